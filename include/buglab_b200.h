@@ -1,0 +1,197 @@
+/*
+ * buglab_b200.h — C ABI of the B200-native gnn-mlp message-passing hot path.
+ *
+ * The reference (microsoft/neurips21-self-supervised-bug-detection-and-repair) is 100 % Python and
+ * has no FFI boundary of its own; the de-facto plugin boundary is the Python operator surface that
+ * buglab/models imports from `ptgnn` and `torch_scatter`.  Every entry point below
+ * names the reference call site whose arithmetic it replaces.  Conventions:
+ *
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless the name ends in _host;
+ *   - row-major contiguous fp32 matrices, int32 indices (the reference's int64 index tensors,
+ *     buglab/models/gnn.py:551-596, are narrowed once per minibatch by the caller);
+ *   - the caller owns and pre-allocates every buffer (outputs and workspace); no allocation inside;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never synchronises;
+ *   - return value 0 on success, negative BL_ERR_* otherwise (bl_error_string() explains);
+ *     no exceptions cross the boundary.
+ */
+#ifndef BUGLAB_B200_H
+#define BUGLAB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BL_OK 0
+#define BL_ERR_INVALID_ARGUMENT (-1)
+#define BL_ERR_CUDA (-2)
+#define BL_ERR_WORKSPACE_TOO_SMALL (-3)
+#define BL_ERR_UNSUPPORTED (-4)
+
+typedef void* bl_stream_t; /* cudaStream_t */
+
+/* Library version (major*10000 + minor*100 + patch). */
+int bl_version(void);
+/* Human-readable text for a BL_ERR_* code; for BL_ERR_CUDA includes the last CUDA error seen. */
+const char* bl_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------------
+ * Typed-edge plan (CSR by target + (node,type) pair tables).
+ *
+ * Replaces the per-layer index handling of ptgnn's MlpMessagePassingLayer.forward
+ * (`torch.cat([adj[1] for adj in adjacency_lists])`, per-type `index_select`; reference call site
+ * buglab/models/gnnlayerdefs.py:6-23 via buglab/models/gnn.py:117) and the edge-typed adjacency
+ * produced by buglab/representations/data.py:139-167.  Built ONCE per minibatch, reused by all 8
+ * message-passing layers, forward and backward.
+ *
+ * Input: the type-major concatenation of the adjacency lists: src/tgt/etype[e], e in [0,E), where
+ * edges of type 0 come first, then type 1, ... (exactly ptgnn's `cat` order, so "original edge
+ * index" == position in this concatenation).
+ *
+ * Output (all int32, caller-allocated):
+ *   e_perm[E]      original edge index of sorted edge i; sorted by (tgt, type, original index)
+ *   e_src[E], e_type[E]   source node / type of sorted edge i
+ *   row_ptr[N+1]   sorted edges of target n are [row_ptr[n], row_ptr[n+1])
+ *   urow[E]        id of the unique (type, src) pair of sorted edge i   (row of the U table)
+ *   vrow[E]        id of the unique (type, tgt) pair of sorted edge i   (row of the V table)
+ *   s_node[E]      node of S-pair p (p < P_s); pairs are ordered by (type, node)
+ *   s_type_ptr[K+1]  S-pairs of type k are [s_type_ptr[k], s_type_ptr[k+1])
+ *   s_by_node_ptr[N+1], s_by_node_idx[E]   CSR node -> S-pair ids (ascending pair id per node)
+ *   t_*            same four tables for the T-pairs (type, tgt)
+ *   counts[2]      {P_s, P_t}
+ * ------------------------------------------------------------------------------------------------ */
+size_t bl_plan_workspace_bytes(int64_t num_edges, int64_t num_nodes, int32_t num_edge_types);
+
+int bl_plan_build(const int32_t* src, const int32_t* tgt, const int32_t* etype,
+                  int64_t num_edges, int64_t num_nodes, int32_t num_edge_types,
+                  int32_t* e_perm, int32_t* e_src, int32_t* e_type, int32_t* row_ptr,
+                  int32_t* urow, int32_t* vrow,
+                  int32_t* s_node, int32_t* s_type_ptr, int32_t* s_by_node_ptr, int32_t* s_by_node_idx,
+                  int32_t* t_node, int32_t* t_type_ptr, int32_t* t_by_node_ptr, int32_t* t_by_node_idx,
+                  int32_t* counts,
+                  void* workspace, size_t workspace_bytes, bl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Row gather / segmented row sum — the `index_select h[src]`, `h[tgt]` of MlpMessagePassingLayer
+ * (P4 in SURVEY.md §8a) restricted to unique (type,node) pairs, and its backward (the scatter-add
+ * of the gathered-row gradients), done as a CSR segmented sum: deterministic, no atomics.
+ * ------------------------------------------------------------------------------------------------ */
+/* out[p,:] = table[idx[p],:]   (p < num_rows; dim % 4 == 0) */
+int bl_rows_gather(const float* table, const int32_t* idx, int64_t num_rows, int32_t dim,
+                   float* out, bl_stream_t stream);
+
+/* out[n,:] (+)= sum_{q in [a_ptr[n],a_ptr[n+1])} a_rows[a_idx[q],:] + sum_{q in b range} b_rows[b_idx[q],:]
+ * b_* may be NULL.  accumulate != 0 adds to the existing contents of out. */
+int bl_rows_segment_sum(const float* a_rows, const int32_t* a_ptr, const int32_t* a_idx,
+                        const float* b_rows, const int32_t* b_ptr, const int32_t* b_idx,
+                        int64_t num_nodes, int32_t dim, int32_t accumulate, float* out, bl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused typed-edge message + aggregate (THE hot kernel).
+ *
+ * Replaces, per layer, ptgnn MlpMessagePassingLayer.forward's
+ *     m = GELU(cat_k Linear_k(cat[h[src_k], h[tgt_k]]));  agg = torch_scatter.scatter_max(m, tgt, dim_size=N)[0]
+ * (reference call sites buglab/models/gnnlayerdefs.py:6-23, aggregation "max" at :11,:20;
+ *  torch_scatter semantics: empty segment -> 0, first maximum wins).
+ *
+ * With Linear_k([h_s;h_t]) = A_k h_s + B_k h_t + b_k hoisted to the unique (type,node) pairs,
+ *     U[urow] = A_k h_src,  V[vrow] = B_k h_tgt + b_k   ([P_s,M] and [P_t,M] tables)
+ * the pre-activation of sorted edge i is x_i = U[urow[i]] + V[vrow[i]].  GELU is quasi-convex
+ * (decreasing left of x0 ~ -0.7518, increasing right of it), so max_i GELU(x_i) is attained at the
+ * minimum or the maximum x_i of the segment; the kernel tracks both extremes per channel and
+ * evaluates erf twice per (node, channel) instead of once per (edge, channel).
+ *
+ * Outputs: agg[N,M] aggregated messages (0 for nodes without in-edges), xwin[N,M] the winning
+ * pre-activation, ewin[N,M] the winning SORTED edge index (-1 for empty) — both kept for backward.
+ * M % 4 == 0 required.
+ * ------------------------------------------------------------------------------------------------ */
+int bl_edge_segmax_fwd(const float* u_rows, const float* v_rows,
+                       const int32_t* row_ptr, const int32_t* urow, const int32_t* vrow,
+                       int64_t num_nodes, int32_t msg_dim,
+                       float* agg, float* xwin, int32_t* ewin, bl_stream_t stream);
+
+/* Backward of the above: g = d_agg * GELU'(xwin) routed to the winning edge only (the arg-routing
+ * backward of torch_scatter.scatter_max).  d_v_rows[P_t,M] is fully written (each (type,tgt) row has
+ * exactly one owner node); d_u_rows[P_s,M] is zero-filled here and accumulated with fp32 REDs. */
+int bl_edge_segmax_bwd(const float* d_agg, const float* xwin, const int32_t* ewin,
+                       const int32_t* row_ptr, const int32_t* urow, const int32_t* vrow,
+                       int64_t num_nodes, int32_t msg_dim, int64_t num_s_pairs, int64_t num_t_pairs,
+                       float* d_u_rows, float* d_v_rows, bl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Node update  LayerNorm(M) -> [Linear(M->D_out) is a library/tensor-core GEMM] -> Tanh -> Dropout
+ * (ptgnn MlpMessagePassingLayer state update).
+ * ------------------------------------------------------------------------------------------------ */
+/* y = (x-mean)*rstd*gamma+beta per row; saves mean[rows], rstd[rows]. dim % 4 == 0, eps as torch. */
+int bl_layernorm_fwd(const float* x, const float* gamma, const float* beta, int64_t rows, int32_t dim,
+                     float eps, float* y, float* mean, float* rstd, bl_stream_t stream);
+/* dx; d_gamma/d_beta accumulated into partial[2, num_partials, dim] then reduced by the same call
+ * into d_gamma[dim], d_beta[dim].  partial must hold 2*BL_LN_PARTIALS*dim floats. */
+#define BL_LN_PARTIALS 256
+int bl_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean,
+                     const float* rstd, int64_t rows, int32_t dim,
+                     float* dx, float* d_gamma, float* d_beta, float* partial, bl_stream_t stream);
+/* y = dropout(tanh(x)) elementwise; keep-mask is regenerated from (seed, element index):
+ * p_drop == 0 disables dropout.  t = tanh(x) is stored for backward. */
+int bl_tanh_dropout_fwd(const float* x, int64_t n, float p_drop, uint64_t seed,
+                        float* y, float* t_out, bl_stream_t stream);
+int bl_tanh_dropout_bwd(const float* dy, const float* t, int64_t n, float p_drop, uint64_t seed,
+                        float* dx, bl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Segment primitives of the heads — replace torch_scatter.scatter_{max,min,sum} and
+ * buglab/models/utils.py:15-48 (scatter_log_softmax and the thin wrappers), used by
+ * buglab/models/layers/localizationmodule.py:59,75,105 and buglab/models/gnn.py:299,305.
+ * src is [L,F] row-major, index[L] in [0,S) in ANY order.
+ * ------------------------------------------------------------------------------------------------ */
+/* out[s,f] = max/min_l src[l,f] over index[l]==s (0 if none); arg[s,f] = first l attaining it (L if none).
+ * is_min != 0 selects minimum. */
+int bl_segment_minmax(const float* src, const int32_t* index, int64_t L, int32_t F, int64_t S,
+                      int32_t is_min, float* out, int32_t* arg, bl_stream_t stream);
+/* d_src[l,f] = (arg[index[l],f]==l) ? d_out[index[l],f] : 0 */
+int bl_segment_minmax_bwd(const float* d_out, const int32_t* arg, const int32_t* index,
+                          int64_t L, int32_t F, float* d_src, bl_stream_t stream);
+/* out[s,f] = sum_l src[l,f] (fp32 REDs; out zero-filled here) */
+int bl_segment_sum(const float* src, const int32_t* index, int64_t L, int32_t F, int64_t S,
+                   float* out, bl_stream_t stream);
+/* scatter_log_softmax over 1-D scores (utils.py:15-28, eps=1e-12 inside the log):
+ * seg_max[S], seg_sum[S] are outputs kept for backward. */
+int bl_segment_log_softmax_fwd(const float* src, const int32_t* index, int64_t L, int64_t S, float eps,
+                               float* out, float* seg_max, float* seg_sum, bl_stream_t stream);
+/* d_src[l] = d_out[l] - exp(out[l]) * sum_{index==index[l]} d_out ; seg_tmp[S] is scratch. */
+int bl_segment_log_softmax_bwd(const float* d_out, const float* out, const int32_t* index,
+                               int64_t L, int64_t S, float* d_src, float* seg_tmp, bl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Subtoken embedding + masked max-pool (ptgnn StrElementRepresentationModel with
+ * token_splitting="subtoken", subtoken_combination="max"; reference wiring
+ * buglab/models/modelregistry.py:57-66,79-82).  ids[N,T] (padded), lens[N] in [1,T].
+ * Dropout (p_drop>0) is applied to the embedded subtokens before the max, mask from (seed, n, t, j).
+ * ------------------------------------------------------------------------------------------------ */
+int bl_subtoken_maxpool_fwd(const float* emb, const int32_t* ids, const int32_t* lens,
+                            int64_t N, int32_t T, int32_t H, float p_drop, uint64_t seed,
+                            float* out, int32_t* arg, bl_stream_t stream);
+/* d_emb[V,H] must be zero-filled (or hold a running gradient) by the caller; accumulated with REDs. */
+int bl_subtoken_maxpool_bwd(const float* d_out, const int32_t* ids, const int32_t* arg,
+                            int64_t N, int32_t T, int32_t H, float p_drop, uint64_t seed,
+                            float* d_emb, bl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimiser step over ONE flat fp32 buffer — Adam(lr, torch defaults) with global-norm clipping,
+ * reference buglab/models/utils.py:51-52 and train.py:104 (clip_gradient_norm=0.5).
+ * The flat gradient buffer is also the NCCL all-reduce bucket.
+ * ------------------------------------------------------------------------------------------------ */
+/* sqnorm[0] = sum g^2  (sqnorm zeroed here; partial[>=1024] scratch) */
+int bl_grad_sqnorm(const float* grad, int64_t n, float* sqnorm, float* partial, bl_stream_t stream);
+/* clip coefficient c = min(1, max_norm / (sqrt(sqnorm[0]) * grad_scale + 1e-6)) (max_norm<=0: no clip);
+ * g' = g*grad_scale*c ; Adam update with bias correction for step `step` (1-based). */
+int bl_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                 float lr, float beta1, float beta2, float eps, int64_t step,
+                 float max_norm, const float* sqnorm, float grad_scale, bl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BUGLAB_B200_H */

@@ -1,0 +1,461 @@
+"""PyTorch-facing operators over the buglab_b200 C ABI (``include/buglab_b200.h``).
+
+PyTorch is plumbing here: it owns device memory, streams and the autograd tape; every arithmetic step of
+the gnn-mlp hot path runs in the hand-written sm_100a kernels of ``csrc/`` (dense per-type projections go
+through ``torch.mm`` = plain cuBLAS fp32 GEMMs, TF32 disabled).
+
+Reference semantics replaced: P4/P5 ``MlpMessagePassingLayer`` message+aggregate,
+A9/A10 scatter ops (``buglab/models/utils.py:15-48``), P2 subtoken max-pool, A12 optimiser.
+"""
+from typing import List, NamedTuple, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, f32, i32, stream_ptr
+
+
+# ---------------------------------------------------------------------------------------------------
+# Typed-edge plan
+# ---------------------------------------------------------------------------------------------------
+class EdgePlan(NamedTuple):
+    """Device tables built once per minibatch by ``bl_plan_build`` (see the header for the layout)."""
+
+    num_nodes: int
+    num_edges: int
+    num_edge_types: int
+    e_perm: torch.Tensor
+    e_src: torch.Tensor
+    e_type: torch.Tensor
+    row_ptr: torch.Tensor
+    urow: torch.Tensor
+    vrow: torch.Tensor
+    s_node: torch.Tensor
+    s_type_ptr: torch.Tensor
+    s_by_node_ptr: torch.Tensor
+    s_by_node_idx: torch.Tensor
+    t_node: torch.Tensor
+    t_type_ptr: torch.Tensor
+    t_by_node_ptr: torch.Tensor
+    t_by_node_idx: torch.Tensor
+    num_s_pairs: int
+    num_t_pairs: int
+    s_type_ptr_host: Tuple[int, ...]
+    t_type_ptr_host: Tuple[int, ...]
+
+
+def build_edge_plan(
+    adjacency_lists: Sequence[Tuple[torch.Tensor, torch.Tensor]], num_nodes: int
+) -> EdgePlan:
+    """Build the plan from ptgnn-style adjacency lists ``[(src_k, tgt_k)]`` (one per edge type, any int dtype).
+
+    The per-type pair counts come back to the host in one small D2H copy (they size the projection GEMMs).
+    """
+    lib = _lib.load()
+    K = len(adjacency_lists)
+    if K == 0:
+        raise ValueError("need at least one edge type")
+    device = adjacency_lists[0][0].device
+    if device.type != "cuda":
+        raise _lib.BuglabB200Error("build_edge_plan needs CUDA tensors; there is no CPU fallback")
+    sizes = [int(a[0].shape[0]) for a in adjacency_lists]
+    E = sum(sizes)
+    src = torch.cat([a[0].reshape(-1) for a in adjacency_lists]).to(torch.int32)
+    tgt = torch.cat([a[1].reshape(-1) for a in adjacency_lists]).to(torch.int32)
+    etype = torch.repeat_interleave(
+        torch.arange(K, device=device, dtype=torch.int32), torch.tensor(sizes, device=device), output_size=E
+    ) if E > 0 else torch.zeros(0, device=device, dtype=torch.int32)
+    return build_edge_plan_from_flat(src, tgt, etype, num_nodes, K)
+
+
+def build_edge_plan_from_flat(
+    src: torch.Tensor, tgt: torch.Tensor, etype: torch.Tensor, num_nodes: int, num_edge_types: int
+) -> EdgePlan:
+    """Same, from the type-major concatenation (int32 CUDA tensors)."""
+    lib = _lib.load()
+    device = src.device
+    E, N, K = int(src.shape[0]), int(num_nodes), int(num_edge_types)
+    opts = dict(device=device, dtype=torch.int32)
+    Ea = max(E, 1)
+    e_perm, e_src, e_type = (torch.empty(Ea, **opts) for _ in range(3))
+    urow, vrow = torch.empty(Ea, **opts), torch.empty(Ea, **opts)
+    row_ptr = torch.empty(N + 1, **opts)
+    s_node, s_by_node_idx = torch.empty(Ea, **opts), torch.empty(Ea, **opts)
+    t_node, t_by_node_idx = torch.empty(Ea, **opts), torch.empty(Ea, **opts)
+    s_by_node_ptr, t_by_node_ptr = torch.empty(N + 1, **opts), torch.empty(N + 1, **opts)
+    # [s_type_ptr (K+1) | t_type_ptr (K+1) | counts (2)] in one buffer -> one D2H copy
+    meta = torch.empty(2 * (K + 1) + 2, **opts)
+    s_type_ptr, t_type_ptr, counts = meta[: K + 1], meta[K + 1 : 2 * (K + 1)], meta[2 * (K + 1) :]
+    ws_bytes = lib.bl_plan_workspace_bytes(E, N, K)
+    workspace = torch.empty(ws_bytes, device=device, dtype=torch.uint8)
+    check(
+        lib.bl_plan_build(
+            i32(src.contiguous()), i32(tgt.contiguous()), i32(etype.contiguous()), E, N, K,
+            i32(e_perm), i32(e_src), i32(e_type), i32(row_ptr), i32(urow), i32(vrow),
+            i32(s_node), s_type_ptr.data_ptr(), i32(s_by_node_ptr), i32(s_by_node_idx),
+            i32(t_node), t_type_ptr.data_ptr(), i32(t_by_node_ptr), i32(t_by_node_idx),
+            counts.data_ptr(), workspace.data_ptr(), ws_bytes, stream_ptr(device),
+        ),
+        "bl_plan_build",
+    )
+    meta_host = meta.cpu().tolist()  # the one host sync of the plan
+    s_tp, t_tp = tuple(meta_host[: K + 1]), tuple(meta_host[K + 1 : 2 * (K + 1)])
+    P_s, P_t = meta_host[-2], meta_host[-1]
+    return EdgePlan(
+        N, E, K, e_perm[:E], e_src[:E], e_type[:E], row_ptr, urow[:E], vrow[:E],
+        s_node[:P_s], s_type_ptr, s_by_node_ptr, s_by_node_idx[:P_s],
+        t_node[:P_t], t_type_ptr, t_by_node_ptr, t_by_node_idx[:P_t],
+        P_s, P_t, s_tp, t_tp,
+    )
+
+
+# ---------------------------------------------------------------------------------------------------
+# Fused typed-edge message + max aggregate (P4 + P5)
+# ---------------------------------------------------------------------------------------------------
+def _rows_gather(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    out = torch.empty((idx.shape[0], table.shape[1]), device=table.device, dtype=torch.float32)
+    check(
+        _lib.load().bl_rows_gather(f32(table), i32(idx), idx.shape[0], table.shape[1], f32(out), stream_ptr(table.device)),
+        "bl_rows_gather",
+    )
+    return out
+
+
+def _project_pairs(rows: torch.Tensor, weight: torch.Tensor, col0: int, type_ptr: Tuple[int, ...],
+                   bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """out[p] = W_k[:, col0:col0+D] @ rows[p] (+ b_k) for the pairs p of type k — per-type fp32 GEMMs."""
+    K, M, _ = weight.shape
+    D = rows.shape[1]
+    out = torch.empty((rows.shape[0], M), device=rows.device, dtype=torch.float32)
+    for k in range(K):
+        lo, hi = type_ptr[k], type_ptr[k + 1]
+        if hi == lo:
+            continue
+        w = weight[k, :, col0 : col0 + D]
+        if bias is not None:
+            torch.addmm(bias[k], rows[lo:hi], w.t(), out=out[lo:hi])
+        else:
+            torch.mm(rows[lo:hi], w.t(), out=out[lo:hi])
+    return out
+
+
+class TypedEdgeMessageMax(torch.autograd.Function):
+    """agg[n] = max over in-edges (s->n, type k) of GELU(W_k [h_s; h_n] + b_k); 0 for isolated nodes.
+
+    ``weight`` is the stack ``[K, M, 2*D]`` of the per-type ``Linear(2D -> M)`` weights, ``bias`` ``[K, M]``
+    or None.  Forward keeps only ``h``, ``weight``, the winning pre-activation and winning edge per
+    (node, channel); the U/V tables are transient.
+    """
+
+    @staticmethod
+    def forward(ctx, h: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], plan: EdgePlan):
+        lib = _lib.load()
+        h = h.contiguous()
+        weight = weight.contiguous()
+        N, D = h.shape
+        K, M, twoD = weight.shape
+        if twoD != 2 * D or K != plan.num_edge_types or N != plan.num_nodes:
+            raise ValueError(f"shape mismatch: h {tuple(h.shape)}, weight {tuple(weight.shape)}, plan K={plan.num_edge_types} N={plan.num_nodes}")
+        with torch.no_grad():
+            hs = _rows_gather(h, plan.s_node)
+            u_rows = _project_pairs(hs, weight, 0, plan.s_type_ptr_host, None)
+            del hs
+            ht = _rows_gather(h, plan.t_node)
+            v_rows = _project_pairs(ht, weight, D, plan.t_type_ptr_host, bias)
+            del ht
+            agg = torch.empty((N, M), device=h.device, dtype=torch.float32)
+            xwin = torch.empty_like(agg)
+            ewin = torch.empty((N, M), device=h.device, dtype=torch.int32)
+            check(
+                lib.bl_edge_segmax_fwd(f32(u_rows), f32(v_rows), i32(plan.row_ptr), i32(plan.urow), i32(plan.vrow),
+                                       N, M, f32(agg), f32(xwin), i32(ewin), stream_ptr(h.device)),
+                "bl_edge_segmax_fwd",
+            )
+        ctx.plan = plan
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(h, weight, xwin, ewin)
+        return agg
+
+    @staticmethod
+    def backward(ctx, d_agg: torch.Tensor):
+        lib = _lib.load()
+        plan: EdgePlan = ctx.plan
+        h, weight, xwin, ewin = ctx.saved_tensors
+        N, D = h.shape
+        K, M, _ = weight.shape
+        d_agg = d_agg.contiguous()
+        dev = h.device
+        du = torch.empty((plan.num_s_pairs, M), device=dev, dtype=torch.float32)
+        dv = torch.empty((plan.num_t_pairs, M), device=dev, dtype=torch.float32)
+        check(
+            lib.bl_edge_segmax_bwd(f32(d_agg), f32(xwin), i32(ewin), i32(plan.row_ptr), i32(plan.urow), i32(plan.vrow),
+                                   N, M, plan.num_s_pairs, plan.num_t_pairs, f32(du), f32(dv), stream_ptr(dev)),
+            "bl_edge_segmax_bwd",
+        )
+        d_weight = torch.zeros_like(weight)
+        d_bias = torch.zeros((K, M), device=dev, dtype=torch.float32) if ctx.has_bias else None
+        d_rows = []
+        for rows_idx, d_tab, col0, type_ptr, is_t in (
+            (plan.s_node, du, 0, plan.s_type_ptr_host, False),
+            (plan.t_node, dv, D, plan.t_type_ptr_host, True),
+        ):
+            rows = _rows_gather(h, rows_idx)  # recomputed instead of kept alive since forward
+            d_in = torch.empty_like(rows)
+            for k in range(K):
+                lo, hi = type_ptr[k], type_ptr[k + 1]
+                if hi == lo:
+                    continue
+                w = weight[k, :, col0 : col0 + D]
+                torch.mm(d_tab[lo:hi], w, out=d_in[lo:hi])
+                d_weight[k, :, col0 : col0 + D].copy_(torch.mm(d_tab[lo:hi].t(), rows[lo:hi]))
+                if is_t and d_bias is not None:
+                    torch.sum(d_tab[lo:hi], dim=0, out=d_bias[k])
+            d_rows.append(d_in)
+            del rows
+        d_h = torch.empty_like(h)
+        check(
+            lib.bl_rows_segment_sum(f32(d_rows[0]), i32(plan.s_by_node_ptr), i32(plan.s_by_node_idx),
+                                    f32(d_rows[1]), i32(plan.t_by_node_ptr), i32(plan.t_by_node_idx),
+                                    N, D, 0, f32(d_h), stream_ptr(dev)),
+            "bl_rows_segment_sum",
+        )
+        return d_h, d_weight, d_bias, None
+
+
+def typed_edge_message_max(h, weight, bias, plan: EdgePlan) -> torch.Tensor:
+    return TypedEdgeMessageMax.apply(h, weight, bias, plan)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Node update pieces
+# ---------------------------------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps: float):
+        x = x.contiguous()
+        rows, dim = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+        rstd = torch.empty_like(mean)
+        check(_lib.load().bl_layernorm_fwd(f32(x), f32(gamma.contiguous()), f32(beta.contiguous()), rows, dim, eps,
+                                            f32(y), f32(mean), f32(rstd), stream_ptr(x.device)), "bl_layernorm_fwd")
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        rows, dim = x.shape
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        d_gamma = torch.empty_like(gamma)
+        d_beta = torch.empty_like(gamma)
+        partial = torch.empty(2 * 256 * dim, device=x.device, dtype=torch.float32)
+        check(_lib.load().bl_layernorm_bwd(f32(dy), f32(x), f32(gamma.contiguous()), f32(mean), f32(rstd), rows, dim,
+                                            f32(dx), f32(d_gamma), f32(d_beta), f32(partial), stream_ptr(x.device)),
+              "bl_layernorm_bwd")
+        return dx, d_gamma, d_beta, None
+
+
+def layer_norm(x, gamma, beta, eps: float = 1e-5):
+    return LayerNormFn.apply(x, gamma, beta, eps)
+
+
+class TanhDropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p_drop: float, seed: int):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        t = torch.empty_like(x)
+        check(_lib.load().bl_tanh_dropout_fwd(f32(x), x.numel(), p_drop, seed, f32(y), f32(t), stream_ptr(x.device)),
+              "bl_tanh_dropout_fwd")
+        ctx.save_for_backward(t)
+        ctx.p_drop, ctx.seed = p_drop, seed
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (t,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(t)
+        check(_lib.load().bl_tanh_dropout_bwd(f32(dy), f32(t), t.numel(), ctx.p_drop, ctx.seed, f32(dx),
+                                               stream_ptr(t.device)), "bl_tanh_dropout_bwd")
+        return dx, None, None
+
+
+_seed_gen = torch.Generator()
+
+
+def fresh_seed() -> int:
+    """A new 63-bit dropout seed drawn from torch's CPU generator state (so torch.manual_seed controls it)."""
+    return int(torch.randint(0, 2**62, (1,)).item())
+
+
+def tanh_dropout(x, p_drop: float, training: bool):
+    p = float(p_drop) if training else 0.0
+    return TanhDropoutFn.apply(x, p, fresh_seed() if p > 0 else 0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Segment primitives (torch_scatter surface)
+# ---------------------------------------------------------------------------------------------------
+def _as_LF(src: torch.Tensor, dim: int):
+    if src.dim() == 1:
+        return src.contiguous().view(-1, 1), True
+    if src.dim() == 2 and dim in (0, -2):
+        return src.contiguous(), False
+    raise NotImplementedError("buglab_b200 segment ops support 1-D src or 2-D src reduced along dim 0")
+
+
+class SegmentMinMaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src2d, index, num_segments: int, is_min: bool):
+        L, F = src2d.shape
+        out = torch.empty((num_segments, F), device=src2d.device, dtype=torch.float32)
+        arg = torch.empty((num_segments, F), device=src2d.device, dtype=torch.int32)
+        check(_lib.load().bl_segment_minmax(f32(src2d), i32(index), L, F, num_segments, 1 if is_min else 0,
+                                             f32(out), i32(arg), stream_ptr(src2d.device)), "bl_segment_minmax")
+        ctx.save_for_backward(arg, index)
+        ctx.shape = (L, F)
+        ctx.mark_non_differentiable(arg)
+        return out, arg
+
+    @staticmethod
+    def backward(ctx, d_out, _d_arg):
+        arg, index = ctx.saved_tensors
+        L, F = ctx.shape
+        d_src = torch.empty((L, F), device=d_out.device, dtype=torch.float32)
+        check(_lib.load().bl_segment_minmax_bwd(f32(d_out.contiguous()), i32(arg), i32(index), L, F, f32(d_src),
+                                                 stream_ptr(d_out.device)), "bl_segment_minmax_bwd")
+        return d_src, None, None, None
+
+
+def _index32(index: torch.Tensor) -> torch.Tensor:
+    return index.contiguous() if index.dtype == torch.int32 else index.to(torch.int32)
+
+
+def _num_segments(index: torch.Tensor, dim_size: Optional[int]) -> int:
+    if dim_size is not None:
+        return int(dim_size)
+    return int(index.max().item()) + 1 if index.numel() > 0 else 0
+
+
+def segment_minmax(src, index, dim=-1, dim_size=None, is_min=False):
+    src2d, was_1d = _as_LF(src.float(), dim)
+    S = _num_segments(index, dim_size)
+    out, arg = SegmentMinMaxFn.apply(src2d, _index32(index), S, is_min)
+    arg = arg.to(torch.int64)
+    if was_1d:
+        return out.view(-1), arg.view(-1)
+    return out, arg
+
+
+class SegmentSumFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src2d, index, num_segments: int):
+        L, F = src2d.shape
+        out = torch.empty((num_segments, F), device=src2d.device, dtype=torch.float32)
+        check(_lib.load().bl_segment_sum(f32(src2d), i32(index), L, F, num_segments, f32(out),
+                                          stream_ptr(src2d.device)), "bl_segment_sum")
+        ctx.save_for_backward(index)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (index,) = ctx.saved_tensors
+        return _rows_gather_any(d_out.contiguous(), index), None, None
+
+
+def _rows_gather_any(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    if table.shape[1] % 4 == 0:
+        return _rows_gather(table, idx)
+    return table[idx.long()]  # tiny head tensors with F not a multiple of 4 (e.g. F == 1)
+
+
+def segment_sum(src, index, dim=-1, dim_size=None):
+    src2d, was_1d = _as_LF(src.float(), dim)
+    S = _num_segments(index, dim_size)
+    out = SegmentSumFn.apply(src2d, _index32(index), S)
+    return out.view(-1) if was_1d else out
+
+
+class SegmentLogSoftmaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, index, num_segments: int, eps: float):
+        src = src.contiguous()
+        L = src.shape[0]
+        out = torch.empty_like(src)
+        seg_max = torch.empty(num_segments, device=src.device, dtype=torch.float32)
+        seg_sum = torch.empty_like(seg_max)
+        check(_lib.load().bl_segment_log_softmax_fwd(f32(src), i32(index), L, num_segments, eps, f32(out), f32(seg_max),
+                                                      f32(seg_sum), stream_ptr(src.device)), "bl_segment_log_softmax_fwd")
+        ctx.save_for_backward(out, index)
+        ctx.num_segments = num_segments
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        out, index = ctx.saved_tensors
+        L = out.shape[0]
+        d_src = torch.empty_like(out)
+        tmp = torch.empty(ctx.num_segments, device=out.device, dtype=torch.float32)
+        check(_lib.load().bl_segment_log_softmax_bwd(f32(d_out.contiguous()), f32(out), i32(index), L, ctx.num_segments,
+                                                      f32(d_src), f32(tmp), stream_ptr(out.device)), "bl_segment_log_softmax_bwd")
+        return d_src, None, None, None
+
+
+def segment_log_softmax(src: torch.Tensor, index: torch.Tensor, eps: float = 1e-12, num_segments: Optional[int] = None):
+    """``scatter_log_softmax`` of buglab/models/utils.py:15-28 for 1-D scores."""
+    if src.dim() != 1:
+        raise NotImplementedError("segment_log_softmax supports 1-D scores")
+    if src.numel() == 0:
+        return src.float()
+    S = _num_segments(index, num_segments)
+    return SegmentLogSoftmaxFn.apply(src.float(), _index32(index), S, eps)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Subtoken embedding max-pool (P2)
+# ---------------------------------------------------------------------------------------------------
+class SubtokenMaxPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, emb, ids, lens, p_drop: float, seed: int):
+        emb = emb.contiguous()
+        N, T = ids.shape
+        H = emb.shape[1]
+        out = torch.empty((N, H), device=emb.device, dtype=torch.float32)
+        arg = torch.empty((N, H), device=emb.device, dtype=torch.int32)
+        check(_lib.load().bl_subtoken_maxpool_fwd(f32(emb), i32(ids), i32(lens), N, T, H, p_drop, seed, f32(out), i32(arg),
+                                                   stream_ptr(emb.device)), "bl_subtoken_maxpool_fwd")
+        ctx.save_for_backward(ids, arg)
+        ctx.meta = (tuple(emb.shape), p_drop, seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        ids, arg = ctx.saved_tensors
+        shape, p_drop, seed = ctx.meta
+        N, T = ids.shape
+        d_emb = torch.zeros(shape, device=d_out.device, dtype=torch.float32)
+        check(_lib.load().bl_subtoken_maxpool_bwd(f32(d_out.contiguous()), i32(ids), i32(arg), N, T, shape[1], p_drop, seed,
+                                                   f32(d_emb), stream_ptr(d_out.device)), "bl_subtoken_maxpool_bwd")
+        return d_emb, None, None, None, None
+
+
+def subtoken_maxpool(emb, ids, lens, p_drop: float = 0.0, training: bool = False):
+    p = float(p_drop) if training else 0.0
+    return SubtokenMaxPoolFn.apply(emb, _index32(ids), _index32(lens), p, fresh_seed() if p > 0 else 0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Flat-buffer optimiser (A12)
+# ---------------------------------------------------------------------------------------------------
+def grad_sqnorm(flat_grad: torch.Tensor, out: torch.Tensor, partial: torch.Tensor) -> None:
+    check(_lib.load().bl_grad_sqnorm(f32(flat_grad), flat_grad.numel(), f32(out), f32(partial),
+                                      stream_ptr(flat_grad.device)), "bl_grad_sqnorm")
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, max_norm, sqnorm, grad_scale=1.0) -> None:
+    check(_lib.load().bl_adam_step(f32(param), f32(grad), f32(exp_avg), f32(exp_avg_sq), param.numel(), lr, beta1, beta2,
+                                    eps, step, max_norm, f32(sqnorm) if sqnorm is not None else None, grad_scale,
+                                    stream_ptr(param.device)), "bl_adam_step")
