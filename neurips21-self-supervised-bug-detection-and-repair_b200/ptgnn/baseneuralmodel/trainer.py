@@ -1,0 +1,333 @@
+"""``ModelTrainer`` — the train/validate loop with the constructor, hooks and method names the reference uses
+(buglab/models/train.py:98-134, buglab/controllers/trainbugdetector.py:73-153).
+
+Per step (reference order): zero_grad -> loss = nn(**minibatch) -> backward ->
+[all-reduce of the flat gradient bucket when torch.distributed is initialised] -> global-norm clip ->
+optimizer.step -> scheduler.step(epoch_idx, epoch_step).
+
+B200-first details: the next minibatch is packed (host, pinned) and copied H2D by a producer thread on a side
+CUDA stream while the current one computes; with a ``FlatAdam`` optimiser the clip + Adam are two fused
+kernels over one flat buffer, which is also the single NCCL bucket; step time is taken with CUDA events.
+"""
+import logging
+import math
+import queue
+import threading
+import time
+from abc import ABC, abstractmethod
+from pathlib import Path
+from typing import Any, Callable, Dict, Iterable, Iterator, List, Optional, Tuple
+
+import torch
+
+from .abstractneuralmodel import AbstractNeuralModel
+from .modulewithmetrics import ModuleWithMetrics
+
+LOGGER = logging.getLogger(__name__)
+
+EndOfEpochHook = Callable[[AbstractNeuralModel, ModuleWithMetrics, int, Dict], None]
+
+
+class AbstractScheduler(ABC):
+    @abstractmethod
+    def step(self, epoch_idx: int, epoch_step: int) -> None:
+        ...
+
+
+def _distributed():
+    from buglab_b200 import distributed
+
+    return distributed
+
+
+class _Prefetcher:
+    """Runs a minibatch iterator in a producer thread, on its own CUDA stream, ``depth`` batches ahead."""
+
+    _END = object()
+
+    def __init__(self, make_iterator: Callable[[], Iterator], device: torch.device, depth: int = 2):
+        self._queue: "queue.Queue" = queue.Queue(maxsize=depth)
+        self._device = device
+        self._error: Optional[BaseException] = None
+        self._stream = torch.cuda.Stream(device) if device.type == "cuda" else None
+        self._thread = threading.Thread(target=self._run, args=(make_iterator,), daemon=True)
+        self._thread.start()
+
+    def _run(self, make_iterator) -> None:
+        try:
+            if self._stream is not None:
+                with torch.cuda.stream(self._stream):
+                    for item in make_iterator():
+                        event = torch.cuda.Event()
+                        event.record(self._stream)
+                        self._queue.put((item, event))
+            else:
+                for item in make_iterator():
+                    self._queue.put((item, None))
+        except BaseException as e:  # surfaced in the consumer
+            self._error = e
+        finally:
+            self._queue.put(self._END)
+
+    def __iter__(self):
+        while True:
+            got = self._queue.get()
+            if got is self._END:
+                if self._error is not None:
+                    raise self._error
+                return
+            item, event = got
+            if event is not None:
+                torch.cuda.current_stream(self._device).wait_event(event)
+            yield item
+
+
+class ModelTrainer:
+    def __init__(
+        self,
+        model: AbstractNeuralModel,
+        save_location: Path,
+        *,
+        max_num_epochs: int = 100,
+        minibatch_size: int = 200,
+        optimizer_creator: Optional[Callable[[Iterable[torch.Tensor]], torch.optim.Optimizer]] = None,
+        scheduler_creator: Optional[Callable[[torch.optim.Optimizer], AbstractScheduler]] = None,
+        clip_gradient_norm: Optional[float] = None,
+        target_validation_metric: Optional[str] = None,
+        target_validation_metric_higher_is_better: bool = False,
+        enable_amp: bool = False,
+        catch_cuda_ooms: bool = False,
+    ):
+        self.__model = model
+        self.__neural_network: Optional[ModuleWithMetrics] = None
+        assert str(save_location).endswith(".pkl.gz"), "All models are stored as .pkl.gz."
+        self.__save_location = Path(save_location)
+        self._max_num_epochs = max_num_epochs
+        self._minibatch_size = minibatch_size
+        self._optimizer_creator = optimizer_creator or (lambda p: torch.optim.Adam(p, lr=1e-4))
+        self._scheduler_creator = scheduler_creator
+        self._clip_gradient_norm = clip_gradient_norm
+        self._target_metric = target_validation_metric
+        self._target_metric_higher_is_better = target_validation_metric_higher_is_better
+        if enable_amp:
+            LOGGER.warning("--amp accepted but ignored: the B200 path computes in fp32 (1e-4 parity target).")
+        self._train_epoch_end_hooks: List[EndOfEpochHook] = []
+        self._validation_epoch_end_hooks: List[EndOfEpochHook] = []
+        self._training_start_hooks: List[Callable] = []
+        self._train_metrics_reporters: List[Callable] = []
+        self.last_epoch_stats: Dict[str, float] = {}
+
+    # ---- accessors ------------------------------------------------------------------------------
+    @property
+    def model(self) -> AbstractNeuralModel:
+        return self.__model
+
+    @property
+    def neural_module(self) -> ModuleWithMetrics:
+        if self.__neural_network is None:
+            raise Exception("Neural network has not been built yet (call load_metadata_and_create_network).")
+        return self.__neural_network
+
+    @neural_module.setter
+    def neural_module(self, nn: ModuleWithMetrics) -> None:
+        self.__neural_network = nn
+
+    # ---- hooks ----------------------------------------------------------------------------------
+    def register_train_epoch_end_hook(self, hook: EndOfEpochHook) -> None:
+        self._train_epoch_end_hooks.append(hook)
+
+    def register_validation_epoch_end_hook(self, hook: EndOfEpochHook) -> None:
+        self._validation_epoch_end_hooks.append(hook)
+
+    def register_training_start_hook(self, hook: Callable[[AbstractNeuralModel, ModuleWithMetrics, torch.optim.Optimizer], None]) -> None:
+        self._training_start_hooks.append(hook)
+
+    # ---- set-up ---------------------------------------------------------------------------------
+    def load_metadata_and_create_network(self, training_data: Iterable, parallelize: bool = True,
+                                         show_progress_bar: bool = True) -> None:
+        LOGGER.info("Computing model metadata...")
+        self.__model.compute_metadata(iter(training_data), parallelize)
+        self.__neural_network = self.__model.build_neural_module()
+        LOGGER.info("Model has %s trainable parameters.",
+                    sum(p.numel() for p in self.__neural_network.parameters() if p.requires_grad))
+
+    def _create_optimizer(self, parameters) -> torch.optim.Optimizer:
+        optimizer = self._optimizer_creator(parameters)
+        if getattr(optimizer, "fused_clip", False) and getattr(optimizer, "max_grad_norm", None) is None:
+            optimizer.max_grad_norm = self._clip_gradient_norm
+        return optimizer
+
+    def _minibatches(self, tensors: Iterable, device, parallelize: bool) -> Iterator:
+        def make():
+            return self.__model.minibatch_iterator(iter(tensors), device=device,
+                                                   max_minibatch_size=self._minibatch_size, parallelize=parallelize)
+
+        if parallelize and torch.device(device).type == "cuda":
+            return iter(_Prefetcher(make, torch.device(device)))
+        return make()
+
+    # ---- one training epoch ---------------------------------------------------------------------
+    def _run_training(self, training_tensors: Iterable, epoch: int, device, optimizer: torch.optim.Optimizer,
+                      scheduler: Optional[AbstractScheduler], parallelize: bool, show_progress_bar: bool) -> float:
+        dist = _distributed()
+        nn = self.neural_module
+        nn.train()
+        nn.reset_metrics()
+        use_cuda = torch.device(device).type == "cuda"
+        fused = getattr(optimizer, "fused_clip", False)
+        params = [p for p in nn.parameters() if p.requires_grad]
+        loss_sum = torch.zeros((), device=device, dtype=torch.float64)
+        num_steps, num_samples = 0, 0
+        start_evt = end_evt = None
+        if use_cuda:
+            start_evt, end_evt = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            start_evt.record()
+        t0 = time.perf_counter()
+        for step_idx, (mb_data, raw_points) in enumerate(self._minibatches(training_tensors, device, parallelize)):
+            optimizer.zero_grad()
+            loss = nn(**mb_data)
+            loss.backward()
+            if fused:
+                scale = dist.allreduce_flat_gradient(optimizer.flat_grad)
+                optimizer.step(grad_scale=scale)
+            else:
+                if dist.is_distributed():
+                    _allreduce_dense_gradients(params, dist.world_size())
+                if self._clip_gradient_norm is not None:
+                    torch.nn.utils.clip_grad_norm_(params, self._clip_gradient_norm)
+                optimizer.step()
+            if scheduler is not None:
+                scheduler.step(epoch_idx=epoch, epoch_step=step_idx)
+            loss_sum += loss.detach().double()
+            num_steps += 1
+            num_samples += len(raw_points)
+        if num_steps == 0:
+            raise RuntimeError("No training minibatches were produced.")
+        if use_cuda:
+            end_evt.record()
+            end_evt.synchronize()
+            elapsed = start_evt.elapsed_time(end_evt) / 1e3
+        else:
+            elapsed = time.perf_counter() - t0
+        self.last_epoch_stats = dict(train_seconds=elapsed, train_steps=num_steps, train_samples=num_samples,
+                                     samples_per_second=num_samples / max(elapsed, 1e-9))
+        mean_loss = float(loss_sum) / num_steps
+        metrics = dict(nn.report_metrics())
+        LOGGER.info("Epoch %i: Train Loss %.4f | %.1f samples/s | %s", epoch + 1, mean_loss,
+                    self.last_epoch_stats["samples_per_second"], metrics)
+        for hook in self._train_epoch_end_hooks:
+            hook(self.__model, nn, epoch, metrics)
+        return mean_loss
+
+    # ---- validation (private name kept: controllers monkey-patch it, trainbugdetector.py:128-143) ---
+    def _run_validation(self, validation_tensors: Iterable, epoch: int, best_target_metric: float, device,
+                        parallelize: bool, show_progress_bar: bool) -> Tuple[float, bool]:
+        dist = _distributed()
+        nn = self.neural_module
+        nn.eval()
+        nn.reset_metrics()
+        loss_sum = torch.zeros((), device=device, dtype=torch.float64)
+        num_steps = 0
+        with torch.no_grad():
+            for mb_data, _raw in self._minibatches(validation_tensors, device, parallelize):
+                loss_sum += nn(**mb_data).double()
+                num_steps += 1
+        total, steps = float(loss_sum), float(num_steps)
+        if dist.is_distributed():
+            total, steps = dist.all_ranks_sum(total, device), dist.all_ranks_sum(steps, device)
+        if steps == 0:
+            raise RuntimeError("No validation minibatches were produced.")
+        validation_loss = total / steps
+        metrics = dict(nn.report_metrics())
+        if self._target_metric is not None:
+            target_metric = metrics[self._target_metric]
+            improved = target_metric > best_target_metric if self._target_metric_higher_is_better \
+                else target_metric < best_target_metric
+        else:
+            target_metric = validation_loss
+            improved = target_metric < best_target_metric
+        LOGGER.info("Epoch %i: Valid Loss %.4f %s", epoch + 1, validation_loss, metrics)
+        for hook in self._validation_epoch_end_hooks:
+            hook(self.__model, nn, epoch, metrics)
+        if improved:
+            LOGGER.info("Best validation metric so far: %.4f (was %.4f).", target_metric, best_target_metric)
+        return target_metric, improved
+
+    def _save_checkpoint(self) -> None:
+        if _distributed().rank() == 0:
+            self.__model.save(self.__save_location, self.neural_module)
+
+    # ---- the loop -------------------------------------------------------------------------------
+    def train(self, training_data: Iterable, validation_data: Iterable, show_progress_bar: bool = True,
+              validate_on_start: bool = True, initialize_metadata: bool = True, parallelize: bool = True,
+              use_multiprocessing: bool = True, patience: int = 5, store_tensorized_data_in_memory: bool = False,
+              shuffle_training_data: bool = True, device: Optional[str] = None) -> None:
+        dist = _distributed()
+        if initialize_metadata:
+            self.load_metadata_and_create_network(training_data, parallelize, show_progress_bar)
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        device = torch.device(device)
+        nn = self.neural_module
+        nn.to(device)
+        dist.broadcast_module(nn)
+        model = self.__model
+
+        def training_tensors():
+            return model.tensorize_dataset(iter(training_data), return_input_data=False, parallelize=parallelize)
+
+        def validation_tensors():
+            return model.tensorize_dataset(iter(validation_data), return_input_data=False, parallelize=parallelize)
+
+        class _Re:
+            def __init__(self, f):
+                self.f = f
+
+            def __iter__(self):
+                return self.f()
+
+        train_it, valid_it = _Re(training_tensors), _Re(validation_tensors)
+        if store_tensorized_data_in_memory:
+            train_list, valid_list = list(train_it), list(valid_it)
+            train_it, valid_it = train_list, valid_list
+
+        optimizer = self._create_optimizer([p for p in nn.parameters() if p.requires_grad])
+        scheduler = None if self._scheduler_creator is None else self._scheduler_creator(optimizer)
+        for hook in self._training_start_hooks:
+            hook(model, nn, optimizer)
+
+        best_metric = -math.inf if (self._target_metric is not None and self._target_metric_higher_is_better) else math.inf
+        if validate_on_start:
+            best_metric, _ = self._run_validation(valid_it, 0, best_metric, device, parallelize, show_progress_bar)
+            self._save_checkpoint()
+        num_epochs_not_improved = 0
+        for epoch in range(self._max_num_epochs):
+            self._run_training(train_it, epoch, device, optimizer, scheduler, parallelize, show_progress_bar)
+            target_metric, improved = self._run_validation(valid_it, epoch, best_metric, device, parallelize,
+                                                           show_progress_bar)
+            if improved:
+                best_metric = target_metric
+                num_epochs_not_improved = 0
+                self._save_checkpoint()
+            else:
+                num_epochs_not_improved += 1
+                if num_epochs_not_improved > patience:
+                    LOGGER.warning("After %s epochs loss has not improved. Stopping.", num_epochs_not_improved)
+                    break
+
+
+def _allreduce_dense_gradients(params: List[torch.nn.Parameter], world: int) -> None:
+    """Bucketed all-reduce for optimisers that do not own a flat buffer (compat path, CPU/gloo tests)."""
+    import torch.distributed as tdist
+
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    tdist.all_reduce(flat, op=tdist.ReduceOp.SUM)
+    flat.div_(world)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off: off + n].view_as(g))
+        off += n

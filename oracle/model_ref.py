@@ -1,0 +1,228 @@
+"""CPU oracle of the whole gnn-mlp detector step — plain PyTorch, per-edge formulation, autograd backward.
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+Restates, with the reference's class / attribute names so that ``state_dict`` keys coincide with the product's:
+  * ptgnn ``GraphNeuralNetwork.forward`` (parity unpinned) over the gnn-mlp layer list of
+    buglab/models/gnnlayerdefs.py:26-39;
+  * ``LocalizationModule`` — buglab/models/layers/localizationmodule.py:54-124;
+  * the three repair heads — buglab/models/layers/fixermodules.py:31-39,65-73,110-124 and layers/mlp.py:6-20
+    (with ``_input_dim`` defined: the reference's F9 bug would raise on every ArgSwap candidate);
+  * ``GnnBugLabModule.forward`` / ``_compute_repair_logprobs`` — buglab/models/gnn.py:144-322 (discriminator branch);
+  * optimiser step — Adam(1e-4) + clip_grad_norm_(0.5) + linear warm-up (utils.py:51-66, train.py:104).
+The in-repo pieces are pinned against the real reference code by tests/golden (make_golden.py).
+"""
+import math
+from typing import Any, Dict, List, Optional
+
+import torch
+from torch import nn
+
+from .mp_ref import MlpMessagePassingLayer, SubtokenUnitEmbedder
+from .scatter_ref import scatter_log_softmax, scatter_max
+
+
+class _NoParams(nn.Module):
+    """Placeholder for the parameter-free dummy / concat-residual entries (keeps ModuleList indices aligned)."""
+
+    def __init__(self, kind: str):
+        super().__init__()
+        self.kind = kind
+
+
+class GraphNeuralNetwork(nn.Module):
+    def __init__(self, hidden: int, num_edge_types: int, vocabulary_size: int, dropout_rate: float = 0.0,
+                 embedding_dropout_rate: float = 0.0, use_message_bias: bool = True):
+        super().__init__()
+
+        def mp(f):
+            return MlpMessagePassingLayer(f * hidden, f * hidden, hidden, num_edge_types, "max", dropout_rate,
+                                          use_message_bias=use_message_bias)
+
+        block = lambda: [_NoParams("remember"), mp(1), mp(1), mp(1), _NoParams("concat"), mp(2)]  # noqa: E731
+        self.__message_passing_layers = nn.ModuleList(block() + block())  # gnnlayerdefs.py:26-39
+        self.__node_embedder = SubtokenUnitEmbedder(vocabulary_size, hidden, embedding_dropout_rate)
+
+    @property
+    def layers(self):
+        return self.__message_passing_layers
+
+    def forward(self, node_data, adjacency_lists, return_all_states: bool = False):
+        state = self.__node_embedder(**node_data)
+        states, remembered = [state], None
+        for layer in self.__message_passing_layers:
+            if isinstance(layer, _NoParams):
+                if layer.kind == "remember":
+                    remembered = state
+                else:
+                    state = torch.cat((remembered, state), dim=-1)
+            else:
+                state = layer(state, adjacency_lists)
+            states.append(state)
+        return torch.cat(states, dim=-1) if return_all_states else state
+
+
+class MLP(nn.Module):
+    def __init__(self, input_dim: int, out_dim: int, hidden_layer_dims: List[int]):
+        super().__init__()
+        layers, d = [], input_dim
+        for h in hidden_layer_dims:
+            layers += [nn.Linear(d, h), nn.ReLU()]
+            d = h
+        layers.append(nn.Linear(d, out_dim))
+        self._layers = nn.Sequential(*layers)
+
+    def forward(self, x):
+        return self._layers(x)
+
+
+class LocalizationModule(nn.Module):
+    def __init__(self, dim: int):
+        super().__init__()
+        self._summary_repr = nn.Linear(dim, dim)
+        self._l1 = nn.Linear(2 * dim, dim)
+        self._repr_to_localization_score = nn.Linear(dim, 1, bias=False)
+
+    def compute_localization_logprobs(self, candidate_reprs, candidate_to_sample_idx, num_samples):  # :54-79
+        summary = scatter_max(self._summary_repr(candidate_reprs), candidate_to_sample_idx, dim=0)[0][candidate_to_sample_idx]
+        l1 = torch.sigmoid(self._l1(torch.cat([candidate_reprs, summary], dim=-1)))
+        scores = self._repr_to_localization_score(l1).squeeze(-1)
+        arange = torch.arange(num_samples, dtype=torch.int64)
+        scores = torch.cat((scores, torch.ones(num_samples, dtype=scores.dtype)))
+        groups = torch.cat((candidate_to_sample_idx, arange))
+        return groups, scatter_log_softmax(scores, groups), arange
+
+    def forward(self, candidate_reprs, candidate_to_sample_idx, has_bug, correct_candidate_idxs, weight: float = 1.0):  # :81-124
+        groups, log_probs, arange = self.compute_localization_logprobs(candidate_reprs, candidate_to_sample_idx, has_bug.shape[0])
+        correct = torch.where(has_bug, correct_candidate_idxs, arange + candidate_reprs.shape[0])
+        per_sample = log_probs[correct].clamp(min=-math.inf, max=math.log(0.995))
+        if weight == 1.0:
+            return -per_sample.mean(), log_probs, groups
+        w = torch.where(has_bug, torch.full_like(per_sample, weight), torch.ones_like(per_sample))
+        return -(per_sample * w).sum() / w.sum(), log_probs, groups
+
+
+class TextRepairModule(nn.Module):
+    def __init__(self, dim: int, rewrite_vocab_size: int):
+        super().__init__()
+        self.__text_rewrite_embeddings = nn.Embedding(rewrite_vocab_size, dim)
+        self.__text_rewrite_scorer = MLP(2 * dim, 1, [dim])
+
+    def compute_rewrite_logits(self, node_reprs, candidate_rewrites):  # fixermodules.py:31-39
+        emb = self.__text_rewrite_embeddings(candidate_rewrites)
+        return self.__text_rewrite_scorer(torch.cat((emb, node_reprs), dim=-1)).squeeze(-1)
+
+
+class SingleCandidateNodeSelectorModule(nn.Module):
+    def __init__(self, dim: int):
+        super().__init__()
+        self.__candidate_scorer = MLP(2 * dim, 1, [dim])
+
+    def compute_per_slot_log_probability(self, slot_reprs, target_reprs):  # fixermodules.py:65-73
+        return self.__candidate_scorer(torch.cat((slot_reprs, target_reprs), dim=-1)).squeeze(-1)
+
+
+class CandidatePairSelectorModule(nn.Module):
+    def __init__(self, dim: int):
+        super().__init__()
+        self._input_dim = dim
+        self.__pair_scorer = MLP(3 * dim, 1, [dim])
+
+    def compute_per_pair_logits(self, slot_reprs, pair_reprs):  # fixermodules.py:110-124
+        return self.__pair_scorer(torch.cat((slot_reprs, pair_reprs.reshape(pair_reprs.shape[0], 2 * self._input_dim)), dim=-1)).squeeze(-1)
+
+
+class GnnBugLabModule(nn.Module):
+    """Discriminator training step of buglab/models/gnn.py:144-251 (selector branch :189-219 not restated)."""
+
+    def __init__(self, hidden: int, num_edge_types: int, vocabulary_size: int, rewrite_vocabulary_size: int,
+                 dropout_rate: float = 0.0, embedding_dropout_rate: float = 0.0, buggy_samples_weight: float = 1.0,
+                 use_message_bias: bool = True):
+        super().__init__()
+        self._gnn = GraphNeuralNetwork(hidden, num_edge_types, vocabulary_size, dropout_rate, embedding_dropout_rate,
+                                       use_message_bias)
+        self.__localization_module = LocalizationModule(hidden)
+        self._text_repair_module = TextRepairModule(hidden, rewrite_vocabulary_size)
+        self._varmisuse_module = SingleCandidateNodeSelectorModule(hidden)
+        self._argswap_module = CandidatePairSelectorModule(hidden)
+        self.buggy_samples_weight = buggy_samples_weight
+
+    def node_representations(self, graph_data):
+        return self._gnn(graph_data["node_data"], graph_data["adjacency_lists"])
+
+    def compute_localization_logprobs(self, graph_data):  # gnn.py:125-142
+        states = self.node_representations(graph_data)
+        cand = states[graph_data["reference_node_ids"]["candidate_nodes"]]
+        groups, lp, arange = self.__localization_module.compute_localization_logprobs(
+            cand, graph_data["reference_node_graph_idx"]["candidate_nodes"], graph_data["num_graphs"])
+        return groups, lp, states, arange
+
+    def _compute_repair_logprobs(self, states, refs, target_rewrites, rewrite_to_location_group,
+                                 candidate_symbol_to_location_group, swapped_pair_to_call_location_group):  # gnn.py:253-322
+        text = (self._text_repair_module.compute_rewrite_logits(states[refs["target_rewrite_nodes"]], target_rewrites)
+                if target_rewrites.shape[0] > 0 else torch.zeros(0, dtype=states.dtype))
+        misuse = (self._varmisuse_module.compute_per_slot_log_probability(
+            states[refs["varmisused_node_ids"]], states[refs["candidate_symbol_node_ids"]])
+            if refs["varmisused_node_ids"].shape[0] > 0 else torch.zeros(0, dtype=states.dtype))
+        swap = (self._argswap_module.compute_per_pair_logits(
+            states[refs["call_node_ids"]], states[refs["candidate_swapped_node_ids"]])
+            if refs["call_node_ids"].shape[0] > 0 else torch.zeros(0, dtype=states.dtype))
+        sizes = [text.shape[0], misuse.shape[0], swap.shape[0]]
+        all_logits = torch.cat((text, misuse, swap))
+        groups = torch.cat((rewrite_to_location_group, candidate_symbol_to_location_group, swapped_pair_to_call_location_group))
+        if all_logits.shape[0] == 0:
+            e = torch.zeros(0, dtype=torch.bool)
+            return swap, text, misuse, (e, e, e)
+        text_lp, misuse_lp, swap_lp = torch.split(scatter_log_softmax(all_logits, groups), sizes)
+        with torch.no_grad():
+            per_rewrite_max = scatter_max(all_logits, groups)[0].gather(-1, groups)
+            text_sel, misuse_sel, swap_sel = torch.split(per_rewrite_max == all_logits, sizes)
+        return swap_lp, text_lp, misuse_lp, (swap_sel, text_sel, misuse_sel)
+
+    def forward(self, *, graph_data, correct_candidate_node_idxs, has_bug, target_rewrites, rewrite_to_location_group,
+                correct_rewrite_idxs, text_rewrite_idxs=None, candidate_symbol_to_location_group=None,
+                correct_candidate_symbols=None, candidate_rewrite_idxs=None, swapped_pair_to_call_location_group=None,
+                correct_swapped_pair=None, pair_rewrite_idxs=None, rewrite_to_graph_id=None, return_details: bool = False, **_):
+        states = self.node_representations(graph_data)
+        refs = graph_data["reference_node_ids"]
+        cand = states[refs["candidate_nodes"]]
+        swap_lp, text_lp, misuse_lp, selected = self._compute_repair_logprobs(
+            states, refs, target_rewrites, rewrite_to_location_group, candidate_symbol_to_location_group,
+            swapped_pair_to_call_location_group)
+        loc_loss, loc_lp, loc_groups = self.__localization_module(
+            cand, graph_data["reference_node_graph_idx"]["candidate_nodes"], has_bug, correct_candidate_node_idxs,
+            self.buggy_samples_weight)
+        repair = (-text_lp[correct_rewrite_idxs]).sum() + (-misuse_lp[correct_candidate_symbols]).sum() \
+            + (-swap_lp[correct_swapped_pair]).sum()
+        loss = loc_loss + repair * self.buggy_samples_weight / has_bug.shape[0]  # gnn.py:240-251
+        if return_details:
+            return loss, dict(node_states=states, localization_logprobs=loc_lp, localization_groups=loc_groups,
+                              text_logprobs=text_lp, varmisuse_logprobs=misuse_lp, argswap_logprobs=swap_lp)
+        return loss
+
+
+def minibatch_to_cpu(mb: Dict[str, Any], dtype: Optional[torch.dtype] = None) -> Dict[str, Any]:
+    """Product minibatch (possibly on a GPU) -> plain CPU tensors / lists the oracle consumes."""
+    def conv(v):
+        if isinstance(v, torch.Tensor):
+            return v.detach().cpu()
+        if isinstance(v, dict):
+            return {k: conv(x) for k, x in v.items()}
+        if isinstance(v, (list, tuple)) and v and isinstance(v[0], (tuple, list)) and len(v[0]) == 2 \
+                and isinstance(v[0][0], torch.Tensor):
+            return [(a.detach().cpu().long(), b.detach().cpu().long()) for a, b in v]
+        return v
+
+    out = {k: conv(v) for k, v in mb.items()}
+    out["graph_data"] = {k: v for k, v in out["graph_data"].items() if k != "h2d_bytes"}
+    return out
+
+
+def train_step_ref(module: nn.Module, optimizer: torch.optim.Optimizer, minibatch: Dict[str, Any],
+                   clip_gradient_norm: float = 0.5) -> float:
+    """zero_grad -> loss -> backward -> clip_grad_norm_ -> Adam step (SURVEY.md §8a P6 order; train.py:98-107)."""
+    optimizer.zero_grad()
+    loss = module(**minibatch)
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_(module.parameters(), clip_gradient_norm)
+    optimizer.step()
+    return float(loss)

@@ -37,42 +37,75 @@ def typed_edge_message_max_ref(h, adjacency_lists, weight, bias):
     return scatter_max(messages, targets, dim=0, dim_size=h.shape[0])
 
 
-class MlpMessagePassingLayerRef(nn.Module):
-    """Parameter names mirror the product module so ``load_state_dict`` moves weights across."""
+class MlpMessagePassingLayer(nn.Module):
+    """Class and attribute names mirror ptgnn's (name-mangled private attributes), so ``state_dict`` keys are
+    identical to the product module's and weights move across with ``load_state_dict``."""
 
     def __init__(self, input_state_dimension: int, message_dimension: int, output_state_dimension: int,
                  num_edge_types: int, message_aggregation_function: str = "max", dropout_rate: float = 0.0,
-                 features_dimension: int = 0, use_message_bias: bool = True):
+                 features_dimension: int = 0, use_message_bias: bool = True, **_unused):
         super().__init__()
         assert features_dimension == 0, "edge features are outside the gnn-mlp default path (modelregistry.py:56)"
-        self.aggregation = message_aggregation_function
-        self.edge_message_transformation_layers = nn.ModuleList(
+        self.__aggregation = message_aggregation_function
+        self.__edge_message_transformation_layers = nn.ModuleList(
             [nn.Linear(2 * input_state_dimension, message_dimension, bias=use_message_bias) for _ in range(num_edge_types)]
         )
-        self.state_update_norm = nn.LayerNorm(message_dimension)
-        self.state_update_dense = nn.Linear(message_dimension, output_state_dimension, bias=False)
-        nn.init.xavier_uniform_(self.state_update_dense.weight)
-        self.dropout = nn.Dropout(dropout_rate)
-        self.output_state_dimension = output_state_dimension
+        dense = nn.Linear(message_dimension, output_state_dimension, bias=False)
+        nn.init.xavier_uniform_(dense.weight)
+        self.__state_update = nn.Sequential(nn.LayerNorm(message_dimension), dense, nn.Tanh(), nn.Dropout(p=dropout_rate))
+        self.__output_state_dim = output_state_dimension
+        self.__input_state_dim = input_state_dimension
 
-    def forward(self, node_states, adjacency_lists, **_):
-        weight = torch.stack([l.weight for l in self.edge_message_transformation_layers])
-        bias = None
-        if self.edge_message_transformation_layers[0].bias is not None:
-            bias = torch.stack([l.bias for l in self.edge_message_transformation_layers])
+    @property
+    def output_state_dimension(self) -> int:
+        return self.__output_state_dim
+
+    @property
+    def input_state_dimension(self) -> int:
+        return self.__input_state_dim
+
+    def aggregated_messages(self, node_states, adjacency_lists):
+        layers = self.__edge_message_transformation_layers
+        weight = torch.stack([l.weight for l in layers])
+        bias = torch.stack([l.bias for l in layers]) if layers[0].bias is not None else None
         messages, targets = edge_messages_ref(node_states, adjacency_lists, weight, bias)
         N = node_states.shape[0]
-        if self.aggregation == "max":
-            agg = scatter_max(messages, targets, dim=0, dim_size=N)[0]
-        elif self.aggregation == "min":
-            agg = scatter_min(messages, targets, dim=0, dim_size=N)[0]
-        elif self.aggregation == "sum":
-            agg = scatter_sum(messages, targets, dim=0, dim_size=N)
-        elif self.aggregation == "mean":
-            agg = scatter_mean(messages, targets, dim=0, dim_size=N)
-        else:
-            raise ValueError(self.aggregation)
-        return self.dropout(torch.tanh(self.state_update_dense(self.state_update_norm(agg))))
+        if self.__aggregation == "max":
+            return scatter_max(messages, targets, dim=0, dim_size=N)[0]
+        if self.__aggregation == "min":
+            return scatter_min(messages, targets, dim=0, dim_size=N)[0]
+        if self.__aggregation == "sum":
+            return scatter_sum(messages, targets, dim=0, dim_size=N)
+        if self.__aggregation == "mean":
+            return scatter_mean(messages, targets, dim=0, dim_size=N)
+        raise ValueError(self.__aggregation)
+
+    def forward(self, node_states, adjacency_lists, node_to_graph_idx=None, reference_node_ids=None,
+                reference_node_graph_idx=None, edge_features=None):
+        return self.__state_update(self.aggregated_messages(node_states, adjacency_lists))
+
+
+MlpMessagePassingLayerRef = MlpMessagePassingLayer
+
+
+class SubtokenUnitEmbedder(nn.Module):
+    """ptgnn subtoken embedder, ``subtoken_combination='max'``: Embedding -> dropout -> masked max."""
+
+    def __init__(self, vocabulary_size: int, embedding_size: int, dropout_rate: float, subtoken_combination: str = "max",
+                 padding_idx: int = 0):
+        super().__init__()
+        assert subtoken_combination == "max"
+        self.__embeddings = nn.Embedding(vocabulary_size, embedding_size, padding_idx=padding_idx)
+        self.__dropout_layer = nn.Dropout(p=dropout_rate)
+
+    @property
+    def embedding_layer(self) -> nn.Embedding:
+        return self.__embeddings
+
+    def forward(self, token_idxs, lengths):
+        emb = self.__dropout_layer(self.__embeddings(token_idxs.long()))  # [N, T, H]
+        mask = torch.arange(token_idxs.shape[1]).view(1, -1) < lengths.long().view(-1, 1)
+        return emb.masked_fill(~mask.unsqueeze(-1), -float("inf")).max(dim=1)[0]
 
 
 def subtoken_maxpool_ref(embedding: torch.Tensor, ids: torch.Tensor, lens: torch.Tensor) -> torch.Tensor:
