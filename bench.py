@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py — code-graphs/sec of the gnn-mlp train step (fwd + bwd + grad all-reduce + clip + Adam) on B200.
+
+Contract: ``python bench.py --gpus N --steps K --warmup W [--impl reference]`` prints ONE JSON line on rank 0.
+Workload = BASELINE.json configs[1]: gnn-mlp, hidden 256, 8 message-passing layers, 256 synthetic code graphs per
+step and GPU (~2k nodes each, 8 forward edge kinds -> 17 kinds per layer), fp32, dropout 0.2.
+  value      graphs/s with the packed minibatch already resident in HBM (plan build + step inside the timed region)
+  e2e        graphs/s through the public API from HOST (tensorised numpy) samples: pack -> pinned -> H2D -> plan ->
+             step -> D2H of the loss, every step
+  roofline   the fused typed-edge message+aggregate kernel, timed alone with CUDA events on its launch stream
+  cpu_baseline / --impl reference   the CPU oracle (port of the reference semantics) on the host cores
+"""
+import argparse
+import copy
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "neurips21-self-supervised-bug-detection-and-repair_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+HIDDEN = 256
+GRAPHS_PER_STEP = 256
+MEAN_NODES = 2000
+DROPOUT = 0.2
+NUM_DISTINCT_BATCHES = 2
+CPU_GRAPHS_PER_STEP = 4
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--graphs", type=int, default=GRAPHS_PER_STEP)
+    ap.add_argument("--hidden", type=int, default=HIDDEN)
+    ap.add_argument("--mean-nodes", type=int, default=MEAN_NODES)
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index, self.proc, self.path = gpu_index, None, None
+
+    def __enter__(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.path or not os.path.exists(self.path):
+            return out
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = max(mx)
+        out["reasons"] = sorted(reasons)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+def make_workload(seed: int, graphs: int, hidden: int, mean_nodes: int, batches: int, dropout: float):
+    """Synthetic samples -> metadata -> tensorised (host numpy) samples grouped into `batches` minibatches."""
+    from pathlib import Path
+
+    from buglab.models.modelregistry import load_model
+    from buglab_b200.synthetic import SyntheticBugLabGenerator
+
+    # metadata from a fixed seed so every rank builds the same vocabulary / edge-type layout
+    meta_gen = SyntheticBugLabGenerator(seed=12345, mean_nodes=mean_nodes)
+    model, _, _ = load_model({"modelName": "gnn-mlp", "hidden_state_size": hidden, "dropout_rate": dropout,
+                              "stop_extending_minibatch_after_num_nodes": 10 ** 9, "max_nodes_per_graph": 10 ** 9},
+                             Path("/tmp/buglab_b200_bench.pkl.gz"))
+    model.compute_metadata(meta_gen.samples(64))
+    gen = SyntheticBugLabGenerator(seed=seed, mean_nodes=mean_nodes)
+    host_batches = []
+    for _ in range(batches):
+        samples = [gen.sample() for _ in range(graphs)]
+        host_batches.append([t for t, _ in model.tensorize_dataset(iter(samples), parallelize=False)])
+    return model, host_batches
+
+
+def pack(model, tensorized, device):
+    mb = model.initialize_minibatch()
+    for t in tensorized:
+        model.extend_minibatch_with(t, mb)
+    return model.finalize_minibatch(mb, device)
+
+
+def run_ours(args):
+    import torch
+
+    from buglab.models.utils import LinearWarmupScheduler, optimizer
+    from buglab_b200 import _lib, distributed, ops
+
+    local_rank = distributed.init_from_env("nccl")
+    rank, world = distributed.rank(), distributed.world_size()
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    torch.manual_seed(0)
+    model, host_batches = make_workload(1000 + rank, args.graphs, args.hidden, args.mean_nodes, NUM_DISTINCT_BATCHES, DROPOUT)
+    nn = model.build_neural_module().to(device)
+    distributed.broadcast_module(nn)
+    opt = optimizer(nn.parameters())
+    opt.max_grad_norm = 0.5
+    sched = LinearWarmupScheduler(opt)
+    nn.train()
+
+    def train_step(mb):
+        opt.zero_grad()
+        loss = nn(**mb)
+        loss.backward()
+        scale = distributed.allreduce_flat_gradient(opt.flat_grad)
+        opt.step(grad_scale=scale)
+        sched.step(0, 0)
+        return loss
+
+    def barrier():
+        if distributed.is_distributed():
+            torch.distributed.barrier()
+        torch.cuda.synchronize(device)
+
+    # ---------------- device-resident throughput ("value") ----------------
+    resident = [pack(model, tb, device) for tb in host_batches]
+    nodes = [int(mb["graph_data"]["node_to_graph_idx"].shape[0]) for mb in resident]
+    edges = [int(mb["graph_data"]["adjacency_lists"].plan.num_edges) for mb in resident]
+    h2d_bytes = [int(mb["graph_data"]["h2d_bytes"]) for mb in resident]
+
+    def resident_step(i):
+        mb = resident[i % len(resident)]
+        mb["graph_data"]["adjacency_lists"].plan = None  # the plan is per-minibatch work: rebuilt inside the step
+        return train_step(mb)
+
+    for i in range(args.warmup):
+        resident_step(i)
+    barrier()
+    _lib.launch_counter["kernels"] = 0
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        start.record()
+        for i in range(args.steps):
+            loss = resident_step(i)
+        end.record()
+        barrier()
+    launches = _lib.launch_counter["kernels"]
+    ms_resident = distributed.all_ranks_max(start.elapsed_time(end), device)
+    clock_summary = clocks.summary()
+    final_loss = float(loss)
+
+    # ---------------- end to end from host samples ("e2e") ----------------
+    for i in range(min(2, args.warmup)):
+        train_step(pack(model, host_batches[i % len(host_batches)], device))
+    barrier()
+    start.record()
+    for i in range(args.steps):
+        mb = pack(model, host_batches[i % len(host_batches)], device)  # numpy -> pinned -> H2D -> device plan
+        loss_host = float(train_step(mb))                               # D2H read of the loss every step
+    end.record()
+    barrier()
+    ms_e2e = distributed.all_ranks_max(start.elapsed_time(end), device)
+
+    total_graphs = args.graphs * world * args.steps
+    result = {
+        "metric": "code-graphs/sec (train step, device-timed)",
+        "value": total_graphs / (ms_resident / 1e3),
+        "unit": "graphs/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_resident / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": f"gnn-mlp hidden={args.hidden}, 8 MP layers, {args.graphs} graphs/step/GPU (~{args.mean_nodes} nodes each, "
+                        f"{model.gnn_model.num_edge_types} edge kinds per layer), train step fwd+bwd+allreduce+clip+Adam, dropout {DROPOUT}",
+            "nodes_per_step": nodes[0], "edges_per_step": edges[0], "parallelism": f"dp{world}",
+            "l2_policy": "inputs larger than L2 (per-layer tables are GBs; 126 MB L2), distinct minibatches cycled",
+        },
+        "e2e": {"value": total_graphs / (ms_e2e / 1e3), "unit": "graphs/s", "h2d_bytes_per_step": h2d_bytes[0],
+                "d2h_bytes_per_step": 4 + 4 * (2 * model.gnn_model.num_edge_types + 4), "ms_per_step": ms_e2e / args.steps,
+                "from": "host tensorised samples (numpy) -> minibatch packing -> pinned staging -> H2D -> device plan -> step -> loss D2H"},
+        "gpu_launches": launches,
+        "clocks": clock_summary,
+        "final_loss": final_loss,
+    }
+
+    if rank == 0:
+        result["roofline"] = edge_kernel_roofline(resident[0], nn, args.hidden, device)
+        if world == 1 and not args.skip_cpu_baseline:
+            result["cpu_baseline"] = cpu_baseline(args, steps=1, warmup=0)
+        print(json.dumps(result), flush=True)
+    if distributed.is_distributed():
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def edge_kernel_roofline(mb, nn, hidden, device):
+    """The fused typed-edge message+aggregate kernel (bl_edge_segmax_fwd) of one H->H layer, timed alone with CUDA
+    events on the stream it is launched on.  Algorithmic bytes per launch (reference formulation):
+    E*(2*D_in*4 + 12) + N*M*4."""
+    import torch
+
+    from buglab_b200 import _lib, ops
+
+    peaks, peak_kind = measured_peaks()
+    graph = mb["graph_data"]
+    adj = graph["adjacency_lists"]
+    plan = ops.build_edge_plan(adj, int(graph["node_to_graph_idx"].shape[0]))
+    N, E, M = plan.num_nodes, plan.num_edges, hidden
+    lib = _lib.load()
+    g = torch.Generator(device=device).manual_seed(0)
+    u = torch.randn(plan.num_s_pairs, M, device=device, generator=g)
+    v = torch.randn(plan.num_t_pairs, M, device=device, generator=g)
+    agg = torch.empty(N, M, device=device); xwin = torch.empty_like(agg)
+    ewin = torch.empty(N, M, device=device, dtype=torch.int32)
+    stream = torch.cuda.current_stream(device)
+
+    def launch():
+        _lib.check(lib.bl_edge_segmax_fwd(u.data_ptr(), v.data_ptr(), plan.row_ptr.data_ptr(), plan.urow.data_ptr(),
+                                          plan.vrow.data_ptr(), N, M, agg.data_ptr(), xwin.data_ptr(), ewin.data_ptr(),
+                                          stream.cuda_stream), "bl_edge_segmax_fwd")
+
+    for _ in range(3):
+        launch()
+    reps = 10
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(device)
+    s.record(stream)
+    for _ in range(reps):
+        launch()
+    e.record(stream)
+    e.synchronize()
+    ms = s.elapsed_time(e) / reps
+    algo_bytes = E * (2 * M * 4 + 12) + N * M * 4
+    achieved = algo_bytes / (ms / 1e3) / 1e9
+    return {"bound": "hbm", "kernel": "edge_segmax_fwd_warp (bl_edge_segmax_fwd), H->H layer", "achieved": achieved,
+            "peak": peaks["hbm_gbs"], "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+            "traffic": None, "algorithmic_bytes": algo_bytes, "ms_per_launch": ms, "nodes": N, "edges": E,
+            "working_set_bytes": int((u.numel() + v.numel()) * 4)}
+
+
+def cpu_baseline(args, steps: int, warmup: int):
+    """The CPU oracle (kind "port": the reference's arithmetic restated in PyTorch, see oracle/) running the same
+    train step on a bounded sample: CPU_GRAPHS_PER_STEP graphs of the same distribution per step."""
+    import torch
+
+    from oracle import model_ref
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model, host_batches = make_workload(777, CPU_GRAPHS_PER_STEP, args.hidden, args.mean_nodes, max(1, min(2, steps + warmup)), DROPOUT)
+    ref = model_ref.GnnBugLabModule(args.hidden, model.gnn_model.num_edge_types,
+                                    len(model.gnn_model.node_representation_model.vocabulary),
+                                    len(model._target_rewrite_ops), dropout_rate=DROPOUT, embedding_dropout_rate=DROPOUT)
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-4)
+    ref.train()
+    mbs = [model_ref.minibatch_to_cpu(pack(model, tb, "cpu")) for tb in host_batches]
+    for i in range(warmup):
+        model_ref.train_step_ref(ref, opt, mbs[i % len(mbs)])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        model_ref.train_step_ref(ref, opt, mbs[i % len(mbs)])
+    dt = time.perf_counter() - t0
+    return {"value": CPU_GRAPHS_PER_STEP * steps / dt, "unit": "graphs/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} train step(s) of {CPU_GRAPHS_PER_STEP} graphs (same generator, hidden={args.hidden}), "
+                      f"PyTorch CPU oracle with {cores} threads", "seconds": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = cpu_baseline(args, steps=args.steps, warmup=min(args.warmup, 1))
+    ms = base["seconds"] * 1e3
+    print(json.dumps({
+        "impl": "reference",
+        "metric": "code-graphs/sec (train step, device-timed)", "value": base["value"], "unit": "graphs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"gnn-mlp hidden={args.hidden}, 8 MP layers, train step on the host CPU; bounded sample of "
+                               f"{CPU_GRAPHS_PER_STEP} graphs/step (~{args.mean_nodes} nodes each)", "parallelism": "cpu"},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -83,7 +83,20 @@ class BuglabB200Error(RuntimeError):
     pass
 
 
+# hand-written kernels launched per successful C-ABI call (CUB sorts/scans, memsets and cuBLAS GEMMs not counted)
+KERNELS_PER_CALL = {
+    "bl_plan_build": 19, "bl_rows_gather": 1, "bl_rows_segment_sum": 1, "bl_edge_segmax_fwd": 1,
+    "bl_edge_segmax_bwd": 1, "bl_layernorm_fwd": 1, "bl_layernorm_bwd": 2, "bl_tanh_dropout_fwd": 1,
+    "bl_tanh_dropout_bwd": 1, "bl_segment_minmax": 5, "bl_segment_minmax_bwd": 1, "bl_segment_sum": 1,
+    "bl_segment_log_softmax_fwd": 5, "bl_segment_log_softmax_bwd": 2, "bl_subtoken_maxpool_fwd": 1,
+    "bl_subtoken_maxpool_bwd": 1, "bl_grad_sqnorm": 2, "bl_adam_step": 1,
+}
+launch_counter = {"kernels": 0, "calls": 0}
+
+
 def check(code: int, what: str) -> None:
+    launch_counter["calls"] += 1
+    launch_counter["kernels"] += KERNELS_PER_CALL.get(what, 1)
     if code != 0:
         msg = load().bl_error_string(code)
         raise BuglabB200Error(f"{what} failed with code {code}: {msg.decode() if msg else '?'}")

@@ -50,7 +50,7 @@ __device__ __forceinline__ float gelu_grad(float x) {
 
 // Order-preserving float <-> int mapping for atomicMax/atomicMin on floats.
 __device__ __forceinline__ int float_to_ordered(float f) {
-    int i = __float_as_int(f);
+    int i = __float_as_int(f + 0.0f);  // -0.0 -> +0.0: the two compare equal, as in the reference's float compare
     return i ^ ((i >> 31) & 0x7fffffff);
 }
 __device__ __forceinline__ float ordered_to_float(int i) {

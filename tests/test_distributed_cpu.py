@@ -1,0 +1,74 @@
+"""Data-parallel host logic with world_size 2 over gloo on CPU: rank sharding, flat-gradient all-reduce, identical
+parameters on every rank after a step, and equality with single-process training on the union batch."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "neurips21-self-supervised-bug-detection-and-repair_b200")
+
+
+def _worker(rank: int, world: int, port: int, out_dir: str):
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from buglab_b200 import distributed
+    from ptgnn.baseneuralmodel.trainer import _allreduce_dense_gradients
+
+    distributed.init_from_env("gloo")
+    assert distributed.is_distributed() and distributed.world_size() == world and distributed.rank() == rank
+    # independent units are sharded round-robin, every unit exactly once
+    mine = list(distributed.shard_for_rank(range(10)))
+    assert mine == list(range(rank, 10, world))
+
+    torch.manual_seed(1234 + rank)  # different initial weights per rank ...
+    net = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.Tanh(), torch.nn.Linear(8, 1))
+    distributed.broadcast_module(net)  # ... until rank 0's are broadcast
+    g = torch.Generator().manual_seed(7)
+    x_all, y_all = torch.randn(8, 4, generator=g), torch.randn(8, 1, generator=g)
+    x, y = x_all[rank::world], y_all[rank::world]  # equal-sized shards -> mean of means == global mean
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    for _ in range(3):
+        opt.zero_grad()
+        torch.nn.functional.mse_loss(net(x), y).backward()
+        # flat-buffer path (what FlatAdam's bucket does on the GPU): sum then scale by 1/world
+        flat = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+        scale = distributed.allreduce_flat_gradient(flat)
+        assert scale == 1.0 / world
+        # compat path used for optimisers without a flat buffer
+        _allreduce_dense_gradients(list(net.parameters()), world)
+        flat2 = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+        torch.testing.assert_close(flat * scale, flat2)
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 0.5)  # after the all-reduce -> identical on all ranks
+        opt.step()
+    assert distributed.all_ranks_max(float(rank), "cpu") == world - 1
+    assert distributed.all_ranks_sum(1.0, "cpu") == world
+    torch.save({k: v.clone() for k, v in net.state_dict().items()}, os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_data_parallel_equals_single_process(tmp_path):
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = torch.load(tmp_path / "rank0.pt"), torch.load(tmp_path / "rank1.pt")
+    for k in a:
+        assert torch.equal(a[k], b[k]), f"ranks diverged on {k}"
+    # single process on the union batch
+    torch.manual_seed(1234)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.Tanh(), torch.nn.Linear(8, 1))
+    g = torch.Generator().manual_seed(7)
+    x_all, y_all = torch.randn(8, 4, generator=g), torch.randn(8, 1, generator=g)
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    for _ in range(3):
+        opt.zero_grad()
+        torch.nn.functional.mse_loss(net(x_all), y_all).backward()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 0.5)
+        opt.step()
+    for k, v in net.state_dict().items():
+        torch.testing.assert_close(a[k], v, atol=1e-6, rtol=1e-5)

@@ -1,0 +1,97 @@
+"""Known-answer tests that pin the UNPINNED part of the oracle (ptgnn / torch_scatter semantics):
+hand-computed tiny cases, per-group log_softmax identities, and the GELU property the fused kernel relies on."""
+import math
+
+import torch
+
+from oracle import scatter_ref
+from oracle.mp_ref import MlpMessagePassingLayer, edge_messages_ref, typed_edge_message_max_ref
+
+
+def test_scatter_max_first_wins_and_empty_is_zero():
+    src = torch.tensor([1.0, 3.0, 3.0, -1.0, 5.0, -2.0])
+    idx = torch.tensor([0, 1, 1, 0, 3, 4])
+    out, arg = scatter_ref.scatter_max(src, idx, dim_size=6)
+    assert out.tolist() == [1.0, 3.0, 0.0, 5.0, -2.0, 0.0]      # segments 2 and 5 are empty -> 0
+    assert arg.tolist() == [0, 1, 6, 4, 5, 6]                    # tie in segment 1 -> first index; empty -> len(src)
+    out, arg = scatter_ref.scatter_min(src, idx, dim_size=5)
+    assert out.tolist() == [-1.0, 3.0, 0.0, 5.0, -2.0] and arg.tolist() == [3, 1, 6, 4, 5]
+
+
+def test_scatter_max_backward_routes_to_arg_only():
+    src = torch.tensor([[1.0, 5.0], [2.0, 5.0], [0.5, 7.0]], requires_grad=True)
+    out, arg = scatter_ref.scatter_max(src, torch.tensor([0, 0, 1]), dim=0, dim_size=2)
+    (out * torch.tensor([[1.0, 10.0], [100.0, 1000.0]])).sum().backward()
+    assert arg.tolist() == [[1, 0], [2, 2]]
+    assert src.grad.tolist() == [[0.0, 10.0], [1.0, 0.0], [100.0, 1000.0]]
+
+
+def test_scatter_log_softmax_is_log_softmax_per_group():
+    g = torch.Generator().manual_seed(0)
+    src = torch.randn(40, generator=g) * 4
+    idx = torch.randint(0, 6, (40,), generator=g)
+    out = scatter_ref.scatter_log_softmax(src, idx)
+    for s in idx.unique():
+        m = idx == s
+        torch.testing.assert_close(out[m], torch.log_softmax(src[m], 0), atol=1e-6, rtol=1e-6)
+
+
+def test_no_bug_slot_identity():
+    """with all-equal candidate scores s and the virtual NO_BUG logit 1.0, the NO_BUG log-prob is
+    1 - logsumexp([s]*C + [1])  (localizationmodule.py:66-77)."""
+    C, s = 7, 0.3
+    scores = torch.cat((torch.full((C,), s), torch.ones(1)))
+    out = scatter_ref.scatter_log_softmax(scores, torch.zeros(C + 1, dtype=torch.int64))
+    expected = 1.0 - math.log(C * math.exp(s) + math.exp(1.0))
+    assert abs(float(out[-1]) - expected) < 1e-6
+
+
+def test_hand_computed_typed_edge_layer():
+    """4 nodes, 2 edge types, D=1, M=1 — every number below is computed by hand.
+       type 0 (W=[1, 0], b=0):   edges 0->2, 1->2   messages GELU(h_s)   = GELU(1), GELU(-3)
+       type 1 (W=[0, 2], b=1):   edge  3->2, 0->1   messages GELU(2*h_t+1) = GELU(2*0.5+1)=GELU(2) at node 2, GELU(-5) at node 1
+       node 0 and node 3 have no in-edge -> 0."""
+    h = torch.tensor([[1.0], [-3.0], [0.5], [4.0]])
+    adj = [(torch.tensor([0, 1]), torch.tensor([2, 2])), (torch.tensor([3, 0]), torch.tensor([2, 1]))]
+    W = torch.tensor([[[1.0, 0.0]], [[0.0, 2.0]]])
+    b = torch.tensor([[0.0], [1.0]])
+    gelu = lambda x: 0.5 * x * (1 + math.erf(x / math.sqrt(2)))  # noqa: E731
+    msgs, tgt = edge_messages_ref(h, adj, W, b)
+    assert tgt.tolist() == [2, 2, 2, 1]
+    torch.testing.assert_close(msgs.view(-1), torch.tensor([gelu(1.0), gelu(-3.0), gelu(2.0), gelu(-5.0)]), atol=1e-6, rtol=1e-6)
+    agg, arg = typed_edge_message_max_ref(h, adj, W, b)
+    torch.testing.assert_close(agg.view(-1), torch.tensor([0.0, gelu(-5.0), gelu(2.0), 0.0]), atol=1e-6, rtol=1e-6)
+    assert arg.view(-1).tolist() == [4, 3, 2, 4]  # edge ids in the type-major concatenation; 4 == "no edge"
+
+
+def test_gelu_is_quasi_convex_so_max_sits_at_an_extreme():
+    """The fused kernel keeps only min(x) and max(x) per segment: max_i GELU(x_i) == max(GELU(min x), GELU(max x))."""
+    g = torch.Generator().manual_seed(1)
+    for scale in (0.3, 1.0, 3.0, 8.0):
+        x = torch.randn(2000, 16, generator=g, dtype=torch.float64) * scale - 0.5
+        direct = torch.nn.functional.gelu(x).max(dim=0)[0]
+        via_extremes = torch.maximum(torch.nn.functional.gelu(x.min(dim=0)[0]), torch.nn.functional.gelu(x.max(dim=0)[0]))
+        torch.testing.assert_close(direct, via_extremes, atol=0, rtol=0)
+    # strictly decreasing left of x0 ~ -0.7518 and increasing right of it; checked on [-5, 12] — further left erf
+    # saturates (GELU rounds to -0.0 with ulp noise), where any choice among the saturated messages has value 0 and
+    # derivative < 1e-6, so the selection is immaterial
+    grid = torch.linspace(-5, 12, 170001, dtype=torch.float64)
+    y = torch.nn.functional.gelu(grid)
+    k = int(y.argmin())
+    assert abs(float(grid[k]) + 0.7518) < 1e-3
+    assert bool((y[:k].diff() < 0).all()) and bool((y[k:].diff() > 0).all())
+
+
+def test_layer_module_matches_functional_and_isolated_nodes():
+    torch.manual_seed(0)
+    layer = MlpMessagePassingLayer(6, 10, 4, num_edge_types=2, message_aggregation_function="max")
+    h = torch.randn(5, 6)
+    adj = [(torch.tensor([0, 1, 1]), torch.tensor([1, 2, 2])), (torch.zeros(0, dtype=torch.int64), torch.zeros(0, dtype=torch.int64))]
+    agg = layer.aggregated_messages(h, adj)
+    assert torch.all(agg[[0, 3, 4]] == 0)
+    out = layer(h, adj)
+    sd = layer.state_dict()
+    ln_w, ln_b = sd["_MlpMessagePassingLayer__state_update.0.weight"], sd["_MlpMessagePassingLayer__state_update.0.bias"]
+    dense = sd["_MlpMessagePassingLayer__state_update.1.weight"]
+    expect = torch.tanh(torch.nn.functional.layer_norm(agg, (10,), ln_w, ln_b) @ dense.t())
+    torch.testing.assert_close(out, expect)
