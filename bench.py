@@ -32,7 +32,7 @@ GRAPHS_PER_STEP = 256
 MEAN_NODES = 2000
 DROPOUT = 0.2
 NUM_DISTINCT_BATCHES = 2
-CPU_GRAPHS_PER_STEP = 4
+CPU_GRAPHS_PER_STEP = 2
 
 
 def parse_args():
@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--hidden", type=int, default=HIDDEN)
     ap.add_argument("--mean-nodes", type=int, default=MEAN_NODES)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="profiling run for ncu: one minibatch, resident steps only (numbers printed under a profiler are not bench values)")
     return ap.parse_args()
 
 
@@ -151,7 +153,8 @@ def run_ours(args):
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     torch.manual_seed(0)
-    model, host_batches = make_workload(1000 + rank, args.graphs, args.hidden, args.mean_nodes, NUM_DISTINCT_BATCHES, DROPOUT)
+    model, host_batches = make_workload(1000 + rank, args.graphs, args.hidden, args.mean_nodes,
+                                        1 if args.profile else NUM_DISTINCT_BATCHES, DROPOUT)
     nn = model.build_neural_module().to(device)
     distributed.broadcast_module(nn)
     opt = optimizer(nn.parameters())
@@ -199,6 +202,11 @@ def run_ours(args):
     ms_resident = distributed.all_ranks_max(start.elapsed_time(end), device)
     clock_summary = clocks.summary()
     final_loss = float(loss)
+
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms_resident / args.steps, "gpu_launches": launches}), flush=True)
+        return
 
     # ---------------- end to end from host samples ("e2e") ----------------
     for i in range(min(2, args.warmup)):
@@ -290,6 +298,31 @@ def edge_kernel_roofline(mb, nn, hidden, device):
             "working_set_bytes": int((u.numel() + v.numel()) * 4)}
 
 
+def best_cpu_thread_count() -> int:
+    """All host threads the process can actually use: os.cpu_count() over-reports inside CPU-limited containers (the
+    first B200 box reported 128 and ran the oracle 30x slower with 128 threads than 8 cores do), so a 1-second SGEMM
+    probe picks the fastest of {8, 16, 32, ..., affinity}."""
+    import torch
+
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    candidates = sorted({min(avail, c) for c in (8, 16, 32, 64, 128, avail)})
+    a = torch.randn(1536, 1536)
+    best, best_t = candidates[0], float("inf")
+    for c in candidates:
+        torch.set_num_threads(c)
+        a @ a
+        t0 = time.perf_counter()
+        for _ in range(3):
+            a @ a
+        dt = time.perf_counter() - t0
+        if dt < best_t * 0.9:
+            best, best_t = c, dt
+    return best
+
+
 def cpu_baseline(args, steps: int, warmup: int):
     """The CPU oracle (kind "port": the reference's arithmetic restated in PyTorch, see oracle/) running the same
     train step on a bounded sample: CPU_GRAPHS_PER_STEP graphs of the same distribution per step."""
@@ -297,7 +330,7 @@ def cpu_baseline(args, steps: int, warmup: int):
 
     from oracle import model_ref
 
-    cores = os.cpu_count() or 1
+    cores = best_cpu_thread_count()
     torch.set_num_threads(cores)
     model, host_batches = make_workload(777, CPU_GRAPHS_PER_STEP, args.hidden, args.mean_nodes, max(1, min(2, steps + warmup)), DROPOUT)
     ref = model_ref.GnnBugLabModule(args.hidden, model.gnn_model.num_edge_types,

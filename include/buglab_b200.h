@@ -89,6 +89,40 @@ int bl_rows_segment_sum(const float* a_rows, const int32_t* a_ptr, const int32_t
                         int64_t num_nodes, int32_t dim, int32_t accumulate, float* out, bl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Pair projections on the tensor cores (split-bf16, fp32-class accuracy) — the hoisted per-type affine
+ *     U[p] = A_k h[s_node[p]],   V[p] = B_k h[t_node[p]] + b_k      with  Linear_k.weight = [A_k | B_k]
+ * of ptgnn MlpMessagePassingLayer (reference call site buglab/models/gnnlayerdefs.py:6-23) and its backward.
+ * fp32 operands are split x = x1 + x2 (bf16 parts) and x.w is evaluated as x1.w1 + x1.w2 + x2.w1 by ONE bf16 GEMM
+ * over the concatenated reduction [x1|x1|x2].[w1|w2|w1] with fp32 accumulation (max error ~1e-5 at D=256; a single
+ * TF32/BF16 pass misses the 1e-4 parity budget).  Row layout of every split table: 3*dim + 8 bf16 per row
+ * (the 8 trailing columns carry [1 1 1 0 0 0 0 0] so that a bias b = b1+b2+b3 folds into the same reduction).
+ * type_ptr_host[K+1] are HOST arrays (they size the per-type GEMMs).
+ * ------------------------------------------------------------------------------------------------ */
+/* out[r,:] = [hi | hi | lo | 1 1 1 0 0 0 0 0] of table[idx[r],:] (idx may be NULL: r itself); out is bf16 [num_rows, 3*dim+8] */
+int bl_rows_split3_bf16(const float* table, const int32_t* idx, int64_t num_rows, int32_t dim, void* out,
+                        bl_stream_t stream);
+/* From weight[K, out_dim, ld] columns [col0, col0+in_dim) (+ bias[K,out_dim] or NULL):
+ *   w3_fwd [K, out_dim, 3*in_dim+8] = [w1 | w2 | w1 | b1 b2 b3 0...]      (forward, "NT" operand)
+ *   b3_bwd [K, 3*out_dim, in_dim]   = [w1 ; w2 ; w1] stacked along rows     (backward w.r.t. the input rows)
+ * either output may be NULL. */
+int bl_weights_split3_bf16(const float* weight, const float* bias, int32_t num_types, int32_t out_dim, int32_t in_dim,
+                           int32_t ld, int32_t col0, void* w3_fwd, void* b3_bwd, bl_stream_t stream);
+/* out[rows of type k, 0:out_dim] = a3[rows] . w3_fwd[k]^T   (fp32 out) */
+int bl_pair_project_fwd(const void* a3, const void* w3_fwd, const int32_t* type_ptr_host, int32_t num_types,
+                        int32_t out_dim, int32_t in_dim, float* out, bl_stream_t stream);
+/* d_rows[rows of type k, 0:in_dim] = g3[rows, 0:3*out_dim] . b3_bwd[k]   (g3 = bl_rows_split3_bf16 of the table gradient) */
+int bl_pair_project_bwd_input(const void* g3, const void* b3_bwd, const int32_t* type_ptr_host, int32_t num_types,
+                              int32_t out_dim, int32_t in_dim, float* d_rows, bl_stream_t stream);
+/* d_weight[k, 0:out_dim, col0:col0+in_dim] = sum over rows of type k of g^T h  (three bf16 GEMMs, fp32 accumulate);
+ * types without rows are zero-filled. */
+int bl_pair_project_bwd_weight(const void* g3, const void* a3, const int32_t* type_ptr_host, int32_t num_types,
+                               int32_t out_dim, int32_t in_dim, float* d_weight, int32_t ld, int32_t col0,
+                               bl_stream_t stream);
+/* out[k, 0:dim] = sum of rows[type_ptr[k] : type_ptr[k+1], :]   (type_ptr on the DEVICE; the bias gradient) */
+int bl_grouped_colsum(const float* rows, const int32_t* type_ptr, int32_t num_types, int32_t dim, float* out,
+                      bl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Fused typed-edge message + aggregate (THE hot kernel).
  *
  * Replaces, per layer, ptgnn MlpMessagePassingLayer.forward's

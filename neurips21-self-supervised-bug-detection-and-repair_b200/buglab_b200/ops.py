@@ -7,6 +7,7 @@ through ``torch.mm`` = plain cuBLAS fp32 GEMMs, TF32 disabled).
 Reference semantics replaced: P4/P5 ``MlpMessagePassingLayer`` message+aggregate,
 A9/A10 scatter ops (``buglab/models/utils.py:15-48``), P2 subtoken max-pool, A12 optimiser.
 """
+import ctypes
 from typing import List, NamedTuple, Optional, Sequence, Tuple
 
 import torch
@@ -139,6 +140,46 @@ def _project_pairs(rows: torch.Tensor, weight: torch.Tensor, col0: int, type_ptr
     return out
 
 
+# Projection arithmetic: "bf16x3" = split-bf16 tensor-core GEMMs (default, see csrc/gemm.cu); "fp32" = cuBLAS SGEMM
+# through torch.mm (kept as an exact referee for tests and error budgeting).
+PROJECTION_MODE = "bf16x3"
+
+
+def _host_i32(values: Tuple[int, ...]):
+    return (ctypes.c_int32 * len(values))(*values)
+
+
+def _split3_rows(table: torch.Tensor, idx: Optional[torch.Tensor]) -> torch.Tensor:
+    rows = int(idx.shape[0]) if idx is not None else int(table.shape[0])
+    dim = int(table.shape[1])
+    out = torch.empty((rows, 3 * dim + 8), device=table.device, dtype=torch.bfloat16)
+    check(_lib.load().bl_rows_split3_bf16(f32(table), i32(idx) if idx is not None else None, rows, dim, out.data_ptr(),
+                                          stream_ptr(table.device)), "bl_rows_split3_bf16")
+    return out
+
+
+def _split3_weights(weight: torch.Tensor, bias: Optional[torch.Tensor], col0: int, in_dim: int, fwd: bool, bwd: bool):
+    K, M, ld = weight.shape
+    w3 = torch.empty((K, M, 3 * in_dim + 8), device=weight.device, dtype=torch.bfloat16) if fwd else None
+    b3 = torch.empty((K, 3 * M, in_dim), device=weight.device, dtype=torch.bfloat16) if bwd else None
+    check(_lib.load().bl_weights_split3_bf16(f32(weight), f32(bias) if bias is not None else None, K, M, in_dim, ld, col0,
+                                             w3.data_ptr() if fwd else None, b3.data_ptr() if bwd else None,
+                                             stream_ptr(weight.device)), "bl_weights_split3_bf16")
+    return w3, b3
+
+
+def _project_pairs_bf16x3(h: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor, col0: int,
+                          type_ptr: Tuple[int, ...], bias: Optional[torch.Tensor]) -> torch.Tensor:
+    K, M, _ = weight.shape
+    D = h.shape[1]
+    a3 = _split3_rows(h, idx)
+    w3, _ = _split3_weights(weight, bias, col0, D, True, False)
+    out = torch.empty((idx.shape[0], M), device=h.device, dtype=torch.float32)
+    check(_lib.load().bl_pair_project_fwd(a3.data_ptr(), w3.data_ptr(), _host_i32(type_ptr), K, M, D, f32(out),
+                                          stream_ptr(h.device)), "bl_pair_project_fwd")
+    return out
+
+
 class TypedEdgeMessageMax(torch.autograd.Function):
     """agg[n] = max over in-edges (s->n, type k) of GELU(W_k [h_s; h_n] + b_k); 0 for isolated nodes.
 
@@ -156,13 +197,18 @@ class TypedEdgeMessageMax(torch.autograd.Function):
         K, M, twoD = weight.shape
         if twoD != 2 * D or K != plan.num_edge_types or N != plan.num_nodes:
             raise ValueError(f"shape mismatch: h {tuple(h.shape)}, weight {tuple(weight.shape)}, plan K={plan.num_edge_types} N={plan.num_nodes}")
+        bias_c = bias.contiguous() if bias is not None else None
         with torch.no_grad():
-            hs = _rows_gather(h, plan.s_node)
-            u_rows = _project_pairs(hs, weight, 0, plan.s_type_ptr_host, None)
-            del hs
-            ht = _rows_gather(h, plan.t_node)
-            v_rows = _project_pairs(ht, weight, D, plan.t_type_ptr_host, bias)
-            del ht
+            if PROJECTION_MODE == "bf16x3":
+                u_rows = _project_pairs_bf16x3(h, plan.s_node, weight, 0, plan.s_type_ptr_host, None)
+                v_rows = _project_pairs_bf16x3(h, plan.t_node, weight, D, plan.t_type_ptr_host, bias_c)
+            else:
+                hs = _rows_gather(h, plan.s_node)
+                u_rows = _project_pairs(hs, weight, 0, plan.s_type_ptr_host, None)
+                del hs
+                ht = _rows_gather(h, plan.t_node)
+                v_rows = _project_pairs(ht, weight, D, plan.t_type_ptr_host, bias_c)
+                del ht
             agg = torch.empty((N, M), device=h.device, dtype=torch.float32)
             xwin = torch.empty_like(agg)
             ewin = torch.empty((N, M), device=h.device, dtype=torch.int32)
@@ -173,6 +219,7 @@ class TypedEdgeMessageMax(torch.autograd.Function):
             )
         ctx.plan = plan
         ctx.has_bias = bias is not None
+        ctx.mode = PROJECTION_MODE
         ctx.save_for_backward(h, weight, xwin, ewin)
         return agg
 
@@ -192,26 +239,45 @@ class TypedEdgeMessageMax(torch.autograd.Function):
                                    N, M, plan.num_s_pairs, plan.num_t_pairs, f32(du), f32(dv), stream_ptr(dev)),
             "bl_edge_segmax_bwd",
         )
-        d_weight = torch.zeros_like(weight)
         d_bias = torch.zeros((K, M), device=dev, dtype=torch.float32) if ctx.has_bias else None
         d_rows = []
-        for rows_idx, d_tab, col0, type_ptr, is_t in (
-            (plan.s_node, du, 0, plan.s_type_ptr_host, False),
-            (plan.t_node, dv, D, plan.t_type_ptr_host, True),
-        ):
-            rows = _rows_gather(h, rows_idx)  # recomputed instead of kept alive since forward
-            d_in = torch.empty_like(rows)
-            for k in range(K):
-                lo, hi = type_ptr[k], type_ptr[k + 1]
-                if hi == lo:
-                    continue
-                w = weight[k, :, col0 : col0 + D]
-                torch.mm(d_tab[lo:hi], w, out=d_in[lo:hi])
-                d_weight[k, :, col0 : col0 + D].copy_(torch.mm(d_tab[lo:hi].t(), rows[lo:hi]))
-                if is_t and d_bias is not None:
-                    torch.sum(d_tab[lo:hi], dim=0, out=d_bias[k])
-            d_rows.append(d_in)
-            del rows
+        if ctx.mode == "bf16x3":
+            d_weight = torch.empty_like(weight)
+            if d_bias is not None:
+                check(lib.bl_grouped_colsum(f32(dv), i32(plan.t_type_ptr), K, M, f32(d_bias), stream_ptr(dev)), "bl_grouped_colsum")
+            for rows_idx, d_tab, col0, type_ptr in ((plan.s_node, du, 0, plan.s_type_ptr_host),
+                                                    (plan.t_node, dv, D, plan.t_type_ptr_host)):
+                tp = _host_i32(type_ptr)
+                g3 = _split3_rows(d_tab, None)
+                _, b3 = _split3_weights(weight, None, col0, D, False, True)
+                d_in = torch.empty((rows_idx.shape[0], D), device=dev, dtype=torch.float32)
+                check(lib.bl_pair_project_bwd_input(g3.data_ptr(), b3.data_ptr(), tp, K, M, D, f32(d_in), stream_ptr(dev)),
+                      "bl_pair_project_bwd_input")
+                a3 = _split3_rows(h, rows_idx)  # recomputed instead of kept alive since forward
+                check(lib.bl_pair_project_bwd_weight(g3.data_ptr(), a3.data_ptr(), tp, K, M, D, f32(d_weight), 2 * D, col0,
+                                                     stream_ptr(dev)), "bl_pair_project_bwd_weight")
+                d_rows.append(d_in)
+                del g3, a3, b3
+            del du, dv
+        else:
+            d_weight = torch.zeros_like(weight)
+            for rows_idx, d_tab, col0, type_ptr, is_t in (
+                (plan.s_node, du, 0, plan.s_type_ptr_host, False),
+                (plan.t_node, dv, D, plan.t_type_ptr_host, True),
+            ):
+                rows = _rows_gather(h, rows_idx)  # recomputed instead of kept alive since forward
+                d_in = torch.empty_like(rows)
+                for k in range(K):
+                    lo, hi = type_ptr[k], type_ptr[k + 1]
+                    if hi == lo:
+                        continue
+                    w = weight[k, :, col0 : col0 + D]
+                    torch.mm(d_tab[lo:hi], w, out=d_in[lo:hi])
+                    d_weight[k, :, col0 : col0 + D].copy_(torch.mm(d_tab[lo:hi].t(), rows[lo:hi]))
+                    if is_t and d_bias is not None:
+                        torch.sum(d_tab[lo:hi], dim=0, out=d_bias[k])
+                d_rows.append(d_in)
+                del rows
         d_h = torch.empty_like(h)
         check(
             lib.bl_rows_segment_sum(f32(d_rows[0]), i32(plan.s_by_node_ptr), i32(plan.s_by_node_idx),

