@@ -83,37 +83,45 @@ int bl_rows_gather(const float* table, const int32_t* idx, int64_t num_rows, int
                    float* out, bl_stream_t stream);
 
 /* out[n,:] (+)= sum_{q in [a_ptr[n],a_ptr[n+1])} a_rows[a_idx[q],:] + sum_{q in b range} b_rows[b_idx[q],:]
- * b_* may be NULL.  accumulate != 0 adds to the existing contents of out. */
+ * b_* may be NULL.  accumulate != 0 adds to the existing contents of out.  amax (device scalar, may be NULL): the rows
+ * come from a table that was pre-scaled by the power of two derived from *amax (see bl_rows_split3_f16); the sum is
+ * multiplied by the exact inverse. */
 int bl_rows_segment_sum(const float* a_rows, const int32_t* a_ptr, const int32_t* a_idx,
                         const float* b_rows, const int32_t* b_ptr, const int32_t* b_idx,
-                        int64_t num_nodes, int32_t dim, int32_t accumulate, float* out, bl_stream_t stream);
+                        int64_t num_nodes, int32_t dim, int32_t accumulate, const float* amax, float* out,
+                        bl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Pair projections on the tensor cores (split-bf16, fp32-class accuracy) — the hoisted per-type affine
+ * Pair projections on the tensor cores (split-fp16, fp32-class accuracy) — the hoisted per-type affine
  *     U[p] = A_k h[s_node[p]],   V[p] = B_k h[t_node[p]] + b_k      with  Linear_k.weight = [A_k | B_k]
  * of ptgnn MlpMessagePassingLayer (reference call site buglab/models/gnnlayerdefs.py:6-23) and its backward.
- * fp32 operands are split x = x1 + x2 (bf16 parts) and x.w is evaluated as x1.w1 + x1.w2 + x2.w1 by ONE bf16 GEMM
- * over the concatenated reduction [x1|x1|x2].[w1|w2|w1] with fp32 accumulation (max error ~1e-5 at D=256; a single
- * TF32/BF16 pass misses the 1e-4 parity budget).  Row layout of every split table: 3*dim + 8 bf16 per row
- * (the 8 trailing columns carry [1 1 1 0 0 0 0 0] so that a bias b = b1+b2+b3 folds into the same reduction).
+ * fp32 operands are split x = x1 + x2 (fp16 parts, 22 bits together) and x.w is evaluated as x1.w1 + x1.w2 + x2.w1 by
+ * ONE fp16 GEMM over the concatenated reduction [x1|x1|x2].[w1|w2|w1] with fp32 accumulation (max error ~2e-6 at D=256,
+ * like fp32 SGEMM; a single TF32/BF16 pass and even a bf16 split miss the 1e-4 parity budget over 8 layers).
+ * Row layout of every split table: 3*dim + 8 fp16 per row (the 8 trailing columns carry [1 1 1 0 0 0 0 0] so that a
+ * bias b = b1+b2+b3 folds into the same reduction).  Gradient tables are pre-scaled by an exact power of two derived
+ * from a device-side absolute maximum (`amax`) so that fp16's narrow exponent range costs no accuracy.
  * type_ptr_host[K+1] are HOST arrays (they size the per-type GEMMs).
  * ------------------------------------------------------------------------------------------------ */
-/* out[r,:] = [hi | hi | lo | 1 1 1 0 0 0 0 0] of table[idx[r],:] (idx may be NULL: r itself); out is bf16 [num_rows, 3*dim+8] */
-int bl_rows_split3_bf16(const float* table, const int32_t* idx, int64_t num_rows, int32_t dim, void* out,
-                        bl_stream_t stream);
+/* out[r,:] = [hi | hi | lo | 1 1 1 0 0 0 0 0] of s*table[idx[r],:] (idx may be NULL: r itself); out is fp16
+ * [num_rows, 3*dim+8]; s = 2^(12-ceil(log2(*amax))) if amax != NULL (device scalar), else 1. */
+int bl_rows_split3_f16(const float* table, const int32_t* idx, int64_t num_rows, int32_t dim, const float* amax,
+                       void* out, bl_stream_t stream);
+/* x[i] /= s  with the same s as above (undoes the pre-scale on a small tensor, e.g. the weight gradient) */
+int bl_unscale_pow2(float* x, int64_t n, const float* amax, bl_stream_t stream);
 /* From weight[K, out_dim, ld] columns [col0, col0+in_dim) (+ bias[K,out_dim] or NULL):
  *   w3_fwd [K, out_dim, 3*in_dim+8] = [w1 | w2 | w1 | b1 b2 b3 0...]      (forward, "NT" operand)
  *   b3_bwd [K, 3*out_dim, in_dim]   = [w1 ; w2 ; w1] stacked along rows     (backward w.r.t. the input rows)
  * either output may be NULL. */
-int bl_weights_split3_bf16(const float* weight, const float* bias, int32_t num_types, int32_t out_dim, int32_t in_dim,
+int bl_weights_split3_f16(const float* weight, const float* bias, int32_t num_types, int32_t out_dim, int32_t in_dim,
                            int32_t ld, int32_t col0, void* w3_fwd, void* b3_bwd, bl_stream_t stream);
 /* out[rows of type k, 0:out_dim] = a3[rows] . w3_fwd[k]^T   (fp32 out) */
 int bl_pair_project_fwd(const void* a3, const void* w3_fwd, const int32_t* type_ptr_host, int32_t num_types,
                         int32_t out_dim, int32_t in_dim, float* out, bl_stream_t stream);
-/* d_rows[rows of type k, 0:in_dim] = g3[rows, 0:3*out_dim] . b3_bwd[k]   (g3 = bl_rows_split3_bf16 of the table gradient) */
+/* d_rows[rows of type k, 0:in_dim] = g3[rows, 0:3*out_dim] . b3_bwd[k]   (g3 = bl_rows_split3_f16 of the table gradient) */
 int bl_pair_project_bwd_input(const void* g3, const void* b3_bwd, const int32_t* type_ptr_host, int32_t num_types,
                               int32_t out_dim, int32_t in_dim, float* d_rows, bl_stream_t stream);
-/* d_weight[k, 0:out_dim, col0:col0+in_dim] = sum over rows of type k of g^T h  (three bf16 GEMMs, fp32 accumulate);
+/* d_weight[k, 0:out_dim, col0:col0+in_dim] = sum over rows of type k of g^T h  (three fp16 GEMMs, fp32 accumulate);
  * types without rows are zero-filled. */
 int bl_pair_project_bwd_weight(const void* g3, const void* a3, const int32_t* type_ptr_host, int32_t num_types,
                                int32_t out_dim, int32_t in_dim, float* d_weight, int32_t ld, int32_t col0,
@@ -148,11 +156,12 @@ int bl_edge_segmax_fwd(const float* u_rows, const float* v_rows,
 
 /* Backward of the above: g = d_agg * GELU'(xwin) routed to the winning edge only (the arg-routing
  * backward of torch_scatter.scatter_max).  d_v_rows[P_t,M] is fully written (each (type,tgt) row has
- * exactly one owner node); d_u_rows[P_s,M] is zero-filled here and accumulated with fp32 REDs. */
+ * exactly one owner node); d_u_rows[P_s,M] is zero-filled here and accumulated with fp32 atomics.  amax (device
+ * scalar, may be NULL) receives an upper bound of max(|d_u_rows|, |d_v_rows|) for the fp16 split's pre-scale. */
 int bl_edge_segmax_bwd(const float* d_agg, const float* xwin, const int32_t* ewin,
                        const int32_t* row_ptr, const int32_t* urow, const int32_t* vrow,
                        int64_t num_nodes, int32_t msg_dim, int64_t num_s_pairs, int64_t num_t_pairs,
-                       float* d_u_rows, float* d_v_rows, bl_stream_t stream);
+                       float* d_u_rows, float* d_v_rows, float* amax, bl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Node update  LayerNorm(M) -> [Linear(M->D_out) is a library/tensor-core GEMM] -> Tanh -> Dropout

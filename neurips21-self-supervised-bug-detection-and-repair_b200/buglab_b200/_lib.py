@@ -32,15 +32,16 @@ _SIGNATURES = {
     "bl_plan_workspace_bytes": (c_size, [c_i64, c_i64, c_i32]),
     "bl_plan_build": (c_i32, [c_ptr] * 3 + [c_i64, c_i64, c_i32] + [c_ptr] * 15 + [c_ptr, c_size, c_ptr]),
     "bl_rows_gather": (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_ptr, c_ptr]),
-    "bl_rows_segment_sum": (c_i32, [c_ptr] * 6 + [c_i64, c_i32, c_i32, c_ptr, c_ptr]),
-    "bl_rows_split3_bf16": (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_ptr, c_ptr]),
-    "bl_weights_split3_bf16": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
+    "bl_rows_segment_sum": (c_i32, [c_ptr] * 6 + [c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
+    "bl_rows_split3_f16": (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_ptr, c_ptr, c_ptr]),
+    "bl_unscale_pow2": (c_i32, [c_ptr, c_i64, c_ptr, c_ptr]),
+    "bl_weights_split3_f16": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
     "bl_pair_project_fwd": (c_i32, [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr, c_ptr]),
     "bl_pair_project_bwd_input": (c_i32, [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr, c_ptr]),
     "bl_pair_project_bwd_weight": (c_i32, [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr, c_i32, c_i32, c_ptr]),
     "bl_grouped_colsum": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_ptr, c_ptr]),
     "bl_edge_segmax_fwd": (c_i32, [c_ptr] * 5 + [c_i64, c_i32] + [c_ptr] * 3 + [c_ptr]),
-    "bl_edge_segmax_bwd": (c_i32, [c_ptr] * 6 + [c_i64, c_i32, c_i64, c_i64] + [c_ptr] * 2 + [c_ptr]),
+    "bl_edge_segmax_bwd": (c_i32, [c_ptr] * 6 + [c_i64, c_i32, c_i64, c_i64] + [c_ptr] * 3 + [c_ptr]),
     "bl_layernorm_fwd": (c_i32, [c_ptr] * 3 + [c_i64, c_i32, c_f32] + [c_ptr] * 3 + [c_ptr]),
     "bl_layernorm_bwd": (c_i32, [c_ptr] * 5 + [c_i64, c_i32] + [c_ptr] * 4 + [c_ptr]),
     "bl_tanh_dropout_fwd": (c_i32, [c_ptr, c_i64, c_f32, c_u64, c_ptr, c_ptr, c_ptr]),
@@ -96,7 +97,7 @@ KERNELS_PER_CALL = {
     "bl_tanh_dropout_bwd": 1, "bl_segment_minmax": 5, "bl_segment_minmax_bwd": 1, "bl_segment_sum": 1,
     "bl_segment_log_softmax_fwd": 5, "bl_segment_log_softmax_bwd": 2, "bl_subtoken_maxpool_fwd": 1,
     "bl_subtoken_maxpool_bwd": 1, "bl_grad_sqnorm": 2, "bl_adam_step": 1,
-    "bl_rows_split3_bf16": 1, "bl_weights_split3_bf16": 2, "bl_pair_project_fwd": 0, "bl_pair_project_bwd_input": 0,
+    "bl_rows_split3_bf16": 1, "bl_weights_split3_f16": 2, "bl_pair_project_fwd": 0, "bl_pair_project_bwd_input": 0,
     "bl_pair_project_bwd_weight": 0, "bl_grouped_colsum": 1,
 }
 launch_counter = {"kernels": 0, "calls": 0}

@@ -140,35 +140,36 @@ def _project_pairs(rows: torch.Tensor, weight: torch.Tensor, col0: int, type_ptr
     return out
 
 
-# Projection arithmetic: "bf16x3" = split-bf16 tensor-core GEMMs (default, see csrc/gemm.cu); "fp32" = cuBLAS SGEMM
+# Projection arithmetic: "f16x3" = split-fp16 tensor-core GEMMs (default, see csrc/gemm.cu); "fp32" = cuBLAS SGEMM
 # through torch.mm (kept as an exact referee for tests and error budgeting).
-PROJECTION_MODE = "bf16x3"
+PROJECTION_MODE = "f16x3"
 
 
 def _host_i32(values: Tuple[int, ...]):
     return (ctypes.c_int32 * len(values))(*values)
 
 
-def _split3_rows(table: torch.Tensor, idx: Optional[torch.Tensor]) -> torch.Tensor:
+def _split3_rows(table: torch.Tensor, idx: Optional[torch.Tensor], amax: Optional[torch.Tensor] = None) -> torch.Tensor:
     rows = int(idx.shape[0]) if idx is not None else int(table.shape[0])
     dim = int(table.shape[1])
-    out = torch.empty((rows, 3 * dim + 8), device=table.device, dtype=torch.bfloat16)
-    check(_lib.load().bl_rows_split3_bf16(f32(table), i32(idx) if idx is not None else None, rows, dim, out.data_ptr(),
-                                          stream_ptr(table.device)), "bl_rows_split3_bf16")
+    out = torch.empty((rows, 3 * dim + 8), device=table.device, dtype=torch.float16)
+    check(_lib.load().bl_rows_split3_f16(f32(table), i32(idx) if idx is not None else None, rows, dim,
+                                         f32(amax) if amax is not None else None, out.data_ptr(),
+                                         stream_ptr(table.device)), "bl_rows_split3_f16")
     return out
 
 
 def _split3_weights(weight: torch.Tensor, bias: Optional[torch.Tensor], col0: int, in_dim: int, fwd: bool, bwd: bool):
     K, M, ld = weight.shape
-    w3 = torch.empty((K, M, 3 * in_dim + 8), device=weight.device, dtype=torch.bfloat16) if fwd else None
-    b3 = torch.empty((K, 3 * M, in_dim), device=weight.device, dtype=torch.bfloat16) if bwd else None
-    check(_lib.load().bl_weights_split3_bf16(f32(weight), f32(bias) if bias is not None else None, K, M, in_dim, ld, col0,
+    w3 = torch.empty((K, M, 3 * in_dim + 8), device=weight.device, dtype=torch.float16) if fwd else None
+    b3 = torch.empty((K, 3 * M, in_dim), device=weight.device, dtype=torch.float16) if bwd else None
+    check(_lib.load().bl_weights_split3_f16(f32(weight), f32(bias) if bias is not None else None, K, M, in_dim, ld, col0,
                                              w3.data_ptr() if fwd else None, b3.data_ptr() if bwd else None,
-                                             stream_ptr(weight.device)), "bl_weights_split3_bf16")
+                                             stream_ptr(weight.device)), "bl_weights_split3_f16")
     return w3, b3
 
 
-def _project_pairs_bf16x3(h: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor, col0: int,
+def _project_pairs_f16x3(h: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor, col0: int,
                           type_ptr: Tuple[int, ...], bias: Optional[torch.Tensor]) -> torch.Tensor:
     K, M, _ = weight.shape
     D = h.shape[1]
@@ -199,9 +200,9 @@ class TypedEdgeMessageMax(torch.autograd.Function):
             raise ValueError(f"shape mismatch: h {tuple(h.shape)}, weight {tuple(weight.shape)}, plan K={plan.num_edge_types} N={plan.num_nodes}")
         bias_c = bias.contiguous() if bias is not None else None
         with torch.no_grad():
-            if PROJECTION_MODE == "bf16x3":
-                u_rows = _project_pairs_bf16x3(h, plan.s_node, weight, 0, plan.s_type_ptr_host, None)
-                v_rows = _project_pairs_bf16x3(h, plan.t_node, weight, D, plan.t_type_ptr_host, bias_c)
+            if PROJECTION_MODE == "f16x3":
+                u_rows = _project_pairs_f16x3(h, plan.s_node, weight, 0, plan.s_type_ptr_host, None)
+                v_rows = _project_pairs_f16x3(h, plan.t_node, weight, D, plan.t_type_ptr_host, bias_c)
             else:
                 hs = _rows_gather(h, plan.s_node)
                 u_rows = _project_pairs(hs, weight, 0, plan.s_type_ptr_host, None)
@@ -234,21 +235,23 @@ class TypedEdgeMessageMax(torch.autograd.Function):
         dev = h.device
         du = torch.empty((plan.num_s_pairs, M), device=dev, dtype=torch.float32)
         dv = torch.empty((plan.num_t_pairs, M), device=dev, dtype=torch.float32)
+        amax = torch.empty(1, device=dev, dtype=torch.float32) if ctx.mode == "f16x3" else None
         check(
             lib.bl_edge_segmax_bwd(f32(d_agg), f32(xwin), i32(ewin), i32(plan.row_ptr), i32(plan.urow), i32(plan.vrow),
-                                   N, M, plan.num_s_pairs, plan.num_t_pairs, f32(du), f32(dv), stream_ptr(dev)),
+                                   N, M, plan.num_s_pairs, plan.num_t_pairs, f32(du), f32(dv),
+                                   f32(amax) if amax is not None else None, stream_ptr(dev)),
             "bl_edge_segmax_bwd",
         )
         d_bias = torch.zeros((K, M), device=dev, dtype=torch.float32) if ctx.has_bias else None
         d_rows = []
-        if ctx.mode == "bf16x3":
+        if ctx.mode == "f16x3":
             d_weight = torch.empty_like(weight)
             if d_bias is not None:
                 check(lib.bl_grouped_colsum(f32(dv), i32(plan.t_type_ptr), K, M, f32(d_bias), stream_ptr(dev)), "bl_grouped_colsum")
             for rows_idx, d_tab, col0, type_ptr in ((plan.s_node, du, 0, plan.s_type_ptr_host),
                                                     (plan.t_node, dv, D, plan.t_type_ptr_host)):
                 tp = _host_i32(type_ptr)
-                g3 = _split3_rows(d_tab, None)
+                g3 = _split3_rows(d_tab, None, amax)  # pre-scaled by a power of two: d_in / d_weight carry that factor
                 _, b3 = _split3_weights(weight, None, col0, D, False, True)
                 d_in = torch.empty((rows_idx.shape[0], D), device=dev, dtype=torch.float32)
                 check(lib.bl_pair_project_bwd_input(g3.data_ptr(), b3.data_ptr(), tp, K, M, D, f32(d_in), stream_ptr(dev)),
@@ -259,6 +262,7 @@ class TypedEdgeMessageMax(torch.autograd.Function):
                 d_rows.append(d_in)
                 del g3, a3, b3
             del du, dv
+            check(lib.bl_unscale_pow2(f32(d_weight), d_weight.numel(), f32(amax), stream_ptr(dev)), "bl_unscale_pow2")
         else:
             d_weight = torch.zeros_like(weight)
             for rows_idx, d_tab, col0, type_ptr, is_t in (
@@ -282,7 +286,7 @@ class TypedEdgeMessageMax(torch.autograd.Function):
         check(
             lib.bl_rows_segment_sum(f32(d_rows[0]), i32(plan.s_by_node_ptr), i32(plan.s_by_node_idx),
                                     f32(d_rows[1]), i32(plan.t_by_node_ptr), i32(plan.t_by_node_idx),
-                                    N, D, 0, f32(d_h), stream_ptr(dev)),
+                                    N, D, 0, f32(amax) if amax is not None else None, f32(d_h), stream_ptr(dev)),
             "bl_rows_segment_sum",
         )
         return d_h, d_weight, d_bias, None

@@ -71,6 +71,13 @@ __device__ __forceinline__ bool keep_element(uint64_t seed, uint64_t idx, float 
     return u >= p_drop;
 }
 
+// Exact power-of-two scale that brings a table with absolute maximum `amax` to ~2^12 before an fp16 split (fp16
+// overflows at 65504 and goes subnormal below 6.1e-5).  amax == 0 or non-finite -> 1.
+__device__ __forceinline__ float pow2_scale_for(float amax) {
+    if (!(amax > 0.f) || !isfinite(amax)) return 1.f;
+    return exp2f(12.f - ceilf(log2f(amax)));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);

@@ -153,9 +153,10 @@ __global__ void __launch_bounds__(256)
 edge_segmax_bwd_warp(const float* __restrict__ d_agg, const float* __restrict__ xwin,
                      const int* __restrict__ ewin, const int* __restrict__ row_ptr,
                      const int* __restrict__ urow, const int* __restrict__ vrow, int num_nodes,
-                     float* __restrict__ dU, float* __restrict__ dV) {
+                     float* __restrict__ dU, float* __restrict__ dV, unsigned* __restrict__ amax_bits) {
     constexpr int M4 = 32 * ITER;
     constexpr int M = 128 * ITER;
+    float local_amax = 0.f;
     const int node = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (node >= num_nodes) return;
@@ -180,8 +181,21 @@ edge_segmax_bwd_warp(const float* __restrict__ d_agg, const float* __restrict__ 
             g[i][c] = dd[c] * gelu_grad(xx[c]);
             wv[i][c] = __ldg(vrow + ee[c]);
             const int wu = __ldg(urow + ee[c]);
-            atomicAdd(dU + (size_t)wu * M + 4 * (lane + 32 * i) + c, g[i][c]);
+            float* dst = dU + (size_t)wu * M + 4 * (lane + 32 * i) + c;
+            if (amax_bits != nullptr) {
+                // the value an entry holds after its LAST add is observed by the thread that made it, so the
+                // maximum over all observed partial sums bounds every final |dU| (and |g| bounds every |dV|)
+                const float after = atomicAdd(dst, g[i][c]) + g[i][c];
+                local_amax = fmaxf(local_amax, fmaxf(fabsf(after), fabsf(g[i][c])));
+            } else {
+                atomicAdd(dst, g[i][c]);
+            }
         }
+    }
+    if (amax_bits != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) local_amax = fmaxf(local_amax, __shfl_xor_sync(FULL_MASK, local_amax, o));
+        if (lane == 0 && local_amax > 0.f) atomicMax(amax_bits, __float_as_uint(local_amax));  // non-negative floats order as uints
     }
     // every V row of this segment is written exactly once (runs of equal vrow are contiguous)
     int prev_v = -1;
@@ -210,7 +224,8 @@ __global__ void __launch_bounds__(256)
 edge_segmax_bwd_generic(const float* __restrict__ d_agg, const float* __restrict__ xwin,
                         const int* __restrict__ ewin, const int* __restrict__ row_ptr,
                         const int* __restrict__ urow, const int* __restrict__ vrow,
-                        int64_t num_nodes, int M, float* __restrict__ dU, float* __restrict__ dV) {
+                        int64_t num_nodes, int M, float* __restrict__ dU, float* __restrict__ dV,
+                        unsigned* __restrict__ amax_bits) {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= num_nodes * M) return;
     const int node = (int)(gid / M);
@@ -220,7 +235,13 @@ edge_segmax_bwd_generic(const float* __restrict__ d_agg, const float* __restrict
     const int e = ewin[gid];
     const float g = d_agg[gid] * gelu_grad(xwin[gid]);
     const int wv = vrow[e];
-    atomicAdd(dU + (size_t)urow[e] * M + j, g);
+    if (amax_bits != nullptr) {
+        const float after = atomicAdd(dU + (size_t)urow[e] * M + j, g) + g;
+        const float a = fmaxf(fabsf(after), fabsf(g));
+        if (a > 0.f) atomicMax(amax_bits, __float_as_uint(a));
+    } else {
+        atomicAdd(dU + (size_t)urow[e] * M + j, g);
+    }
     int prev_v = -1;
     for (int i = beg; i < end; ++i) {
         const int v = vrow[i];
@@ -260,7 +281,7 @@ extern "C" int bl_edge_segmax_fwd(const float* u_rows, const float* v_rows, cons
 extern "C" int bl_edge_segmax_bwd(const float* d_agg, const float* xwin, const int32_t* ewin,
                                   const int32_t* row_ptr, const int32_t* urow, const int32_t* vrow,
                                   int64_t num_nodes, int32_t msg_dim, int64_t num_s_pairs,
-                                  int64_t num_t_pairs, float* d_u_rows, float* d_v_rows,
+                                  int64_t num_t_pairs, float* d_u_rows, float* d_v_rows, float* amax,
                                   bl_stream_t stream_) {
     if (num_nodes < 0 || msg_dim <= 0 || (msg_dim & 3) || num_nodes > 0x7fffffffLL) return BL_ERR_INVALID_ARGUMENT;
     (void)num_t_pairs;
@@ -270,19 +291,24 @@ extern "C" int bl_edge_segmax_bwd(const float* d_agg, const float* xwin, const i
                             "bl_edge_segmax_bwd memset");
         if (rc) return rc;
     }
+    unsigned* amax_bits = reinterpret_cast<unsigned*>(amax);
+    if (amax != nullptr) {
+        int rc = check_cuda(cudaMemsetAsync(amax, 0, sizeof(float), stream), "bl_edge_segmax_bwd amax memset");
+        if (rc) return rc;
+    }
     if (num_nodes == 0) return BL_OK;
     const int threads = 256;
     const unsigned warp_grid = grid_for(num_nodes * 32, threads);
     const int n = (int)num_nodes;
     if (msg_dim == 128) {
-        edge_segmax_bwd_warp<1><<<warp_grid, threads, 0, stream>>>(d_agg, xwin, ewin, row_ptr, urow, vrow, n, d_u_rows, d_v_rows);
+        edge_segmax_bwd_warp<1><<<warp_grid, threads, 0, stream>>>(d_agg, xwin, ewin, row_ptr, urow, vrow, n, d_u_rows, d_v_rows, amax_bits);
     } else if (msg_dim == 256) {
-        edge_segmax_bwd_warp<2><<<warp_grid, threads, 0, stream>>>(d_agg, xwin, ewin, row_ptr, urow, vrow, n, d_u_rows, d_v_rows);
+        edge_segmax_bwd_warp<2><<<warp_grid, threads, 0, stream>>>(d_agg, xwin, ewin, row_ptr, urow, vrow, n, d_u_rows, d_v_rows, amax_bits);
     } else if (msg_dim == 512) {
-        edge_segmax_bwd_warp<4><<<warp_grid, threads, 0, stream>>>(d_agg, xwin, ewin, row_ptr, urow, vrow, n, d_u_rows, d_v_rows);
+        edge_segmax_bwd_warp<4><<<warp_grid, threads, 0, stream>>>(d_agg, xwin, ewin, row_ptr, urow, vrow, n, d_u_rows, d_v_rows, amax_bits);
     } else {
         edge_segmax_bwd_generic<<<grid_for(num_nodes * msg_dim, threads), threads, 0, stream>>>(
-            d_agg, xwin, ewin, row_ptr, urow, vrow, num_nodes, msg_dim, d_u_rows, d_v_rows);
+            d_agg, xwin, ewin, row_ptr, urow, vrow, num_nodes, msg_dim, d_u_rows, d_v_rows, amax_bits);
     }
     return check_launch("bl_edge_segmax_bwd");
 }

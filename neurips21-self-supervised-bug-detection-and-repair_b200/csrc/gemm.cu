@@ -1,18 +1,20 @@
-// Pair projections on the tensor cores with fp32-class accuracy: split-bf16 ("bf16x3") GEMMs.
+// Pair projections on the tensor cores with fp32-class accuracy: split-fp16 ("f16x3") GEMMs.
 //
 // The hoisted per-type affine of ptgnn's MlpMessagePassingLayer (U = A_k h_src, V = B_k h_tgt + b_k; reference
 // call site buglab/models/gnnlayerdefs.py:6-23) is a true dense GEMM over the unique (type,node) pairs, but the
-// path must match the reference's fp32 CPU arithmetic to 1e-4, which single-pass TF32/BF16 cannot (measured
-// 1.6e-3 / 5e-3 max error on a 256-long dot product).  Each fp32 operand is therefore split into two bf16 parts
-// (x = x1 + x2 + O(2^-16 x)) and the product is evaluated as x1*w1 + x1*w2 + x2*w1 by ONE bf16 GEMM whose reduction
-// dimension is the concatenation [x1 | x1 | x2] . [w1 | w2 | w1] (3*D long, fp32 accumulation in the tensor-core
-// accumulators; measured max error 9e-6 at D=256, i.e. ~10x inside the budget).  The bias rides along as three extra
-// reduction columns [1 1 1] . [b1 b2 b3] (b = b1+b2+b3 to 24 bits), padded to 8 columns for 16-byte rows.
+// path must match the reference's fp32 CPU arithmetic to 1e-4 through 8 layers, which a single TF32/BF16 pass cannot
+// (1.6e-3 / 5e-3 max error on a 256-long dot product).  Each fp32 operand is split into two fp16 parts
+// (x = x1 + x2 + O(2^-22 x); fp16 keeps 11 significand bits per part, bf16 only 8) and the product is evaluated as
+// x1*w1 + x1*w2 + x2*w1 by ONE fp16 GEMM whose reduction dimension is the concatenation [x1 | x1 | x2] . [w1 | w2 | w1]
+// (3*D long, fp32 accumulation in the tensor-core accumulators).  Emulated max error at D=256: 1.9e-6, the same as
+// fp32 SGEMM (1.4e-6); the bf16 split (9e-6) accumulated past 1e-4 after 8 layers and was rejected on the GPU.
+// fp16's narrow exponent is handled by an exact power-of-two pre-scale of gradient tables (scale from a device-side
+// amax, undone downstream).  The bias rides along as three extra reduction columns [1 1 1] . [b1 b2 b3], padded to 8.
 //
-// The GEMMs themselves are plain library GEMMs (cublasGemmEx, bf16 x bf16 -> fp32); the split / gather / transposed
+// The GEMMs themselves are plain library GEMMs (cublasGemmEx, fp16 x fp16 -> fp32); the split / gather / transposed
 // stacking kernels around them are hand-written here.
 #include <cublas_v2.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <mutex>
 
@@ -53,37 +55,41 @@ static int check_blas(cublasStatus_t s, const char* where) {
     return BL_OK;
 }
 
-__device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-    hi = __float2bfloat16_rn(x);
-    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+__device__ __forceinline__ void split2(float x, __half& hi, __half& lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(x - __half2float(hi));
 }
 
-// out[r, :] = [hi | hi | lo | 1 1 1 0 0 0 0 0]  of row idx[r] (or r) of `table`; one thread per 4 source floats.
+// out[r, :] = [hi | hi | lo | 1 1 1 0 0 0 0 0]  of row idx[r] (or r) of `table` (times the pow2 scale if amax is given)
 __global__ void __launch_bounds__(256)
 rows_split3_kernel(const float* __restrict__ table, const int* __restrict__ idx, int64_t num_rows, int D,
-                   __nv_bfloat16* __restrict__ out) {
+                   const float* __restrict__ amax, __half* __restrict__ out) {
     const int D4 = D / 4;
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= num_rows * (D4 + 1)) return;
     const int64_t r = gid / (D4 + 1);
     const int c = (int)(gid - r * (D4 + 1));
     const int64_t row_stride = 3 * (int64_t)D + BIAS_PAD;
-    __nv_bfloat16* orow = out + r * row_stride;
+    __half* orow = out + r * row_stride;
     if (c == D4) {  // the bias columns
-        const __nv_bfloat16 one = __float2bfloat16_rn(1.0f), zero = __float2bfloat16_rn(0.0f);
+        const __half one = __float2half_rn(1.0f), zero = __float2half_rn(0.0f);
 #pragma unroll
         for (int j = 0; j < BIAS_PAD; ++j) orow[3 * D + j] = (j < 3) ? one : zero;
         return;
     }
     const int64_t src_row = idx ? (int64_t)__ldg(idx + r) : r;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(table + src_row * D) + c);
-    __nv_bfloat16 h[4], l[4];
+    float4 v = __ldg(reinterpret_cast<const float4*>(table + src_row * D) + c);
+    if (amax != nullptr) {
+        const float sc = pow2_scale_for(__ldg(amax));
+        v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+    }
+    __half h[4], l[4];
     split2(v.x, h[0], l[0]); split2(v.y, h[1], l[1]); split2(v.z, h[2], l[2]); split2(v.w, h[3], l[3]);
     uint2 hp, lp;
-    hp.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
-    hp.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
-    lp.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
-    lp.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+    hp.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+    hp.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+    lp.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
+    lp.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
     *reinterpret_cast<uint2*>(orow + 4 * c) = hp;
     *reinterpret_cast<uint2*>(orow + D + 4 * c) = hp;
     *reinterpret_cast<uint2*>(orow + 2 * D + 4 * c) = lp;
@@ -91,23 +97,23 @@ rows_split3_kernel(const float* __restrict__ table, const int* __restrict__ idx,
 
 // Forward weights: w3[k, m, :] = [w1 | w2 | w1 | b1 b2 b3 0..] of W[k, m, col0:col0+D] (row stride ld) and bias[k, m].
 __global__ void weights_split3_fwd_kernel(const float* __restrict__ W, const float* __restrict__ bias, int64_t KM, int D,
-                                          int ld, int col0, __nv_bfloat16* __restrict__ out) {
+                                          int ld, int col0, __half* __restrict__ out) {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= KM * (D + 1)) return;
     const int64_t km = gid / (D + 1);
     const int d = (int)(gid - km * (D + 1));
-    __nv_bfloat16* orow = out + km * (3 * (int64_t)D + BIAS_PAD);
+    __half* orow = out + km * (3 * (int64_t)D + BIAS_PAD);
     if (d == D) {
         const float b = bias ? bias[km] : 0.f;
-        const __nv_bfloat16 b1 = __float2bfloat16_rn(b);
-        const float r1 = b - __bfloat162float(b1);
-        const __nv_bfloat16 b2 = __float2bfloat16_rn(r1);
-        const __nv_bfloat16 b3 = __float2bfloat16_rn(r1 - __bfloat162float(b2));
+        const __half b1 = __float2half_rn(b);
+        const float r1 = b - __half2float(b1);
+        const __half b2 = __float2half_rn(r1);
+        const __half b3 = __float2half_rn(r1 - __half2float(b2));
         orow[3 * D + 0] = b1; orow[3 * D + 1] = b2; orow[3 * D + 2] = b3;
-        for (int j = 3; j < BIAS_PAD; ++j) orow[3 * D + j] = __float2bfloat16_rn(0.f);
+        for (int j = 3; j < BIAS_PAD; ++j) orow[3 * D + j] = __float2half_rn(0.f);
         return;
     }
-    __nv_bfloat16 hi, lo;
+    __half hi, lo;
     split2(W[km * ld + col0 + d], hi, lo);
     orow[d] = hi;
     orow[D + d] = lo;
@@ -116,15 +122,15 @@ __global__ void weights_split3_fwd_kernel(const float* __restrict__ W, const flo
 
 // Backward weights, row-stacked for dX = G3 @ B3:  b3[k, j*M + m, d] = part_j(W[k, m, col0 + d]), parts (hi, lo, hi).
 __global__ void weights_stack3_bwd_kernel(const float* __restrict__ W, int64_t K, int M, int D, int ld, int col0,
-                                          __nv_bfloat16* __restrict__ out) {
+                                          __half* __restrict__ out) {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= K * M * D) return;
     const int d = (int)(gid % D);
     const int m = (int)((gid / D) % M);
     const int64_t k = gid / ((int64_t)D * M);
-    __nv_bfloat16 hi, lo;
+    __half hi, lo;
     split2(W[(k * M + m) * ld + col0 + d], hi, lo);
-    __nv_bfloat16* base = out + k * 3 * (int64_t)M * D;
+    __half* base = out + k * 3 * (int64_t)M * D;
     base[((int64_t)0 * M + m) * D + d] = hi;
     base[((int64_t)1 * M + m) * D + d] = lo;
     base[((int64_t)2 * M + m) * D + d] = hi;
@@ -151,20 +157,31 @@ grouped_colsum_kernel(const float* __restrict__ dv, const int* __restrict__ type
     }
 }
 
-}  // namespace bl
+__global__ void unscale_kernel(float* __restrict__ x, int64_t n, const float* __restrict__ amax) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] *= 1.0f / pow2_scale_for(__ldg(amax));
+}
 
+}  // namespace bl
 using namespace bl;
 
-extern "C" int bl_rows_split3_bf16(const float* table, const int32_t* idx, int64_t num_rows, int32_t dim, void* out,
-                                   bl_stream_t stream) {
+extern "C" int bl_unscale_pow2(float* x, int64_t n, const float* amax, bl_stream_t stream) {
+    if (n < 0 || amax == nullptr) return BL_ERR_INVALID_ARGUMENT;
+    if (n == 0) return BL_OK;
+    unscale_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, amax);
+    return check_launch("bl_unscale_pow2");
+}
+
+extern "C" int bl_rows_split3_f16(const float* table, const int32_t* idx, int64_t num_rows, int32_t dim,
+                                  const float* amax, void* out, bl_stream_t stream) {
     if (num_rows < 0 || dim <= 0 || (dim & 3)) return BL_ERR_INVALID_ARGUMENT;
     if (num_rows == 0) return BL_OK;
     rows_split3_kernel<<<grid_for(num_rows * (dim / 4 + 1), 256), 256, 0, (cudaStream_t)stream>>>(
-        table, idx, num_rows, dim, (__nv_bfloat16*)out);
-    return check_launch("bl_rows_split3_bf16");
+        table, idx, num_rows, dim, amax, (__half*)out);
+    return check_launch("bl_rows_split3_f16");
 }
 
-extern "C" int bl_weights_split3_bf16(const float* weight, const float* bias, int32_t num_types, int32_t out_dim,
+extern "C" int bl_weights_split3_f16(const float* weight, const float* bias, int32_t num_types, int32_t out_dim,
                                       int32_t in_dim, int32_t ld, int32_t col0, void* w3_fwd, void* b3_bwd,
                                       bl_stream_t stream_) {
     if (num_types <= 0 || out_dim <= 0 || in_dim <= 0 || (in_dim & 3)) return BL_ERR_INVALID_ARGUMENT;
@@ -172,11 +189,11 @@ extern "C" int bl_weights_split3_bf16(const float* weight, const float* bias, in
     const int64_t KM = (int64_t)num_types * out_dim;
     if (w3_fwd)
         weights_split3_fwd_kernel<<<grid_for(KM * (in_dim + 1), 256), 256, 0, stream>>>(weight, bias, KM, in_dim, ld, col0,
-                                                                                   (__nv_bfloat16*)w3_fwd);
+                                                                                   (__half*)w3_fwd);
     if (b3_bwd)
         weights_stack3_bwd_kernel<<<grid_for(KM * in_dim, 256), 256, 0, stream>>>(weight, num_types, out_dim, in_dim, ld,
-                                                                                col0, (__nv_bfloat16*)b3_bwd);
-    return check_launch("bl_weights_split3_bf16");
+                                                                                col0, (__half*)b3_bwd);
+    return check_launch("bl_weights_split3_f16");
 }
 
 // out[rows of type k, 0:M] = a3[rows, 0:Kp] . w3[k, 0:M, 0:Kp]^T      (row-major; Kp = 3*D + 8)
@@ -188,15 +205,15 @@ extern "C" int bl_pair_project_fwd(const void* a3, const void* w3, const int32_t
     if (rc) return rc;
     const int Kp = 3 * in_dim + BIAS_PAD;
     const float one = 1.f, zero = 0.f;
-    const __nv_bfloat16* A = (const __nv_bfloat16*)a3;
-    const __nv_bfloat16* W = (const __nv_bfloat16*)w3;
+    const __half* A = (const __half*)a3;
+    const __half* W = (const __half*)w3;
     for (int k = 0; k < num_types; ++k) {
         const int lo = type_ptr_host[k], hi = type_ptr_host[k + 1];
         if (hi <= lo) continue;
         // column-major view: C^T[M, P] = W_k[M, Kp] . A^T[Kp, P]
         rc = check_blas(cublasGemmEx(h, CUBLAS_OP_T, CUBLAS_OP_N, out_dim, hi - lo, Kp, &one,
-                                     W + (size_t)k * out_dim * Kp, CUDA_R_16BF, Kp,
-                                     A + (size_t)lo * Kp, CUDA_R_16BF, Kp, &zero,
+                                     W + (size_t)k * out_dim * Kp, CUDA_R_16F, Kp,
+                                     A + (size_t)lo * Kp, CUDA_R_16F, Kp, &zero,
                                      out + (size_t)lo * out_dim, CUDA_R_32F, out_dim,
                                      CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT), "bl_pair_project_fwd");
         if (rc) return rc;
@@ -214,15 +231,15 @@ extern "C" int bl_pair_project_bwd_input(const void* g3, const void* b3, const i
     const int M = out_dim, D = in_dim;
     const int gstride = 3 * M + BIAS_PAD;
     const float one = 1.f, zero = 0.f;
-    const __nv_bfloat16* G = (const __nv_bfloat16*)g3;
-    const __nv_bfloat16* B = (const __nv_bfloat16*)b3;
+    const __half* G = (const __half*)g3;
+    const __half* B = (const __half*)b3;
     for (int k = 0; k < num_types; ++k) {
         const int lo = type_ptr_host[k], hi = type_ptr_host[k + 1];
         if (hi <= lo) continue;
         // C^T[D, P] = B3^T[D, 3M] . G3^T[3M, P]
         rc = check_blas(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, D, hi - lo, 3 * M, &one,
-                                     B + (size_t)k * 3 * M * D, CUDA_R_16BF, D,
-                                     G + (size_t)lo * gstride, CUDA_R_16BF, gstride, &zero,
+                                     B + (size_t)k * 3 * M * D, CUDA_R_16F, D,
+                                     G + (size_t)lo * gstride, CUDA_R_16F, gstride, &zero,
                                      d_rows + (size_t)lo * D, CUDA_R_32F, D,
                                      CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT), "bl_pair_project_bwd_input");
         if (rc) return rc;
@@ -241,8 +258,8 @@ extern "C" int bl_pair_project_bwd_weight(const void* g3, const void* a3, const 
     const int M = out_dim, D = in_dim;
     const int gstride = 3 * M + BIAS_PAD, astride = 3 * D + BIAS_PAD;
     const float one = 1.f, zero = 0.f;
-    const __nv_bfloat16* G = (const __nv_bfloat16*)g3;
-    const __nv_bfloat16* A = (const __nv_bfloat16*)a3;
+    const __half* G = (const __half*)g3;
+    const __half* A = (const __half*)a3;
     // (g part offset, a part offset): g1.h1, g1.h2, g2.h1   (g3 = [g1|g1|g2], a3 = [h1|h1|h2])
     const int goff[3] = {0, 0, 2 * M};
     const int aoff[3] = {0, 2 * D, 0};
@@ -257,8 +274,8 @@ extern "C" int bl_pair_project_bwd_weight(const void* g3, const void* a3, const 
         for (int t = 0; t < 3; ++t) {
             // C^T[D, M] (+)= H^T[D, P] . G[P, M]
             rc = check_blas(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, D, M, hi - lo, &one,
-                                         A + (size_t)lo * astride + aoff[t], CUDA_R_16BF, astride,
-                                         G + (size_t)lo * gstride + goff[t], CUDA_R_16BF, gstride,
+                                         A + (size_t)lo * astride + aoff[t], CUDA_R_16F, astride,
+                                         G + (size_t)lo * gstride + goff[t], CUDA_R_16F, gstride,
                                          t == 0 ? &zero : &one, C, CUDA_R_32F, ld,
                                          CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT), "bl_pair_project_bwd_weight");
             if (rc) return rc;

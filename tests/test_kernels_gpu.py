@@ -55,7 +55,7 @@ def test_plan_no_edges(cuda_device):
     (2000, 128, 256, 5, [9000, 3000, 50], False, True),     # ITER=2, isolated nodes
     (1200, 256, 512, 7, [5000, 2000, 700], True, True),     # ITER=4 (the wide post-residual layer)
 ])
-@pytest.mark.parametrize("mode", ["bf16x3", "fp32"])
+@pytest.mark.parametrize("mode", ["f16x3", "fp32"])
 def test_typed_edge_message_max_fwd_bwd(cuda_device, monkeypatch, mode, N, D, M, K, epk, self_edges, use_bias):
     from buglab_b200 import ops
     from oracle.mp_ref import typed_edge_message_max_ref
