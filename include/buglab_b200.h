@@ -126,9 +126,24 @@ int bl_pair_project_bwd_input(const void* g3, const void* b3_bwd, const int32_t*
 int bl_pair_project_bwd_weight(const void* g3, const void* a3, const int32_t* type_ptr_host, int32_t num_types,
                                int32_t out_dim, int32_t in_dim, float* d_weight, int32_t ld, int32_t col0,
                                bl_stream_t stream);
-/* out[k, 0:dim] = sum of rows[type_ptr[k] : type_ptr[k+1], :]   (type_ptr on the DEVICE; the bias gradient) */
+/* out[k, 0:dim] = sum of rows[type_ptr[k] : type_ptr[k+1], :]   (type_ptr on the DEVICE; the bias gradient; dim <= 1024) */
 int bl_grouped_colsum(const float* rows, const int32_t* type_ptr, int32_t num_types, int32_t dim, float* out,
                       bl_stream_t stream);
+
+/* amax[0] = max_i |x[i]|  (n % 4 == 0) — the device-side scale source for an fp16 split of a gradient tensor */
+int bl_absmax(const float* x, int64_t n, float* amax, bl_stream_t stream);
+
+/* Hand-written tcgen05/TMEM version of the pair projection: gathers + splits the fp32 rows inside the GEMM loader, so
+ * the split table never exists in HBM.   out[p, 0:n_out] = s * src[idx[p], 0:k_in] . W_k^T (+ bias_k),  p in type k.
+ *   parts  = bl_weight_parts_f16 output [num_types, 2 (hi,lo), n_out, k_in] fp16
+ *   idx    may be NULL (identity), amax may be NULL (s = 1), bias may be NULL; type_ptr is a DEVICE array.
+ * Supported shapes: k_in % 64 == 0 and n_out in {128, 256, 512, 768, 1024} (bl_pair_project_tc_supported). */
+int bl_weight_parts_f16(const float* weight, int32_t num_types, int32_t n_out, int32_t k_in, int32_t ld, int32_t col0,
+                        int32_t transposed, void* parts, bl_stream_t stream);
+int bl_pair_project_tc_supported(int32_t n_out, int32_t k_in);
+int bl_pair_project_tc(const float* src, const int32_t* idx, const float* amax, const void* parts, const float* bias,
+                       const int32_t* type_ptr, int32_t num_types, int64_t num_rows, int32_t n_out, int32_t k_in,
+                       float* out, bl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused typed-edge message + aggregate (THE hot kernel).

@@ -143,6 +143,9 @@ def _project_pairs(rows: torch.Tensor, weight: torch.Tensor, col0: int, type_ptr
 # Projection arithmetic: "f16x3" = split-fp16 tensor-core GEMMs (default, see csrc/gemm.cu); "fp32" = cuBLAS SGEMM
 # through torch.mm (kept as an exact referee for tests and error budgeting).
 PROJECTION_MODE = "f16x3"
+# With "f16x3": run the forward projections through the hand-written tcgen05 kernel (csrc/pair_project_tc.cu: gather +
+# split inside the GEMM loader, no split table in HBM) whenever the shape is supported; else split kernel + cuBLAS.
+USE_TCGEN05 = False
 
 
 def _host_i32(values: Tuple[int, ...]):
@@ -169,10 +172,33 @@ def _split3_weights(weight: torch.Tensor, bias: Optional[torch.Tensor], col0: in
     return w3, b3
 
 
+def weight_parts(weight: torch.Tensor, n_out: int, k_in: int, col0: int, transposed: bool) -> torch.Tensor:
+    """fp16 hi/lo parts [K, 2, n_out, k_in] of weight[:, :, col0:...] (or of its transpose) for the tcgen05 kernel."""
+    K, _, ld = weight.shape
+    parts = torch.empty((K, 2, n_out, k_in), device=weight.device, dtype=torch.float16)
+    check(_lib.load().bl_weight_parts_f16(f32(weight), K, n_out, k_in, ld, col0, 1 if transposed else 0, parts.data_ptr(),
+                                          stream_ptr(weight.device)), "bl_weight_parts_f16")
+    return parts
+
+
+def pair_project_tc(src: torch.Tensor, idx: Optional[torch.Tensor], parts: torch.Tensor, bias: Optional[torch.Tensor],
+                    type_ptr_dev: torch.Tensor, num_rows: int, amax: Optional[torch.Tensor] = None) -> torch.Tensor:
+    K, _, n_out, k_in = parts.shape
+    out = torch.empty((num_rows, n_out), device=src.device, dtype=torch.float32)
+    check(_lib.load().bl_pair_project_tc(f32(src), i32(idx) if idx is not None else None,
+                                         f32(amax) if amax is not None else None, parts.data_ptr(),
+                                         f32(bias) if bias is not None else None, i32(type_ptr_dev), K, num_rows, n_out, k_in,
+                                         f32(out), stream_ptr(src.device)), "bl_pair_project_tc")
+    return out
+
+
 def _project_pairs_f16x3(h: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor, col0: int,
-                          type_ptr: Tuple[int, ...], bias: Optional[torch.Tensor]) -> torch.Tensor:
+                          type_ptr: Tuple[int, ...], bias: Optional[torch.Tensor],
+                          type_ptr_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     K, M, _ = weight.shape
     D = h.shape[1]
+    if USE_TCGEN05 and type_ptr_dev is not None and _lib.load().bl_pair_project_tc_supported(M, D):
+        return pair_project_tc(h, idx, weight_parts(weight, M, D, col0, False), bias, type_ptr_dev, int(idx.shape[0]))
     a3 = _split3_rows(h, idx)
     w3, _ = _split3_weights(weight, bias, col0, D, True, False)
     out = torch.empty((idx.shape[0], M), device=h.device, dtype=torch.float32)
@@ -201,8 +227,8 @@ class TypedEdgeMessageMax(torch.autograd.Function):
         bias_c = bias.contiguous() if bias is not None else None
         with torch.no_grad():
             if PROJECTION_MODE == "f16x3":
-                u_rows = _project_pairs_f16x3(h, plan.s_node, weight, 0, plan.s_type_ptr_host, None)
-                v_rows = _project_pairs_f16x3(h, plan.t_node, weight, D, plan.t_type_ptr_host, bias_c)
+                u_rows = _project_pairs_f16x3(h, plan.s_node, weight, 0, plan.s_type_ptr_host, None, plan.s_type_ptr)
+                v_rows = _project_pairs_f16x3(h, plan.t_node, weight, D, plan.t_type_ptr_host, bias_c, plan.t_type_ptr)
             else:
                 hs = _rows_gather(h, plan.s_node)
                 u_rows = _project_pairs(hs, weight, 0, plan.s_type_ptr_host, None)
@@ -294,6 +320,63 @@ class TypedEdgeMessageMax(torch.autograd.Function):
 
 def typed_edge_message_max(h, weight, bias, plan: EdgePlan) -> torch.Tensor:
     return TypedEdgeMessageMax.apply(h, weight, bias, plan)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Dense Linear (no bias) on the tensor cores with the same split-fp16 scheme — the node-update Linear(M -> D_out)
+# ---------------------------------------------------------------------------------------------------
+class DenseLinearF16x3(torch.autograd.Function):
+    """y = x @ weight.T for x [R, K_in], weight [N_out, K_in] (fp32 in/out, fp16x3 tensor-core arithmetic)."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, weight: torch.Tensor):
+        lib = _lib.load()
+        x = x.contiguous()
+        weight = weight.contiguous()
+        R, K_in = x.shape
+        N_out = weight.shape[0]
+        w = weight.view(1, N_out, K_in)
+        tp = _host_i32((0, R))
+        a3 = _split3_rows(x, None)
+        w3, _ = _split3_weights(w, None, 0, K_in, True, False)
+        y = torch.empty((R, N_out), device=x.device, dtype=torch.float32)
+        check(lib.bl_pair_project_fwd(a3.data_ptr(), w3.data_ptr(), tp, 1, N_out, K_in, f32(y), stream_ptr(x.device)),
+              "bl_pair_project_fwd")
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: torch.Tensor):
+        lib = _lib.load()
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        R, K_in = x.shape
+        N_out = weight.shape[0]
+        dev = x.device
+        w = weight.view(1, N_out, K_in)
+        tp = _host_i32((0, R))
+        amax = torch.empty(1, device=dev, dtype=torch.float32)
+        check(lib.bl_absmax(f32(dy), dy.numel(), f32(amax), stream_ptr(dev)), "bl_absmax")
+        g3 = _split3_rows(dy, None, amax)
+        _, b3 = _split3_weights(w, None, 0, K_in, False, True)
+        dx = torch.empty_like(x)
+        check(lib.bl_pair_project_bwd_input(g3.data_ptr(), b3.data_ptr(), tp, 1, N_out, K_in, f32(dx), stream_ptr(dev)),
+              "bl_pair_project_bwd_input")
+        check(lib.bl_unscale_pow2(f32(dx), dx.numel(), f32(amax), stream_ptr(dev)), "bl_unscale_pow2")
+        a3 = _split3_rows(x, None)
+        dw = torch.empty_like(weight)
+        check(lib.bl_pair_project_bwd_weight(g3.data_ptr(), a3.data_ptr(), tp, 1, N_out, K_in, f32(dw), K_in, 0,
+                                             stream_ptr(dev)), "bl_pair_project_bwd_weight")
+        check(lib.bl_unscale_pow2(f32(dw), dw.numel(), f32(amax), stream_ptr(dev)), "bl_unscale_pow2")
+        return dx, dw
+
+
+def dense_linear(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """Bias-free Linear: split-fp16 tensor-core GEMMs by default, plain fp32 library GEMM in "fp32" mode or for odd widths."""
+    if PROJECTION_MODE == "f16x3" and x.shape[1] % 4 == 0 and weight.shape[0] % 4 == 0 and x.shape[0] * 4 % 4 == 0 \
+            and (x.shape[0] * weight.shape[0]) % 4 == 0:
+        return DenseLinearF16x3.apply(x, weight)
+    return torch.nn.functional.linear(x, weight)
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -136,25 +136,62 @@ __global__ void weights_stack3_bwd_kernel(const float* __restrict__ W, int64_t K
     base[((int64_t)2 * M + m) * D + d] = hi;
 }
 
-// d_bias[k, m] = sum over the rows of type k of dv[row, m]; one block per (k, 32-channel slab), fixed order.
+// out[k, :] += sum of a slab of rows of type k.  Work items = (type, slab of COLSUM_ROWS rows), enumerated like GEMM
+// tiles from the device-side type_ptr; a block reads whole rows with 128-bit loads (dim4 float4 per row, 256/dim4
+// row lanes), reduces the lanes through shared memory and adds one float4 per column group with atomics.
+constexpr int COLSUM_ROWS = 2048;
 __global__ void __launch_bounds__(256)
-grouped_colsum_kernel(const float* __restrict__ dv, const int* __restrict__ type_ptr, int M, float* __restrict__ out) {
-    const int k = blockIdx.x;
-    const int m = blockIdx.y * 32 + (threadIdx.x & 31);
-    const int sub = threadIdx.x >> 5;  // 8 row lanes
-    const int lo = type_ptr[k], hi = type_ptr[k + 1];
-    float acc = 0.f;
-    if (m < M)
-        for (int r = lo + sub; r < hi; r += 8) acc += dv[(size_t)r * M + m];
-    __shared__ float part[8][32];
-    part[sub][threadIdx.x & 31] = acc;
-    __syncthreads();
-    if (sub == 0 && m < M) {
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s += part[j][threadIdx.x & 31];
-        out[(size_t)k * M + m] = s;
+grouped_colsum_kernel(const float4* __restrict__ rows, const int* __restrict__ type_ptr, int num_types, int dim4,
+                      float* __restrict__ out) {
+    __shared__ int prefix[130];
+    __shared__ float4 part[256];
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int k = 0; k < num_types; ++k) {
+            prefix[k] = acc;
+            acc += (type_ptr[k + 1] - type_ptr[k] + COLSUM_ROWS - 1) / COLSUM_ROWS;
+        }
+        prefix[num_types] = acc;
     }
+    __syncthreads();
+    const int total = prefix[num_types];
+    const int lanes = 256 / dim4;            // row lanes per block (dim4 <= 256)
+    const int col = threadIdx.x % dim4, lane = threadIdx.x / dim4;
+    for (int work = blockIdx.x; work < total; work += gridDim.x) {
+        int k = 0;
+        while (work >= prefix[k + 1]) ++k;
+        const int lo = type_ptr[k] + (work - prefix[k]) * COLSUM_ROWS;
+        const int hi = min(lo + COLSUM_ROWS, type_ptr[k + 1]);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < lanes)
+            for (int r = lo + lane; r < hi; r += lanes) {
+                const float4 v = __ldg(rows + (size_t)r * dim4 + col);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        part[threadIdx.x] = acc;
+        __syncthreads();
+        if (lane == 0) {
+            for (int l = 1; l < lanes; ++l) {
+                const float4 v = part[l * dim4 + col];
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            float* o = out + ((size_t)k * dim4 + col) * 4;
+            atomicAdd(o + 0, acc.x); atomicAdd(o + 1, acc.y); atomicAdd(o + 2, acc.z); atomicAdd(o + 3, acc.w);
+        }
+        __syncthreads();
+    }
+}
+
+// amax[0] = max |x[i]|  (non-negative floats order as unsigned ints; amax zeroed by the caller side of the launch)
+__global__ void __launch_bounds__(256) absmax_kernel(const float4* __restrict__ x, int64_t n4, unsigned* __restrict__ amax_bits) {
+    float m = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(x + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));
 }
 
 __global__ void unscale_kernel(float* __restrict__ x, int64_t n, const float* __restrict__ amax) {
@@ -285,9 +322,20 @@ extern "C" int bl_pair_project_bwd_weight(const void* g3, const void* a3, const 
 }
 
 extern "C" int bl_grouped_colsum(const float* rows, const int32_t* type_ptr, int32_t num_types, int32_t dim, float* out,
-                                 bl_stream_t stream) {
-    if (num_types <= 0 || dim <= 0) return BL_ERR_INVALID_ARGUMENT;
-    dim3 grid(num_types, (dim + 31) / 32);
-    grouped_colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rows, type_ptr, dim, out);
+                                 bl_stream_t stream_) {
+    if (num_types <= 0 || num_types > 128 || dim <= 0 || (dim & 3) || dim > 1024) return BL_ERR_INVALID_ARGUMENT;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = check_cuda(cudaMemsetAsync(out, 0, (size_t)num_types * dim * sizeof(float), stream), "bl_grouped_colsum memset");
+    if (rc) return rc;
+    grouped_colsum_kernel<<<4 * kNumSMs, 256, 0, stream>>>((const float4*)rows, type_ptr, num_types, dim / 4, out);
     return check_launch("bl_grouped_colsum");
+}
+
+extern "C" int bl_absmax(const float* x, int64_t n, float* amax, bl_stream_t stream_) {
+    if (n < 0 || (n & 3) || amax == nullptr) return BL_ERR_INVALID_ARGUMENT;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = check_cuda(cudaMemsetAsync(amax, 0, sizeof(float), stream), "bl_absmax memset");
+    if (rc || n == 0) return rc;
+    absmax_kernel<<<4 * kNumSMs, 256, 0, stream>>>((const float4*)x, n / 4, (unsigned*)amax);
+    return check_launch("bl_absmax");
 }

@@ -1,0 +1,331 @@
+// Fused gather + fp16-split + grouped GEMM on the 5th-gen tensor cores (tcgen05 / TMEM), sm_100a only.
+//
+//   out[p, 0:N] = scale * src[idx[p], 0:Kin] . W_k[0:N, 0:Kin]^T (+ bias_k)      for the pair rows p of type k
+//
+// This is the hoisted per-type affine of ptgnn's MlpMessagePassingLayer (U = A_k h_src, V = B_k h_tgt + b_k; reference
+// call site buglab/models/gnnlayerdefs.py:6-23) and, with src = the table gradient and W transposed, its backward with
+// respect to the gathered rows.  Compared with bl_rows_split3_f16 + cublasGemmEx it never materialises the split table
+// A3[P, 3*Kin+8] in HBM: the loader gathers the fp32 rows, splits them into fp16 hi/lo parts in registers and writes the
+// 128-byte-swizzled K-major smem tiles the UMMA descriptors expect; one gathered 128x64 fp32 chunk feeds 12 MMAs
+// (hi.w1, hi.w2, lo.w1 for 4 k-steps of 16), all accumulating into one fp32 TMEM tile of 128 lanes x N columns.
+//
+// CTA = 256 threads, persistent over (type, 128-row tile[, 256-column half]) work items; per 64-wide K chunk:
+//   all threads : wait until the MMAs that last read this smem stage committed (mbarrier), gather+split A (8 float4
+//                 each), cp.async the w1/w2 chunk rows (K-major, 128 B per row, 16-byte units XOR-swizzled by row&7),
+//                 fence.proxy.async, bar.sync
+//   thread 0    : 12 x tcgen05.mma.cta_group::1.kind::f16 (M=128, N=128|256, K=16), tcgen05.commit -> mbarrier[stage]
+// so the tensor core works on chunk i while the threads load chunk i+1 into the other stage.  Epilogue: tcgen05.ld
+// (32 lanes x 32 columns per warp and step) -> + bias -> 128-byte row segments to global.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace bl {
+namespace tc {
+
+constexpr int TILE_M = 128;     // pair rows per tile = TMEM lanes
+constexpr int CHUNK_K = 64;     // fp16 elements per smem row = 128 bytes = one swizzle atom
+constexpr int THREADS = 256;
+constexpr int MAX_TYPES = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+// Bounded spin: a protocol bug must trap (and fail the launch) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spin > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in
+// [0,14), leading byte offset (unused for one 128-byte atom along K) in [16,30), stride byte offset = 8 rows * 128 B
+// = 1024 >> 4 in [32,46), descriptor version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 (1 at [4,6)), A=B=F16 (0), both K-major, N>>3 at [17,23),
+// M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc_f16_f32(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// byte offset of (row, 16-byte unit j) inside a [rows x 128 B] K-major SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t sw128(int row, int unit) { return (uint32_t)(row * 128 + ((unit ^ (row & 7)) << 4)); }
+
+struct Params {
+    const float* src;       // [*, Kin] fp32
+    const int* idx;         // [P] rows of src, or nullptr (identity)
+    const float* amax;      // device scalar for the pow2 pre-scale, or nullptr
+    const __half* wparts;   // [num_types, 2 (hi,lo), N, Kin] fp16, Kin contiguous
+    const float* bias;      // [num_types, N] or nullptr
+    const int* type_ptr;    // [num_types+1] on the device
+    float* out;             // [P, N]
+    int num_types, N, Kin;
+};
+
+// NT = columns handled per work item (128 or 256); N is a multiple of NT.
+template <int NT>
+__global__ void __launch_bounds__(THREADS, 1) pair_project_tc_kernel(const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // stage layout: A_hi [128x128B] | A_lo [128x128B] | B_hi [NT x 128B] | B_lo [NT x 128B]
+    constexpr uint32_t A_BYTES = TILE_M * 128;
+    constexpr uint32_t B_BYTES = NT * 128;
+    constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+
+    __shared__ uint64_t mbar[2];       // stage free (MMAs that read it have completed)
+    __shared__ uint64_t mbar_acc;      // accumulator complete
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ int tile_prefix[MAX_TYPES + 1];
+    __shared__ int row_index[TILE_M];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_splits = p.N / NT;
+
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        mbar_init(&mbar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        int acc = 0;
+        for (int k = 0; k < p.num_types; ++k) {
+            tile_prefix[k] = acc;
+            acc += (p.type_ptr[k + 1] - p.type_ptr[k] + TILE_M - 1) / TILE_M;
+        }
+        tile_prefix[p.num_types] = acc;
+    }
+    if (warp == 0) {  // TMEM: NT fp32 columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(NT));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    const int total_tiles = tile_prefix[p.num_types] * n_splits;
+    const float scale = (p.amax != nullptr) ? pow2_scale_for(__ldg(p.amax)) : 1.0f;
+    const uint32_t idesc = umma_idesc_f16_f32(TILE_M, NT);
+    const int num_chunks = p.Kin / CHUNK_K;
+
+    uint32_t commits[2] = {0, 0};  // commits issued so far per stage (identical in all threads)
+    uint32_t acc_commits = 0;
+
+    for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+        const int tile = work / n_splits, split = work - tile * n_splits;
+        int k = 0;
+        while (tile >= tile_prefix[k + 1]) ++k;  // num_types is small
+        const int row0 = p.type_ptr[k] + (tile - tile_prefix[k]) * TILE_M;
+        const int row_end = p.type_ptr[k + 1];
+        const int col0 = split * NT;
+
+        if (tid < TILE_M) {
+            const int r = row0 + tid;
+            row_index[tid] = (r < row_end) ? (p.idx ? __ldg(p.idx + r) : r) : -1;
+        }
+        __syncthreads();
+        const __half* w_hi = p.wparts + ((size_t)(k * 2 + 0) * p.N + col0) * p.Kin;
+        const __half* w_lo = p.wparts + ((size_t)(k * 2 + 1) * p.N + col0) * p.Kin;
+
+        for (int c = 0; c < num_chunks; ++c) {
+            const int s = c & 1;
+            uint8_t* stage = smem + (size_t)s * STAGE_BYTES;
+            if (commits[s] > 0) mbar_wait(&mbar[s], (commits[s] - 1) & 1);  // MMAs of the previous use of this stage are done
+            // ---- A: gather 128 rows x 64 fp32, split, write hi / lo tiles ----
+#pragma unroll
+            for (int i = 0; i < (TILE_M * CHUNK_K / 4) / THREADS; ++i) {
+                const int f = i * THREADS + tid;
+                const int r = f >> 4, c4 = f & 15;  // 16 float4 per row chunk
+                const int src_row = row_index[r];
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (src_row >= 0) v = __ldg(reinterpret_cast<const float4*>(p.src + (size_t)src_row * p.Kin + c * CHUNK_K) + c4);
+                v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+                const __half h0 = __float2half_rn(v.x), h1 = __float2half_rn(v.y), h2 = __float2half_rn(v.z), h3 = __float2half_rn(v.w);
+                const __half l0 = __float2half_rn(v.x - __half2float(h0)), l1 = __float2half_rn(v.y - __half2float(h1));
+                const __half l2 = __float2half_rn(v.z - __half2float(h2)), l3 = __float2half_rn(v.w - __half2float(h3));
+                uint2 hp, lp;
+                hp.x = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                hp.y = (uint32_t)__half_as_ushort(h2) | ((uint32_t)__half_as_ushort(h3) << 16);
+                lp.x = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                lp.y = (uint32_t)__half_as_ushort(l2) | ((uint32_t)__half_as_ushort(l3) << 16);
+                const uint32_t off = sw128(r, c4 >> 1) + ((c4 & 1) << 3);  // 4 halfs = 8 bytes inside a 16-byte unit
+                *reinterpret_cast<uint2*>(stage + off) = hp;
+                *reinterpret_cast<uint2*>(stage + A_BYTES + off) = lp;
+            }
+            // ---- B: NT rows x 128 B of w_hi and w_lo (K-major rows of Kin halfs) ----
+#pragma unroll
+            for (int i = 0; i < (NT * 8) / THREADS; ++i) {
+                const int f = i * THREADS + tid;
+                const int r = f >> 3, u = f & 7;
+                const size_t goff = (size_t)r * p.Kin + c * CHUNK_K + u * 8;
+                cp_async16(smem_u32(stage + 2 * A_BYTES + sw128(r, u)), w_hi + goff);
+                cp_async16(smem_u32(stage + 2 * A_BYTES + B_BYTES + sw128(r, u)), w_lo + goff);
+            }
+            cp_async_wait_all();
+            fence_async_proxy();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(stage), a_lo = a_hi + A_BYTES;
+                const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < CHUNK_K / 16; ++kk) {
+                    const uint32_t koff = kk * 32;  // 16 halfs = 32 bytes along K inside the swizzle atom
+                    umma_f16(tmem_base, umma_desc_sw128(a_hi + koff), umma_desc_sw128(b_hi + koff), idesc, (c | kk) ? 1u : 0u);
+                    umma_f16(tmem_base, umma_desc_sw128(a_hi + koff), umma_desc_sw128(b_lo + koff), idesc, 1u);
+                    umma_f16(tmem_base, umma_desc_sw128(a_lo + koff), umma_desc_sw128(b_hi + koff), idesc, 1u);
+                }
+                tc_commit(&mbar[s]);                       // frees this stage when the 12 MMAs have read it
+                if (c == num_chunks - 1) tc_commit(&mbar_acc);  // accumulator complete
+            }
+            commits[s] += 1;
+        }
+        // ---- epilogue: TMEM -> registers -> (+bias) -> global ----
+        mbar_wait(&mbar_acc, acc_commits & 1);
+        acc_commits += 1;
+        tc_fence_after();
+        {
+            const int lane_base = (warp & 3) * 32;           // a warp may only touch its own quarter of the 128 lanes
+            const int r = lane_base + lane;
+            const bool valid = (row0 + r) < row_end;
+            float* orow = p.out + (size_t)(row0 + r) * p.N + col0;
+            const float* brow = p.bias ? p.bias + (size_t)k * p.N + col0 : nullptr;
+            constexpr int COLS_PER_GROUP = NT / 2;           // warps 0-3 take the first half of the columns, 4-7 the second
+            const int cbase = (warp >> 2) * COLS_PER_GROUP;
+#pragma unroll 1
+            for (int j = 0; j < COLS_PER_GROUP / 32; ++j) {
+                float v[32];
+                const int col = cbase + j * 32;
+                tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)col, v);
+                if (valid) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        if (brow) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(brow + col) + q);
+                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                        }
+                        reinterpret_cast<float4*>(orow + col)[q] = o;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();  // accumulator drained (and row_index free) before the next tile's first MMA / index load
+    }
+
+    // all MMAs this CTA issued have completed (every accumulator was waited for); release TMEM
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(NT));
+    }
+}
+
+// wparts[k, part, n, kin] = hi/lo of W[k, n, col0 + kin]              (transposed == 0, W is [K, N, ld])
+//                         = hi/lo of W[k, kin, col0 + n]              (transposed != 0, W is [K, Kin, ld])
+__global__ void weight_parts_kernel(const float* __restrict__ W, int num_types, int N, int Kin, int ld, int col0,
+                                    int transposed, __half* __restrict__ out) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (int64_t)num_types * N * Kin) return;
+    const int kin = (int)(gid % Kin);
+    const int n = (int)((gid / Kin) % N);
+    const int64_t k = gid / ((int64_t)Kin * N);
+    const float w = transposed ? W[(k * Kin + kin) * ld + col0 + n] : W[(k * N + n) * ld + col0 + kin];
+    const __half hi = __float2half_rn(w);
+    const __half lo = __float2half_rn(w - __half2float(hi));
+    out[((k * 2 + 0) * N + n) * Kin + kin] = hi;
+    out[((k * 2 + 1) * N + n) * Kin + kin] = lo;
+}
+
+}  // namespace tc
+}  // namespace bl
+
+using namespace bl;
+
+extern "C" int bl_weight_parts_f16(const float* weight, int32_t num_types, int32_t n_out, int32_t k_in, int32_t ld,
+                                   int32_t col0, int32_t transposed, void* parts, bl_stream_t stream) {
+    if (num_types <= 0 || n_out <= 0 || k_in <= 0) return BL_ERR_INVALID_ARGUMENT;
+    tc::weight_parts_kernel<<<grid_for((int64_t)num_types * n_out * k_in, 256), 256, 0, (cudaStream_t)stream>>>(
+        weight, num_types, n_out, k_in, ld, col0, transposed, (__half*)parts);
+    return check_launch("bl_weight_parts_f16");
+}
+
+extern "C" int bl_pair_project_tc_supported(int32_t n_out, int32_t k_in) {
+    return (k_in % tc::CHUNK_K == 0) && (n_out == 128 || (n_out % 256 == 0 && n_out <= 1024));
+}
+
+extern "C" int bl_pair_project_tc(const float* src, const int32_t* idx, const float* amax, const void* parts,
+                                  const float* bias, const int32_t* type_ptr, int32_t num_types, int64_t num_rows,
+                                  int32_t n_out, int32_t k_in, float* out, bl_stream_t stream_) {
+    if (num_types <= 0 || num_types > tc::MAX_TYPES || num_rows < 0) return BL_ERR_INVALID_ARGUMENT;
+    if (!bl_pair_project_tc_supported(n_out, k_in)) return BL_ERR_UNSUPPORTED;
+    if (num_rows == 0) return BL_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    tc::Params p{src, idx, amax, (const __half*)parts, bias, type_ptr, out, num_types, n_out, k_in};
+    const int64_t max_tiles = (num_rows + tc::TILE_M - 1) / tc::TILE_M + num_types;
+    if (n_out == 128) {
+        constexpr uint32_t smem = 2 * (2 * 128 * 128 + 2 * 128 * 128) + 1024;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(tc::pair_project_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            attr_set = true;
+        }
+        const int grid = (int)std::min<int64_t>(kNumSMs, max_tiles);
+        tc::pair_project_tc_kernel<128><<<grid, tc::THREADS, smem, stream>>>(p);
+    } else {
+        constexpr uint32_t smem = 2 * (2 * 128 * 128 + 2 * 256 * 128) + 1024;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(tc::pair_project_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            attr_set = true;
+        }
+        const int grid = (int)std::min<int64_t>(kNumSMs, max_tiles * (n_out / 256));
+        tc::pair_project_tc_kernel<256><<<grid, tc::THREADS, smem, stream>>>(p);
+    }
+    return check_launch("bl_pair_project_tc");
+}

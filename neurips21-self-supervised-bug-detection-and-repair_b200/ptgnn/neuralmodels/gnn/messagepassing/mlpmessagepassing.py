@@ -67,5 +67,5 @@ class MlpMessagePassingLayer(AbstractMessagePassingLayer):
         aggregated = ops.typed_edge_message_max(node_states, weight, bias, plan)  # [N, M]
         norm, dense = self.__state_update[0], self.__state_update[1]
         normed = ops.layer_norm(aggregated, norm.weight, norm.bias, norm.eps)
-        updated = torch.nn.functional.linear(normed, dense.weight)  # plain fp32 library GEMM
+        updated = ops.dense_linear(normed, dense.weight)  # split-fp16 tensor-core GEMM (fp32-class accuracy)
         return ops.tanh_dropout(updated, self.__dropout_rate, self.training)
