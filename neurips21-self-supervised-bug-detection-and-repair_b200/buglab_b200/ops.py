@@ -8,6 +8,7 @@ Reference semantics replaced: P4/P5 ``MlpMessagePassingLayer`` 
 A9/A10 scatter ops (``buglab/models/utils.py:15-48``), P2 subtoken max-pool, A12 optimiser.
 """
 import ctypes
+import os
 from typing import List, NamedTuple, Optional, Sequence, Tuple
 
 import torch
@@ -145,7 +146,7 @@ def _project_pairs(rows: torch.Tensor, weight: torch.Tensor, col0: int, type_ptr
 PROJECTION_MODE = "f16x3"
 # With "f16x3": run the forward projections through the hand-written tcgen05 kernel (csrc/pair_project_tc.cu: gather +
 # split inside the GEMM loader, no split table in HBM) whenever the shape is supported; else split kernel + cuBLAS.
-USE_TCGEN05 = False
+USE_TCGEN05 = os.environ.get("BUGLAB_B200_TCGEN05", "1") != "0"
 
 
 def _host_i32(values: Tuple[int, ...]):
