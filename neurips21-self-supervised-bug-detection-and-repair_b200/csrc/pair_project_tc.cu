@@ -169,6 +169,9 @@ __global__ void __launch_bounds__(THREADS, 1) pair_project_tc_kernel(const Param
             row_index[tid] = (r < row_end) ? (p.idx ? __ldg(p.idx + r) : r) : -1;
         }
         __syncthreads();
+        int my_rows[(TILE_M * CHUNK_K / 4) / THREADS];
+#pragma unroll
+        for (int i = 0; i < (TILE_M * CHUNK_K / 4) / THREADS; ++i) my_rows[i] = row_index[(i * THREADS + tid) >> 4];
         const __half* w_hi = p.wparts + ((size_t)(k * 2 + 0) * p.N + col0) * p.Kin;
         const __half* w_lo = p.wparts + ((size_t)(k * 2 + 1) * p.N + col0) * p.Kin;
 
@@ -176,14 +179,31 @@ __global__ void __launch_bounds__(THREADS, 1) pair_project_tc_kernel(const Param
             const int s = c & 1;
             uint8_t* stage = smem + (size_t)s * STAGE_BYTES;
             if (commits[s] > 0) mbar_wait(&mbar[s], (commits[s] - 1) & 1);  // MMAs of the previous use of this stage are done
-            // ---- A: gather 128 rows x 64 fp32, split, write hi / lo tiles ----
+            // ---- B: NT rows x 128 B of w_hi and w_lo (K-major rows of Kin halfs), asynchronous ----
 #pragma unroll
-            for (int i = 0; i < (TILE_M * CHUNK_K / 4) / THREADS; ++i) {
+            for (int i = 0; i < (NT * 8) / THREADS; ++i) {
+                const int f = i * THREADS + tid;
+                const int r = f >> 3, u = f & 7;
+                const size_t goff = (size_t)r * p.Kin + c * CHUNK_K + u * 8;
+                cp_async16(smem_u32(stage + 2 * A_BYTES + sw128(r, u)), w_hi + goff);
+                cp_async16(smem_u32(stage + 2 * A_BYTES + B_BYTES + sw128(r, u)), w_lo + goff);
+            }
+            // ---- A: gather 128 rows x 64 fp32 (all loads in flight first), split, write hi / lo tiles ----
+            constexpr int A_ITERS = (TILE_M * CHUNK_K / 4) / THREADS;  // 8 float4 per thread
+            float4 av[A_ITERS];
+#pragma unroll
+            for (int i = 0; i < A_ITERS; ++i) {
+                const int f = i * THREADS + tid;
+                const int src_row = my_rows[i];  // row_index[f >> 4], hoisted per tile
+                av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (src_row >= 0)
+                    av[i] = __ldg(reinterpret_cast<const float4*>(p.src + (size_t)src_row * p.Kin + c * CHUNK_K) + (f & 15));
+            }
+#pragma unroll
+            for (int i = 0; i < A_ITERS; ++i) {
                 const int f = i * THREADS + tid;
                 const int r = f >> 4, c4 = f & 15;  // 16 float4 per row chunk
-                const int src_row = row_index[r];
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (src_row >= 0) v = __ldg(reinterpret_cast<const float4*>(p.src + (size_t)src_row * p.Kin + c * CHUNK_K) + c4);
+                float4 v = av[i];
                 v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
                 const __half h0 = __float2half_rn(v.x), h1 = __float2half_rn(v.y), h2 = __float2half_rn(v.z), h3 = __float2half_rn(v.w);
                 const __half l0 = __float2half_rn(v.x - __half2float(h0)), l1 = __float2half_rn(v.y - __half2float(h1));
@@ -196,15 +216,6 @@ __global__ void __launch_bounds__(THREADS, 1) pair_project_tc_kernel(const Param
                 const uint32_t off = sw128(r, c4 >> 1) + ((c4 & 1) << 3);  // 4 halfs = 8 bytes inside a 16-byte unit
                 *reinterpret_cast<uint2*>(stage + off) = hp;
                 *reinterpret_cast<uint2*>(stage + A_BYTES + off) = lp;
-            }
-            // ---- B: NT rows x 128 B of w_hi and w_lo (K-major rows of Kin halfs) ----
-#pragma unroll
-            for (int i = 0; i < (NT * 8) / THREADS; ++i) {
-                const int f = i * THREADS + tid;
-                const int r = f >> 3, u = f & 7;
-                const size_t goff = (size_t)r * p.Kin + c * CHUNK_K + u * 8;
-                cp_async16(smem_u32(stage + 2 * A_BYTES + sw128(r, u)), w_hi + goff);
-                cp_async16(smem_u32(stage + 2 * A_BYTES + B_BYTES + sw128(r, u)), w_lo + goff);
             }
             cp_async_wait_all();
             fence_async_proxy();  // generic-proxy smem writes -> visible to the tensor core (async proxy)

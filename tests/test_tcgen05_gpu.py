@@ -77,9 +77,12 @@ def test_pair_project_tc_transposed_with_prescale(cuda_device):
 
 
 @pytest.mark.parametrize("R,K_in,N_out", [(1000, 256, 256), (777, 512, 256), (64, 32, 16)])
-def test_dense_linear_f16x3(cuda_device, R, K_in, N_out):
+@pytest.mark.parametrize("exact_forward", [True, False])
+def test_dense_linear_f16x3(cuda_device, monkeypatch, exact_forward, R, K_in, N_out):
     from buglab_b200 import ops
     from oracle import parity
+
+    monkeypatch.setattr(ops.DenseLinearF16x3, "exact_forward", exact_forward)
 
     g = torch.Generator().manual_seed(R)
     x = torch.randn(R, K_in, generator=g)
