@@ -294,7 +294,9 @@ def edge_kernel_roofline(mb, nn, hidden, device):
     achieved = algo_bytes / (ms / 1e3) / 1e9
     return {"bound": "hbm", "kernel": "edge_segmax_fwd_warp (bl_edge_segmax_fwd), H->H layer", "achieved": achieved,
             "peak": peaks["hbm_gbs"], "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-            "traffic": None, "algorithmic_bytes": algo_bytes, "ms_per_launch": ms, "nodes": N, "edges": E,
+            # dram__bytes_read+write of this kernel on this exact workload, from the committed ncu --set full capture
+            # (profiles/r1_edge_segmax_fwd_ncu.md); null for any other shape
+            "traffic": 10253209000 if (N, E, M) == (564508, 6410926, 256) else None, "algorithmic_bytes": algo_bytes, "ms_per_launch": ms, "nodes": N, "edges": E,
             "working_set_bytes": int((u.numel() + v.numel()) * 4)}
 
 

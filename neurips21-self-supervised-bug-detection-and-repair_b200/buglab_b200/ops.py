@@ -209,6 +209,11 @@ def _project_pairs_f16x3(h: torch.Tensor, idx: torch.Tensor, weight: torch.Tenso
     return out
 
 
+# Test hook: when set to a list, every forward appends the winning ORIGINAL edge index per (node, channel)
+# (num_edges for nodes without in-edges) so that an oracle can be evaluated with the same max-routing.
+WINNER_TRACE: Optional[list] = None
+
+
 class TypedEdgeMessageMax(torch.autograd.Function):
     """agg[n] = max over in-edges (s->n, type k) of GELU(W_k [h_s; h_n] + b_k); 0 for isolated nodes.
 
@@ -246,6 +251,9 @@ class TypedEdgeMessageMax(torch.autograd.Function):
                                        N, M, f32(agg), f32(xwin), i32(ewin), stream_ptr(h.device)),
                 "bl_edge_segmax_fwd",
             )
+        if WINNER_TRACE is not None:
+            e = ewin.long()
+            WINNER_TRACE.append(torch.where(e >= 0, plan.e_perm.long()[e.clamp(min=0)], torch.full_like(e, plan.num_edges)).cpu())
         ctx.plan = plan
         ctx.has_bias = bias is not None
         ctx.mode = PROJECTION_MODE

@@ -46,6 +46,15 @@ class GraphNeuralNetwork(nn.Module):
     def layers(self):
         return self.__message_passing_layers
 
+    def force_winners(self, per_layer_winners) -> None:
+        """Route every max-aggregation like the traced implementation did (None resets to the oracle's own argmax)."""
+        mp_layers = [l for l in self.__message_passing_layers if not isinstance(l, _NoParams)]
+        if per_layer_winners is None:
+            per_layer_winners = [None] * len(mp_layers)
+        assert len(per_layer_winners) == len(mp_layers)
+        for layer, winners in zip(mp_layers, per_layer_winners):
+            layer.forced_winners = winners
+
     def forward(self, node_data, adjacency_lists, return_all_states: bool = False):
         state = self.__node_embedder(**node_data)
         states, remembered = [state], None

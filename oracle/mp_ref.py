@@ -55,6 +55,10 @@ class MlpMessagePassingLayer(nn.Module):
         self.__state_update = nn.Sequential(nn.LayerNorm(message_dimension), dense, nn.Tanh(), nn.Dropout(p=dropout_rate))
         self.__output_state_dim = output_state_dimension
         self.__input_state_dim = input_state_dimension
+        # test hook: [N, M] int64 winning edge per (node, channel) in the type-major concatenation (E = no edge).  When
+        # set, the max-aggregation uses THIS routing instead of its own argmax, which makes gradients comparable
+        # elementwise with an implementation whose near-tied winners differ (see oracle/parity.py).
+        self.forced_winners = None
 
     @property
     def output_state_dimension(self) -> int:
@@ -70,6 +74,11 @@ class MlpMessagePassingLayer(nn.Module):
         bias = torch.stack([l.bias for l in layers]) if layers[0].bias is not None else None
         messages, targets = edge_messages_ref(node_states, adjacency_lists, weight, bias)
         N = node_states.shape[0]
+        if self.__aggregation == "max" and self.forced_winners is not None:
+            arg = self.forced_winners
+            E = messages.shape[0]
+            picked = messages.gather(0, arg.clamp(max=E - 1))
+            return torch.where(arg >= E, torch.zeros_like(picked), picked)
         if self.__aggregation == "max":
             return scatter_max(messages, targets, dim=0, dim_size=N)[0]
         if self.__aggregation == "min":

@@ -7,11 +7,13 @@ channel's gradient to different edges.  Measured on the smoke workload (scripts/
 oracle itself differs from its own fp64 run by up to 3.7e-3 in dW (values up to 0.37) because ~2.5e-6 of the
 (node, channel) winners flip, while the GPU path is within 2-4e-4 of fp64.  One flipped winner near the loss re-routes a whole back-propagation path (the loss gradient enters at ~40 candidate
 nodes per graph and max-aggregation forwards each channel to exactly one in-edge), so it can move most entries of an
-early layer's dW by ~1 %.  Gradient parity is therefore:
-  * relative Frobenius error of every gradient tensor below 2e-2 (a routing bug — wrong edge, wrong type, missing
-    term — fails this by orders of magnitude), and
-  * at least 99.5 % of the entries within 1e-4 (abs + rel) whenever the sample is not routing-ambiguous, i.e. whenever
-    the fp32 CPU oracle agrees elementwise with its own fp64 run on that tensor.
+early layer's dW by ~1 %.  Gradient parity is therefore established in two ways:
+  * ROUTING-CONDITIONED (model tests, smoke): the GPU path exports its winning edge per (node, channel)
+    (`ops.WINNER_TRACE`), the oracle re-runs with that routing forced (`force_winners`) and every gradient tensor must
+    then agree elementwise to 1e-4 (abs + rel) — this checks every backward kernel exactly;
+  * UNCONDITIONED (goldens from the real reference, where routing cannot be forced): relative Frobenius error of every
+    gradient tensor below 5e-2, which a routing bug (wrong edge, wrong type, missing term) fails by orders of
+    magnitude while winner flips stay below it (CPU fp32 vs CPU fp64 reach ~1e-2).
 """
 import torch
 
@@ -53,17 +55,20 @@ def grad_mismatch(actual: torch.Tensor, expected: torch.Tensor):
     return frac_bad, rel_l2, float((a - e).abs().max()) if a.numel() else 0.0
 
 
-def assert_grad_close(actual: torch.Tensor, expected: torch.Tensor, what: str = "", expected_fp64: torch.Tensor = None,
-                      max_frac_bad: float = 5e-3, max_rel_l2: float = 2e-2) -> None:
-    """Norm-wise check always; elementwise check unless the fp32 oracle itself disagrees elementwise with its own fp64
-    run on this tensor (``expected_fp64``), which marks the sample as routing-ambiguous (near-tied max winners)."""
+def assert_grad_close_normwise(actual: torch.Tensor, expected: torch.Tensor, what: str = "", max_rel_l2: float = 5e-2) -> None:
+    """Unconditioned gradient check (routing may differ at near-ties): relative Frobenius error only."""
+    _, rel_l2, max_abs = grad_mismatch(actual, expected)
+    assert rel_l2 <= max_rel_l2, (
+        f"{what}: relative L2 error {rel_l2:.2e} (allowed {max_rel_l2:.0e}), max abs diff {max_abs:.2e}")
+
+
+def assert_grad_close(actual: torch.Tensor, expected: torch.Tensor, what: str = "", max_frac_bad: float = 5e-3,
+                      max_rel_l2: float = 2e-2) -> None:
+    """Elementwise (>= 99.5 % of entries within 1e-4 abs+rel) and norm-wise check; use with identical max-routing
+    (forced winners) or on data without near-ties."""
     frac_bad, rel_l2, max_abs = grad_mismatch(actual, expected)
     assert rel_l2 <= max_rel_l2, (
         f"{what}: relative L2 error {rel_l2:.2e} (allowed {max_rel_l2:.0e}), max abs diff {max_abs:.2e}")
-    if expected_fp64 is not None:
-        oracle_frac_bad, _, _ = grad_mismatch(expected, expected_fp64)
-        if oracle_frac_bad > 1e-4:
-            return  # the CPU fp32 reference is itself > 1e-4 away from exact arithmetic here: winners flipped
     assert frac_bad <= max_frac_bad, (
         f"{what}: {frac_bad:.3%} of entries off by more than 1e-4 (allowed {max_frac_bad:.2%}), "
         f"relative L2 error {rel_l2:.2e}, max abs diff {max_abs:.2e}")
