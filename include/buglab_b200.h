@@ -121,10 +121,18 @@ int bl_pair_project_fwd(const void* a3, const void* w3_fwd, const int32_t* type_
 /* d_rows[rows of type k, 0:in_dim] = g3[rows, 0:3*out_dim] . b3_bwd[k]   (g3 = bl_rows_split3_f16 of the table gradient) */
 int bl_pair_project_bwd_input(const void* g3, const void* b3_bwd, const int32_t* type_ptr_host, int32_t num_types,
                               int32_t out_dim, int32_t in_dim, float* d_rows, bl_stream_t stream);
-/* d_weight[k, 0:out_dim, col0:col0+in_dim] = sum over rows of type k of g^T h  (three fp16 GEMMs, fp32 accumulate);
- * types without rows are zero-filled. */
-int bl_pair_project_bwd_weight(const void* g3, const void* a3, const int32_t* type_ptr_host, int32_t num_types,
-                               int32_t out_dim, int32_t in_dim, float* d_weight, int32_t ld, int32_t col0,
+/* out[r,:] = [hi | lo] of s*table[idx[r],:]  (fp16 [num_rows, 2*dim]) — the operand of the weight-gradient GEMM */
+int bl_rows_split2_f16(const float* table, const int32_t* idx, int64_t num_rows, int32_t dim, const float* amax,
+                       void* out, bl_stream_t stream);
+/* d_weight[k, 0:out_dim, col0:col0+in_dim] = (1/s) * sum over rows of type k of g^T h.  One fp16 GEMM per type forms all
+ * four hi/lo cross products T_k[2*out_dim, 2*in_dim] = [g1|g2]^T.[h1|h2] into tmp (fp32, [num_types, 2*out_dim,
+ * 2*in_dim]); a fold kernel adds the blocks and undoes the pow2 pre-scale of g (amax may be NULL: s = 1).
+ * g holds [g1|g2] at columns [g_col0, g_col0 + 2*out_dim) of a split table with row stride g_stride (three-part table:
+ * g_stride = 3*out_dim+8, g_col0 = out_dim; two-part table: g_stride = 2*out_dim, g_col0 = 0);
+ * a2 = bl_rows_split2_f16 of the gathered inputs. */
+int bl_pair_project_bwd_weight(const void* g, int32_t g_stride, int32_t g_col0, const void* a2,
+                               const int32_t* type_ptr_host, int32_t num_types, int32_t out_dim, int32_t in_dim,
+                               const float* amax, float* tmp, float* d_weight, int32_t ld, int32_t col0,
                                bl_stream_t stream);
 /* out[k, 0:dim] = sum of rows[type_ptr[k] : type_ptr[k+1], :]   (type_ptr on the DEVICE; the bias gradient; dim <= 1024) */
 int bl_grouped_colsum(const float* rows, const int32_t* type_ptr, int32_t num_types, int32_t dim, float* out,

@@ -38,7 +38,8 @@ _SIGNATURES = {
     "bl_weights_split3_f16": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
     "bl_pair_project_fwd": (c_i32, [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr, c_ptr]),
     "bl_pair_project_bwd_input": (c_i32, [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr, c_ptr]),
-    "bl_pair_project_bwd_weight": (c_i32, [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr, c_i32, c_i32, c_ptr]),
+    "bl_rows_split2_f16": (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_ptr, c_ptr, c_ptr]),
+    "bl_pair_project_bwd_weight": (c_i32, [c_ptr, c_i32, c_i32, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_ptr]),
     "bl_grouped_colsum": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_ptr, c_ptr]),
     "bl_absmax": (c_i32, [c_ptr, c_i64, c_ptr, c_ptr]),
     "bl_weight_parts_f16": (c_i32, [c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr, c_ptr]),
@@ -102,7 +103,7 @@ KERNELS_PER_CALL = {
     "bl_segment_log_softmax_fwd": 5, "bl_segment_log_softmax_bwd": 2, "bl_subtoken_maxpool_fwd": 1,
     "bl_subtoken_maxpool_bwd": 1, "bl_grad_sqnorm": 2, "bl_adam_step": 1,
     "bl_rows_split3_bf16": 1, "bl_weights_split3_f16": 2, "bl_pair_project_fwd": 0, "bl_pair_project_bwd_input": 0,
-    "bl_pair_project_bwd_weight": 0, "bl_grouped_colsum": 1, "bl_absmax": 1, "bl_weight_parts_f16": 1,
+    "bl_pair_project_bwd_weight": 1, "bl_rows_split2_f16": 1, "bl_grouped_colsum": 1, "bl_absmax": 1, "bl_weight_parts_f16": 1,
     "bl_pair_project_tc": 1,
 }
 launch_counter = {"kernels": 0, "calls": 0}

@@ -163,6 +163,16 @@ def _split3_rows(table: torch.Tensor, idx: Optional[torch.Tensor], amax: Optiona
     return out
 
 
+def _split2_rows(table: torch.Tensor, idx: Optional[torch.Tensor], amax: Optional[torch.Tensor] = None) -> torch.Tensor:
+    rows = int(idx.shape[0]) if idx is not None else int(table.shape[0])
+    dim = int(table.shape[1])
+    out = torch.empty((rows, 2 * dim), device=table.device, dtype=torch.float16)
+    check(_lib.load().bl_rows_split2_f16(f32(table), i32(idx) if idx is not None else None, rows, dim,
+                                         f32(amax) if amax is not None else None, out.data_ptr(),
+                                         stream_ptr(table.device)), "bl_rows_split2_f16")
+    return out
+
+
 def _split3_weights(weight: torch.Tensor, bias: Optional[torch.Tensor], col0: int, in_dim: int, fwd: bool, bwd: bool):
     K, M, ld = weight.shape
     w3 = torch.empty((K, M, 3 * in_dim + 8), device=weight.device, dtype=torch.float16) if fwd else None
@@ -284,21 +294,33 @@ class TypedEdgeMessageMax(torch.autograd.Function):
             d_weight = torch.empty_like(weight)
             if d_bias is not None:
                 check(lib.bl_grouped_colsum(f32(dv), i32(plan.t_type_ptr), K, M, f32(d_bias), stream_ptr(dev)), "bl_grouped_colsum")
-            for rows_idx, d_tab, col0, type_ptr in ((plan.s_node, du, 0, plan.s_type_ptr_host),
-                                                    (plan.t_node, dv, D, plan.t_type_ptr_host)):
+            use_tc = USE_TCGEN05 and D <= 256 and bool(lib.bl_pair_project_tc_supported(D, M))
+            for rows_idx, d_tab, col0, type_ptr, type_ptr_dev in (
+                    (plan.s_node, du, 0, plan.s_type_ptr_host, plan.s_type_ptr),
+                    (plan.t_node, dv, D, plan.t_type_ptr_host, plan.t_type_ptr)):
                 tp = _host_i32(type_ptr)
-                g3 = _split3_rows(d_tab, None, amax)  # pre-scaled by a power of two: d_in / d_weight carry that factor
-                _, b3 = _split3_weights(weight, None, col0, D, False, True)
-                d_in = torch.empty((rows_idx.shape[0], D), device=dev, dtype=torch.float32)
-                check(lib.bl_pair_project_bwd_input(g3.data_ptr(), b3.data_ptr(), tp, K, M, D, f32(d_in), stream_ptr(dev)),
-                      "bl_pair_project_bwd_input")
-                a3 = _split3_rows(h, rows_idx)  # recomputed instead of kept alive since forward
-                check(lib.bl_pair_project_bwd_weight(g3.data_ptr(), a3.data_ptr(), tp, K, M, D, f32(d_weight), 2 * D, col0,
-                                                     stream_ptr(dev)), "bl_pair_project_bwd_weight")
+                # both results below carry the power-of-two pre-scale of the gradient table; it is undone in
+                # bl_rows_segment_sum (d_in) and in the fold kernel of bl_pair_project_bwd_weight (d_weight)
+                if use_tc:
+                    # d(rows) = dTable @ W_k[:, col0:col0+D] on the hand-written tcgen05 kernel (reads the fp32 table directly)
+                    d_in = pair_project_tc(d_tab, None, weight_parts(weight, D, M, col0, True), None, type_ptr_dev,
+                                           int(rows_idx.shape[0]), amax=amax)
+                    g, g_stride, g_col0 = _split2_rows(d_tab, None, amax), 2 * M, 0
+                else:
+                    g, g_stride, g_col0 = _split3_rows(d_tab, None, amax), 3 * M + 8, M
+                    _, b3 = _split3_weights(weight, None, col0, D, False, True)
+                    d_in = torch.empty((rows_idx.shape[0], D), device=dev, dtype=torch.float32)
+                    check(lib.bl_pair_project_bwd_input(g.data_ptr(), b3.data_ptr(), tp, K, M, D, f32(d_in), stream_ptr(dev)),
+                          "bl_pair_project_bwd_input")
+                    del b3
+                a2 = _split2_rows(h, rows_idx)  # recomputed instead of kept alive since forward
+                tmp = torch.empty((K, 2 * M, 2 * D), device=dev, dtype=torch.float32)
+                check(lib.bl_pair_project_bwd_weight(g.data_ptr(), g_stride, g_col0, a2.data_ptr(), tp, K, M, D, f32(amax),
+                                                     f32(tmp), f32(d_weight), 2 * D, col0, stream_ptr(dev)),
+                      "bl_pair_project_bwd_weight")
                 d_rows.append(d_in)
-                del g3, a3, b3
+                del g, a2, tmp
             del du, dv
-            check(lib.bl_unscale_pow2(f32(d_weight), d_weight.numel(), f32(amax), stream_ptr(dev)), "bl_unscale_pow2")
         else:
             d_weight = torch.zeros_like(weight)
             for rows_idx, d_tab, col0, type_ptr, is_t in (
@@ -381,11 +403,11 @@ class DenseLinearF16x3(torch.autograd.Function):
         check(lib.bl_pair_project_bwd_input(g3.data_ptr(), b3.data_ptr(), tp, 1, N_out, K_in, f32(dx), stream_ptr(dev)),
               "bl_pair_project_bwd_input")
         check(lib.bl_unscale_pow2(f32(dx), dx.numel(), f32(amax), stream_ptr(dev)), "bl_unscale_pow2")
-        a3 = _split3_rows(x, None)
+        a2 = _split2_rows(x, None)
         dw = torch.empty_like(weight)
-        check(lib.bl_pair_project_bwd_weight(g3.data_ptr(), a3.data_ptr(), tp, 1, N_out, K_in, f32(dw), K_in, 0,
-                                             stream_ptr(dev)), "bl_pair_project_bwd_weight")
-        check(lib.bl_unscale_pow2(f32(dw), dw.numel(), f32(amax), stream_ptr(dev)), "bl_unscale_pow2")
+        tmp = torch.empty((1, 2 * N_out, 2 * K_in), device=dev, dtype=torch.float32)
+        check(lib.bl_pair_project_bwd_weight(g3.data_ptr(), 3 * N_out + 8, N_out, a2.data_ptr(), tp, 1, N_out, K_in, f32(amax),
+                                             f32(tmp), f32(dw), K_in, 0, stream_ptr(dev)), "bl_pair_project_bwd_weight")
         return dx, dw
 
 

@@ -95,6 +95,48 @@ rows_split3_kernel(const float* __restrict__ table, const int* __restrict__ idx,
     *reinterpret_cast<uint2*>(orow + 2 * D + 4 * c) = lp;
 }
 
+// out[r, :] = [hi | lo] of row idx[r] (or r): the two-part table the weight-gradient GEMM consumes (2*D fp16 per row)
+__global__ void __launch_bounds__(256)
+rows_split2_kernel(const float* __restrict__ table, const int* __restrict__ idx, int64_t num_rows, int D,
+                   const float* __restrict__ amax, __half* __restrict__ out) {
+    const int D4 = D / 4;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= num_rows * D4) return;
+    const int64_t r = gid / D4;
+    const int c = (int)(gid - r * D4);
+    const int64_t src_row = idx ? (int64_t)__ldg(idx + r) : r;
+    float4 v = __ldg(reinterpret_cast<const float4*>(table + src_row * D) + c);
+    if (amax != nullptr) {
+        const float sc = pow2_scale_for(__ldg(amax));
+        v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+    }
+    __half h[4], l[4];
+    split2(v.x, h[0], l[0]); split2(v.y, h[1], l[1]); split2(v.z, h[2], l[2]); split2(v.w, h[3], l[3]);
+    uint2 hp, lp;
+    hp.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+    hp.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+    lp.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
+    lp.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
+    __half* orow = out + r * 2 * (int64_t)D;
+    *reinterpret_cast<uint2*>(orow + 4 * c) = hp;
+    *reinterpret_cast<uint2*>(orow + D + 4 * c) = lp;
+}
+
+// d_weight[k, m, col0 + d] = T[k, m, d] + T[k, m, D + d] + T[k, M + m, d] + T[k, M + m, D + d]   (T is [K, 2M, 2D])
+__global__ void combine_weight_grad_kernel(const float* __restrict__ T, int64_t K, int M, int D, int ld, int col0,
+                                           const float* __restrict__ amax, float* __restrict__ dW) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= K * M * D) return;
+    const int d = (int)(gid % D);
+    const int m = (int)((gid / D) % M);
+    const int64_t k = gid / ((int64_t)D * M);
+    const float* t = T + k * 4 * (int64_t)M * D;
+    const int64_t r1 = (int64_t)m * 2 * D, r2 = (int64_t)(M + m) * 2 * D;
+    float v = (t[r1 + d] + t[r1 + D + d]) + (t[r2 + d] + t[r2 + D + d]);
+    if (amax != nullptr) v *= 1.0f / pow2_scale_for(__ldg(amax));
+    dW[(k * M + m) * ld + col0 + d] = v;
+}
+
 // Forward weights: w3[k, m, :] = [w1 | w2 | w1 | b1 b2 b3 0..] of W[k, m, col0:col0+D] (row stride ld) and bias[k, m].
 __global__ void weights_split3_fwd_kernel(const float* __restrict__ W, const float* __restrict__ bias, int64_t KM, int D,
                                           int ld, int col0, __half* __restrict__ out) {
@@ -218,6 +260,15 @@ extern "C" int bl_rows_split3_f16(const float* table, const int32_t* idx, int64_
     return check_launch("bl_rows_split3_f16");
 }
 
+extern "C" int bl_rows_split2_f16(const float* table, const int32_t* idx, int64_t num_rows, int32_t dim,
+                                  const float* amax, void* out, bl_stream_t stream) {
+    if (num_rows < 0 || dim <= 0 || (dim & 3)) return BL_ERR_INVALID_ARGUMENT;
+    if (num_rows == 0) return BL_OK;
+    rows_split2_kernel<<<grid_for(num_rows * (dim / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+        table, idx, num_rows, dim, amax, (__half*)out);
+    return check_launch("bl_rows_split2_f16");
+}
+
 extern "C" int bl_weights_split3_f16(const float* weight, const float* bias, int32_t num_types, int32_t out_dim,
                                       int32_t in_dim, int32_t ld, int32_t col0, void* w3_fwd, void* b3_bwd,
                                       bl_stream_t stream_) {
@@ -284,41 +335,46 @@ extern "C" int bl_pair_project_bwd_input(const void* g3, const void* b3, const i
     return BL_OK;
 }
 
-// d_weight[k, 0:M, col0:col0+D] = g1^T h1 + g1^T h2 + g2^T h1 over the rows of type k (fp32 accumulate, beta chain)
-extern "C" int bl_pair_project_bwd_weight(const void* g3, const void* a3, const int32_t* type_ptr_host, int32_t num_types,
-                                          int32_t out_dim, int32_t in_dim, float* d_weight, int32_t ld, int32_t col0,
-                                          bl_stream_t stream_) {
-    if (num_types <= 0 || out_dim <= 0 || in_dim <= 0) return BL_ERR_INVALID_ARGUMENT;
+// d_weight[k, 0:M, col0:col0+D] = sum over the rows of type k of g^T h.  ONE fp16 GEMM per type computes all four
+// hi/lo cross products at once,  T_k[2M, 2D] = [g1|g2]^T . [h1|h2]  (operands read once; the g2.h2 block comes for
+// free and is added too), then combine_weight_grad_kernel folds the four blocks (and undoes the pow2 pre-scale).
+//   g : [g1|g2] at columns [g_col0, g_col0+2M) of a table with row stride g_stride: either the three-part table
+//       [P, 3M+8] = [g1|g1|g2|..] (g_col0 = M) or a two-part table [P, 2M] from bl_rows_split2_f16 (g_col0 = 0)
+//   a2: [P, 2D]   = [h1|h2]        (bl_rows_split2_f16)
+//   tmp: [num_types, 2M, 2D] fp32 scratch
+extern "C" int bl_pair_project_bwd_weight(const void* g, int32_t g_stride, int32_t g_col0, const void* a2,
+                                          const int32_t* type_ptr_host, int32_t num_types, int32_t out_dim,
+                                          int32_t in_dim, const float* amax, float* tmp, float* d_weight, int32_t ld,
+                                          int32_t col0, bl_stream_t stream_) {
+    if (num_types <= 0 || out_dim <= 0 || in_dim <= 0 || g_stride < 2 * out_dim) return BL_ERR_INVALID_ARGUMENT;
     cublasHandle_t h;
     int rc = get_handle((cudaStream_t)stream_, &h);
     if (rc) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
     const int M = out_dim, D = in_dim;
-    const int gstride = 3 * M + BIAS_PAD, astride = 3 * D + BIAS_PAD;
+    const int gstride = g_stride, astride = 2 * D;
     const float one = 1.f, zero = 0.f;
-    const __half* G = (const __half*)g3;
-    const __half* A = (const __half*)a3;
-    // (g part offset, a part offset): g1.h1, g1.h2, g2.h1   (g3 = [g1|g1|g2], a3 = [h1|h1|h2])
-    const int goff[3] = {0, 0, 2 * M};
-    const int aoff[3] = {0, 2 * D, 0};
+    const __half* G = (const __half*)g + g_col0;
+    const __half* A = (const __half*)a2;
     for (int k = 0; k < num_types; ++k) {
         const int lo = type_ptr_host[k], hi = type_ptr_host[k + 1];
-        float* C = d_weight + (size_t)k * M * ld + col0;
+        float* C = tmp + (size_t)k * 4 * M * D;
         if (hi <= lo) {
-            rc = check_cuda(cudaMemset2DAsync(C, (size_t)ld * 4, 0, (size_t)D * 4, M, (cudaStream_t)stream_), "dW memset");
+            rc = check_cuda(cudaMemsetAsync(C, 0, (size_t)4 * M * D * sizeof(float), stream), "dW tmp memset");
             if (rc) return rc;
             continue;
         }
-        for (int t = 0; t < 3; ++t) {
-            // C^T[D, M] (+)= H^T[D, P] . G[P, M]
-            rc = check_blas(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, D, M, hi - lo, &one,
-                                         A + (size_t)lo * astride + aoff[t], CUDA_R_16F, astride,
-                                         G + (size_t)lo * gstride + goff[t], CUDA_R_16F, gstride,
-                                         t == 0 ? &zero : &one, C, CUDA_R_32F, ld,
-                                         CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT), "bl_pair_project_bwd_weight");
-            if (rc) return rc;
-        }
+        // column-major: C^T[2D, 2M] = H_all^T[2D, P] . G_all[P, 2M]
+        rc = check_blas(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, 2 * D, 2 * M, hi - lo, &one,
+                                     A + (size_t)lo * astride, CUDA_R_16F, astride,
+                                     G + (size_t)lo * gstride, CUDA_R_16F, gstride, &zero,
+                                     C, CUDA_R_32F, 2 * D, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT),
+                        "bl_pair_project_bwd_weight");
+        if (rc) return rc;
     }
-    return BL_OK;
+    combine_weight_grad_kernel<<<grid_for((int64_t)num_types * M * D, 256), 256, 0, stream>>>(tmp, num_types, M, D, ld, col0,
+                                                                                          amax, d_weight);
+    return check_launch("bl_pair_project_bwd_weight");
 }
 
 extern "C" int bl_grouped_colsum(const float* rows, const int32_t* type_ptr, int32_t num_types, int32_t dim, float* out,
