@@ -179,8 +179,9 @@ int bl_edge_segmax_fwd(const float* u_rows, const float* v_rows,
 
 /* Backward of the above: g = d_agg * GELU'(xwin) routed to the winning edge only (the arg-routing
  * backward of torch_scatter.scatter_max).  d_v_rows[P_t,M] is fully written (each (type,tgt) row has
- * exactly one owner node); d_u_rows[P_s,M] is zero-filled here and accumulated with fp32 atomics.  amax (device
- * scalar, may be NULL) receives an upper bound of max(|d_u_rows|, |d_v_rows|) for the fp16 split's pre-scale. */
+ * exactly one owner node); d_u_rows[P_s,M] is zero-filled here and accumulated with fp32 REDs.  amax (device scalar,
+ * may be NULL) receives 256 * max|g|: the scale source of the fp16 split of both tables (|d_v_rows| <= max|g|; a
+ * d_u_rows entry sums the g of the targets sharing its pair — 256x headroom, and the split saturates, never infs). */
 int bl_edge_segmax_bwd(const float* d_agg, const float* xwin, const int32_t* ewin,
                        const int32_t* row_ptr, const int32_t* urow, const int32_t* vrow,
                        int64_t num_nodes, int32_t msg_dim, int64_t num_s_pairs, int64_t num_t_pairs,

@@ -148,6 +148,8 @@ edge_segmax_fwd_generic(const float* __restrict__ U, const float* __restrict__ V
 // share a (type,src) pair) and V row (plain stores: a (type,tgt) row belongs to exactly one target,
 // so the owner warp writes every one of its V rows in full — winners get g, the rest 0).
 // ---------------------------------------------------------------------------------------------
+constexpr float kFanInHeadroom = 256.f;  // see the amax comment in edge_segmax_bwd_warp
+
 template <int ITER>
 __global__ void __launch_bounds__(256)
 edge_segmax_bwd_warp(const float* __restrict__ d_agg, const float* __restrict__ xwin,
@@ -181,21 +183,16 @@ edge_segmax_bwd_warp(const float* __restrict__ d_agg, const float* __restrict__ 
             g[i][c] = dd[c] * gelu_grad(xx[c]);
             wv[i][c] = __ldg(vrow + ee[c]);
             const int wu = __ldg(urow + ee[c]);
-            float* dst = dU + (size_t)wu * M + 4 * (lane + 32 * i) + c;
-            if (amax_bits != nullptr) {
-                // the value an entry holds after its LAST add is observed by the thread that made it, so the
-                // maximum over all observed partial sums bounds every final |dU| (and |g| bounds every |dV|)
-                const float after = atomicAdd(dst, g[i][c]) + g[i][c];
-                local_amax = fmaxf(local_amax, fmaxf(fabsf(after), fabsf(g[i][c])));
-            } else {
-                atomicAdd(dst, g[i][c]);
-            }
+            atomicAdd(dU + (size_t)wu * M + 4 * (lane + 32 * i) + c, g[i][c]);  // result unused -> RED
+            local_amax = fmaxf(local_amax, fabsf(g[i][c]));
         }
     }
     if (amax_bits != nullptr) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) local_amax = fmaxf(local_amax, __shfl_xor_sync(FULL_MASK, local_amax, o));
-        if (lane == 0 && local_amax > 0.f) atomicMax(amax_bits, __float_as_uint(local_amax));  // non-negative floats order as uints
+        // |dV| <= max|g| exactly; a dU entry sums the g of the targets that share its (type,src) pair.  The published
+        // bound leaves room for sums of kFanInHeadroom maximal terms; the fp16 split additionally saturates (never inf).
+        if (lane == 0 && local_amax > 0.f) atomicMax(amax_bits, __float_as_uint(local_amax * kFanInHeadroom));
     }
     // every V row of this segment is written exactly once (runs of equal vrow are contiguous)
     int prev_v = -1;
@@ -235,13 +232,8 @@ edge_segmax_bwd_generic(const float* __restrict__ d_agg, const float* __restrict
     const int e = ewin[gid];
     const float g = d_agg[gid] * gelu_grad(xwin[gid]);
     const int wv = vrow[e];
-    if (amax_bits != nullptr) {
-        const float after = atomicAdd(dU + (size_t)urow[e] * M + j, g) + g;
-        const float a = fmaxf(fabsf(after), fabsf(g));
-        if (a > 0.f) atomicMax(amax_bits, __float_as_uint(a));
-    } else {
-        atomicAdd(dU + (size_t)urow[e] * M + j, g);
-    }
+    atomicAdd(dU + (size_t)urow[e] * M + j, g);
+    if (amax_bits != nullptr && g != 0.f) atomicMax(amax_bits, __float_as_uint(fabsf(g) * kFanInHeadroom));
     int prev_v = -1;
     for (int i = beg; i < end; ++i) {
         const int v = vrow[i];

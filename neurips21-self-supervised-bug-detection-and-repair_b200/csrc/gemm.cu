@@ -56,6 +56,7 @@ static int check_blas(cublasStatus_t s, const char* where) {
 }
 
 __device__ __forceinline__ void split2(float x, __half& hi, __half& lo) {
+    x = fminf(fmaxf(x, -65000.f), 65000.f);  // saturate instead of overflowing to inf (pre-scaled tables stay far below)
     hi = __float2half_rn(x);
     lo = __float2half_rn(x - __half2float(hi));
 }

@@ -204,7 +204,8 @@ __global__ void __launch_bounds__(THREADS, 1) pair_project_tc_kernel(const Param
                 const int f = i * THREADS + tid;
                 const int r = f >> 4, c4 = f & 15;  // 16 float4 per row chunk
                 float4 v = av[i];
-                v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+                v.x = fminf(fmaxf(v.x * scale, -65000.f), 65000.f); v.y = fminf(fmaxf(v.y * scale, -65000.f), 65000.f);
+                v.z = fminf(fmaxf(v.z * scale, -65000.f), 65000.f); v.w = fminf(fmaxf(v.w * scale, -65000.f), 65000.f);
                 const __half h0 = __float2half_rn(v.x), h1 = __float2half_rn(v.y), h2 = __float2half_rn(v.z), h3 = __float2half_rn(v.w);
                 const __half l0 = __float2half_rn(v.x - __half2float(h0)), l1 = __float2half_rn(v.y - __half2float(h1));
                 const __half l2 = __float2half_rn(v.z - __half2float(h2)), l3 = __float2half_rn(v.w - __half2float(h3));

@@ -40,6 +40,24 @@ def _distributed():
     return distributed
 
 
+def _record_stream(obj, stream, _depth: int = 0) -> None:
+    """Tell the caching allocator that every tensor reachable from ``obj`` is also used on ``stream`` (they were
+    allocated on the producer's side stream; without this their blocks could be recycled while still in use)."""
+    if isinstance(obj, torch.Tensor):
+        if obj.is_cuda:
+            obj.record_stream(stream)
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            _record_stream(v, stream, _depth + 1)
+    elif isinstance(obj, (list, tuple)):
+        if _depth < 6 and (not obj or not isinstance(obj[0], (int, float, str))):
+            for v in obj:
+                _record_stream(v, stream, _depth + 1)
+        plan = getattr(obj, "plan", None)  # PlannedAdjacency carries the device plan as an attribute
+        if plan is not None:
+            _record_stream(tuple(plan), stream, _depth + 1)
+
+
 class _Prefetcher:
     """Runs a minibatch iterator in a producer thread, on its own CUDA stream, ``depth`` batches ahead."""
 
@@ -78,7 +96,9 @@ class _Prefetcher:
                 return
             item, event = got
             if event is not None:
-                torch.cuda.current_stream(self._device).wait_event(event)
+                consumer = torch.cuda.current_stream(self._device)
+                consumer.wait_event(event)
+                _record_stream(item, consumer)
             yield item
 
 
