@@ -45,6 +45,8 @@ _SIGNATURES = {
     "bl_weight_parts_f16": (c_i32, [c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr, c_ptr]),
     "bl_pair_project_tc_supported": (c_i32, [c_i32, c_i32]),
     "bl_pair_project_tc": (c_i32, [c_ptr] * 6 + [c_i32, c_i64, c_i32, c_i32, c_ptr, c_ptr]),
+    "bl_pair_weight_grad_tc_supported": (c_i32, [c_i32, c_i32]),
+    "bl_pair_weight_grad_tc": (c_i32, [c_ptr] * 5 + [c_i32, c_i64, c_i32, c_i32, c_ptr, c_i32, c_i32, c_ptr]),
     "bl_edge_segmax_fwd": (c_i32, [c_ptr] * 5 + [c_i64, c_i32] + [c_ptr] * 3 + [c_ptr]),
     "bl_edge_segmax_bwd": (c_i32, [c_ptr] * 6 + [c_i64, c_i32, c_i64, c_i64] + [c_ptr] * 3 + [c_ptr]),
     "bl_layernorm_fwd": (c_i32, [c_ptr] * 3 + [c_i64, c_i32, c_f32] + [c_ptr] * 3 + [c_ptr]),
@@ -104,7 +106,7 @@ KERNELS_PER_CALL = {
     "bl_subtoken_maxpool_bwd": 1, "bl_grad_sqnorm": 2, "bl_adam_step": 1,
     "bl_rows_split3_bf16": 1, "bl_weights_split3_f16": 2, "bl_pair_project_fwd": 0, "bl_pair_project_bwd_input": 0,
     "bl_pair_project_bwd_weight": 1, "bl_rows_split2_f16": 1, "bl_grouped_colsum": 1, "bl_absmax": 1, "bl_weight_parts_f16": 1,
-    "bl_pair_project_tc": 1,
+    "bl_pair_project_tc": 1, "bl_pair_weight_grad_tc": 1,
 }
 launch_counter = {"kernels": 0, "calls": 0}
 

@@ -203,6 +203,15 @@ def pair_project_tc(src: torch.Tensor, idx: Optional[torch.Tensor], parts: torch
     return out
 
 
+def pair_weight_grad_tc(g: torch.Tensor, x: torch.Tensor, idx: torch.Tensor, amax: Optional[torch.Tensor],
+                        type_ptr_dev: torch.Tensor, d_weight: torch.Tensor, col0: int) -> None:
+    """d_weight[k, :, col0:col0+x.shape[1]] = sum over pair rows of type k of g[p]^T x[idx[p]] (tcgen05 kernel)."""
+    K, M, ld = d_weight.shape
+    check(_lib.load().bl_pair_weight_grad_tc(f32(g), f32(x), i32(idx), f32(amax) if amax is not None else None,
+                                             i32(type_ptr_dev), K, int(idx.shape[0]), M, int(x.shape[1]), f32(d_weight), ld, col0,
+                                             stream_ptr(g.device)), "bl_pair_weight_grad_tc")
+
+
 def _project_pairs_f16x3(h: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor, col0: int,
                           type_ptr: Tuple[int, ...], bias: Optional[torch.Tensor],
                           type_ptr_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -301,11 +310,14 @@ class TypedEdgeMessageMax(torch.autograd.Function):
                 tp = _host_i32(type_ptr)
                 # both results below carry the power-of-two pre-scale of the gradient table; it is undone in
                 # bl_rows_segment_sum (d_in) and in the fold kernel of bl_pair_project_bwd_weight (d_weight)
+                use_tc_wg = USE_TCGEN05 and bool(lib.bl_pair_weight_grad_tc_supported(M, D))
+                g = None
                 if use_tc:
                     # d(rows) = dTable @ W_k[:, col0:col0+D] on the hand-written tcgen05 kernel (reads the fp32 table directly)
                     d_in = pair_project_tc(d_tab, None, weight_parts(weight, D, M, col0, True), None, type_ptr_dev,
                                            int(rows_idx.shape[0]), amax=amax)
-                    g, g_stride, g_col0 = _split2_rows(d_tab, None, amax), 2 * M, 0
+                    if not use_tc_wg:
+                        g, g_stride, g_col0 = _split2_rows(d_tab, None, amax), 2 * M, 0
                 else:
                     g, g_stride, g_col0 = _split3_rows(d_tab, None, amax), 3 * M + 8, M
                     _, b3 = _split3_weights(weight, None, col0, D, False, True)
@@ -313,11 +325,16 @@ class TypedEdgeMessageMax(torch.autograd.Function):
                     check(lib.bl_pair_project_bwd_input(g.data_ptr(), b3.data_ptr(), tp, K, M, D, f32(d_in), stream_ptr(dev)),
                           "bl_pair_project_bwd_input")
                     del b3
-                a2 = _split2_rows(h, rows_idx)  # recomputed instead of kept alive since forward
-                tmp = torch.empty((K, 2 * M, 2 * D), device=dev, dtype=torch.float32)
-                check(lib.bl_pair_project_bwd_weight(g.data_ptr(), g_stride, g_col0, a2.data_ptr(), tp, K, M, D, f32(amax),
-                                                     f32(tmp), f32(d_weight), 2 * D, col0, stream_ptr(dev)),
-                      "bl_pair_project_bwd_weight")
+                if use_tc_wg:
+                    # dW_k = dTable^T h[rows] with the transposing tcgen05 loader: no split tables at all
+                    pair_weight_grad_tc(d_tab, h, rows_idx, amax, type_ptr_dev, d_weight, col0)
+                    a2 = tmp = None
+                else:
+                    a2 = _split2_rows(h, rows_idx)  # recomputed instead of kept alive since forward
+                    tmp = torch.empty((K, 2 * M, 2 * D), device=dev, dtype=torch.float32)
+                    check(lib.bl_pair_project_bwd_weight(g.data_ptr(), g_stride, g_col0, a2.data_ptr(), tp, K, M, D, f32(amax),
+                                                         f32(tmp), f32(d_weight), 2 * D, col0, stream_ptr(dev)),
+                          "bl_pair_project_bwd_weight")
                 d_rows.append(d_in)
                 del g, a2, tmp
             del du, dv

@@ -294,6 +294,185 @@ __global__ void weight_parts_kernel(const float* __restrict__ W, int num_types, 
     out[((k * 2 + 1) * N + n) * Kin + kin] = lo;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradient on the tensor cores:  dW_k[m, n] (+)= (1/s) * sum_{p in type k} (s*g[p, m]) * x[idx[p], n]
+// (dA_k = dU^T h_src, dB_k = dV^T h_tgt of the hoisted affine).  The reduction runs over PAIR ROWS, so both operands
+// are needed "row-index-minor": the loader transposes while it splits — lane = output row (m or n), 8 consecutive
+// pair rows per thread are packed into one 16-byte smem unit, which is bank-conflict free under the 128B swizzle and
+// reuses exactly the K-major descriptors validated in the projection kernel.  Work item = (type, slab of ROWS_PER_ITEM
+// pair rows, 128-row m tile, 256-column n tile); the fp32 TMEM accumulator is added to dW with REDs (dW pre-zeroed).
+constexpr int WG_ROWS_PER_ITEM = 8192;
+
+struct WgParams {
+    const float* g;        // [P, M]   table gradient (dU or dV), fp32
+    const float* x;        // [*, Nin] node states, gathered through idx
+    const int* idx;        // [P]
+    const float* amax;     // pow2 pre-scale source for g (nullable)
+    const int* type_ptr;   // [num_types + 1], device
+    float* d_weight;       // [num_types, M, ld]; this call fills columns [col0, col0 + Nin)
+    int num_types, M, Nin, ld, col0;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) pair_weight_grad_tc_kernel(const WgParams p) {
+    constexpr int NT = 256;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr uint32_t A_BYTES = TILE_M * 128;
+    constexpr uint32_t B_BYTES = NT * 128;
+    constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+
+    __shared__ uint64_t mbar[2];
+    __shared__ uint64_t mbar_acc;
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ int slab_prefix[MAX_TYPES + 1];
+    __shared__ int chunk_rows[2][CHUNK_K];  // gathered source row of each of the 64 pair rows of a chunk (-1 = past the end)
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m_tiles = p.M / TILE_M, n_tiles = p.Nin / NT;
+
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        mbar_init(&mbar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        int acc = 0;
+        for (int k = 0; k < p.num_types; ++k) {
+            slab_prefix[k] = acc;
+            acc += (p.type_ptr[k + 1] - p.type_ptr[k] + WG_ROWS_PER_ITEM - 1) / WG_ROWS_PER_ITEM;
+        }
+        slab_prefix[p.num_types] = acc;
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(NT));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    const int total_items = slab_prefix[p.num_types] * m_tiles * n_tiles;
+    const float scale = (p.amax != nullptr) ? pow2_scale_for(__ldg(p.amax)) : 1.0f;
+    const float inv_scale = 1.0f / scale;
+    const uint32_t idesc = umma_idesc_f16_f32(TILE_M, NT);
+
+    uint32_t commits[2] = {0, 0};
+    uint32_t acc_commits = 0;
+
+    for (int work = blockIdx.x; work < total_items; work += gridDim.x) {
+        const int slab = work / (m_tiles * n_tiles);
+        const int mn = work - slab * (m_tiles * n_tiles);
+        const int mt = mn / n_tiles, nt = mn - mt * n_tiles;
+        int k = 0;
+        while (slab >= slab_prefix[k + 1]) ++k;
+        const int row_begin = p.type_ptr[k] + (slab - slab_prefix[k]) * WG_ROWS_PER_ITEM;
+        const int row_end = min(row_begin + WG_ROWS_PER_ITEM, p.type_ptr[k + 1]);
+        const int num_chunks = (row_end - row_begin + CHUNK_K - 1) / CHUNK_K;
+        const int m0 = mt * TILE_M, n0 = nt * NT;
+
+        for (int c = 0; c < num_chunks; ++c) {
+            const int s = c & 1;
+            uint8_t* stage = smem + (size_t)s * STAGE_BYTES;
+            const int p0 = row_begin + c * CHUNK_K;
+            if (commits[s] > 0) mbar_wait(&mbar[s], (commits[s] - 1) & 1);
+            if (tid < CHUNK_K) {
+                const int r = p0 + tid;
+                chunk_rows[s][tid] = (r < row_end) ? __ldg(p.idx + r) : -1;
+            }
+            // ---- A = g^T tile: 128 output rows (m) x 64 pair rows; thread item = (m, group of 8 pair rows) ----
+#pragma unroll
+            for (int it = 0; it < (TILE_M * 8) / THREADS; ++it) {
+                const int item = it * THREADS + tid;
+                const int m = item & (TILE_M - 1), grp = item >> 7;
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int r = p0 + grp * 8 + j;
+                    v[j] = (r < row_end) ? __ldg(p.g + (size_t)r * p.M + m0 + m) : 0.f;
+                }
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float a = fminf(fmaxf(v[2 * j] * scale, -65000.f), 65000.f);
+                    const float b = fminf(fmaxf(v[2 * j + 1] * scale, -65000.f), 65000.f);
+                    const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+                    const __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b - __half2float(hb));
+                    hi[j] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
+                    lo[j] = (uint32_t)__half_as_ushort(la) | ((uint32_t)__half_as_ushort(lb) << 16);
+                }
+                const uint32_t off = sw128(m, grp);
+                *reinterpret_cast<uint4*>(stage + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(stage + A_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            __syncthreads();  // chunk_rows[s] visible
+            // ---- B = x^T tile: 256 output columns (n) x 64 pair rows, gathered through idx ----
+#pragma unroll
+            for (int it = 0; it < (NT * 8) / THREADS; ++it) {
+                const int item = it * THREADS + tid;
+                const int n = item & (NT - 1), grp = item >> 8;
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int src_row = chunk_rows[s][grp * 8 + j];
+                    v[j] = (src_row >= 0) ? __ldg(p.x + (size_t)src_row * p.Nin + n0 + n) : 0.f;
+                }
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const __half ha = __float2half_rn(v[2 * j]), hb = __float2half_rn(v[2 * j + 1]);
+                    const __half la = __float2half_rn(v[2 * j] - __half2float(ha)), lb = __float2half_rn(v[2 * j + 1] - __half2float(hb));
+                    hi[j] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
+                    lo[j] = (uint32_t)__half_as_ushort(la) | ((uint32_t)__half_as_ushort(lb) << 16);
+                }
+                const uint32_t off = 2 * A_BYTES + sw128(n, grp);
+                *reinterpret_cast<uint4*>(stage + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(stage + B_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            fence_async_proxy();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(stage), a_lo = a_hi + A_BYTES;
+                const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < CHUNK_K / 16; ++kk) {
+                    const uint32_t koff = kk * 32;
+                    umma_f16(tmem_base, umma_desc_sw128(a_hi + koff), umma_desc_sw128(b_hi + koff), idesc, (c | kk) ? 1u : 0u);
+                    umma_f16(tmem_base, umma_desc_sw128(a_hi + koff), umma_desc_sw128(b_lo + koff), idesc, 1u);
+                    umma_f16(tmem_base, umma_desc_sw128(a_lo + koff), umma_desc_sw128(b_hi + koff), idesc, 1u);
+                }
+                tc_commit(&mbar[s]);
+                if (c == num_chunks - 1) tc_commit(&mbar_acc);
+            }
+            commits[s] += 1;
+        }
+        // ---- epilogue: TMEM partial [128 m x 256 n] -> scaled fp32 REDs into dW_k ----
+        if (num_chunks > 0) {
+            mbar_wait(&mbar_acc, acc_commits & 1);
+            acc_commits += 1;
+            tc_fence_after();
+            const int lane_base = (warp & 3) * 32;
+            const int m = m0 + lane_base + lane;
+            float* wrow = p.d_weight + ((size_t)k * p.M + m) * p.ld + p.col0 + n0;
+            const int cbase = (warp >> 2) * (NT / 2);
+#pragma unroll 1
+            for (int j = 0; j < (NT / 2) / 32; ++j) {
+                float v[32];
+                const int col = cbase + j * 32;
+                tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)col, v);
+#pragma unroll
+                for (int q = 0; q < 32; ++q) atomicAdd(wrow + col + q, v[q] * inv_scale);
+            }
+            tc_fence_before();
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(NT));
+    }
+}
+
 }  // namespace tc
 }  // namespace bl
 
@@ -340,4 +519,33 @@ extern "C" int bl_pair_project_tc(const float* src, const int32_t* idx, const fl
         tc::pair_project_tc_kernel<256><<<grid, tc::THREADS, smem, stream>>>(p);
     }
     return check_launch("bl_pair_project_tc");
+}
+
+extern "C" int bl_pair_weight_grad_tc_supported(int32_t m_out, int32_t n_in) {
+    return (m_out % tc::TILE_M == 0) && (n_in % 256 == 0) && m_out <= 1024 && n_in <= 1024;
+}
+
+/* d_weight[k, 0:m_out, col0:col0+n_in] = sum over the pair rows p of type k of g[p, :]^T x[idx[p], :] */
+extern "C" int bl_pair_weight_grad_tc(const float* g, const float* x, const int32_t* idx, const float* amax,
+                                      const int32_t* type_ptr, int32_t num_types, int64_t num_rows, int32_t m_out,
+                                      int32_t n_in, float* d_weight, int32_t ld, int32_t col0, bl_stream_t stream_) {
+    if (num_types <= 0 || num_types > tc::MAX_TYPES || num_rows < 0 || idx == nullptr) return BL_ERR_INVALID_ARGUMENT;
+    if (!bl_pair_weight_grad_tc_supported(m_out, n_in)) return BL_ERR_UNSUPPORTED;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    // zero the destination block (columns [col0, col0+n_in) of every [m_out, ld] matrix): partials are added with REDs
+    int rc = check_cuda(cudaMemset2DAsync(d_weight + col0, (size_t)ld * sizeof(float), 0, (size_t)n_in * sizeof(float),
+                                          (size_t)num_types * m_out, stream), "bl_pair_weight_grad_tc memset");
+    if (rc) return rc;
+    if (num_rows == 0) return BL_OK;
+    tc::WgParams p{g, x, idx, amax, type_ptr, d_weight, num_types, m_out, n_in, ld, col0};
+    constexpr uint32_t smem = 2 * (2 * 128 * 128 + 2 * 256 * 128) + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(tc::pair_weight_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+    const int64_t items = ((num_rows + tc::WG_ROWS_PER_ITEM - 1) / tc::WG_ROWS_PER_ITEM + num_types) * (m_out / tc::TILE_M) * (n_in / 256);
+    const int grid = (int)std::min<int64_t>(kNumSMs, items);
+    tc::pair_weight_grad_tc_kernel<<<grid, tc::THREADS, smem, stream>>>(p);
+    return check_launch("bl_pair_weight_grad_tc");
 }

@@ -76,6 +76,42 @@ def test_pair_project_tc_transposed_with_prescale(cuda_device):
     assert float(err) < 1e-5, float(err)
 
 
+@pytest.mark.parametrize("counts,M,D,col0", [
+    ([40], 128, 256, 0),                       # a single partial chunk
+    ([64, 0, 1000, 129], 128, 256, 256),       # exact chunk, empty type, several chunks (both stages), column offset
+    ([9000, 300], 256, 256, 0),                # > 8192 rows: two slabs accumulate into the same block (REDs), 2 m tiles
+    ([2500, 1200, 700], 512, 512, 512),        # the wide layer: 4 m tiles x 2 n tiles
+])
+def test_pair_weight_grad_tc_matches_fp64(cuda_device, counts, M, D, col0):
+    from buglab_b200 import _lib, ops
+
+    g_ = torch.Generator().manual_seed(sum(counts) + M)
+    K = len(counts)
+    tp = _ragged_type_ptr(counts)
+    P = tp[-1]
+    n_src = 2000
+    grad = torch.randn(P, M, generator=g_) * 1e-3
+    x = torch.randn(n_src, D, generator=g_)
+    idx = torch.randint(0, n_src, (P,), generator=g_, dtype=torch.int32)
+    ref = torch.zeros(K, M, D, dtype=torch.float64)
+    for k in range(K):
+        lo, hi = tp[k], tp[k + 1]
+        ref[k] = grad[lo:hi].double().t() @ x[idx[lo:hi].long()].double()
+    dev = cuda_device
+    gd = grad.to(dev)
+    amax = torch.empty(1, device=dev)
+    _lib.check(_lib.load().bl_absmax(gd.data_ptr(), gd.numel(), amax.data_ptr(), torch.cuda.current_stream().cuda_stream), "bl_absmax")
+    ld = 2 * D + (256 if col0 else 0)
+    d_weight = torch.full((K, M, ld), 7.0, device=dev)  # untouched columns must keep their contents
+    ops.pair_weight_grad_tc(gd, x.to(dev), idx.to(dev), amax, torch.tensor(tp, dtype=torch.int32, device=dev), d_weight, col0)
+    torch.cuda.synchronize()
+    got = d_weight[:, :, col0:col0 + D].cpu().double()
+    scale = float(ref.abs().max())
+    assert float((got - ref).abs().max()) < 2e-6 * max(scale, 1.0) + 1e-7, float((got - ref).abs().max())
+    outside = torch.ones(ld, dtype=torch.bool); outside[col0:col0 + D] = False
+    assert torch.all(d_weight[:, :, outside.to(dev)] == 7.0)
+
+
 @pytest.mark.parametrize("R,K_in,N_out", [(1000, 256, 256), (777, 512, 256), (64, 32, 16)])
 @pytest.mark.parametrize("exact_forward", [True, False])
 def test_dense_linear_f16x3(cuda_device, monkeypatch, exact_forward, R, K_in, N_out):
