@@ -156,7 +156,7 @@ int bl_pair_project_tc(const float* src, const int32_t* idx, const float* amax, 
 /* Hand-written tcgen05/TMEM weight gradient of the pair projection (no split tables in HBM):
  *   d_weight[k, 0:m_out, col0:col0+n_in] = (1/s) * sum over pair rows p of type k of (s*g[p,:])^T x[idx[p],:]
  * g = the table gradient [P, m_out] (dU or dV), x = node states [*, n_in], s from *amax (NULL: 1).  The destination
- * block is zero-filled here and accumulated with fp32 REDs (one partial per 8192-row slab).
+ * block is zero-filled here and accumulated with fp32 REDs (one partial per 4096-row slab).
  * Supported: m_out % 128 == 0, n_in % 256 == 0, both <= 1024 (bl_pair_weight_grad_tc_supported). */
 int bl_pair_weight_grad_tc_supported(int32_t m_out, int32_t n_in);
 int bl_pair_weight_grad_tc(const float* g, const float* x, const int32_t* idx, const float* amax,

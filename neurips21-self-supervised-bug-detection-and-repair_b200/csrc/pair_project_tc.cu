@@ -62,10 +62,17 @@ __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// MN-major, SWIZZLE_128B: the tile is stored as K rows of 128 bytes (64 fp16 along M/N), 8-row groups 1024 B apart
+// (stride byte offset), further 64-wide M/N blocks `lbo_bytes` apart (leading byte offset) — canonical layout
+// Swizzle<3,4,3> o ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)) of cute::UMMA::make_umma_desc<Major::MN>.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 (1 at [4,6)), A=B=F16 (0), both K-major, N>>3 at [17,23),
 // M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t umma_idesc_f16_f32(int m, int n) {
-    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+__host__ __device__ constexpr uint32_t umma_idesc_f16_f32(int m, int n, bool mn_major = false) {
+    return (1u << 4) | (mn_major ? ((1u << 15) | (1u << 16)) : 0u) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -297,12 +304,13 @@ __global__ void weight_parts_kernel(const float* __restrict__ W, int num_types, 
 
 // ---------------------------------------------------------------------------------------------------------------
 // Weight gradient on the tensor cores:  dW_k[m, n] (+)= (1/s) * sum_{p in type k} (s*g[p, m]) * x[idx[p], n]
-// (dA_k = dU^T h_src, dB_k = dV^T h_tgt of the hoisted affine).  The reduction runs over PAIR ROWS, so both operands
-// are needed "row-index-minor": the loader transposes while it splits — lane = output row (m or n), 8 consecutive
-// pair rows per thread are packed into one 16-byte smem unit, which is bank-conflict free under the 128B swizzle and
-// reuses exactly the K-major descriptors validated in the projection kernel.  Work item = (type, slab of ROWS_PER_ITEM
-// pair rows, 128-row m tile, 256-column n tile); the fp32 TMEM accumulator is added to dW with REDs (dW pre-zeroed).
-constexpr int WG_ROWS_PER_ITEM = 8192;
+// (dA_k = dU^T h_src, dB_k = dV^T h_tgt of the hoisted affine).  The reduction runs over PAIR ROWS, i.e. both operands
+// are naturally "M/N-major" (a row of g or x is contiguous along the OUTPUT dimension), so the loader copies rows
+// exactly like the projection kernel (128-bit gathers, fp16 hi/lo split, 8-byte swizzled stores) and the MMAs use
+// MN-major descriptors.  Work item = (type, slab of WG_ROWS_PER_ITEM pair rows, 128-row m tile, 256-column n tile);
+// the fp32 TMEM partial is added to dW with REDs (dW pre-zeroed).  The slab length also bounds the accumulation chain:
+// tensor-core accumulation truncates, so very long chains drift (measured 3e-5 relative after 1500 MMAs).
+constexpr int WG_ROWS_PER_ITEM = 4096;
 
 struct WgParams {
     const float* g;        // [P, M]   table gradient (dU or dV), fp32
@@ -317,8 +325,10 @@ struct WgParams {
 __global__ void __launch_bounds__(THREADS, 1) pair_weight_grad_tc_kernel(const WgParams p) {
     constexpr int NT = 256;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    constexpr uint32_t A_BYTES = TILE_M * 128;
-    constexpr uint32_t B_BYTES = NT * 128;
+    // stage: A_hi | A_lo  (each 2 blocks of [64 rows x 128 B])  |  B_hi | B_lo  (each 4 blocks of [64 rows x 128 B])
+    constexpr uint32_t BLOCK_BYTES = CHUNK_K * 128;           // one 64(pair rows) x 64(outputs) fp16 block
+    constexpr uint32_t A_BYTES = (TILE_M / 64) * BLOCK_BYTES;  // 16 KB
+    constexpr uint32_t B_BYTES = (NT / 64) * BLOCK_BYTES;      // 32 KB
     constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 
@@ -326,7 +336,6 @@ __global__ void __launch_bounds__(THREADS, 1) pair_weight_grad_tc_kernel(const W
     __shared__ uint64_t mbar_acc;
     __shared__ uint32_t tmem_base_smem;
     __shared__ int slab_prefix[MAX_TYPES + 1];
-    __shared__ int chunk_rows[2][CHUNK_K];  // gathered source row of each of the 64 pair rows of a chunk (-1 = past the end)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m_tiles = p.M / TILE_M, n_tiles = p.Nin / NT;
@@ -354,7 +363,7 @@ __global__ void __launch_bounds__(THREADS, 1) pair_weight_grad_tc_kernel(const W
     const int total_items = slab_prefix[p.num_types] * m_tiles * n_tiles;
     const float scale = (p.amax != nullptr) ? pow2_scale_for(__ldg(p.amax)) : 1.0f;
     const float inv_scale = 1.0f / scale;
-    const uint32_t idesc = umma_idesc_f16_f32(TILE_M, NT);
+    const uint32_t idesc = umma_idesc_f16_f32(TILE_M, NT, /*mn_major=*/true);
 
     uint32_t commits[2] = {0, 0};
     uint32_t acc_commits = 0;
@@ -375,58 +384,54 @@ __global__ void __launch_bounds__(THREADS, 1) pair_weight_grad_tc_kernel(const W
             uint8_t* stage = smem + (size_t)s * STAGE_BYTES;
             const int p0 = row_begin + c * CHUNK_K;
             if (commits[s] > 0) mbar_wait(&mbar[s], (commits[s] - 1) & 1);
-            if (tid < CHUNK_K) {
-                const int r = p0 + tid;
-                chunk_rows[s][tid] = (r < row_end) ? __ldg(p.idx + r) : -1;
+            // ---- loads first (all in flight), then split + swizzled stores ----
+            // A: 64 pair rows x 128 outputs of g  = 2048 float4, 8 per thread;  f -> (row = f / 32, float4 col = f % 32)
+            // B: 64 pair rows x 256 outputs of x  = 4096 float4, 16 per thread; f -> (row = f / 64, float4 col = f % 64)
+            float4 av[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int f = i * THREADS + tid;
+                const int r = p0 + (f >> 5);
+                av[i] = (r < row_end) ? __ldg(reinterpret_cast<const float4*>(p.g + (size_t)r * p.M + m0) + (f & 31))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            // ---- A = g^T tile: 128 output rows (m) x 64 pair rows; thread item = (m, group of 8 pair rows) ----
+            float4 bv[16];
 #pragma unroll
-            for (int it = 0; it < (TILE_M * 8) / THREADS; ++it) {
-                const int item = it * THREADS + tid;
-                const int m = item & (TILE_M - 1), grp = item >> 7;
-                float v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int r = p0 + grp * 8 + j;
-                    v[j] = (r < row_end) ? __ldg(p.g + (size_t)r * p.M + m0 + m) : 0.f;
+            for (int i = 0; i < 16; ++i) {
+                const int f = i * THREADS + tid;
+                const int r = p0 + (f >> 6);
+                bv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < row_end) {
+                    const int src_row = __ldg(p.idx + r);
+                    bv[i] = __ldg(reinterpret_cast<const float4*>(p.x + (size_t)src_row * p.Nin + n0) + (f & 63));
                 }
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float a = fminf(fmaxf(v[2 * j] * scale, -65000.f), 65000.f);
-                    const float b = fminf(fmaxf(v[2 * j + 1] * scale, -65000.f), 65000.f);
-                    const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
-                    const __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b - __half2float(hb));
-                    hi[j] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
-                    lo[j] = (uint32_t)__half_as_ushort(la) | ((uint32_t)__half_as_ushort(lb) << 16);
-                }
-                const uint32_t off = sw128(m, grp);
-                *reinterpret_cast<uint4*>(stage + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(stage + A_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
-            __syncthreads();  // chunk_rows[s] visible
-            // ---- B = x^T tile: 256 output columns (n) x 64 pair rows, gathered through idx ----
+            auto store_split = [&](const float4 v, float sc, uint8_t* hi_base, uint8_t* lo_base, int row, int col4) {
+                // col4 = float4 index along the output dimension; 16 float4 per 64-wide block
+                const float a0 = fminf(fmaxf(v.x * sc, -65000.f), 65000.f), a1 = fminf(fmaxf(v.y * sc, -65000.f), 65000.f);
+                const float a2 = fminf(fmaxf(v.z * sc, -65000.f), 65000.f), a3 = fminf(fmaxf(v.w * sc, -65000.f), 65000.f);
+                const __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1), h2 = __float2half_rn(a2), h3 = __float2half_rn(a3);
+                const __half l0 = __float2half_rn(a0 - __half2float(h0)), l1 = __float2half_rn(a1 - __half2float(h1));
+                const __half l2 = __float2half_rn(a2 - __half2float(h2)), l3 = __float2half_rn(a3 - __half2float(h3));
+                uint2 hp, lp;
+                hp.x = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                hp.y = (uint32_t)__half_as_ushort(h2) | ((uint32_t)__half_as_ushort(h3) << 16);
+                lp.x = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                lp.y = (uint32_t)__half_as_ushort(l2) | ((uint32_t)__half_as_ushort(l3) << 16);
+                const int block = col4 >> 4, c4 = col4 & 15;
+                const uint32_t off = block * BLOCK_BYTES + sw128(row, c4 >> 1) + ((c4 & 1) << 3);
+                *reinterpret_cast<uint2*>(hi_base + off) = hp;
+                *reinterpret_cast<uint2*>(lo_base + off) = lp;
+            };
 #pragma unroll
-            for (int it = 0; it < (NT * 8) / THREADS; ++it) {
-                const int item = it * THREADS + tid;
-                const int n = item & (NT - 1), grp = item >> 8;
-                float v[8];
+            for (int i = 0; i < 8; ++i) {
+                const int f = i * THREADS + tid;
+                store_split(av[i], scale, stage, stage + A_BYTES, f >> 5, f & 31);
+            }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int src_row = chunk_rows[s][grp * 8 + j];
-                    v[j] = (src_row >= 0) ? __ldg(p.x + (size_t)src_row * p.Nin + n0 + n) : 0.f;
-                }
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const __half ha = __float2half_rn(v[2 * j]), hb = __float2half_rn(v[2 * j + 1]);
-                    const __half la = __float2half_rn(v[2 * j] - __half2float(ha)), lb = __float2half_rn(v[2 * j + 1] - __half2float(hb));
-                    hi[j] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
-                    lo[j] = (uint32_t)__half_as_ushort(la) | ((uint32_t)__half_as_ushort(lb) << 16);
-                }
-                const uint32_t off = 2 * A_BYTES + sw128(n, grp);
-                *reinterpret_cast<uint4*>(stage + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(stage + B_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            for (int i = 0; i < 16; ++i) {
+                const int f = i * THREADS + tid;
+                store_split(bv[i], 1.0f, stage + 2 * A_BYTES, stage + 2 * A_BYTES + B_BYTES, f >> 6, f & 63);
             }
             fence_async_proxy();
             __syncthreads();
@@ -436,10 +441,12 @@ __global__ void __launch_bounds__(THREADS, 1) pair_weight_grad_tc_kernel(const W
                 const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < CHUNK_K / 16; ++kk) {
-                    const uint32_t koff = kk * 32;
-                    umma_f16(tmem_base, umma_desc_sw128(a_hi + koff), umma_desc_sw128(b_hi + koff), idesc, (c | kk) ? 1u : 0u);
-                    umma_f16(tmem_base, umma_desc_sw128(a_hi + koff), umma_desc_sw128(b_lo + koff), idesc, 1u);
-                    umma_f16(tmem_base, umma_desc_sw128(a_lo + koff), umma_desc_sw128(b_hi + koff), idesc, 1u);
+                    const uint32_t koff = kk * 16 * 128;  // 16 pair rows = two 8-row groups of 1024 B
+                    const uint64_t dah = umma_desc_mn_sw128(a_hi + koff, BLOCK_BYTES), dal = umma_desc_mn_sw128(a_lo + koff, BLOCK_BYTES);
+                    const uint64_t dbh = umma_desc_mn_sw128(b_hi + koff, BLOCK_BYTES), dbl = umma_desc_mn_sw128(b_lo + koff, BLOCK_BYTES);
+                    umma_f16(tmem_base, dah, dbh, idesc, (c | kk) ? 1u : 0u);
+                    umma_f16(tmem_base, dah, dbl, idesc, 1u);
+                    umma_f16(tmem_base, dal, dbh, idesc, 1u);
                 }
                 tc_commit(&mbar[s]);
                 if (c == num_chunks - 1) tc_commit(&mbar_acc);

@@ -79,7 +79,7 @@ def test_pair_project_tc_transposed_with_prescale(cuda_device):
 @pytest.mark.parametrize("counts,M,D,col0", [
     ([40], 128, 256, 0),                       # a single partial chunk
     ([64, 0, 1000, 129], 128, 256, 256),       # exact chunk, empty type, several chunks (both stages), column offset
-    ([9000, 300], 256, 256, 0),                # > 8192 rows: two slabs accumulate into the same block (REDs), 2 m tiles
+    ([9000, 300], 256, 256, 0),                # > 4096 rows: three slabs accumulate into the same block (REDs), 2 m tiles
     ([2500, 1200, 700], 512, 512, 512),        # the wide layer: 4 m tiles x 2 n tiles
 ])
 def test_pair_weight_grad_tc_matches_fp64(cuda_device, counts, M, D, col0):
@@ -107,7 +107,8 @@ def test_pair_weight_grad_tc_matches_fp64(cuda_device, counts, M, D, col0):
     torch.cuda.synchronize()
     got = d_weight[:, :, col0:col0 + D].cpu().double()
     scale = float(ref.abs().max())
-    assert float((got - ref).abs().max()) < 2e-6 * max(scale, 1.0) + 1e-7, float((got - ref).abs().max())
+    # tensor-core accumulation truncates: error grows with the chain length (<= 4096 rows = 768 MMAs per partial)
+    assert float((got - ref).abs().max()) < 3e-5 * scale + 1e-7, (float((got - ref).abs().max()), scale)
     outside = torch.ones(ld, dtype=torch.bool); outside[col0:col0 + D] = False
     assert torch.all(d_weight[:, :, outside.to(dev)] == 7.0)
 
