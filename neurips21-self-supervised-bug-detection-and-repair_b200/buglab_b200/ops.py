@@ -310,7 +310,9 @@ class TypedEdgeMessageMax(torch.autograd.Function):
                 tp = _host_i32(type_ptr)
                 # both results below carry the power-of-two pre-scale of the gradient table; it is undone in
                 # bl_rows_segment_sum (d_in) and in the fold kernel of bl_pair_project_bwd_weight (d_weight)
-                use_tc_wg = USE_TCGEN05 and bool(lib.bl_pair_weight_grad_tc_supported(M, D))
+                # measured (scripts/bench_project.py, B200): 5.8 ms vs 6.2 ms for split2 + cuBLAS at D=M=256; the 512-wide layers
+                # would re-load operands per 128x256 output tile and stay on the library path
+                use_tc_wg = USE_TCGEN05 and M <= 256 and D <= 256 and bool(lib.bl_pair_weight_grad_tc_supported(M, D))
                 g = None
                 if use_tc:
                     # d(rows) = dTable @ W_k[:, col0:col0+D] on the hand-written tcgen05 kernel (reads the fp32 table directly)
