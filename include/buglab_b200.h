@@ -206,7 +206,7 @@ int bl_layernorm_fwd(const float* x, const float* gamma, const float* beta, int6
                      float eps, float* y, float* mean, float* rstd, bl_stream_t stream);
 /* dx; d_gamma/d_beta accumulated into partial[2, num_partials, dim] then reduced by the same call
  * into d_gamma[dim], d_beta[dim].  partial must hold 2*BL_LN_PARTIALS*dim floats. */
-#define BL_LN_PARTIALS 256
+#define BL_LN_PARTIALS 1184 /* 8 x 148 SMs */
 int bl_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean,
                      const float* rstd, int64_t rows, int32_t dim,
                      float* dx, float* d_gamma, float* d_beta, float* partial, bl_stream_t stream);

@@ -441,6 +441,9 @@ def dense_linear(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
 # ---------------------------------------------------------------------------------------------------
 # Node update pieces
 # ---------------------------------------------------------------------------------------------------
+LN_PARTIALS = 1184  # BL_LN_PARTIALS in include/buglab_b200.h (8 blocks per SM)
+
+
 class LayerNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, eps: float):
@@ -462,7 +465,7 @@ class LayerNormFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         d_gamma = torch.empty_like(gamma)
         d_beta = torch.empty_like(gamma)
-        partial = torch.empty(2 * 256 * dim, device=x.device, dtype=torch.float32)
+        partial = torch.empty(2 * LN_PARTIALS * dim, device=x.device, dtype=torch.float32)
         check(_lib.load().bl_layernorm_bwd(f32(dy), f32(x), f32(gamma.contiguous()), f32(mean), f32(rstd), rows, dim,
                                             f32(dx), f32(d_gamma), f32(d_beta), f32(partial), stream_ptr(x.device)),
               "bl_layernorm_bwd")

@@ -59,6 +59,7 @@ layernorm_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ ga
 }
 
 // grid = BL_LN_PARTIALS blocks x 256 threads; block b handles rows {b*8+w + k*PARTIALS*8}.
+template <int LN_MAX_CHUNKS>  // float4 chunks per lane: dim <= 128 * LN_MAX_CHUNKS (fewer chunks -> fewer registers -> more CTAs/SM)
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
                      const float4* __restrict__ gamma, const float* __restrict__ mean,
@@ -205,13 +206,19 @@ extern "C" int bl_layernorm_bwd(const float* dy, const float* x, const float* ga
     cudaStream_t stream = (cudaStream_t)stream_;
     const size_t smem = (size_t)2 * 8 * dim * sizeof(float);
     static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * 1024 * 4);
+    if (!attr_set) {  // only the 1024-wide instantiation needs more than the default 48 KB of dynamic shared memory
+        cudaFuncSetAttribute(layernorm_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * 1024 * 4);
         attr_set = true;
     }
-    layernorm_bwd_kernel<<<BL_LN_PARTIALS, 256, smem, stream>>>((const float4*)dy, (const float4*)x,
-                                                               (const float4*)gamma, mean, rstd, rows,
-                                                               dim / 4, (float4*)dx, partial);
+#define BL_LAUNCH_LN_BWD(C)                                                                                         \
+    layernorm_bwd_kernel<C><<<BL_LN_PARTIALS, 256, smem, stream>>>((const float4*)dy, (const float4*)x,            \
+                                                                  (const float4*)gamma, mean, rstd, rows, dim / 4, \
+                                                                  (float4*)dx, partial)
+    if (dim <= 128) BL_LAUNCH_LN_BWD(1);
+    else if (dim <= 256) BL_LAUNCH_LN_BWD(2);
+    else if (dim <= 512) BL_LAUNCH_LN_BWD(4);
+    else BL_LAUNCH_LN_BWD(8);
+#undef BL_LAUNCH_LN_BWD
     layernorm_bwd_reduce<<<grid_for(dim, 128), 128, 0, stream>>>(partial, BL_LN_PARTIALS, dim, d_gamma, d_beta);
     return check_launch("bl_layernorm_bwd");
 }
