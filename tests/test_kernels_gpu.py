@@ -258,3 +258,63 @@ def test_flat_adam_with_clip(cuda_device):
         torch.testing.assert_close(sq.cpu()[0], (grad.double() ** 2).sum().float(), rtol=1e-5, atol=1e-6)
         ops.adam_step(p, gg, m, v, 1e-3, 0.9, 0.999, 1e-8, step, 0.5, sq)
         torch.testing.assert_close(p.cpu(), ref_p.detach().float(), atol=1e-6, rtol=1e-5)
+
+
+def test_full_size_properties_c3(cuda_device):
+    """BASELINE.json configs[2] at FULL size (1M nodes, 10M edges, 14 edge kinds, hidden 256): size-independent properties
+    of the plan (permutation, sortedness, pair-table consistency) and of the fused edge kernel (equals a max over the
+    per-edge messages evaluated by library ops on the same tables; winners are edges of the right segment)."""
+    from buglab_b200 import _lib, ops
+    from buglab_b200.synthetic import packed_edge_batch
+
+    N, E, K, M = 1_000_000, 10_000_000, 14, 256
+    src, tgt, etype = (torch.from_numpy(a).to(cuda_device) for a in packed_edge_batch(N, E, K, seed=3))
+    plan = ops.build_edge_plan_from_flat(src, tgt, etype, N, K)
+    perm = plan.e_perm.long()
+    # e_perm is a permutation; sorted by (tgt, type, original index)
+    assert int(torch.bincount(perm, minlength=E).max()) == 1
+    t_sorted, k_sorted = tgt[perm].long(), etype[perm].long()
+    key = (t_sorted * K + k_sorted) * E + perm
+    assert bool((key[1:] > key[:-1]).all())
+    assert torch.equal(plan.e_src, src[perm]) and torch.equal(plan.e_type, etype[perm])
+    # CSR: row_ptr is the exclusive prefix sum of the in-degrees
+    deg = torch.bincount(tgt.long(), minlength=N)
+    assert torch.equal(plan.row_ptr.long(), torch.cat((torch.zeros(1, dtype=torch.int64, device=cuda_device), deg.cumsum(0))))
+    # pair tables: every edge points at the pair that holds its (type, node); pairs are unique and (type, node)-sorted
+    assert torch.equal(plan.s_node[plan.urow.long()], plan.e_src) and torch.equal(plan.t_node[plan.vrow.long()].long(), t_sorted)
+    for node, type_ptr, rows in ((plan.s_node, plan.s_type_ptr, plan.urow), (plan.t_node, plan.t_type_ptr, plan.vrow)):
+        tp = type_ptr.long()
+        pair_type = torch.bucketize(torch.arange(node.shape[0], device=cuda_device), tp[1:], right=True)
+        pkey = pair_type * N + node.long()
+        assert bool((pkey[1:] > pkey[:-1]).all())                      # unique and sorted
+        assert torch.equal(pair_type[rows.long()], k_sorted)            # an edge's pair has the edge's type
+    assert plan.num_s_pairs <= E and plan.num_t_pairs <= E
+    # edge kernel at full size vs library ops on the SAME U/V tables
+    g = torch.Generator(device=cuda_device).manual_seed(0)
+    u = torch.randn(plan.num_s_pairs, M, device=cuda_device, generator=g)
+    v = torch.randn(plan.num_t_pairs, M, device=cuda_device, generator=g)
+    agg = torch.empty(N, M, device=cuda_device); xwin = torch.empty_like(agg)
+    ewin = torch.empty(N, M, device=cuda_device, dtype=torch.int32)
+    _lib.check(_lib.load().bl_edge_segmax_fwd(u.data_ptr(), v.data_ptr(), plan.row_ptr.data_ptr(), plan.urow.data_ptr(),
+                                               plan.vrow.data_ptr(), N, M, agg.data_ptr(), xwin.data_ptr(), ewin.data_ptr(),
+                                               torch.cuda.current_stream().cuda_stream), "bl_edge_segmax_fwd")
+    expect = torch.full((N, M), -float("inf"), device=cuda_device)
+    step = 2_000_000  # chunked so the [E, M] message tensor never exists at once
+    for lo in range(0, E, step):
+        hi = min(E, lo + step)
+        m = torch.nn.functional.gelu(u[plan.urow[lo:hi].long()] + v[plan.vrow[lo:hi].long()])
+        expect = expect.scatter_reduce(0, t_sorted[lo:hi].view(-1, 1).expand(-1, M), m, "amax", include_self=True)
+        del m
+    expect = torch.where(torch.isinf(expect), torch.zeros_like(expect), expect)  # nodes without in-edges aggregate to 0
+    torch.testing.assert_close(agg, expect, atol=1e-6, rtol=1e-6)
+    assert bool((agg[deg == 0] == 0).all()) and bool((ewin[deg == 0] == -1).all())
+    # winners lie inside their target's segment and reproduce the stored pre-activation
+    has = deg > 0
+    e = ewin[has].long()
+    lo_ = plan.row_ptr[:-1].long()[has].view(-1, 1); hi_ = plan.row_ptr[1:].long()[has].view(-1, 1)
+    assert bool(((e >= lo_) & (e < hi_)).all())
+    sample = torch.randint(0, int(has.sum()), (4096,), device=cuda_device, generator=g)
+    es = e[sample]
+    cols = torch.arange(M, device=cuda_device).view(1, -1).expand_as(es)
+    x_re = u[plan.urow.long()[es], cols] + v[plan.vrow.long()[es], cols]
+    torch.testing.assert_close(x_re, xwin[has][sample], atol=0, rtol=0)
