@@ -22,7 +22,7 @@ from buglab.models.layers.fixermodules import (
     TextRepairModule,
 )
 from buglab.models.layers.localizationmodule import LocalizationModule
-from buglab.models.utils import scatter_log_softmax, scatter_max
+from buglab.models.utils import compute_generator_loss, scatter_log_softmax, scatter_max
 from buglab.representations.data import BugLabData
 
 LOGGER = logging.getLogger(__name__)
@@ -136,9 +136,16 @@ class GnnBugLabModule(ModuleWithMetrics):
             gnn_output, target_rewrites, rewrite_to_location_group, candidate_symbol_to_location_group,
             swapped_pair_to_call_location_group)
 
-        if rewrite_logprobs is not None:
-            raise NotImplementedError(
-                "the selector / generator loss (buglab/models/utils.py:101-179) is a SURVEY.md §8f 'next' row, not built yet")
+        if rewrite_logprobs is not None:  # selector ("bug generator") training — reference gnn.py:189-219
+            _, localization_logprobs, arange = self.__localization_module.compute_localization_logprobs(
+                candidate_reprs=candidate_reprs, candidate_to_sample_idx=candidate_to_sample, num_samples=has_bug.shape[0])
+            loss = compute_generator_loss(
+                swap_lp, arange, candidate_rewrite_idxs, candidate_symbol_to_location_group, localization_logprobs,
+                self.__generator_loss_type, pair_rewrite_idxs, rewrite_logprobs, rewrite_to_graph_id,
+                rewrite_to_location_group, swapped_pair_to_call_location_group, text_lp, text_rewrite_idxs, misuse_lp)
+            zero = torch.zeros((), device=loss.device)
+            self.__accumulate(loss, zero, zero)
+            return loss
 
         localization_loss = self.__localization_module(
             candidate_reprs=candidate_reprs, candidate_to_sample_idx=candidate_to_sample, has_bug=has_bug,

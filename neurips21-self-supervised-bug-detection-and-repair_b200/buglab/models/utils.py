@@ -54,3 +54,45 @@ class LinearWarmupScheduler(AbstractScheduler):
 
     def step(self, epoch_idx: int, epoch_step: int) -> None:
         self.__scheduler.step()
+
+
+def compute_generator_loss(arg_swap_logprobs, arrange, candidate_rewrite_idxs, candidate_symbol_to_location_group,
+                           localization_logprobs, loss_type, pair_rewrite_idxs, rewrite_logprobs, rewrite_to_graph_id,
+                           rewrite_to_location_group, swapped_pair_to_call_location_group, text_repair_logprobs,
+                           text_rewrite_idxs, varmisuse_logprobs):
+    """Selector ("bug generator") loss — reference buglab/models/utils.py:101-179, same argument order.
+
+    Every candidate rewrite r of every graph gets the model's joint log-probability of GENERATING it,
+    log P(location of r) + log P(r | location), the per-graph NO_BUG slot gets log P(NO_BUG); ``rewrite_logprobs`` holds
+    the detector's log-probabilities for the same slots (-inf = not observed).  Over the observed slots, grouped by
+    graph, the loss pushes the generator towards rewrites the detector finds hard (five variants).  All segment
+    reductions run on the buglab_b200 segment kernels."""
+    num_graphs = arrange.shape[0]
+    num_rewrites = rewrite_logprobs.shape[0] - num_graphs
+    slots = torch.cat((text_rewrite_idxs, candidate_rewrite_idxs, pair_rewrite_idxs, arrange + num_rewrites))
+    values = torch.cat((
+        localization_logprobs[rewrite_to_location_group] + text_repair_logprobs,
+        localization_logprobs[candidate_symbol_to_location_group] + varmisuse_logprobs,
+        localization_logprobs[swapped_pair_to_call_location_group] + arg_swap_logprobs,
+        localization_logprobs[-num_graphs:],
+    ))
+    generation_logprobs = torch.zeros_like(rewrite_logprobs).index_put((slots,), values)  # slots are unique
+
+    observed = torch.isinf(rewrite_logprobs).logical_not()
+    index = torch.cat((rewrite_to_graph_id, arrange))[observed]
+    detection = rewrite_logprobs[observed]
+    generation = generation_logprobs[observed]
+    if loss_type in ("norm-kl", "norm-rmse", "classify-max-loss"):
+        generation = scatter_log_softmax(generation, index=index)  # renormalise over the observed slots of each graph
+        if loss_type == "norm-rmse":
+            log_total = torch.logaddexp(scatter_log_softmax(detection, index=index), generation)
+            return (log_total ** 2).mean()
+        if loss_type == "norm-kl":
+            failed = torch.log(torch.clamp(1.0 - detection.exp(), min=1e-30))  # log P(detector misses the rewrite)
+            kl_terms = failed.exp() * (scatter_log_softmax(failed, index=index) - generation)
+            return scatter_sum(kl_terms, index=index).mean()
+        _, hardest = scatter_min(detection, index=index)  # the rewrite the detector is least sure about, per graph
+        return -generation[hardest].mean()
+    if loss_type == "expectation":
+        return scatter_sum(generation.exp() * detection, index=index).mean()
+    raise ValueError(f"Unknown loss type `{loss_type}`")

@@ -18,7 +18,37 @@ import torch
 from torch import nn
 
 from .mp_ref import MlpMessagePassingLayer, SubtokenUnitEmbedder
-from .scatter_ref import scatter_log_softmax, scatter_max
+from .scatter_ref import scatter_log_softmax, scatter_max, scatter_min, scatter_sum
+
+
+def compute_generator_loss_ref(arg_swap_logprobs, arrange, candidate_rewrite_idxs, candidate_symbol_to_location_group,
+                               localization_logprobs, loss_type, pair_rewrite_idxs, rewrite_logprobs, rewrite_to_graph_id,
+                               rewrite_to_location_group, swapped_pair_to_call_location_group, text_repair_logprobs,
+                               text_rewrite_idxs, varmisuse_logprobs):
+    """Follows buglab/models/utils.py:101-179 step by step (in-place accumulation into a zero vector, masked_select)."""
+    gen = torch.zeros_like(rewrite_logprobs)
+    num_graphs = arrange.shape[0]
+    gen[-num_graphs:] = localization_logprobs[-num_graphs:]                                   # :118-120
+    gen[text_rewrite_idxs] += localization_logprobs[rewrite_to_location_group] + text_repair_logprobs          # :122-124
+    gen[candidate_rewrite_idxs] += localization_logprobs[candidate_symbol_to_location_group] + varmisuse_logprobs  # :126-128
+    gen[pair_rewrite_idxs] += localization_logprobs[swapped_pair_to_call_location_group] + arg_swap_logprobs    # :130-132
+    observed = torch.isinf(rewrite_logprobs).logical_not()                                  # :135
+    index = torch.cat((rewrite_to_graph_id, arrange)).masked_select(observed)
+    det = rewrite_logprobs.masked_select(observed)
+    g = gen.masked_select(observed)
+    if loss_type in ("norm-kl", "norm-rmse", "classify-max-loss"):                           # :139-168
+        g = scatter_log_softmax(g, index)
+        if loss_type == "norm-rmse":
+            return (torch.logaddexp(scatter_log_softmax(det, index), g) ** 2).mean()
+        if loss_type == "norm-kl":
+            failed = torch.log(torch.max(1.0 - det.exp(), torch.full_like(det, 1e-30)))
+            kl = failed.exp() * (scatter_log_softmax(failed, index) - g)
+            return scatter_sum(kl, index).mean()
+        _, min_idx = scatter_min(det, index)
+        return -g[min_idx].mean()
+    if loss_type == "expectation":                                                           # :172-175
+        return scatter_sum(g.exp() * det, index).mean()
+    raise ValueError(loss_type)
 
 
 class _NoParams(nn.Module):
@@ -145,7 +175,7 @@ class GnnBugLabModule(nn.Module):
 
     def __init__(self, hidden: int, num_edge_types: int, vocabulary_size: int, rewrite_vocabulary_size: int,
                  dropout_rate: float = 0.0, embedding_dropout_rate: float = 0.0, buggy_samples_weight: float = 1.0,
-                 use_message_bias: bool = True):
+                 use_message_bias: bool = True, generator_loss_type: str = "classify-max-loss"):
         super().__init__()
         self._gnn = GraphNeuralNetwork(hidden, num_edge_types, vocabulary_size, dropout_rate, embedding_dropout_rate,
                                        use_message_bias)
@@ -154,6 +184,7 @@ class GnnBugLabModule(nn.Module):
         self._varmisuse_module = SingleCandidateNodeSelectorModule(hidden)
         self._argswap_module = CandidatePairSelectorModule(hidden)
         self.buggy_samples_weight = buggy_samples_weight
+        self.generator_loss_type = generator_loss_type
 
     def node_representations(self, graph_data):
         return self._gnn(graph_data["node_data"], graph_data["adjacency_lists"])
@@ -190,13 +221,21 @@ class GnnBugLabModule(nn.Module):
     def forward(self, *, graph_data, correct_candidate_node_idxs, has_bug, target_rewrites, rewrite_to_location_group,
                 correct_rewrite_idxs, text_rewrite_idxs=None, candidate_symbol_to_location_group=None,
                 correct_candidate_symbols=None, candidate_rewrite_idxs=None, swapped_pair_to_call_location_group=None,
-                correct_swapped_pair=None, pair_rewrite_idxs=None, rewrite_to_graph_id=None, return_details: bool = False, **_):
+                correct_swapped_pair=None, pair_rewrite_idxs=None, rewrite_to_graph_id=None, rewrite_logprobs=None,
+                return_details: bool = False, **_):
         states = self.node_representations(graph_data)
         refs = graph_data["reference_node_ids"]
         cand = states[refs["candidate_nodes"]]
         swap_lp, text_lp, misuse_lp, selected = self._compute_repair_logprobs(
             states, refs, target_rewrites, rewrite_to_location_group, candidate_symbol_to_location_group,
             swapped_pair_to_call_location_group)
+        if rewrite_logprobs is not None:  # selector branch, gnn.py:189-219
+            _, loc_lp, arange = self.__localization_module.compute_localization_logprobs(
+                cand, graph_data["reference_node_graph_idx"]["candidate_nodes"], has_bug.shape[0])
+            return compute_generator_loss_ref(
+                swap_lp, arange, candidate_rewrite_idxs, candidate_symbol_to_location_group, loc_lp, self.generator_loss_type,
+                pair_rewrite_idxs, rewrite_logprobs.to(loc_lp.dtype), rewrite_to_graph_id, rewrite_to_location_group,
+                swapped_pair_to_call_location_group, text_lp, text_rewrite_idxs, misuse_lp)
         loc_loss, loc_lp, loc_groups = self.__localization_module(
             cand, graph_data["reference_node_graph_idx"]["candidate_nodes"], has_bug, correct_candidate_node_idxs,
             self.buggy_samples_weight)

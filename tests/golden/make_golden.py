@@ -175,6 +175,32 @@ def main():
         out[f"predict/{i}/location_logprobs"] = np.array([loc[k] for k in keys], dtype=np.float64)
         out[f"predict/{i}/rewrite_logprobs"] = np.array(rewrites, dtype=np.float64)
 
+    # selector ("bug generator") mode: samples carry the detector's log-probs for every rewrite + NO_BUG, rewrites are
+    # tensorised at ALL locations (gnn.py:365-366), and the loss is compute_generator_loss (utils.py:101-179)
+    rng = np.random.default_rng(SEED)
+    selector_samples = load()
+    for s in selector_samples:
+        lp = np.log(rng.uniform(0.02, 0.98, size=len(s["candidate_rewrites"]) + 1))
+        lp[rng.random(lp.shape[0]) < 0.2] = -np.inf   # unobserved slots
+        lp[-1] = np.log(0.5)                           # keep NO_BUG observed so no graph is empty
+        s["candidate_rewrite_logprobs"] = [float(x) for x in lp]
+    selector_shard = os.path.join(HERE, "selector_samples.msgpack.l.gz")
+    save_msgpack_l_gz(selector_samples, selector_shard)
+    with model._tensorize_all_location_rewrites():
+        sel_tensorized = [t for t, _ in model.tensorize_dataset(iter(load_msgpack_l_gz(selector_shard)), parallelize=False)]
+        sel_mb, _ = next(model.minibatch_iterator(((t, None) for t in sel_tensorized), "cpu", max_minibatch_size=100,
+                                                  parallelize=False))
+    for k, v in sel_mb.items():
+        if isinstance(v, torch.Tensor):
+            out["selector_mb/" + k] = v.numpy()
+    for loss_type in ("classify-max-loss", "norm-kl", "norm-rmse", "expectation"):
+        nn._GnnBugLabModule__generator_loss_type = loss_type
+        nn.zero_grad()
+        sel_loss = nn(**sel_mb)
+        sel_loss.backward()
+        out[f"selector/{loss_type}/loss"] = sel_loss.detach().numpy()
+        out[f"selector/{loss_type}/grad_l1"] = nn._GnnBugLabModule__localization_module._l1.weight.grad.numpy().copy()
+
     # schedules (modelregistry.py:18-41, utils.py:55-66)
     sched_fn = buggy_sample_weight_schedule("warmdown(4, 0.25)")
     out["sched/warmdown"] = np.array([sched_fn(e) for e in range(8)])

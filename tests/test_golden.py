@@ -184,3 +184,65 @@ def test_gpu_path_matches_reference_outputs(golden, mirror, cuda_device):
         np.testing.assert_array_equal(np.array(keys), golden[f"predict/{i}/location_nodes"])
         np.testing.assert_allclose([loc[k] for k in keys], golden[f"predict/{i}/location_logprobs"], atol=1e-4, rtol=1e-4)
         np.testing.assert_allclose(rewrites, golden[f"predict/{i}/rewrite_logprobs"], atol=1e-4, rtol=1e-4)
+
+
+# ---- selector ("bug generator") mode: all-location rewrites + compute_generator_loss (reference utils.py:101-179) ----
+SELECTOR_SAMPLES = os.path.join(HERE, "golden", "selector_samples.msgpack.l.gz")
+LOSS_TYPES = ("classify-max-loss", "norm-kl", "norm-rmse", "expectation")
+
+
+def _selector_minibatch(model, device):
+    from buglab.utils.msgpackutils import load_msgpack_l_gz
+
+    with model._tensorize_all_location_rewrites():
+        tensorized = [t for t, _ in model.tensorize_dataset(iter(load_msgpack_l_gz(SELECTOR_SAMPLES)), parallelize=False)]
+        return _pack(model, tensorized, device)
+
+
+def test_selector_minibatch_bit_exact(golden, mirror):
+    model, _ = mirror
+    mb = _selector_minibatch(model, "cpu")
+    checked = 0
+    for key in golden.files:
+        if key.startswith("selector_mb/"):
+            got = mb[key[len("selector_mb/"):]]
+            if got.dtype.is_floating_point:
+                np.testing.assert_array_equal(got.numpy(), golden[key])  # rewrite_logprobs incl. -inf, exact
+            else:
+                np.testing.assert_array_equal(got.numpy(), golden[key], err_msg=key)
+            checked += 1
+    assert checked >= 14 and "rewrite_logprobs" in mb
+
+
+@pytest.mark.parametrize("loss_type", LOSS_TYPES)
+def test_oracle_generator_loss_matches_reference(golden, mirror, loss_type):
+    from oracle import model_ref
+
+    model, _ = mirror
+    ref = _oracle(golden, mirror)
+    ref.generator_loss_type = loss_type
+    mb = model_ref.minibatch_to_cpu(_selector_minibatch(model, "cpu"))
+    loss = ref(**mb)
+    loss.backward()
+    torch.testing.assert_close(loss.detach(), torch.from_numpy(golden[f"selector/{loss_type}/loss"]), atol=1e-5, rtol=1e-5)
+    grad = dict(ref.named_parameters())["_GnnBugLabModule__localization_module._l1.weight"].grad
+    torch.testing.assert_close(grad, torch.from_numpy(golden[f"selector/{loss_type}/grad_l1"]), atol=1e-5, rtol=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("loss_type", LOSS_TYPES)
+def test_gpu_generator_loss_matches_reference(golden, mirror, cuda_device, loss_type):
+    from oracle import parity
+
+    model, _ = mirror
+    nn = model.build_neural_module()
+    nn.load_state_dict(_state_dict(golden), strict=True)
+    nn.to(cuda_device).train()
+    nn._GnnBugLabModule__generator_loss_type = loss_type
+    mb = _selector_minibatch(model, cuda_device)
+    loss = nn(**mb)
+    loss.backward()
+    parity.assert_forward_close(loss, torch.from_numpy(golden[f"selector/{loss_type}/loss"]), f"{loss_type} loss")
+    grad = dict(nn.named_parameters())["_GnnBugLabModule__localization_module._l1.weight"].grad
+    parity.assert_grad_close_normwise(grad, torch.from_numpy(golden[f"selector/{loss_type}/grad_l1"]), f"{loss_type} d l1.weight")
+    assert abs(nn.report_metrics()["Loss"] - float(golden[f"selector/{loss_type}/loss"])) < 1e-4
