@@ -17,6 +17,9 @@
 // so the tensor core works on chunk i while the threads load chunk i+1 into the other stage.  Epilogue: tcgen05.ld
 // (32 lanes x 32 columns per warp and step) -> + bias -> 128-byte row segments to global.
 #include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -285,6 +288,204 @@ __global__ void __launch_bounds__(THREADS, 1) pair_project_tc_kernel(const Param
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// v2: warp-specialised pipeline.  Same arithmetic and smem/TMEM layouts as pair_project_tc_kernel, different schedule:
+//   warps 0-3  PRODUCERS  gather + split A, cp.async B into stage s, then arrive on full[s]           (128 arrivals)
+//   warp  8    MMA        waits full[s], issues the 12 MMAs of the chunk, tcgen05.commit -> empty[s];
+//                         after a tile's last chunk tcgen05.commit -> acc_full[a]
+//   warps 4-7  EPILOGUE   waits acc_full[a], tcgen05.ld -> +bias -> global, arrives on acc_empty[a]    (128 arrivals)
+// Two smem stages and TWO TMEM accumulators (2*NT columns): the epilogue of tile i overlaps the main loop of tile
+// i+1, and the producers run up to two chunks ahead of the tensor core.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int THREADS_V2 = 288;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int NT>
+__global__ void __launch_bounds__(THREADS_V2, 1) pair_project_tc_v2_kernel(const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr uint32_t A_BYTES = TILE_M * 128;
+    constexpr uint32_t B_BYTES = NT * 128;
+    constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+
+    __shared__ uint64_t full[2], empty[2], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ int tile_prefix[MAX_TYPES + 1];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_splits = p.N / NT;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&full[i], 128);
+            mbar_init(&empty[i], 1);
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        int acc = 0;
+        for (int k = 0; k < p.num_types; ++k) {
+            tile_prefix[k] = acc;
+            acc += (p.type_ptr[k + 1] - p.type_ptr[k] + TILE_M - 1) / TILE_M;
+        }
+        tile_prefix[p.num_types] = acc;
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(2 * NT));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    const int total_tiles = tile_prefix[p.num_types] * n_splits;
+    const int num_chunks = p.Kin / CHUNK_K;
+
+    auto locate = [&](int work, int& k, int& row0, int& row_end, int& col0) {
+        const int tile = work / n_splits, split = work - tile * n_splits;
+        k = 0;
+        while (tile >= tile_prefix[k + 1]) ++k;
+        row0 = p.type_ptr[k] + (tile - tile_prefix[k]) * TILE_M;
+        row_end = p.type_ptr[k + 1];
+        col0 = split * NT;
+    };
+
+    if (warp < 4) {
+        // ======================= PRODUCERS (128 threads) =======================
+        const float scale = (p.amax != nullptr) ? pow2_scale_for(__ldg(p.amax)) : 1.0f;
+        constexpr int A_ITERS = (TILE_M * CHUNK_K / 4) / 128;  // 16 float4 per thread and chunk
+        uint32_t chunk_counter = 0;
+        for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+            int k, row0, row_end, col0;
+            locate(work, k, row0, row_end, col0);
+            int my_rows[A_ITERS];
+#pragma unroll
+            for (int i = 0; i < A_ITERS; ++i) {
+                const int r = row0 + ((i * 128 + tid) >> 4);
+                my_rows[i] = (r < row_end) ? (p.idx ? __ldg(p.idx + r) : r) : -1;
+            }
+            const __half* w_hi = p.wparts + ((size_t)(k * 2 + 0) * p.N + col0) * p.Kin;
+            const __half* w_lo = p.wparts + ((size_t)(k * 2 + 1) * p.N + col0) * p.Kin;
+            for (int c = 0; c < num_chunks; ++c, ++chunk_counter) {
+                const int s = chunk_counter & 1;
+                const uint32_t use = chunk_counter >> 1;
+                uint8_t* stage = smem + (size_t)s * STAGE_BYTES;
+                if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+#pragma unroll
+                for (int i = 0; i < (NT * 8) / 128; ++i) {
+                    const int f = i * 128 + tid;
+                    const int r = f >> 3, u = f & 7;
+                    const size_t goff = (size_t)r * p.Kin + c * CHUNK_K + u * 8;
+                    cp_async16(smem_u32(stage + 2 * A_BYTES + sw128(r, u)), w_hi + goff);
+                    cp_async16(smem_u32(stage + 2 * A_BYTES + B_BYTES + sw128(r, u)), w_lo + goff);
+                }
+                float4 av[A_ITERS];
+#pragma unroll
+                for (int i = 0; i < A_ITERS; ++i) {
+                    const int f = i * 128 + tid;
+                    av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (my_rows[i] >= 0)
+                        av[i] = __ldg(reinterpret_cast<const float4*>(p.src + (size_t)my_rows[i] * p.Kin + c * CHUNK_K) + (f & 15));
+                }
+#pragma unroll
+                for (int i = 0; i < A_ITERS; ++i) {
+                    const int f = i * 128 + tid;
+                    const int r = f >> 4, c4 = f & 15;
+                    float4 v = av[i];
+                    v.x = fminf(fmaxf(v.x * scale, -65000.f), 65000.f); v.y = fminf(fmaxf(v.y * scale, -65000.f), 65000.f);
+                    v.z = fminf(fmaxf(v.z * scale, -65000.f), 65000.f); v.w = fminf(fmaxf(v.w * scale, -65000.f), 65000.f);
+                    const __half h0 = __float2half_rn(v.x), h1 = __float2half_rn(v.y), h2 = __float2half_rn(v.z), h3 = __float2half_rn(v.w);
+                    const __half l0 = __float2half_rn(v.x - __half2float(h0)), l1 = __float2half_rn(v.y - __half2float(h1));
+                    const __half l2 = __float2half_rn(v.z - __half2float(h2)), l3 = __float2half_rn(v.w - __half2float(h3));
+                    uint2 hp, lp;
+                    hp.x = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                    hp.y = (uint32_t)__half_as_ushort(h2) | ((uint32_t)__half_as_ushort(h3) << 16);
+                    lp.x = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                    lp.y = (uint32_t)__half_as_ushort(l2) | ((uint32_t)__half_as_ushort(l3) << 16);
+                    const uint32_t off = sw128(r, c4 >> 1) + ((c4 & 1) << 3);
+                    *reinterpret_cast<uint2*>(stage + off) = hp;
+                    *reinterpret_cast<uint2*>(stage + A_BYTES + off) = lp;
+                }
+                cp_async_wait_all();
+                fence_async_proxy();
+                mbar_arrive(&full[s]);
+            }
+        }
+    } else if (warp == 8) {
+        // ======================= MMA ISSUER (one elected lane) =======================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16_f32(TILE_M, NT);
+            uint32_t chunk_counter = 0, tile_counter = 0;
+            for (int work = blockIdx.x; work < total_tiles; work += gridDim.x, ++tile_counter) {
+                const int a = tile_counter & 1;
+                const uint32_t ause = tile_counter >> 1;
+                if (ause > 0) mbar_wait(&acc_empty[a], (ause - 1) & 1);  // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_acc = tmem_base + (uint32_t)(a * NT);
+                for (int c = 0; c < num_chunks; ++c, ++chunk_counter) {
+                    const int s = chunk_counter & 1;
+                    const uint32_t use = chunk_counter >> 1;
+                    mbar_wait(&full[s], use & 1);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + (size_t)s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < CHUNK_K / 16; ++kk) {
+                        const uint32_t koff = kk * 32;
+                        umma_f16(tmem_acc, umma_desc_sw128(a_hi + koff), umma_desc_sw128(b_hi + koff), idesc, (c | kk) ? 1u : 0u);
+                        umma_f16(tmem_acc, umma_desc_sw128(a_hi + koff), umma_desc_sw128(b_lo + koff), idesc, 1u);
+                        umma_f16(tmem_acc, umma_desc_sw128(a_lo + koff), umma_desc_sw128(b_hi + koff), idesc, 1u);
+                    }
+                    tc_commit(&empty[s]);
+                }
+                tc_commit(&acc_full[a]);
+            }
+        }
+    } else {
+        // ======================= EPILOGUE (warps 4-7, 128 threads) =======================
+        uint32_t tile_counter = 0;
+        const int lane_base = (warp & 3) * 32;
+        for (int work = blockIdx.x; work < total_tiles; work += gridDim.x, ++tile_counter) {
+            int k, row0, row_end, col0;
+            locate(work, k, row0, row_end, col0);
+            const int a = tile_counter & 1;
+            const uint32_t ause = tile_counter >> 1;
+            mbar_wait(&acc_full[a], ause & 1);
+            tc_fence_after();
+            const int r = lane_base + lane;
+            const bool valid = (row0 + r) < row_end;
+            float* orow = p.out + (size_t)(row0 + r) * p.N + col0;
+            const float* brow = p.bias ? p.bias + (size_t)k * p.N + col0 : nullptr;
+#pragma unroll 1
+            for (int j = 0; j < NT / 32; ++j) {
+                float v[32];
+                const int col = j * 32;
+                tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(a * NT + col), v);
+                if (valid) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        if (brow) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(brow + col) + q);
+                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                        }
+                        reinterpret_cast<float4*>(orow + col)[q] = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[a]);
+        }
+    }
+    __syncthreads();
+    if (warp == 8) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * NT));
+    }
+}
+
 // wparts[k, part, n, kin] = hi/lo of W[k, n, col0 + kin]              (transposed == 0, W is [K, N, ld])
 //                         = hi/lo of W[k, kin, col0 + n]              (transposed != 0, W is [K, Kin, ld])
 __global__ void weight_parts_kernel(const float* __restrict__ W, int num_types, int N, int Kin, int ld, int col0,
@@ -506,6 +707,30 @@ extern "C" int bl_pair_project_tc(const float* src, const int32_t* idx, const fl
     cudaStream_t stream = (cudaStream_t)stream_;
     tc::Params p{src, idx, amax, (const __half*)parts, bias, type_ptr, out, num_types, n_out, k_in};
     const int64_t max_tiles = (num_rows + tc::TILE_M - 1) / tc::TILE_M + num_types;
+    static const bool use_v2 = []() {
+        const char* e = getenv("BUGLAB_B200_TC_V1");
+        return !(e && e[0] == '1');
+    }();
+    if (use_v2) {
+        if (n_out == 128) {
+            constexpr uint32_t smem = 2 * (2 * 128 * 128 + 2 * 128 * 128) + 1024;
+            static bool attr_set = false;
+            if (!attr_set) {
+                cudaFuncSetAttribute(tc::pair_project_tc_v2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                attr_set = true;
+            }
+            tc::pair_project_tc_v2_kernel<128><<<(int)std::min<int64_t>(kNumSMs, max_tiles), tc::THREADS_V2, smem, stream>>>(p);
+        } else {
+            constexpr uint32_t smem = 2 * (2 * 128 * 128 + 2 * 256 * 128) + 1024;
+            static bool attr_set = false;
+            if (!attr_set) {
+                cudaFuncSetAttribute(tc::pair_project_tc_v2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                attr_set = true;
+            }
+            tc::pair_project_tc_v2_kernel<256><<<(int)std::min<int64_t>(kNumSMs, max_tiles * (n_out / 256)), tc::THREADS_V2, smem, stream>>>(p);
+        }
+        return check_launch("bl_pair_project_tc(v2)");
+    }
     if (n_out == 128) {
         constexpr uint32_t smem = 2 * (2 * 128 * 128 + 2 * 128 * 128) + 1024;
         static bool attr_set = false;
