@@ -36,20 +36,35 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-// Bounded spin: a protocol bug must trap (and fail the launch) instead of hanging the GPU.
+// Bounded wait: a protocol bug must trap (and fail the launch) within ~2 s instead of hanging the GPU.  test_wait never
+// suspends the thread, so the wall-clock bound below is real.
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __noinline__ void mbar_timeout(uint32_t addr, uint32_t parity) {
+    printf("buglab_b200: mbarrier wait timed out (block %d thread %d smem 0x%x parity %u)\n", blockIdx.x, threadIdx.x, addr, parity);
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
+    uint64_t t0 = 0;
     for (uint32_t spin = 0;; ++spin) {
         uint32_t done;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) return;
-        if (spin > (1u << 26)) __trap();
+        if ((spin & 1023u) == 1023u) {
+            const uint64_t now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) mbar_timeout(addr, parity);
+        }
     }
 }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -415,21 +430,23 @@ __global__ void __launch_bounds__(THREADS_V2, 1) pair_project_tc_v2_kernel(const
             }
         }
     } else if (warp == 8) {
-        // ======================= MMA ISSUER (one elected lane) =======================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16_f32(TILE_M, NT);
-            uint32_t chunk_counter = 0, tile_counter = 0;
-            for (int work = blockIdx.x; work < total_tiles; work += gridDim.x, ++tile_counter) {
-                const int a = tile_counter & 1;
-                const uint32_t ause = tile_counter >> 1;
-                if (ause > 0) mbar_wait(&acc_empty[a], (ause - 1) & 1);  // epilogue drained this accumulator
+        // ======================= MMA ISSUER =======================
+        // The whole warp walks the schedule and waits on the barriers together (a lone lane racing ahead of its warp to
+        // the final bar.sync is undefined behaviour); only lane 0 issues the single-thread tcgen05 instructions.
+        const uint32_t idesc = umma_idesc_f16_f32(TILE_M, NT);
+        uint32_t chunk_counter = 0, tile_counter = 0;
+        for (int work = blockIdx.x; work < total_tiles; work += gridDim.x, ++tile_counter) {
+            const int a = tile_counter & 1;
+            const uint32_t ause = tile_counter >> 1;
+            if (ause > 0) mbar_wait(&acc_empty[a], (ause - 1) & 1);  // epilogue drained this accumulator
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + (uint32_t)(a * NT);
+            for (int c = 0; c < num_chunks; ++c, ++chunk_counter) {
+                const int s = chunk_counter & 1;
+                const uint32_t use = chunk_counter >> 1;
+                mbar_wait(&full[s], use & 1);
                 tc_fence_after();
-                const uint32_t tmem_acc = tmem_base + (uint32_t)(a * NT);
-                for (int c = 0; c < num_chunks; ++c, ++chunk_counter) {
-                    const int s = chunk_counter & 1;
-                    const uint32_t use = chunk_counter >> 1;
-                    mbar_wait(&full[s], use & 1);
-                    tc_fence_after();
+                if (lane == 0) {
                     const uint32_t a_hi = smem_u32(smem + (size_t)s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
                     const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
 #pragma unroll
@@ -440,8 +457,9 @@ __global__ void __launch_bounds__(THREADS_V2, 1) pair_project_tc_v2_kernel(const
                         umma_f16(tmem_acc, umma_desc_sw128(a_lo + koff), umma_desc_sw128(b_hi + koff), idesc, 1u);
                     }
                     tc_commit(&empty[s]);
+                    if (c == num_chunks - 1) tc_commit(&acc_full[a]);
                 }
-                tc_commit(&acc_full[a]);
+                __syncwarp();
             }
         }
     } else {
