@@ -305,14 +305,15 @@ __global__ void __launch_bounds__(THREADS, 1) pair_project_tc_kernel(const Param
 
 // ---------------------------------------------------------------------------------------------------------------
 // v2: warp-specialised pipeline.  Same arithmetic and smem/TMEM layouts as pair_project_tc_kernel, different schedule:
-//   warps 0-3  PRODUCERS  gather + split A, cp.async B into stage s, then arrive on full[s]           (128 arrivals)
-//   warp  8    MMA        waits full[s], issues the 12 MMAs of the chunk, tcgen05.commit -> empty[s];
-//                         after a tile's last chunk tcgen05.commit -> acc_full[a]
-//   warps 4-7  EPILOGUE   waits acc_full[a], tcgen05.ld -> +bias -> global, arrives on acc_empty[a]    (128 arrivals)
-// Two smem stages and TWO TMEM accumulators (2*NT columns): the epilogue of tile i overlaps the main loop of tile
-// i+1, and the producers run up to two chunks ahead of the tensor core.
+//   warps 0-7   PRODUCERS  two groups of 4 warps; group g owns smem stage g and loads every chunk with
+//                          (running chunk index & 1) == g: gather + split A, cp.async B, then arrive on full[g] (128
+//                          arrivals) — while one group waits for its loads the other converts and stores
+//   warp  12    MMA        waits full[s], issues the 12 MMAs of the chunk, tcgen05.commit -> empty[s];
+//                          after a tile's last chunk tcgen05.commit -> acc_full[a]
+//   warps 8-11  EPILOGUE   waits acc_full[a], tcgen05.ld -> +bias -> global, arrives on acc_empty[a]    (128 arrivals)
+// Two smem stages and TWO TMEM accumulators (2*NT columns): the epilogue of tile i overlaps the main loop of tile i+1.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int THREADS_V2 = 288;
+constexpr int THREADS_V2 = 416;  // 8 producer warps + 4 epilogue warps + 1 MMA warp
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(THREADS_V2, 1) pair_project_tc_v2_kernel(const
         }
         tile_prefix[p.num_types] = acc;
     }
-    if (warp == 8) {
+    if (warp == 12) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(2 * NT));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -368,10 +369,12 @@ __global__ void __launch_bounds__(THREADS_V2, 1) pair_project_tc_v2_kernel(const
         col0 = split * NT;
     };
 
-    if (warp < 4) {
-        // ======================= PRODUCERS (128 threads) =======================
+    if (warp < 8) {
+        // ======================= PRODUCERS (2 groups x 128 threads) =======================
+        const int group = warp >> 2, t = tid & 127;
         const float scale = (p.amax != nullptr) ? pow2_scale_for(__ldg(p.amax)) : 1.0f;
-        constexpr int A_ITERS = (TILE_M * CHUNK_K / 4) / 128;  // 16 float4 per thread and chunk
+        constexpr int A_ITERS = (TILE_M * CHUNK_K / 4) / 128;  // 16 float4 per thread and chunk, in two batches of 8
+        uint8_t* stage = smem + (size_t)group * STAGE_BYTES;
         uint32_t chunk_counter = 0;
         for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
             int k, row0, row_end, col0;
@@ -379,57 +382,60 @@ __global__ void __launch_bounds__(THREADS_V2, 1) pair_project_tc_v2_kernel(const
             int my_rows[A_ITERS];
 #pragma unroll
             for (int i = 0; i < A_ITERS; ++i) {
-                const int r = row0 + ((i * 128 + tid) >> 4);
+                const int r = row0 + ((i * 128 + t) >> 4);
                 my_rows[i] = (r < row_end) ? (p.idx ? __ldg(p.idx + r) : r) : -1;
             }
             const __half* w_hi = p.wparts + ((size_t)(k * 2 + 0) * p.N + col0) * p.Kin;
             const __half* w_lo = p.wparts + ((size_t)(k * 2 + 1) * p.N + col0) * p.Kin;
             for (int c = 0; c < num_chunks; ++c, ++chunk_counter) {
-                const int s = chunk_counter & 1;
+                if ((int)(chunk_counter & 1) != group) continue;  // the other group's chunk
                 const uint32_t use = chunk_counter >> 1;
-                uint8_t* stage = smem + (size_t)s * STAGE_BYTES;
-                if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+                if (use > 0) mbar_wait(&empty[group], (use - 1) & 1);
 #pragma unroll
                 for (int i = 0; i < (NT * 8) / 128; ++i) {
-                    const int f = i * 128 + tid;
+                    const int f = i * 128 + t;
                     const int r = f >> 3, u = f & 7;
                     const size_t goff = (size_t)r * p.Kin + c * CHUNK_K + u * 8;
                     cp_async16(smem_u32(stage + 2 * A_BYTES + sw128(r, u)), w_hi + goff);
                     cp_async16(smem_u32(stage + 2 * A_BYTES + B_BYTES + sw128(r, u)), w_lo + goff);
                 }
-                float4 av[A_ITERS];
 #pragma unroll
-                for (int i = 0; i < A_ITERS; ++i) {
-                    const int f = i * 128 + tid;
-                    av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (my_rows[i] >= 0)
-                        av[i] = __ldg(reinterpret_cast<const float4*>(p.src + (size_t)my_rows[i] * p.Kin + c * CHUNK_K) + (f & 15));
-                }
+                for (int half = 0; half < 2; ++half) {
+                    float4 av[A_ITERS / 2];
 #pragma unroll
-                for (int i = 0; i < A_ITERS; ++i) {
-                    const int f = i * 128 + tid;
-                    const int r = f >> 4, c4 = f & 15;
-                    float4 v = av[i];
-                    v.x = fminf(fmaxf(v.x * scale, -65000.f), 65000.f); v.y = fminf(fmaxf(v.y * scale, -65000.f), 65000.f);
-                    v.z = fminf(fmaxf(v.z * scale, -65000.f), 65000.f); v.w = fminf(fmaxf(v.w * scale, -65000.f), 65000.f);
-                    const __half h0 = __float2half_rn(v.x), h1 = __float2half_rn(v.y), h2 = __float2half_rn(v.z), h3 = __float2half_rn(v.w);
-                    const __half l0 = __float2half_rn(v.x - __half2float(h0)), l1 = __float2half_rn(v.y - __half2float(h1));
-                    const __half l2 = __float2half_rn(v.z - __half2float(h2)), l3 = __float2half_rn(v.w - __half2float(h3));
-                    uint2 hp, lp;
-                    hp.x = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                    hp.y = (uint32_t)__half_as_ushort(h2) | ((uint32_t)__half_as_ushort(h3) << 16);
-                    lp.x = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-                    lp.y = (uint32_t)__half_as_ushort(l2) | ((uint32_t)__half_as_ushort(l3) << 16);
-                    const uint32_t off = sw128(r, c4 >> 1) + ((c4 & 1) << 3);
-                    *reinterpret_cast<uint2*>(stage + off) = hp;
-                    *reinterpret_cast<uint2*>(stage + A_BYTES + off) = lp;
+                    for (int j = 0; j < A_ITERS / 2; ++j) {
+                        const int i = half * (A_ITERS / 2) + j;
+                        const int f = i * 128 + t;
+                        av[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (my_rows[i] >= 0)
+                            av[j] = __ldg(reinterpret_cast<const float4*>(p.src + (size_t)my_rows[i] * p.Kin + c * CHUNK_K) + (f & 15));
+                    }
+#pragma unroll
+                    for (int j = 0; j < A_ITERS / 2; ++j) {
+                        const int f = (half * (A_ITERS / 2) + j) * 128 + t;
+                        const int r = f >> 4, c4 = f & 15;
+                        float4 v = av[j];
+                        v.x = fminf(fmaxf(v.x * scale, -65000.f), 65000.f); v.y = fminf(fmaxf(v.y * scale, -65000.f), 65000.f);
+                        v.z = fminf(fmaxf(v.z * scale, -65000.f), 65000.f); v.w = fminf(fmaxf(v.w * scale, -65000.f), 65000.f);
+                        const __half h0 = __float2half_rn(v.x), h1 = __float2half_rn(v.y), h2 = __float2half_rn(v.z), h3 = __float2half_rn(v.w);
+                        const __half l0 = __float2half_rn(v.x - __half2float(h0)), l1 = __float2half_rn(v.y - __half2float(h1));
+                        const __half l2 = __float2half_rn(v.z - __half2float(h2)), l3 = __float2half_rn(v.w - __half2float(h3));
+                        uint2 hp, lp;
+                        hp.x = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                        hp.y = (uint32_t)__half_as_ushort(h2) | ((uint32_t)__half_as_ushort(h3) << 16);
+                        lp.x = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                        lp.y = (uint32_t)__half_as_ushort(l2) | ((uint32_t)__half_as_ushort(l3) << 16);
+                        const uint32_t off = sw128(r, c4 >> 1) + ((c4 & 1) << 3);
+                        *reinterpret_cast<uint2*>(stage + off) = hp;
+                        *reinterpret_cast<uint2*>(stage + A_BYTES + off) = lp;
+                    }
                 }
                 cp_async_wait_all();
                 fence_async_proxy();
-                mbar_arrive(&full[s]);
+                mbar_arrive(&full[group]);
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == 12) {
         // ======================= MMA ISSUER =======================
         // The whole warp walks the schedule and waits on the barriers together (a lone lane racing ahead of its warp to
         // the final bar.sync is undefined behaviour); only lane 0 issues the single-thread tcgen05 instructions.
@@ -463,7 +469,7 @@ __global__ void __launch_bounds__(THREADS_V2, 1) pair_project_tc_v2_kernel(const
             }
         }
     } else {
-        // ======================= EPILOGUE (warps 4-7, 128 threads) =======================
+        // ======================= EPILOGUE (warps 8-11, 128 threads) =======================
         uint32_t tile_counter = 0;
         const int lane_base = (warp & 3) * 32;
         for (int work = blockIdx.x; work < total_tiles; work += gridDim.x, ++tile_counter) {
@@ -499,7 +505,7 @@ __global__ void __launch_bounds__(THREADS_V2, 1) pair_project_tc_v2_kernel(const
         }
     }
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 12) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * NT));
     }
 }
