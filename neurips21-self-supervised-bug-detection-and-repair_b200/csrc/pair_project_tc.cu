@@ -123,6 +123,21 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // byte offset of (row, 16-byte unit j) inside a [rows x 128 B] K-major SWIZZLE_128B tile
 __device__ __forceinline__ uint32_t sw128(int row, int unit) { return (uint32_t)(row * 128 + ((unit ^ (row & 7)) << 4)); }
 
+// fp32x4 -> fp16 hi/lo parts with packed conversions (cvt.rn.f16x2.f32): ~14 instructions per float4 instead of ~40 —
+// the loader, not the tensor pipe, is what bounds these kernels.  SCALED adds the pow2 pre-scale + fp16 saturation.
+template <bool SCALED>
+__device__ __forceinline__ void split_f32x4(float4 v, float scale, uint2& hi, uint2& lo) {
+    if (SCALED) {
+        v.x = fminf(fmaxf(v.x * scale, -65000.f), 65000.f); v.y = fminf(fmaxf(v.y * scale, -65000.f), 65000.f);
+        v.z = fminf(fmaxf(v.z * scale, -65000.f), 65000.f); v.w = fminf(fmaxf(v.w * scale, -65000.f), 65000.f);
+    }
+    const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+    const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn(v.x - b01.x, v.y - b01.y), l23 = __floats2half2_rn(v.z - b23.x, v.w - b23.y);
+    hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
+    lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
+}
+
 struct Params {
     const float* src;       // [*, Kin] fp32
     const int* idx;         // [P] rows of src, or nullptr (identity)
@@ -228,17 +243,8 @@ __global__ void __launch_bounds__(THREADS, 1) pair_project_tc_kernel(const Param
             for (int i = 0; i < A_ITERS; ++i) {
                 const int f = i * THREADS + tid;
                 const int r = f >> 4, c4 = f & 15;  // 16 float4 per row chunk
-                float4 v = av[i];
-                v.x = fminf(fmaxf(v.x * scale, -65000.f), 65000.f); v.y = fminf(fmaxf(v.y * scale, -65000.f), 65000.f);
-                v.z = fminf(fmaxf(v.z * scale, -65000.f), 65000.f); v.w = fminf(fmaxf(v.w * scale, -65000.f), 65000.f);
-                const __half h0 = __float2half_rn(v.x), h1 = __float2half_rn(v.y), h2 = __float2half_rn(v.z), h3 = __float2half_rn(v.w);
-                const __half l0 = __float2half_rn(v.x - __half2float(h0)), l1 = __float2half_rn(v.y - __half2float(h1));
-                const __half l2 = __float2half_rn(v.z - __half2float(h2)), l3 = __float2half_rn(v.w - __half2float(h3));
                 uint2 hp, lp;
-                hp.x = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                hp.y = (uint32_t)__half_as_ushort(h2) | ((uint32_t)__half_as_ushort(h3) << 16);
-                lp.x = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-                lp.y = (uint32_t)__half_as_ushort(l2) | ((uint32_t)__half_as_ushort(l3) << 16);
+                if (p.amax != nullptr) split_f32x4<true>(av[i], scale, hp, lp); else split_f32x4<false>(av[i], 1.f, hp, lp);
                 const uint32_t off = sw128(r, c4 >> 1) + ((c4 & 1) << 3);  // 4 halfs = 8 bytes inside a 16-byte unit
                 *reinterpret_cast<uint2*>(stage + off) = hp;
                 *reinterpret_cast<uint2*>(stage + A_BYTES + off) = lp;
@@ -414,17 +420,8 @@ __global__ void __launch_bounds__(THREADS_V2, 1) pair_project_tc_v2_kernel(const
                     for (int j = 0; j < A_ITERS / 2; ++j) {
                         const int f = (half * (A_ITERS / 2) + j) * 128 + t;
                         const int r = f >> 4, c4 = f & 15;
-                        float4 v = av[j];
-                        v.x = fminf(fmaxf(v.x * scale, -65000.f), 65000.f); v.y = fminf(fmaxf(v.y * scale, -65000.f), 65000.f);
-                        v.z = fminf(fmaxf(v.z * scale, -65000.f), 65000.f); v.w = fminf(fmaxf(v.w * scale, -65000.f), 65000.f);
-                        const __half h0 = __float2half_rn(v.x), h1 = __float2half_rn(v.y), h2 = __float2half_rn(v.z), h3 = __float2half_rn(v.w);
-                        const __half l0 = __float2half_rn(v.x - __half2float(h0)), l1 = __float2half_rn(v.y - __half2float(h1));
-                        const __half l2 = __float2half_rn(v.z - __half2float(h2)), l3 = __float2half_rn(v.w - __half2float(h3));
                         uint2 hp, lp;
-                        hp.x = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                        hp.y = (uint32_t)__half_as_ushort(h2) | ((uint32_t)__half_as_ushort(h3) << 16);
-                        lp.x = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-                        lp.y = (uint32_t)__half_as_ushort(l2) | ((uint32_t)__half_as_ushort(l3) << 16);
+                        if (p.amax != nullptr) split_f32x4<true>(av[j], scale, hp, lp); else split_f32x4<false>(av[j], 1.f, hp, lp);
                         const uint32_t off = sw128(r, c4 >> 1) + ((c4 & 1) << 3);
                         *reinterpret_cast<uint2*>(stage + off) = hp;
                         *reinterpret_cast<uint2*>(stage + A_BYTES + off) = lp;
@@ -633,16 +630,8 @@ __global__ void __launch_bounds__(THREADS, 1) pair_weight_grad_tc_kernel(const W
             }
             auto store_split = [&](const float4 v, float sc, uint8_t* hi_base, uint8_t* lo_base, int row, int col4) {
                 // col4 = float4 index along the output dimension; 16 float4 per 64-wide block
-                const float a0 = fminf(fmaxf(v.x * sc, -65000.f), 65000.f), a1 = fminf(fmaxf(v.y * sc, -65000.f), 65000.f);
-                const float a2 = fminf(fmaxf(v.z * sc, -65000.f), 65000.f), a3 = fminf(fmaxf(v.w * sc, -65000.f), 65000.f);
-                const __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1), h2 = __float2half_rn(a2), h3 = __float2half_rn(a3);
-                const __half l0 = __float2half_rn(a0 - __half2float(h0)), l1 = __float2half_rn(a1 - __half2float(h1));
-                const __half l2 = __float2half_rn(a2 - __half2float(h2)), l3 = __float2half_rn(a3 - __half2float(h3));
                 uint2 hp, lp;
-                hp.x = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                hp.y = (uint32_t)__half_as_ushort(h2) | ((uint32_t)__half_as_ushort(h3) << 16);
-                lp.x = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-                lp.y = (uint32_t)__half_as_ushort(l2) | ((uint32_t)__half_as_ushort(l3) << 16);
+                if (sc != 1.0f) split_f32x4<true>(v, sc, hp, lp); else split_f32x4<false>(v, 1.f, hp, lp);
                 const int block = col4 >> 4, c4 = col4 & 15;
                 const uint32_t off = block * BLOCK_BYTES + sw128(row, c4 >> 1) + ((c4 & 1) << 3);
                 *reinterpret_cast<uint2*>(hi_base + off) = hp;
