@@ -147,6 +147,9 @@ PROJECTION_MODE = "f16x3"
 # With "f16x3": run the forward projections through the hand-written tcgen05 kernel (csrc/pair_project_tc.cu: gather +
 # split inside the GEMM loader, no split table in HBM) whenever the shape is supported; else split kernel + cuBLAS.
 USE_TCGEN05 = os.environ.get("BUGLAB_B200_TCGEN05", "1") != "0"
+# Largest width that goes through the tcgen05 kernels; the 512-wide post-residual layers stay on split + cuBLAS by default
+# (measured parity there: 12.6 vs 12.1 ms per table), BUGLAB_B200_TC_MAX_WIDTH=512 switches them over.
+TC_MAX_WIDTH = int(os.environ.get("BUGLAB_B200_TC_MAX_WIDTH", "256"))
 
 
 def _host_i32(values: Tuple[int, ...]):
@@ -218,7 +221,7 @@ def _project_pairs_f16x3(h: torch.Tensor, idx: torch.Tensor, weight: torch.Tenso
     K, M, _ = weight.shape
     D = h.shape[1]
     # measured on B200 (scripts/bench_project.py): fused 4.6 ms vs split+cuBLAS 4.8 ms at D=M=256, 14.3 vs 11.8 ms at 512
-    if USE_TCGEN05 and type_ptr_dev is not None and M <= 256 and _lib.load().bl_pair_project_tc_supported(M, D):
+    if USE_TCGEN05 and type_ptr_dev is not None and M <= TC_MAX_WIDTH and _lib.load().bl_pair_project_tc_supported(M, D):
         return pair_project_tc(h, idx, weight_parts(weight, M, D, col0, False), bias, type_ptr_dev, int(idx.shape[0]))
     a3 = _split3_rows(h, idx)
     w3, _ = _split3_weights(weight, bias, col0, D, True, False)
@@ -303,7 +306,7 @@ class TypedEdgeMessageMax(torch.autograd.Function):
             d_weight = torch.empty_like(weight)
             if d_bias is not None:
                 check(lib.bl_grouped_colsum(f32(dv), i32(plan.t_type_ptr), K, M, f32(d_bias), stream_ptr(dev)), "bl_grouped_colsum")
-            use_tc = USE_TCGEN05 and D <= 256 and bool(lib.bl_pair_project_tc_supported(D, M))
+            use_tc = USE_TCGEN05 and D <= TC_MAX_WIDTH and bool(lib.bl_pair_project_tc_supported(D, M))
             for rows_idx, d_tab, col0, type_ptr, type_ptr_dev in (
                     (plan.s_node, du, 0, plan.s_type_ptr_host, plan.s_type_ptr),
                     (plan.t_node, dv, D, plan.t_type_ptr_host, plan.t_type_ptr)):
@@ -312,7 +315,7 @@ class TypedEdgeMessageMax(torch.autograd.Function):
                 # bl_rows_segment_sum (d_in) and in the fold kernel of bl_pair_project_bwd_weight (d_weight)
                 # measured (scripts/bench_project.py, B200): 5.8 ms vs 6.2 ms for split2 + cuBLAS at D=M=256; the 512-wide layers
                 # would re-load operands per 128x256 output tile and stay on the library path
-                use_tc_wg = USE_TCGEN05 and M <= 256 and D <= 256 and bool(lib.bl_pair_weight_grad_tc_supported(M, D))
+                use_tc_wg = USE_TCGEN05 and M <= TC_MAX_WIDTH and D <= TC_MAX_WIDTH and bool(lib.bl_pair_weight_grad_tc_supported(M, D))
                 g = None
                 if use_tc:
                     # d(rows) = dTable @ W_k[:, col0:col0+D] on the hand-written tcgen05 kernel (reads the fp32 table directly)
