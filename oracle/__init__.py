@@ -11,7 +11,7 @@ What it restates (plain PyTorch fp32 / fp64 and numpy, straightforward per-edge 
     pieces the oracle is **parity unpinned**: it follows the published semantics of
     ptgnn.MlpMessagePassingLayer / torch_scatter (CPU) restated in SURVEY.md §8a P1-P7 and is pinned only
     by the hand-computed known-answer tests in tests/test_oracle_kat.py.
-  * the in-repo pieces (heads, losses, rewrite bookkeeping, data schema) — restated with file:line
+  * the in-repo pieces (heads, detector and selector/generator losses, rewrite bookkeeping, data schema) — restated with file:line
     citations and pinned against the REAL reference code imported from /root/reference
     (tests/golden/make_golden.py wrote the fixtures under tests/golden/).
 """
