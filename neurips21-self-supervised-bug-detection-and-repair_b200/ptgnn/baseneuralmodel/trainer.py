@@ -102,6 +102,31 @@ class _Prefetcher:
             yield item
 
 
+def _while_all_ranks_have_data(batches: Iterator, device) -> Iterator:
+    """Data-parallel ranks read different shards and may run out of minibatches at different times; every step contains
+    a collective, so the epoch must end for all ranks as soon as ANY rank is exhausted (otherwise the others would wait in
+    the gradient all-reduce forever).  One tiny MIN all-reduce per step; a no-op without torch.distributed."""
+    dist = _distributed()
+    if not dist.is_distributed():
+        yield from batches
+        return
+    import torch.distributed as tdist
+
+    it = iter(batches)
+    flag_device = device if torch.device(device).type == "cuda" else "cpu"
+    while True:
+        try:
+            item = next(it)
+            have = 1
+        except StopIteration:
+            item, have = None, 0
+        flag = torch.tensor([have], dtype=torch.int32, device=flag_device)
+        tdist.all_reduce(flag, op=tdist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            return
+        yield item
+
+
 class ModelTrainer:
     def __init__(
         self,
@@ -203,7 +228,8 @@ class ModelTrainer:
             start_evt, end_evt = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             start_evt.record()
         t0 = time.perf_counter()
-        for step_idx, (mb_data, raw_points) in enumerate(self._minibatches(training_tensors, device, parallelize)):
+        batches = _while_all_ranks_have_data(self._minibatches(training_tensors, device, parallelize), device)
+        for step_idx, (mb_data, raw_points) in enumerate(batches):
             optimizer.zero_grad()
             loss = nn(**mb_data)
             loss.backward()
@@ -261,6 +287,9 @@ class ModelTrainer:
         metrics = dict(nn.report_metrics())
         if self._target_metric is not None:
             target_metric = metrics[self._target_metric]
+            if dist.is_distributed():
+                # every rank must take the same improved / early-stopping decision: use the mean over the ranks' shards
+                target_metric = dist.all_ranks_sum(float(target_metric), device) / dist.world_size()
             improved = target_metric > best_target_metric if self._target_metric_higher_is_better \
                 else target_metric < best_target_metric
         else:

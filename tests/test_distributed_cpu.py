@@ -72,3 +72,32 @@ def test_two_rank_data_parallel_equals_single_process(tmp_path):
         opt.step()
     for k, v in net.state_dict().items():
         torch.testing.assert_close(a[k], v, atol=1e-6, rtol=1e-5)
+
+
+def _uneven_worker(rank: int, world: int, port: int, out_dir: str):
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from buglab_b200 import distributed
+    from ptgnn.baseneuralmodel.trainer import _allreduce_dense_gradients, _while_all_ranks_have_data
+
+    distributed.init_from_env("gloo")
+    my_batches = list(range(5 if rank == 0 else 3))  # rank 0 has two more minibatches than rank 1
+    seen = []
+    w = torch.nn.Parameter(torch.zeros(2))
+    for b in _while_all_ranks_have_data(iter(my_batches), "cpu"):
+        w.grad = torch.full((2,), float(b + rank))
+        _allreduce_dense_gradients([w], world)  # the per-step collective that would dead-lock on uneven epochs
+        seen.append((b, w.grad.tolist()))
+    torch.save(seen, os.path.join(out_dir, f"uneven{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_uneven_shards_end_the_epoch_together(tmp_path):
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_uneven_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = torch.load(tmp_path / "uneven0.pt"), torch.load(tmp_path / "uneven1.pt")
+    assert [x[0] for x in a] == [0, 1, 2] and [x[0] for x in b] == [0, 1, 2]   # both stop after 3 steps, nobody hangs
+    assert a == b and a[1][1] == [1.5, 1.5]                                     # averaged gradient (1 + 2) / 2
