@@ -68,20 +68,26 @@ class AbstractBugLabModel:
 
     def _compute_rewrite_data(self, datapoint: BugLabData, candidate_node_idxs):
         graph = datapoint["graph"]
-        target_action = datapoint["target_fix_action_idx"]
-        target_node = None if target_action is None else graph["reference_nodes"][target_action]
-        only_target = self._tensorize_only_at_target_location_rewrites
-
         # positional arguments of every Call node, in Child-edge order (needed by the arg-swap family)
         nodes = graph["nodes"]
         call_args: Dict[int, List[int]] = defaultdict(list)
         for edge in graph["edges"]["Child"]:
             if len(edge) == 3 and edge[2] == "args" and nodes[edge[0]] == "Call":
                 call_args[edge[0]].append(edge[1])
+        return self._compute_rewrite_data_from(
+            graph["reference_nodes"], datapoint["candidate_rewrites"], datapoint["candidate_rewrite_metadata"],
+            datapoint["target_fix_action_idx"], call_args, candidate_node_idxs)
+
+    def _compute_rewrite_data_from(self, reference_nodes, candidate_rewrites, candidate_rewrite_metadata, target_action,
+                                   call_args, candidate_node_idxs):
+        """The rewrite families of one sample from its already-decoded fields (shared by the dict path above and the
+        native shard path, buglab_b200/shards.py)."""
+        target_node = None if target_action is None else reference_nodes[target_action]
+        only_target = self._tensorize_only_at_target_location_rewrites
 
         text, varmisuse, argswap = _Family(), _Family(), _Family()
         for i, (location, rewrite, metadata) in enumerate(
-                zip(graph["reference_nodes"], datapoint["candidate_rewrites"], datapoint["candidate_rewrite_metadata"])):
+                zip(reference_nodes, candidate_rewrites, candidate_rewrite_metadata)):
             if only_target and location != target_node:
                 continue  # training only scores rewrites at the target location
             scout, scout_metadata = metadata

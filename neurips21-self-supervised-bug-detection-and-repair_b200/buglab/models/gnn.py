@@ -237,12 +237,18 @@ class GnnBugLabModel(AbstractNeuralModel[BugLabData, BaseTensorizedBugLabGnn, Gn
         graph_data, target_location_node_idx = BugLabData.as_graph_data(datapoint)
         if "candidate_rewrite_logprobs" in datapoint:
             assert not self._tensorize_only_at_target_location_rewrites
-        (text_nodes, text_ops, text_groups, text_correct, text_orig,
-         misuse_nodes, misuse_groups, misuse_candidates, misuse_correct, misuse_orig,
-         call_nodes, swapped_pairs, swap_correct, swap_groups, swap_orig,
-         location_groups) = self._compute_rewrite_data(datapoint, graph_data.reference_nodes["candidate_nodes"])
+        rewrite_data = self._compute_rewrite_data(datapoint, graph_data.reference_nodes["candidate_nodes"])
+        self._add_rewrite_reference_nodes(graph_data.reference_nodes, rewrite_data)
+        tensorized_graph = self.__gnn_model.tensorize(graph_data)
+        if tensorized_graph is None:
+            return None
+        return self._assemble_tensorized(tensorized_graph, target_location_node_idx, rewrite_data,
+                                         datapoint.get("candidate_rewrite_logprobs", None))
 
-        refs = graph_data.reference_nodes
+    @staticmethod
+    def _add_rewrite_reference_nodes(refs: Dict[str, Any], rewrite_data) -> None:
+        (text_nodes, _ops, _tg, text_correct, _to, misuse_nodes, _mg, misuse_candidates, misuse_correct, _mo,
+         call_nodes, swapped_pairs, swap_correct, _sg, _so, _groups) = rewrite_data
         refs["target_rewrite_nodes"] = text_nodes
         refs["varmisused_node_ids"] = misuse_nodes
         refs["candidate_symbol_node_ids"] = misuse_candidates
@@ -251,9 +257,11 @@ class GnnBugLabModel(AbstractNeuralModel[BugLabData, BaseTensorizedBugLabGnn, Gn
         assert sum(c is not None for c in (text_correct, misuse_correct, swap_correct)) <= 1, \
             "No more than one node should be correct."
 
-        tensorized_graph = self.__gnn_model.tensorize(graph_data)
-        if tensorized_graph is None:
-            return None
+    @staticmethod
+    def _assemble_tensorized(tensorized_graph, target_location_node_idx, rewrite_data,
+                             rewrite_logprobs) -> BaseTensorizedBugLabGnn:
+        (_tn, text_ops, text_groups, text_correct, text_orig, _mn, misuse_groups, _mc, misuse_correct, misuse_orig,
+         _cn, _sp, swap_correct, swap_groups, swap_orig, location_groups) = rewrite_data
         return BaseTensorizedBugLabGnn(
             graph_data=tensorized_graph,
             target_location_node_idx=target_location_node_idx,
@@ -263,7 +271,7 @@ class GnnBugLabModel(AbstractNeuralModel[BugLabData, BaseTensorizedBugLabGnn, Gn
             candidate_rewrite_original_idx=misuse_orig,
             swapped_pair_to_call=swap_groups, correct_swapped_pair=swap_correct, pair_rewrite_original_idx=swap_orig,
             num_rewrite_locations_considered=len(location_groups),
-            rewrite_logprobs=datapoint.get("candidate_rewrite_logprobs", None))
+            rewrite_logprobs=rewrite_logprobs)
 
     # ---- minibatch ------------------------------------------------------------------------------
     def initialize_minibatch(self) -> Dict[str, Any]:

@@ -14,6 +14,7 @@ Options:
     --restore-path=<path>         The path to previous model file for starting from previous checkpoint.
     --model-spec=<json>           Extra registry keyword arguments as JSON, e.g. '{"hidden_state_size": 256}'.
     --sequential                  Do not parallelize data loading. Makes debugging easier.
+    --host-loader                 Decode shards with the Python msgpack path instead of the native shard decoder.
     --quiet                       Do not show progress bar.
     -h --help                     Show this screen.
     --debug                       Enable debug routines. [default: False]
@@ -59,13 +60,25 @@ def run(arguments):
     max_files_per_fold = arguments["--max-files-per-fold"]
     max_files_per_fold = None if max_files_per_fold is None else int(max_files_per_fold)
 
-    training_data = LazyDataIterable(construct_data_loading_callable(
-        RichPath.create(arguments["TRAIN_DATA_PATH"], azure_info_path), shuffle=True,
-        max_files_per_fold=max_files_per_fold, limit_num_yielded_elements=int(arguments["--validate-after"]),
-        rank=rank, world_size=world))
-    validation_data = LazyDataIterable(construct_data_loading_callable(
-        RichPath.create(arguments["VALID_DATA_PATH"], azure_info_path), max_files_per_fold=max_files_per_fold,
-        rank=rank, world_size=world))
+    train_path = RichPath.create(arguments["TRAIN_DATA_PATH"], azure_info_path)
+    valid_path = RichPath.create(arguments["VALID_DATA_PATH"], azure_info_path)
+    validate_after = int(arguments["--validate-after"])
+    if arguments.get("--host-loader"):
+        training_data = LazyDataIterable(construct_data_loading_callable(
+            train_path, shuffle=True, max_files_per_fold=max_files_per_fold, limit_num_yielded_elements=validate_after,
+            rank=rank, world_size=world))
+        validation_data = LazyDataIterable(construct_data_loading_callable(
+            valid_path, max_files_per_fold=max_files_per_fold, rank=rank, world_size=world))
+    else:
+        # same file selection / sharding / limits; samples go file -> packed arrays in native code (include/buglab_shards.h)
+        from buglab_b200.shards import ShardDataset
+
+        threads = 1 if arguments["--sequential"] else None
+        training_data = ShardDataset(train_path, shuffle=True, take_only_first_n_files=max_files_per_fold,
+                                     limit_num_yielded_elements=validate_after, rank=rank, world_size=world,
+                                     num_threads=threads)
+        validation_data = ShardDataset(valid_path, take_only_first_n_files=max_files_per_fold, rank=rank,
+                                       world_size=world, num_threads=threads)
 
     model_path = Path(arguments["MODEL_FILENAME"])
     model_spec = {"modelName": arguments["MODEL_NAME"]}

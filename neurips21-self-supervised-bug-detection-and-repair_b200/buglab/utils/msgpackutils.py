@@ -22,10 +22,11 @@ def save_msgpack_l_gz(data: Iterable[Any], filename: PathLike) -> None:
             stream.write(packer.pack(element))
 
 
-def load_all_msgpack_l_gz(path: RichPath, shuffle: bool = False, take_only_first_n_files: Optional[int] = None,
-                          limit_num_yielded_elements: Optional[int] = None, rank: int = 0, world_size: int = 1) -> Iterator:
-    """All non-None elements of every ``*.msgpack.l.gz`` under ``path`` (sorted, optionally shuffled file order).
-    ``rank`` / ``world_size`` shard the (sorted) file list round-robin for data-parallel training."""
+def select_shard_files(path: RichPath, shuffle: bool = False, take_only_first_n_files: Optional[int] = None,
+                       rank: int = 0, world_size: int = 1):
+    """The ``*.msgpack.l.gz`` files one rank reads: the sorted list (optionally truncated), split round-robin across
+    ranks when there are enough files — otherwise every rank reads every file and keeps each ``world_size``-th element
+    (second return value) — then optionally shuffled."""
     files = sorted(path.iterate_filtered_files_in_dir("*.msgpack.l.gz"))
     if take_only_first_n_files is not None:
         files = files[:take_only_first_n_files]
@@ -36,6 +37,14 @@ def load_all_msgpack_l_gz(path: RichPath, shuffle: bool = False, take_only_first
         shard_elements = world_size > 1
     if shuffle:
         random.shuffle(files)
+    return files, shard_elements
+
+
+def load_all_msgpack_l_gz(path: RichPath, shuffle: bool = False, take_only_first_n_files: Optional[int] = None,
+                          limit_num_yielded_elements: Optional[int] = None, rank: int = 0, world_size: int = 1) -> Iterator:
+    """All non-None elements of every ``*.msgpack.l.gz`` under ``path`` (sorted, optionally shuffled file order).
+    ``rank`` / ``world_size`` shard the (sorted) file list round-robin for data-parallel training."""
+    files, shard_elements = select_shard_files(path, shuffle, take_only_first_n_files, rank, world_size)
     num_yielded = 0
     for file in files:
         try:

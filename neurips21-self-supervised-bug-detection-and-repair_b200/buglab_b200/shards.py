@@ -1,0 +1,428 @@
+"""Native ``.msgpack.l.gz`` shard path: file -> packed per-graph tensors without building Python objects.
+
+ctypes binding of ``include/buglab_shards.h`` (host-only ``libbuglab_shards.so``, built by ``csrc/build.sh``) plus the
+glue that turns its arrays into the same ``BaseTensorizedBugLabGnn`` tuples ``GnnBugLabModel.tensorize`` produces
+(reference call chain: buglab/utils/msgpackutils.py:11-45 -> buglab/representations/data.py:139-167 ->
+buglab/models/gnn.py:463-520).  The decode runs outside the GIL, so the loader's worker threads scale with cores.
+
+Samples the native code declines (``BL_SAMPLE_NEEDS_HOST``: exotic Unicode case mapping, malformed fields, ...) are
+unpacked with ``msgpack`` and go through ``model.tensorize`` — the reference-shaped path — so results and exceptions are
+the same either way.  There is no silent degradation: a missing library raises at construction.
+"""
+import ctypes
+import os
+import threading
+from collections import defaultdict
+from concurrent.futures import ThreadPoolExecutor
+from typing import Any, Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
+
+import msgpack
+import numpy as np
+
+_LIB_NAME = "libbuglab_shards.so"
+_lib: Optional[ctypes.CDLL] = None
+_lock = threading.Lock()
+
+c_i32, c_i64, c_ptr = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p
+
+SAMPLE_OK, SAMPLE_NIL, SAMPLE_NEEDS_HOST = 0, 1, 2
+SPLIT_TOKEN, SPLIT_SUBTOKEN = 0, 1
+
+
+class SampleView(ctypes.Structure):
+    """``bl_sample_view`` (include/buglab_shards.h), field for field."""
+    _fields_ = [
+        ("status", c_i32), ("num_file_nodes", c_i32), ("num_nodes", c_i32), ("max_subtokens", c_i32),
+        ("node_ids", c_ptr), ("node_lens", c_ptr),
+        ("num_edge_types", c_i32), ("num_reference_nodes", c_i32),
+        ("edge_offsets", c_ptr), ("edge_src", c_ptr), ("edge_tgt", c_ptr), ("reference_nodes", c_ptr),
+        ("num_call_args", c_i32), ("has_target", c_i32),
+        ("call_args", c_ptr),
+        ("target_fix_action_idx", c_i64),
+        ("raw", c_ptr), ("raw_len", c_i64),
+        ("rewrites_off", c_i64), ("rewrites_len", c_i64),
+        ("metadata_off", c_i64), ("metadata_len", c_i64),
+        ("logprobs_off", c_i64), ("logprobs_len", c_i64),
+    ]
+
+
+_SIGNATURES = {
+    "bl_shards_version": (c_i32, []),
+    "bl_shards_error_string": (ctypes.c_char_p, [c_i32]),
+    "bl_shard_open": (c_i32, [ctypes.c_char_p, ctypes.POINTER(c_ptr)]),
+    "bl_shard_open_buffer": (c_i32, [c_ptr, c_i64, ctypes.POINTER(c_ptr)]),
+    "bl_shard_close": (None, [c_ptr]),
+    "bl_shard_num_objects": (c_i64, [c_ptr]),
+    "bl_shard_raw_bytes": (c_i64, [c_ptr]),
+    "bl_shard_status": (c_i32, [c_ptr]),
+    "bl_shard_object": (c_i32, [c_ptr, c_i64, ctypes.POINTER(c_ptr), ctypes.POINTER(c_i64)]),
+    "bl_tokenizer_create": (c_i32, [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_ptr, c_i32, ctypes.POINTER(c_ptr)]),
+    "bl_tokenizer_destroy": (None, [c_ptr]),
+    "bl_tokenizer_ids": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr]),
+    "bl_sample_create": (c_i32, [ctypes.POINTER(c_ptr)]),
+    "bl_sample_destroy": (None, [c_ptr]),
+    "bl_sample_decode": (c_i32, [c_ptr, c_i64, c_ptr, c_ptr, c_i32, c_ptr, ctypes.POINTER(SampleView)]),
+    "bl_pyset_iteration_order": (c_i64, [c_ptr, c_i64, c_ptr]),
+}
+
+
+def library_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                path = library_path()
+                if not os.path.exists(path):
+                    raise RuntimeError(f"{_LIB_NAME} is not built ({path}); run csrc/build.sh or __graft_entry__.build()")
+                handle = ctypes.CDLL(path)
+                for name, (restype, argtypes) in _SIGNATURES.items():
+                    fn = getattr(handle, name)
+                    fn.restype, fn.argtypes = restype, argtypes
+                _check_set_order(handle)
+                _lib = handle
+    return _lib
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        raise RuntimeError(f"{what}: {lib().bl_shards_error_string(code).decode()}")
+
+
+def pyset_iteration_order(values: Sequence[int], handle: Optional[ctypes.CDLL] = None) -> List[int]:
+    handle = handle or lib()
+    a = np.ascontiguousarray(values, dtype=np.int64)
+    out = np.empty(max(1, a.size), dtype=np.int64)
+    k = handle.bl_pyset_iteration_order(a.ctypes.data, a.size, out.ctypes.data)
+    if k < 0:
+        raise ValueError("unsupported set element")
+    return out[:k].tolist()
+
+
+def _check_set_order(handle: ctypes.CDLL) -> None:
+    """data.py:103-108 makes the iteration order of a CPython ``set`` of token ids load-bearing (it numbers the subtoken
+    nodes).  The native model of that order is verified against the running interpreter before first use; an interpreter
+    with a different set implementation must not silently produce differently numbered graphs."""
+    rng = np.random.default_rng(7)
+    probes = [list(range(0, 400, 3)) + list(range(1, 400, 3)),
+              rng.integers(0, 5000, size=3000).tolist(),
+              rng.integers(0, 1 << 40, size=500).tolist(),
+              [i // 2 + (i % 2) for i in range(70000)]]
+    for values in probes:
+        expected = set()
+        for v in values:
+            expected.add(v)
+        if pyset_iteration_order(values, handle) != list(expected):
+            raise RuntimeError("libbuglab_shards: CPython set-order model does not match this interpreter; "
+                               "use the host-language loader (buglab.utils.msgpackutils.load_msgpack_l_gz)")
+
+
+def lower_variant_codepoints() -> np.ndarray:
+    """Non-ASCII code points that ``str.lower()`` changes, from THIS interpreter's Unicode tables (labels containing one
+    are left to the host path, so native and host case folding cannot disagree)."""
+    global _LOWER_VARIANT
+    if _LOWER_VARIANT is None:
+        cps = [c for c in range(0x80, 0x110000) if not (0xD800 <= c <= 0xDFFF) and chr(c).lower() != chr(c)]
+        _LOWER_VARIANT = np.array(cps, dtype=np.int32)
+    return _LOWER_VARIANT
+
+
+_LOWER_VARIANT: Optional[np.ndarray] = None
+
+
+class Shard:
+    """One inflated + indexed ``.msgpack.l.gz`` file."""
+
+    def __init__(self, path: Optional[str] = None, gz_bytes: Optional[bytes] = None):
+        handle = c_ptr()
+        if path is not None:
+            check(lib().bl_shard_open(os.fsencode(path), ctypes.byref(handle)), f"open {path}")
+        else:
+            buf = (ctypes.c_char * len(gz_bytes)).from_buffer_copy(gz_bytes) if gz_bytes else None
+            check(lib().bl_shard_open_buffer(ctypes.cast(buf, c_ptr) if buf is not None else None, len(gz_bytes or b""),
+                                             ctypes.byref(handle)), "open buffer")
+        self._h = handle
+        self.path = path
+
+    def __len__(self) -> int:
+        return int(lib().bl_shard_num_objects(self._h))
+
+    @property
+    def raw_bytes(self) -> int:
+        return int(lib().bl_shard_raw_bytes(self._h))
+
+    @property
+    def status(self) -> int:
+        """0, or the error code that cut the stream short (objects before the break are still served)."""
+        return int(lib().bl_shard_status(self._h))
+
+    def object_bytes(self, index: int) -> bytes:
+        data, n = c_ptr(), c_i64()
+        check(lib().bl_shard_object(self._h, index, ctypes.byref(data), ctypes.byref(n)), "object")
+        return ctypes.string_at(data.value, n.value)
+
+    def close(self) -> None:
+        if self._h is not None and self._h.value:
+            lib().bl_shard_close(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Tokenizer:
+    """The node-label vocabulary handed to the native side (ptgnn StrElementRepresentationModel semantics)."""
+
+    def __init__(self, vocabulary, splitting_kind: str, max_num_subtokens: int):
+        tokens = list(vocabulary.token_to_id.items())
+        encoded = [t.encode("utf-8", "surrogatepass") for t, _ in tokens]
+        offsets = np.zeros(len(encoded) + 1, dtype=np.int64)
+        np.cumsum([len(e) for e in encoded], out=offsets[1:])
+        blob = np.frombuffer(b"".join(encoded) or b"\0", dtype=np.uint8)
+        ids = np.array([i for _, i in tokens], dtype=np.int32)
+        unk = vocabulary.token_to_id.get(vocabulary.get_unk(), -1)
+        variants = lower_variant_codepoints()
+        kind = {"token": SPLIT_TOKEN, "subtoken": SPLIT_SUBTOKEN}[splitting_kind]
+        handle = c_ptr()
+        check(lib().bl_tokenizer_create(blob.ctypes.data, offsets.ctypes.data, ids.ctypes.data, len(tokens), int(unk), kind,
+                                        int(max_num_subtokens), variants.ctypes.data, variants.size, ctypes.byref(handle)),
+              "tokenizer")
+        self._h = handle
+        self.max_subtokens = 1 if kind == SPLIT_TOKEN else int(max_num_subtokens)
+
+    def ids(self, label: str) -> Optional[Tuple[int, ...]]:
+        raw = label.encode("utf-8", "surrogatepass")
+        out = np.zeros(self.max_subtokens, dtype=np.int32)
+        n = lib().bl_tokenizer_ids(self._h, raw, len(raw), out.ctypes.data)
+        return None if n < 0 else tuple(out[:n].tolist())
+
+    def __del__(self):
+        try:
+            if self._h is not None and self._h.value:
+                lib().bl_tokenizer_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def _as_array(ptr: Optional[int], count: int, dtype) -> np.ndarray:
+    if count == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    ctype = {np.int32: ctypes.c_int32, np.int64: ctypes.c_int64}[dtype]
+    return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctype)), shape=(count,)).copy()
+
+
+class _SampleBuffer:
+    """Per-thread ``bl_sample`` handle (its vectors are reused from sample to sample)."""
+
+    def __init__(self):
+        self.handle = c_ptr()
+        check(lib().bl_sample_create(ctypes.byref(self.handle)), "sample")
+        self.view = SampleView()
+
+    def __del__(self):
+        try:
+            if self.handle is not None and self.handle.value:
+                lib().bl_sample_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class NativeShardTensorizer:
+    """``shard file -> BaseTensorizedBugLabGnn`` for a ``GnnBugLabModel`` whose metadata is finalised."""
+
+    def __init__(self, model):
+        lib()
+        self._model = model
+        gnn_model = model.gnn_model
+        node_model = gnn_model.node_representation_model
+        self._gnn_model = gnn_model
+        self._tokenizer = Tokenizer(node_model.vocabulary, node_model.splitting_kind, node_model.max_num_subtokens)
+        self._splitting_kind = node_model.splitting_kind
+        names = [n.encode("utf-8") for n in gnn_model.edge_types]
+        self._edge_names = (ctypes.c_char_p * max(1, len(names)))(*names)
+        self._num_edge_types = len(names)
+        self._local = threading.local()
+        self.num_native = 0   # samples produced by the native path / handed to the host path (statistics)
+        self.num_host = 0
+
+    # ---- one sample -----------------------------------------------------------------------------
+    def _buffer(self) -> _SampleBuffer:
+        buf = getattr(self._local, "buf", None)
+        if buf is None:
+            buf = self._local.buf = _SampleBuffer()
+        return buf
+
+    def tensorize_object(self, shard: Shard, index: int):
+        """Tensorised sample ``index`` of ``shard``; ``None`` for nil objects and for samples the model drops."""
+        buf = self._buffer()
+        v = buf.view
+        check(lib().bl_sample_decode(shard._h, index, self._tokenizer._h, self._edge_names, self._num_edge_types,
+                                     buf.handle, ctypes.byref(v)), "decode")
+        if v.status == SAMPLE_NIL:
+            return None
+        if v.status == SAMPLE_NEEDS_HOST:
+            self.num_host += 1
+            datapoint = msgpack.unpackb(ctypes.string_at(v.raw, v.raw_len), raw=False)
+            return self._model.tensorize(datapoint)
+        self.num_native += 1
+        model, gnn_model = self._model, self._gnn_model
+
+        raw = ctypes.string_at(v.raw, v.raw_len)
+        rewrites = msgpack.unpackb(raw[v.rewrites_off: v.rewrites_off + v.rewrites_len], raw=False)
+        metadata = msgpack.unpackb(raw[v.metadata_off: v.metadata_off + v.metadata_len], raw=False)
+        logprobs = None
+        has_logprobs = v.logprobs_len > 0
+        if has_logprobs:
+            assert not model._tensorize_only_at_target_location_rewrites
+            logprobs = msgpack.unpackb(raw[v.logprobs_off: v.logprobs_off + v.logprobs_len], raw=False)
+
+        reference_nodes = _as_array(v.reference_nodes, v.num_reference_nodes, np.int32).tolist()
+        target_action = int(v.target_fix_action_idx) if v.has_target else None
+        candidate_nodes, inverse = np.unique(reference_nodes, return_inverse=True)
+        target_node_idx = None if target_action is None else inverse[target_action]
+
+        call_args: Dict[int, List[int]] = defaultdict(list)
+        pairs = _as_array(v.call_args, 2 * v.num_call_args, np.int32).tolist()
+        for k in range(0, len(pairs), 2):
+            call_args[pairs[k]].append(pairs[k + 1])
+        rewrite_data = model._compute_rewrite_data_from(reference_nodes, rewrites, metadata, target_action, call_args,
+                                                        candidate_nodes)
+        refs: Dict[str, Any] = {"candidate_nodes": candidate_nodes}
+        model._add_rewrite_reference_nodes(refs, rewrite_data)
+
+        n, T = v.num_nodes, v.max_subtokens
+        ids = _as_array(v.node_ids, n * T, np.int32).reshape(n, T)
+        lens = _as_array(v.node_lens, n, np.int32)
+        offsets = _as_array(v.edge_offsets, self._num_edge_types + 1, np.int64)
+        src = _as_array(v.edge_src, int(offsets[-1]) if offsets.size else 0, np.int32)
+        tgt = _as_array(v.edge_tgt, int(offsets[-1]) if offsets.size else 0, np.int32)
+        forward = [(src[offsets[k]: offsets[k + 1]], tgt[offsets[k]: offsets[k + 1]]) for k in range(self._num_edge_types)]
+        tensorized_graph = gnn_model.tensorize_arrays(n, (ids, lens), forward, refs)
+        if tensorized_graph is None:
+            return None
+        return model._assemble_tensorized(tensorized_graph, target_node_idx, rewrite_data, logprobs)
+
+    # ---- whole shards ---------------------------------------------------------------------------
+    _DROPPED = object()  # a sample the model declined (too many nodes): counted by the loader, not yielded
+
+    def _shard_items(self, path: str, rank: int, world_size: int) -> List:
+        out: List = []
+        with Shard(path) as shard:
+            for i in range(len(shard)):
+                if world_size > 1 and i % world_size != rank:
+                    continue
+                buf = self._buffer()
+                t = self.tensorize_object(shard, i)
+                if t is None and buf.view.status == SAMPLE_NIL:
+                    continue
+                out.append(self._DROPPED if t is None else t)
+            if shard.status != 0:
+                print(f"Error loading {path}: {lib().bl_shards_error_string(shard.status).decode()}.")
+        return out
+
+    def tensorize_shard(self, path: str, rank: int = 0, world_size: int = 1) -> Iterator:
+        """All tensorised samples of one file, in file order (``rank``/``world_size``: element-level sharding used when
+        there are fewer files than ranks, msgpackutils.load_all_msgpack_l_gz)."""
+        for t in self._shard_items(path, rank, world_size):
+            if t is not self._DROPPED:
+                yield t
+
+    def tensorize_files(self, paths: Iterable[str], num_threads: Optional[int] = None, rank: int = 0, world_size: int = 1,
+                        element_sharding: bool = False, limit_num_elements: Optional[int] = None
+                        ) -> Iterator[Tuple[Any, None]]:
+        """``(tensorised, None)`` pairs — the shape ``tensorize_dataset`` yields — over many shard files.  Files are
+        decoded by ``num_threads`` workers (the native calls run outside the GIL); results come back in file order.
+        ``limit_num_elements`` counts non-nil file elements the way load_all_msgpack_l_gz does (it stops after the
+        element that EXCEEDS the limit, as the reference's loop does)."""
+        paths = list(paths)
+        if num_threads is None:
+            num_threads = max(1, min(8, (os.cpu_count() or 2) - 1))
+        shard_args = (rank, world_size) if element_sharding else (0, 1)
+
+        def work(path):
+            try:
+                return self._shard_items(path, *shard_args)
+            except RuntimeError as e:  # unreadable shard: skipped like the reference does (msgpackutils.py:44-45)
+                print(f"Error loading {path}: {e}.")
+                return []
+
+        def per_file() -> Iterator[List]:
+            if num_threads <= 1 or len(paths) <= 1:
+                for path in paths:
+                    yield work(path)
+                return
+            pool = ThreadPoolExecutor(max_workers=num_threads)
+            try:
+                window: List = []
+                it = iter(paths)
+                for _ in range(num_threads + 1):
+                    p = next(it, None)
+                    if p is None:
+                        break
+                    window.append(pool.submit(work, p))
+                while window:
+                    fut = window.pop(0)
+                    p = next(it, None)
+                    if p is not None:
+                        window.append(pool.submit(work, p))
+                    yield fut.result()
+            finally:
+                pool.shutdown(wait=True, cancel_futures=True)
+
+        num_seen = 0
+        for items in per_file():
+            for t in items:
+                num_seen += 1
+                if t is not self._DROPPED:
+                    yield t, None
+                if limit_num_elements is not None and num_seen > limit_num_elements:
+                    return
+
+
+class ShardDataset:
+    """A directory of ``.msgpack.l.gz`` shards as the trainer's data source.
+
+    Iterating it yields raw datapoints through the host decoder (metadata pass, ``predict``); ``tensorized(model)`` yields
+    ``(tensorised, None)`` pairs straight from the native decoder — ``ModelTrainer.train`` picks that up when present.
+    File selection, rank sharding and the element limit are those of ``load_all_msgpack_l_gz``."""
+
+    def __init__(self, data_path, shuffle: bool = False, take_only_first_n_files: Optional[int] = None,
+                 limit_num_yielded_elements: Optional[int] = None, rank: int = 0, world_size: int = 1,
+                 num_threads: Optional[int] = None):
+        self._path, self._shuffle, self._first_n = data_path, shuffle, take_only_first_n_files
+        self._limit, self._rank, self._world, self._threads = limit_num_yielded_elements, rank, world_size, num_threads
+        self._tensorizer: Optional[NativeShardTensorizer] = None
+        self._tensorizer_model = None
+
+    def __iter__(self):
+        from buglab.utils.msgpackutils import load_all_msgpack_l_gz
+
+        return load_all_msgpack_l_gz(self._path, shuffle=self._shuffle, take_only_first_n_files=self._first_n,
+                                     limit_num_yielded_elements=self._limit, rank=self._rank, world_size=self._world)
+
+    def tensorized(self, model) -> Iterator[Tuple[Any, None]]:
+        from buglab.utils.msgpackutils import select_shard_files
+
+        if self._tensorizer is None or self._tensorizer_model is not model:
+            self._tensorizer, self._tensorizer_model = NativeShardTensorizer(model), model
+        files, shard_elements = select_shard_files(self._path, self._shuffle, self._first_n, self._rank, self._world)
+        paths = [f.to_local_path().path for f in files]
+        return self._tensorizer.tensorize_files(paths, self._threads, self._rank, self._world, shard_elements, self._limit)
+
+    @property
+    def tensorizer(self) -> Optional[NativeShardTensorizer]:
+        return self._tensorizer

@@ -21,3 +21,9 @@ done
 for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
 "$NVCC" -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT" "${OBJS[@]}" -lcudart -lcublas
 echo "built $OUT"
+# host-only shard decoder (no CUDA): include/buglab_shards.h
+SHARDS_OUT=../buglab_b200/libbuglab_shards.so
+if [[ ! -f "$SHARDS_OUT" || shards/shards.cpp -nt "$SHARDS_OUT" || ../../include/buglab_shards.h -nt "$SHARDS_OUT" ]]; then
+  ${CXX:-g++} -O3 -std=c++17 -fPIC -shared -Wall -Wextra -o "$SHARDS_OUT" shards/shards.cpp -lz
+fi
+echo "built $SHARDS_OUT"

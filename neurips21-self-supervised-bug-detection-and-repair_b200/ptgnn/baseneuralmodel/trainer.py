@@ -322,11 +322,18 @@ class ModelTrainer:
         dist.broadcast_module(nn)
         model = self.__model
 
+        def tensors_of(data):
+            # a data source that can tensorise itself (buglab_b200.shards.ShardDataset: native shard decoder) is asked to;
+            # anything else is a plain iterable of raw datapoints, as in the reference
+            if hasattr(data, "tensorized"):
+                return data.tensorized(model)
+            return model.tensorize_dataset(iter(data), return_input_data=False, parallelize=parallelize)
+
         def training_tensors():
-            return model.tensorize_dataset(iter(training_data), return_input_data=False, parallelize=parallelize)
+            return tensors_of(training_data)
 
         def validation_tensors():
-            return model.tensorize_dataset(iter(validation_data), return_input_data=False, parallelize=parallelize)
+            return tensors_of(validation_data)
 
         class _Re:
             def __init__(self, f):

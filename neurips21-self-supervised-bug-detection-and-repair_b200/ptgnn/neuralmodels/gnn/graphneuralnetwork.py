@@ -148,6 +148,21 @@ class GraphNeuralNetworkModel(AbstractNeuralModel[GraphData, TensorizedGraphData
             else:
                 adj = np.asarray(adj, dtype=np.int32)
                 forward.append((np.ascontiguousarray(adj[:, 0]), np.ascontiguousarray(adj[:, 1])))
+        node_model = self.__node_embedding_model
+        if hasattr(node_model, "tensorize_many"):
+            node_data = node_model.tensorize_many(datapoint.node_information)
+        else:
+            node_data = [node_model.tensorize(n) for n in datapoint.node_information]
+        return self.tensorize_arrays(num_nodes, node_data, forward, datapoint.reference_nodes)
+
+    def tensorize_arrays(self, num_nodes: int, node_data, forward: List[Tuple[np.ndarray, np.ndarray]],
+                         reference_nodes: Dict[str, Any]) -> Optional[TensorizedGraphData]:
+        """The per-graph tensors from already-packed parts: ``node_data`` as the node model tensorises it and one
+        ``(sources, targets)`` int32 pair per forward edge type, in ``edge_types`` order.  Shared by ``tensorize`` and the
+        native shard path (buglab_b200/shards.py), which produces these arrays without building Python objects."""
+        if num_nodes > self.max_nodes_per_graph:
+            LOGGER.warning("Dropping graph with %s nodes.", num_nodes)
+            return None
         adjacency = list(forward)
         if self.introduce_backwards_edges:
             adjacency.extend((tgt, src) for src, tgt in forward)
@@ -156,16 +171,11 @@ class GraphNeuralNetworkModel(AbstractNeuralModel[GraphData, TensorizedGraphData
             adjacency.append((ar, ar))
         if sum(a[0].shape[0] for a in adjacency) > 2 ** 31 - 16:
             return None
-        node_model = self.__node_embedding_model
-        if hasattr(node_model, "tensorize_many"):
-            node_data = node_model.tensorize_many(datapoint.node_information)
-        else:
-            node_data = [node_model.tensorize(n) for n in datapoint.node_information]
         return TensorizedGraphData(
             num_nodes=num_nodes,
             node_tensorized_data=node_data,
             adjacency_lists=adjacency,
-            reference_nodes={k: np.asarray(v, dtype=np.int32) for k, v in datapoint.reference_nodes.items()},
+            reference_nodes={k: np.asarray(v, dtype=np.int32) for k, v in reference_nodes.items()},
         )
 
     # ---- minibatch packing ----------------------------------------------------------------------

@@ -1,0 +1,350 @@
+"""Native shard decoder (include/buglab_shards.h) against the host-language path.
+
+The checker is the reference-shaped Python chain load_msgpack_l_gz -> BugLabData.as_graph_data -> GnnBugLabModel.tensorize
+(itself pinned by tests/golden).  The bar is bit-identity: same arrays, same dtypes, same Python scalars, same order."""
+import copy
+import gzip
+import io
+import os
+import random
+import re
+import sys
+
+import msgpack
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "neurips21-self-supervised-bug-detection-and-repair_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from buglab_b200 import shards  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def assert_same(a, b, where="sample"):
+    if isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
+        assert isinstance(a, np.ndarray) and isinstance(b, np.ndarray), (where, type(a), type(b))
+        assert a.dtype == b.dtype and a.shape == b.shape, (where, a.dtype, b.dtype, a.shape, b.shape)
+        assert np.array_equal(a, b), where
+    elif hasattr(a, "_fields"):
+        assert type(a) is type(b), where
+        for f in a._fields:
+            assert_same(getattr(a, f), getattr(b, f), f"{where}.{f}")
+    elif isinstance(a, dict):
+        assert isinstance(b, dict) and list(a.keys()) == list(b.keys()), where
+        for k in a:
+            assert_same(a[k], b[k], f"{where}.{k}")
+    elif isinstance(a, (list, tuple)):
+        assert isinstance(b, (list, tuple)) and len(a) == len(b), (where, a, b)
+        for i, (x, y) in enumerate(zip(a, b)):
+            assert_same(x, y, f"{where}[{i}]")
+    else:
+        assert type(a) is type(b) and a == b, (where, a, b)
+
+
+@pytest.fixture(scope="module")
+def model():
+    from pathlib import Path
+
+    from buglab.models.modelregistry import load_model
+    from buglab_b200.synthetic import SyntheticBugLabGenerator
+
+    m, _, _ = load_model({"modelName": "gnn-mlp", "hidden_state_size": 16}, Path("/tmp/_buglab_shards_test.pkl.gz"))
+    m.compute_metadata(SyntheticBugLabGenerator(seed=12345, mean_nodes=200, min_nodes=40).samples(48))
+    return m
+
+
+def host_tensorize_file(model, path):
+    from buglab.utils.msgpackutils import load_msgpack_l_gz
+
+    return [model.tensorize(dp) for dp in load_msgpack_l_gz(path) if dp is not None]
+
+
+def write_objects(path, objects, **packer_kwargs):
+    packer = msgpack.Packer(use_bin_type=True, **packer_kwargs)
+    with gzip.GzipFile(path, "wb") as f:
+        for o in objects:
+            f.write(packer.pack(o))
+
+
+# ---------------------------------------------------------------------------------------------- C ABI surface
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "buglab_shards.h")).read()
+    declared = set(re.findall(r"\b(bl_[a-z0-9_]+)\s*\(", header))
+    declared -= {"bl_sample_view"}
+    assert len(declared) >= 16
+    lib = shards.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in buglab_shards.h but not exported"
+        assert name in shards._SIGNATURES, f"{name} has no ctypes signature"
+    assert lib.bl_shards_version() == 1
+    assert lib.bl_shards_error_string(2) == b"corrupt or truncated gzip stream"
+
+
+# ---------------------------------------------------------------------------------------------- CPython set order
+def test_set_iteration_order_matches_the_interpreter():
+    rng = random.Random(3)
+    for trial in range(400):
+        n = rng.choice([0, 1, 2, 5, 8, 9, 21, 85, 341, 1500, 6000])
+        hi = rng.choice([8, 64, 1000, 50_000, 10 ** 9, 2 ** 50])
+        if trial % 2:
+            start = rng.randrange(hi)
+            values = []
+            for i in range(n):  # NextToken-like chains (a, a+1), (a+1, a+2), ...
+                values += [start + i, start + i + rng.choice([1, 1, 1, 3])]
+        else:
+            values = [rng.randrange(hi) for _ in range(n)]
+        expected = set()
+        for v in values:
+            expected.add(v)
+        assert shards.pyset_iteration_order(values) == list(expected)
+    with pytest.raises(ValueError):
+        shards.pyset_iteration_order([3, -1])
+
+
+# ---------------------------------------------------------------------------------------------- tokeniser
+LABELS = ["", "_", "___", "a", "A", "aB", "ABc", "AB", "HTTPServer", "fooBar_baz2", "__init__", "CamelCASE", "iOS",
+          "x+y", " ", "a1B2c3", "snake_case_name", "UPPER_CASE", "Call", "Name", "<=", "'a string literal'", "f00Bar",
+          "naïve", "日本語", "caféAu_lait", "\U0001F600smile", "aßb", "x" * 300, "aB" * 200,
+          "Élan", "ΑΒΓ", "STRASSEẞ", "İstanbul", "mixedΣigma"]
+
+
+@pytest.mark.parametrize("kind", ["subtoken", "token"])
+def test_tokenizer_matches_host_ids(kind):
+    from dpu_utils.mlutils import Vocabulary
+    from ptgnn.neuralmodels.embeddings.strelementrepresentationmodel import StrElementRepresentationModel
+
+    node_model = StrElementRepresentationModel(token_splitting=kind, embedding_size=8, vocabulary_size=500,
+                                               min_freq_threshold=1, max_num_subtokens=6, subtoken_combination="max")
+    for label in LABELS[::2] * 2:
+        node_model.update_metadata_from(label)
+    node_model.finalize_metadata()
+    vocab: Vocabulary = node_model.vocabulary
+    tok = shards.Tokenizer(vocab, kind, node_model.max_num_subtokens)
+    needs_host = 0
+    for label in LABELS:
+        got = tok.ids(label)
+        if got is None:
+            needs_host += 1
+            assert any(ord(c) >= 0x80 and c.lower() != c for c in label), label  # only case-variant non-ASCII is declined
+            continue
+        assert got == tuple(node_model._ids_of(label)), label
+    assert needs_host == 5
+
+
+def test_vocabulary_without_unk_routes_misses_to_host():
+    from dpu_utils.mlutils import Vocabulary
+
+    vocab = Vocabulary(add_unk=False, add_pad=True)
+    vocab.add_or_get_id("foo")
+    tok = shards.Tokenizer(vocab, "subtoken", 4)
+    assert tok.ids("foo_Foo") == (vocab.get_id_or_unk("foo"),) * 2
+    assert tok.ids("foo_bar") is None
+
+
+# ---------------------------------------------------------------------------------------------- whole samples
+def test_synthetic_shard_is_bit_identical(model, tmp_path):
+    from buglab_b200.synthetic import write_shards
+
+    path = write_shards(str(tmp_path), 1, 24, seed=5, mean_nodes=300, min_nodes=30)[0]
+    expected = host_tensorize_file(model, path)
+    tensorizer = shards.NativeShardTensorizer(model)
+    got = list(tensorizer.tensorize_shard(path))
+    assert len(got) == len(expected) == 24
+    assert tensorizer.num_native == 24 and tensorizer.num_host == 0
+    for i, (a, b) in enumerate(zip(expected, got)):
+        assert_same(a, b, f"sample{i}")
+
+
+def test_golden_reference_samples_are_bit_identical(model):
+    """The samples the golden vectors were generated from (tests/golden/make_golden.py), incl. the selector ones that
+    carry candidate_rewrite_logprobs."""
+    tensorizer = shards.NativeShardTensorizer(model)
+    path = os.path.join(GOLDEN, "samples.msgpack.l.gz")
+    for a, b in zip(host_tensorize_file(model, path), tensorizer.tensorize_shard(path)):
+        assert_same(a, b)
+    path = os.path.join(GOLDEN, "selector_samples.msgpack.l.gz")
+    with model._tensorize_all_location_rewrites():
+        expected = host_tensorize_file(model, path)
+        got = list(tensorizer.tensorize_shard(path))
+    assert len(expected) == len(got) > 0
+    for a, b in zip(expected, got):
+        assert_same(a, b)
+        assert (a.rewrite_logprobs is None) == (b.rewrite_logprobs is None)
+    assert tensorizer.num_host == 0
+
+
+def _variants(base):
+    """Hand-made irregular samples: each must come out exactly as the host path makes it (natively or by deferring)."""
+    def v(mutate):
+        s = copy.deepcopy(base)
+        mutate(s)
+        return s
+
+    g = "graph"
+    out = {
+        "plain": v(lambda s: None),
+        "no_next_token_keeps_file_has_subtoken": v(lambda s: (s[g]["edges"].pop("NextToken"),
+                                                               s[g]["edges"].__setitem__("HasSubtoken", [[0, 1], [2, 3]]))),
+        "stale_has_subtoken_is_replaced": v(lambda s: s[g]["edges"].__setitem__("HasSubtoken", [[0, 1]])),
+        "empty_edge_lists": v(lambda s: [s[g]["edges"].__setitem__(k, []) for k in list(s[g]["edges"])
+                                         if k not in ("NextToken", "Child")]),
+        "unknown_edge_type": v(lambda s: s[g]["edges"].__setitem__("NeverSeenInMetadata", [[0, 1, "meta"], [1, 2]])),
+        "edge_metadata_of_other_types": v(lambda s: s[g]["edges"].__setitem__(
+            "NextToken", [[a, b, None] for a, b, *_ in s[g]["edges"]["NextToken"]])),
+        "out_of_vocabulary_labels": v(lambda s: [s[g]["nodes"].__setitem__(i, f"zzQq{i}_neverSeen") for i in range(0, 12, 3)]),
+        "lower_invariant_unicode": v(lambda s: s[g]["nodes"].__setitem__(1, "caféCrème_日本")),
+        "case_variant_unicode_goes_to_host": v(lambda s: s[g]["nodes"].__setitem__(1, "ÉlanVital")),
+        "long_labels_str8_str16": v(lambda s: (s[g]["nodes"].__setitem__(2, "longName" * 9),
+                                               s[g]["nodes"].__setitem__(3, "x" * 70000))),
+        "extra_keys_everywhere": v(lambda s: (s.__setitem__("unheard_of", {"a": [1, 2.5, None, True, b"bytes"]}),
+                                              s[g].__setitem__("more", [[], {}, -1, 2 ** 40, -2 ** 40, 1.5]))),
+        "no_bug": v(lambda s: s.__setitem__("target_fix_action_idx", None)),
+    }
+    return out
+
+
+@pytest.fixture(scope="module")
+def base_sample():
+    from buglab_b200.synthetic import SyntheticBugLabGenerator
+
+    return SyntheticBugLabGenerator(seed=77, mean_nodes=120, min_nodes=60).sample()
+
+
+def test_irregular_samples_match_host_path(model, base_sample, tmp_path):
+    variants = _variants(base_sample)
+    path = str(tmp_path / "variants.msgpack.l.gz")
+    # nil elements between the samples are skipped by both loaders (msgpackutils.py:38)
+    write_objects(path, [None] + [x for s in variants.values() for x in (s, None)])
+    expected = host_tensorize_file(model, path)
+    tensorizer = shards.NativeShardTensorizer(model)
+    got = list(tensorizer.tensorize_shard(path))
+    assert len(expected) == len(got) == len(variants)
+    for name, a, b in zip(variants, expected, got):
+        assert_same(a, b, name)
+    assert tensorizer.num_host == 1 and tensorizer.num_native == len(variants) - 1
+    # the no-bug variant really exercised the nil target
+    assert got[list(variants).index("no_bug")].target_location_node_idx is None
+
+
+def test_host_path_exceptions_are_preserved(model, base_sample, tmp_path):
+    """Samples the reference would crash on crash the same way here (the native side defers instead of guessing)."""
+    broken = copy.deepcopy(base_sample)
+    del broken["graph"]["edges"]["Child"]           # basemodel.py:84 indexes ["Child"]
+    path = str(tmp_path / "broken.msgpack.l.gz")
+    write_objects(path, [broken])
+    tensorizer = shards.NativeShardTensorizer(model)
+    with pytest.raises(KeyError):
+        host_tensorize_file(model, path)
+    with pytest.raises(KeyError):
+        list(tensorizer.tensorize_shard(path))
+
+    out_of_range = copy.deepcopy(base_sample)
+    out_of_range["graph"]["edges"]["NextToken"].append([0, len(out_of_range["graph"]["nodes"]) + 10 ** 6])
+    write_objects(path, [out_of_range])
+    with pytest.raises(IndexError):
+        host_tensorize_file(model, path)
+    with pytest.raises(IndexError):
+        list(tensorizer.tensorize_shard(path))
+
+
+def test_oversized_graph_is_dropped_like_the_host_path(model, base_sample, tmp_path):
+    path = str(tmp_path / "big.msgpack.l.gz")
+    write_objects(path, [base_sample, base_sample])
+    gnn_model = model.gnn_model
+    saved = gnn_model.max_nodes_per_graph
+    try:
+        gnn_model.max_nodes_per_graph = 10
+        assert host_tensorize_file(model, path) == [None, None]
+        assert list(shards.NativeShardTensorizer(model).tensorize_shard(path)) == []
+    finally:
+        gnn_model.max_nodes_per_graph = saved
+
+
+# ---------------------------------------------------------------------------------------------- container format
+def test_multi_member_gzip_and_truncated_streams(model, base_sample, tmp_path):
+    packer = msgpack.Packer(use_bin_type=True)
+    one = packer.pack(base_sample)
+    member = lambda payload: gzip.compress(payload)  # noqa: E731
+    two_members = member(one + one) + member(one)
+    with shards.Shard(gz_bytes=two_members) as shard:
+        assert len(shard) == 3 and shard.status == 0
+        assert shard.object_bytes(2) == one and shard.raw_bytes == 3 * len(one)
+    # python's reader agrees on the concatenated-members semantics
+    assert len(list(msgpack.Unpacker(gzip.GzipFile(fileobj=io.BytesIO(two_members)), raw=False))) == 3
+
+    whole = member(one + one + one)
+    with shards.Shard(gz_bytes=whole[: len(whole) - 12]) as shard:  # cut inside the deflate stream: no trailer, tail lost
+        assert shard.status == 2 and 2 <= len(shard) <= 3
+        assert shard.object_bytes(0) == one
+    with shards.Shard(gz_bytes=member(one + one[: len(one) // 2])) as shard:  # complete gzip, incomplete last object
+        assert len(shard) == 1 and shard.status == 4
+    with shards.Shard(gz_bytes=member(one + b"\xc1" + one)) as shard:  # 0xc1 is never a valid msgpack type byte
+        assert len(shard) == 1 and shard.status == 4
+    with shards.Shard(gz_bytes=member(packer.pack({"k": "ok"}) + packer.pack({"bad": b"\xff\xfe".decode("latin1")})
+                                      .replace("ÿþ".encode(), b"\xff\xfe\xfe\xfe"))) as shard:
+        assert len(shard) == 1 and shard.status == 4          # invalid UTF-8 in a str, as raw=False rejects it
+    with shards.Shard(gz_bytes=member(packer.pack({"k": 1}) + msgpack.packb({1: 2}))) as shard:
+        assert len(shard) == 1 and shard.status == 4          # non-str map key (strict_map_key)
+    with pytest.raises(RuntimeError):
+        shards.Shard(path=str(tmp_path / "does_not_exist.msgpack.l.gz"))
+    with shards.Shard(gz_bytes=b"this is not gzip") as shard:
+        assert len(shard) == 0 and shard.status == 2
+
+
+# ---------------------------------------------------------------------------------------------- dataset level
+def test_shard_dataset_matches_host_loader(model, tmp_path):
+    from buglab.utils.msgpackutils import load_all_msgpack_l_gz
+    from buglab_b200.synthetic import write_shards
+    from dpu_utils.utils import RichPath
+
+    write_shards(str(tmp_path / "d"), 5, 7, seed=9, mean_nodes=120, min_nodes=30)
+    rich = RichPath.create(str(tmp_path / "d"))
+
+    def host(**kw):
+        return [t for t in (model.tensorize(dp) for dp in load_all_msgpack_l_gz(rich, **kw)) if t is not None]
+
+    def native(threads, **kw):
+        ds = shards.ShardDataset(rich, num_threads=threads, **kw)
+        return [t for t, raw in ds.tensorized(model) if raw is None]
+
+    cases = [dict(), dict(take_only_first_n_files=3), dict(limit_num_yielded_elements=10),
+             dict(rank=1, world_size=2),             # 5 files >= 2 ranks: file-level sharding
+             dict(rank=3, world_size=8),             # fewer files than ranks: element-level sharding
+             dict(rank=0, world_size=8, limit_num_yielded_elements=2)]
+    for kw in cases:
+        expected = host(**kw)
+        for threads in (1, 4):
+            got = native(threads, **kw)
+            assert len(got) == len(expected), kw
+            for a, b in zip(expected, got):
+                assert_same(a, b, str(kw))
+    assert len(host()) == 35 and len(host(rank=1, world_size=2)) == 14 and len(host(limit_num_yielded_elements=10)) == 11
+
+    # raw iteration (metadata pass) is the host loader itself
+    assert len(list(shards.ShardDataset(rich))) == 35
+
+
+def test_trainer_consumes_self_tensorizing_datasets(model, tmp_path):
+    """ModelTrainer.train asks a data source with ``tensorized`` for tensors; minibatches packed from them are the ones the
+    host loader gives (host-side packing only — no device work)."""
+    from buglab.utils.msgpackutils import load_all_msgpack_l_gz
+    from buglab_b200.synthetic import write_shards
+    from dpu_utils.utils import RichPath
+
+    write_shards(str(tmp_path / "d"), 2, 6, seed=4, mean_nodes=100, min_nodes=30)
+    rich = RichPath.create(str(tmp_path / "d"))
+
+    def pack(tensorized):
+        mb = model.initialize_minibatch()
+        for t in tensorized:
+            model.extend_minibatch_with(t, mb)
+        return mb
+
+    host_mb = pack(model.tensorize(dp) for dp in load_all_msgpack_l_gz(rich))
+    native_mb = pack(t for t, _ in shards.ShardDataset(rich, num_threads=2).tensorized(model))
+    assert_same(host_mb, native_mb, "minibatch")
