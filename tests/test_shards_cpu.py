@@ -265,6 +265,114 @@ def test_oversized_graph_is_dropped_like_the_host_path(model, base_sample, tmp_p
         gnn_model.max_nodes_per_graph = saved
 
 
+def mutate_sample(sample, rng):
+    """One to three random structural mutations of a decoded sample (used by the differential test below)."""
+    graph = sample["graph"]
+    nodes, edges = graph["nodes"], graph["edges"]
+    weird_labels = ["", "_", "ÉCOLE", "naïveBayes", "日本_語", "ΣΑΣ", "a" * 40, "HTTPServer2Go", "__x__", "\x00nul", "x y",
+                    "İ", "ǅ", "ß", "tab\there", "😀", "Call", "call", "CALL_ME"]
+
+    def random_edge_type():
+        return rng.choice(list(edges))
+
+    def m_label():
+        nodes[rng.randrange(len(nodes))] = rng.choice(weird_labels)
+
+    def m_label_type():
+        nodes[rng.randrange(len(nodes))] = rng.choice([7, None, b"bytes", 1.5, ["x"]])
+
+    def m_edge_value():
+        lst = edges[random_edge_type()]
+        if lst:
+            e = list(lst[rng.randrange(len(lst))])
+            e[rng.randrange(2)] = rng.choice([-1, -len(nodes), len(nodes), len(nodes) + 3, 2 ** 31, 2 ** 40, 0, 1.0, "3", None])
+            lst[rng.randrange(len(lst))] = e
+
+    def m_edge_arity():
+        lst = edges[random_edge_type()]
+        if lst:
+            i = rng.randrange(len(lst))
+            e = list(lst[i])
+            lst[i] = rng.choice([e[:1], e[:2], e[:2] + ["args"], e[:2] + [b"args"], e[:2] + ["args", 1], e[:2] + [None], []])
+
+    def m_drop_edge_type():
+        edges.pop(random_edge_type())
+
+    def m_edge_container():
+        edges[random_edge_type()] = rng.choice([None, {}, "str", 5, [[0, 1]], []])
+
+    def m_reference_nodes():
+        refs = graph["reference_nodes"]
+        if refs:
+            refs[rng.randrange(len(refs))] = rng.choice([-1, 0, len(nodes) + 7, 2 ** 33, "1", None, 2.0])
+
+    def m_target():
+        sample["target_fix_action_idx"] = rng.choice([None, 0, -1, 10 ** 6, "0", 1.0, True])
+
+    def m_drop_key():
+        holder = rng.choice([sample, graph])
+        holder.pop(rng.choice(list(holder)))
+
+    def m_rewrites():
+        key = rng.choice(["candidate_rewrites", "candidate_rewrite_metadata"])
+        if sample.get(key):
+            i = rng.randrange(len(sample[key]))
+            sample[key][i] = rng.choice([None, [], ["only one"], ["ArgSwapRewriteScout", None], ["X", [0, 9]], 5])
+
+    def m_call_label():
+        child = edges.get("Child") or []
+        marked = [e for e in child if len(e) == 3 and e[2] == "args"]
+        if marked:
+            nodes[marked[rng.randrange(len(marked))][0]] = rng.choice(["Call", "call", "Name"])
+
+    def m_more_keys():
+        sample[rng.choice(["zzz", "graph2", "candidate_rewrite_logprobs_x"])] = rng.choice([None, [1, 2], {"a": {"b": []}}])
+
+    def m_next_token_gone():
+        edges.pop("NextToken", None)
+
+    moves = [m_label] * 4 + [m_label_type, m_edge_value, m_edge_value, m_edge_arity, m_edge_arity, m_drop_edge_type,
+                             m_edge_container, m_reference_nodes, m_target, m_drop_key, m_rewrites, m_call_label,
+                             m_call_label, m_more_keys, m_next_token_gone]
+    for _ in range(rng.choice([1, 1, 2, 3])):
+        try:
+            rng.choice(moves)()
+        except (KeyError, IndexError, TypeError, AttributeError, ValueError):
+            pass  # an earlier mutation removed what this one wanted to touch
+    return sample
+
+
+def test_randomly_mutated_samples_behave_like_the_host_path(model):
+    """Differential test: structurally mutated samples give bit-identical tensors, or raise the same exception type."""
+    from buglab_b200.synthetic import SyntheticBugLabGenerator
+
+    gen = SyntheticBugLabGenerator(seed=5, mean_nodes=60, min_nodes=30)
+    bases = [gen.sample() for _ in range(4)]
+    rng = random.Random(20210921)
+    tensorizer = shards.NativeShardTensorizer(model)
+    same = raised = 0
+    for it in range(300):
+        sample = mutate_sample(copy.deepcopy(rng.choice(bases)), rng)
+        blob = msgpack.packb(sample, use_bin_type=True)
+        try:
+            expected, host_error = model.tensorize(msgpack.unpackb(blob, raw=False)), None
+        except Exception as e:  # noqa: BLE001 - whatever the reference-shaped path raises is the expectation
+            expected, host_error = None, e
+        with shards.Shard(gz_bytes=gzip.compress(blob, 1)) as shard:
+            assert len(shard) == 1
+            try:
+                got, native_error = tensorizer.tensorize_object(shard, 0), None
+            except Exception as e:  # noqa: BLE001
+                got, native_error = None, e
+        if host_error is not None or native_error is not None:
+            assert type(host_error) is type(native_error), (it, repr(host_error), repr(native_error))
+            raised += 1
+        else:
+            assert_same(expected, got, f"mutation {it}")
+            same += 1
+    assert same > 100 and raised > 30 and tensorizer.num_native > 60 and tensorizer.num_host > 60
+
+
 # ---------------------------------------------------------------------------------------------- container format
 def test_multi_member_gzip_and_truncated_streams(model, base_sample, tmp_path):
     packer = msgpack.Packer(use_bin_type=True)
