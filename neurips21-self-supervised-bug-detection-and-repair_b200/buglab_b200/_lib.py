@@ -104,7 +104,7 @@ KERNELS_PER_CALL = {
     "bl_tanh_dropout_bwd": 1, "bl_segment_minmax": 5, "bl_segment_minmax_bwd": 1, "bl_segment_sum": 1,
     "bl_segment_log_softmax_fwd": 5, "bl_segment_log_softmax_bwd": 2, "bl_subtoken_maxpool_fwd": 1,
     "bl_subtoken_maxpool_bwd": 1, "bl_grad_sqnorm": 2, "bl_adam_step": 1,
-    "bl_rows_split3_bf16": 1, "bl_weights_split3_f16": 2, "bl_pair_project_fwd": 0, "bl_pair_project_bwd_input": 0,
+    "bl_rows_split3_f16": 1, "bl_unscale_pow2": 1, "bl_weights_split3_f16": 2, "bl_pair_project_fwd": 0, "bl_pair_project_bwd_input": 0,
     "bl_pair_project_bwd_weight": 1, "bl_rows_split2_f16": 1, "bl_grouped_colsum": 1, "bl_absmax": 1, "bl_weight_parts_f16": 1,
     "bl_pair_project_tc": 1, "bl_pair_weight_grad_tc": 1,
 }

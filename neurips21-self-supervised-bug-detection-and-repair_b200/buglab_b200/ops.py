@@ -1,8 +1,10 @@
 """PyTorch-facing operators over the buglab_b200 C ABI (``include/buglab_b200.h``).
 
 PyTorch is plumbing here: it owns device memory, streams and the autograd tape; every arithmetic step of
-the gnn-mlp hot path runs in the hand-written sm_100a kernels of ``csrc/`` (dense per-type projections go
-through ``torch.mm`` = plain cuBLAS fp32 GEMMs, TF32 disabled).
+the gnn-mlp hot path runs in the kernels of ``csrc/``.  The per-type projections are split-fp16 ("f16x3") tensor-core
+GEMMs — the hand-written tcgen05 kernels of ``csrc/pair_project_tc.cu`` for widths <= ``TC_MAX_WIDTH``, split kernels +
+cuBLAS fp16 GEMMs otherwise; ``PROJECTION_MODE = "fp32"`` (plain cuBLAS SGEMM through ``torch.mm``, TF32 disabled) is
+kept as the exact referee for tests.
 
 Reference semantics replaced: P4/P5 ``MlpMessagePassingLayer`` message+aggregate,
 A9/A10 scatter ops (``buglab/models/utils.py:15-48``), P2 subtoken max-pool, A12 optimiser.
@@ -435,8 +437,7 @@ class DenseLinearF16x3(torch.autograd.Function):
 
 def dense_linear(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     """Bias-free Linear: split-fp16 tensor-core GEMMs by default, plain fp32 library GEMM in "fp32" mode or for odd widths."""
-    if PROJECTION_MODE == "f16x3" and x.shape[1] % 4 == 0 and weight.shape[0] % 4 == 0 and x.shape[0] * 4 % 4 == 0 \
-            and (x.shape[0] * weight.shape[0]) % 4 == 0:
+    if PROJECTION_MODE == "f16x3" and x.shape[1] % 4 == 0 and weight.shape[0] % 4 == 0:
         return DenseLinearF16x3.apply(x, weight)
     return torch.nn.functional.linear(x, weight)
 
@@ -499,9 +500,6 @@ class TanhDropoutFn(torch.autograd.Function):
         check(_lib.load().bl_tanh_dropout_bwd(f32(dy), f32(t), t.numel(), ctx.p_drop, ctx.seed, f32(dx),
                                                stream_ptr(t.device)), "bl_tanh_dropout_bwd")
         return dx, None, None
-
-
-_seed_gen = torch.Generator()
 
 
 def fresh_seed() -> int:

@@ -59,7 +59,11 @@ def _record_stream(obj, stream, _depth: int = 0) -> None:
 
 
 class _Prefetcher:
-    """Runs a minibatch iterator in a producer thread, on its own CUDA stream, ``depth`` batches ahead."""
+    """Runs a minibatch iterator in a producer thread, on its own CUDA stream, ``depth`` batches ahead.
+
+    A consumer that stops early (an exception in the step, or a data-parallel epoch cut short because another rank ran
+    out of data) closes the generator; that stops the producer and releases the queued minibatches instead of leaving a
+    thread blocked on a full queue with device memory attached."""
 
     _END = object()
 
@@ -67,9 +71,19 @@ class _Prefetcher:
         self._queue: "queue.Queue" = queue.Queue(maxsize=depth)
         self._device = device
         self._error: Optional[BaseException] = None
+        self._stop = threading.Event()
         self._stream = torch.cuda.Stream(device) if device.type == "cuda" else None
         self._thread = threading.Thread(target=self._run, args=(make_iterator,), daemon=True)
         self._thread.start()
+
+    def _put(self, entry) -> bool:
+        while not self._stop.is_set():
+            try:
+                self._queue.put(entry, timeout=0.05)
+                return True
+            except queue.Full:
+                continue
+        return False
 
     def _run(self, make_iterator) -> None:
         try:
@@ -78,28 +92,42 @@ class _Prefetcher:
                     for item in make_iterator():
                         event = torch.cuda.Event()
                         event.record(self._stream)
-                        self._queue.put((item, event))
+                        if not self._put((item, event)):
+                            break
             else:
                 for item in make_iterator():
-                    self._queue.put((item, None))
+                    if not self._put((item, None)):
+                        break
         except BaseException as e:  # surfaced in the consumer
             self._error = e
         finally:
-            self._queue.put(self._END)
+            self._put(self._END)
+
+    def close(self) -> None:
+        self._stop.set()
+        while True:  # drop whatever is queued so the minibatches (and their device memory) can be freed
+            try:
+                self._queue.get_nowait()
+            except queue.Empty:
+                break
+        self._thread.join(timeout=5.0)
 
     def __iter__(self):
-        while True:
-            got = self._queue.get()
-            if got is self._END:
-                if self._error is not None:
-                    raise self._error
-                return
-            item, event = got
-            if event is not None:
-                consumer = torch.cuda.current_stream(self._device)
-                consumer.wait_event(event)
-                _record_stream(item, consumer)
-            yield item
+        try:
+            while True:
+                got = self._queue.get()
+                if got is self._END:
+                    if self._error is not None:
+                        raise self._error
+                    return
+                item, event = got
+                if event is not None:
+                    consumer = torch.cuda.current_stream(self._device)
+                    consumer.wait_event(event)
+                    _record_stream(item, consumer)
+                yield item
+        finally:
+            self.close()
 
 
 def _while_all_ranks_have_data(batches: Iterator, device) -> Iterator:

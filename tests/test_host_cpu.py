@@ -252,3 +252,43 @@ def test_modules_are_picklable_with_stable_paths(tmp_path):
     model3, nn3 = type(model).restore_model(tmp_path / "m.pkl.gz", "cpu")
     for (k, a), (_, b) in zip(nn.state_dict().items(), nn3.state_dict().items()):
         assert torch.equal(a, b), k
+
+
+def test_prefetcher_stops_its_producer_when_the_consumer_leaves_early():
+    """An abandoned epoch (exception, or a data-parallel rank that ran out of data first) must not leave a producer
+    thread blocked on a full queue."""
+    import threading
+    import time
+
+    import torch
+    from ptgnn.baseneuralmodel.trainer import _Prefetcher
+
+    produced = []
+
+    def endless():
+        i = 0
+        while True:
+            produced.append(i)
+            yield i
+            i += 1
+
+    before = threading.active_count()
+    pf = _Prefetcher(endless, torch.device("cpu"), depth=2)
+    it = iter(pf)
+    assert [next(it), next(it), next(it)] == [0, 1, 2]
+    it.close()                      # what happens when the training loop's generator chain is dropped
+    assert not pf._thread.is_alive() and threading.active_count() == before
+    n = len(produced)
+    time.sleep(0.2)
+    assert len(produced) == n       # nothing is produced after the close
+
+    # normal exhaustion and error propagation still work
+    assert list(_Prefetcher(lambda: iter(range(5)), torch.device("cpu"))) == [0, 1, 2, 3, 4]
+
+    def failing():
+        yield 1
+        raise ValueError("boom")
+
+    import pytest
+    with pytest.raises(ValueError):
+        list(_Prefetcher(failing, torch.device("cpu")))
