@@ -12,6 +12,7 @@ kernels over one flat buffer, which is also the single NCCL bucket; step time is
 import logging
 import math
 import queue
+import random
 import threading
 import time
 from abc import ABC, abstractmethod
@@ -130,6 +131,22 @@ class _Prefetcher:
             self.close()
 
 
+def _buffered_shuffle(items: Iterator, buffer_size: int, rng=random) -> Iterator:
+    """Streaming shuffle of the tensorised training samples (``shuffle_training_data=True``, ptgnn's default): fill a
+    buffer, shuffle it, emit half, refill.  Shard files are already visited in random order (msgpackutils); this mixes
+    samples across neighbouring files without holding the data set in memory."""
+    buffer: List = []
+    for item in items:
+        buffer.append(item)
+        if len(buffer) >= buffer_size:
+            rng.shuffle(buffer)
+            half = len(buffer) // 2
+            yield from buffer[half:]
+            del buffer[half:]
+    rng.shuffle(buffer)
+    yield from buffer
+
+
 def _while_all_ranks_have_data(batches: Iterator, device) -> Iterator:
     """Data-parallel ranks read different shards and may run out of minibatches at different times; every step contains
     a collective, so the epoch must end for all ranks as soon as ANY rank is exhausted (otherwise the others would wait in
@@ -189,6 +206,7 @@ class ModelTrainer:
         self._training_start_hooks: List[Callable] = []
         self._train_metrics_reporters: List[Callable] = []
         self.last_epoch_stats: Dict[str, float] = {}
+        self.shuffle_buffer_size = 2048  # tensorised samples held by the streaming shuffle of the training data
 
     # ---- accessors ------------------------------------------------------------------------------
     @property
@@ -358,6 +376,8 @@ class ModelTrainer:
             return model.tensorize_dataset(iter(data), return_input_data=False, parallelize=parallelize)
 
         def training_tensors():
+            if shuffle_training_data and not store_tensorized_data_in_memory:
+                return _buffered_shuffle(tensors_of(training_data), self.shuffle_buffer_size)
             return tensors_of(training_data)
 
         def validation_tensors():
@@ -373,7 +393,13 @@ class ModelTrainer:
         train_it, valid_it = _Re(training_tensors), _Re(validation_tensors)
         if store_tensorized_data_in_memory:
             train_list, valid_list = list(train_it), list(valid_it)
-            train_it, valid_it = train_list, valid_list
+
+            def reshuffled():
+                if shuffle_training_data:
+                    random.shuffle(train_list)
+                return iter(train_list)
+
+            train_it, valid_it = _Re(reshuffled), valid_list
 
         optimizer = self._create_optimizer([p for p in nn.parameters() if p.requires_grad])
         scheduler = None if self._scheduler_creator is None else self._scheduler_creator(optimizer)

@@ -292,3 +292,26 @@ def test_prefetcher_stops_its_producer_when_the_consumer_leaves_early():
     import pytest
     with pytest.raises(ValueError):
         list(_Prefetcher(failing, torch.device("cpu")))
+
+
+def test_buffered_shuffle_is_a_permutation_and_streams():
+    import random
+
+    from ptgnn.baseneuralmodel.trainer import _buffered_shuffle
+
+    pulled = []
+
+    def source():
+        for i in range(1000):
+            pulled.append(i)
+            yield i
+
+    out = []
+    for x in _buffered_shuffle(source(), 64, random.Random(0)):
+        if not out:
+            assert len(pulled) == 64          # the first sample leaves as soon as one buffer is full, not at the end
+        out.append(x)
+    assert sorted(out) == list(range(1000)) and out != list(range(1000))
+    assert max(abs(pos - x) for pos, x in enumerate(out)) < 600      # local mixing: nothing travels arbitrarily far ...
+    assert sum(1 for pos, x in enumerate(out) if abs(pos - x) > 16) > 500   # ... but most samples do move
+    assert list(_buffered_shuffle(iter([]), 8)) == [] and sorted(_buffered_shuffle(iter([3, 1, 2]), 8)) == [1, 2, 3]
