@@ -273,4 +273,4 @@ def train_step_ref(module: nn.Module, optimizer: torch.optim.Optimizer, minibatc
     loss.backward()
     torch.nn.utils.clip_grad_norm_(module.parameters(), clip_gradient_norm)
     optimizer.step()
-    return float(loss)
+    return float(loss.detach())
