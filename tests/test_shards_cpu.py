@@ -456,3 +456,32 @@ def test_trainer_consumes_self_tensorizing_datasets(model, tmp_path):
     host_mb = pack(model.tensorize(dp) for dp in load_all_msgpack_l_gz(rich))
     native_mb = pack(t for t, _ in shards.ShardDataset(rich, num_threads=2).tensorized(model))
     assert_same(host_mb, native_mb, "minibatch")
+
+
+def test_native_dataset_through_the_trainers_producer_thread(model, tmp_path):
+    """The exact chain ModelTrainer.train runs per epoch — ShardDataset.tensorized -> (streaming shuffle) ->
+    minibatch_iterator -> _Prefetcher's producer thread — with the device work left out (device="cpu")."""
+    import random
+
+    import torch
+    from buglab.utils.msgpackutils import load_all_msgpack_l_gz
+    from buglab_b200.synthetic import write_shards
+    from dpu_utils.utils import RichPath
+    from ptgnn.baseneuralmodel.trainer import _buffered_shuffle, _Prefetcher
+
+    write_shards(str(tmp_path / "d"), 3, 8, seed=11, mean_nodes=100, min_nodes=30)
+    rich = RichPath.create(str(tmp_path / "d"))
+    dataset = shards.ShardDataset(rich, shuffle=True)
+
+    def make():
+        tensors = _buffered_shuffle(dataset.tensorized(model), 8, random.Random(1))
+        return model.minibatch_iterator(tensors, device="cpu", max_minibatch_size=5)
+
+    for epoch in range(2):  # the tensoriser is created in the first epoch's thread and reused from another one
+        batches = list(_Prefetcher(make, torch.device("cpu")))
+        assert [len(raw) for _, raw in batches] == [5, 5, 5, 5, 4]
+        assert sum(int(mb["graph_data"]["num_graphs"]) for mb, _ in batches) == 24
+    total_nodes = sum(int(mb["graph_data"]["node_to_graph_idx"].shape[0]) for mb, _ in batches)
+    expected_nodes = sum(model.tensorize(dp).graph_data.num_nodes for dp in load_all_msgpack_l_gz(rich))
+    assert total_nodes == expected_nodes
+    assert dataset.tensorizer.num_native == 48 and dataset.tensorizer.num_host == 0
