@@ -147,29 +147,45 @@ def _buffered_shuffle(items: Iterator, buffer_size: int, rng=random) -> Iterator
     yield from buffer
 
 
-def _while_all_ranks_have_data(batches: Iterator, device) -> Iterator:
-    """Data-parallel ranks read different shards and may run out of minibatches at different times; every step contains
-    a collective, so the epoch must end for all ranks as soon as ANY rank is exhausted (otherwise the others would wait in
-    the gradient all-reduce forever).  One tiny MIN all-reduce per step; a no-op without torch.distributed."""
-    dist = _distributed()
-    if not dist.is_distributed():
-        yield from batches
-        return
-    import torch.distributed as tdist
+class _RankSync:
+    """Per-step agreement between data-parallel ranks (one tiny all-gather; a no-op without torch.distributed).
 
-    it = iter(batches)
-    flag_device = device if torch.device(device).type == "cuda" else "cpu"
-    while True:
-        try:
-            item = next(it)
-            have = 1
-        except StopIteration:
-            item, have = None, 0
-        flag = torch.tensor([have], dtype=torch.int32, device=flag_device)
-        tdist.all_reduce(flag, op=tdist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
+    * Ranks read different shards and may run out of minibatches at different times; every step contains a collective,
+      so the epoch ends for all ranks as soon as ANY rank is exhausted (the others would otherwise wait in the gradient
+      all-reduce forever).
+    * The losses are means over the graphs of the LOCAL minibatch (gnn.py:251, localizationmodule.py:117).  When ranks
+      hold different numbers of graphs, averaging the ranks' gradients is not the gradient of the mean over the union;
+      ``weight`` = B_rank * world / sum(B) is what the local gradient must be scaled by BEFORE the all-reduce so that the
+      data-parallel step equals the single-device step on the union minibatch (1.0 when every rank has the same B)."""
+
+    def __init__(self, device):
+        self.weight = 1.0
+        self._device = device if torch.device(device).type == "cuda" else "cpu"
+
+    def batches(self, batches: Iterator) -> Iterator:
+        dist = _distributed()
+        if not dist.is_distributed():
+            yield from batches
             return
-        yield item
+        import torch.distributed as tdist
+
+        world = dist.world_size()
+        it = iter(batches)
+        while True:
+            try:
+                item = next(it)
+                local = len(item[1])  # (minibatch, raw datapoints)
+            except StopIteration:
+                item, local = None, -1
+            mine = torch.tensor([local], dtype=torch.int64, device=self._device)
+            everyone = [torch.empty_like(mine) for _ in range(world)]
+            tdist.all_gather(everyone, mine)
+            sizes = [int(t.item()) for t in everyone]
+            if min(sizes) < 0:
+                return
+            total = sum(sizes)
+            self.weight = float(local) * world / total if total > 0 else 1.0
+            yield item
 
 
 class ModelTrainer:
@@ -274,17 +290,19 @@ class ModelTrainer:
             start_evt, end_evt = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             start_evt.record()
         t0 = time.perf_counter()
-        batches = _while_all_ranks_have_data(self._minibatches(training_tensors, device, parallelize), device)
-        for step_idx, (mb_data, raw_points) in enumerate(batches):
+        sync = _RankSync(device)
+        for step_idx, (mb_data, raw_points) in enumerate(sync.batches(self._minibatches(training_tensors, device, parallelize))):
             optimizer.zero_grad()
             loss = nn(**mb_data)
             loss.backward()
             if fused:
+                if sync.weight != 1.0:
+                    optimizer.flat_grad.mul_(sync.weight)  # uneven minibatches only (typically the last step of an epoch)
                 scale = dist.allreduce_flat_gradient(optimizer.flat_grad)
                 optimizer.step(grad_scale=scale)
             else:
                 if dist.is_distributed():
-                    _allreduce_dense_gradients(params, dist.world_size())
+                    _allreduce_dense_gradients(params, dist.world_size(), sync.weight)
                 if self._clip_gradient_norm is not None:
                     torch.nn.utils.clip_grad_norm_(params, self._clip_gradient_norm)
                 optimizer.step()
@@ -426,14 +444,17 @@ class ModelTrainer:
                     break
 
 
-def _allreduce_dense_gradients(params: List[torch.nn.Parameter], world: int) -> None:
-    """Bucketed all-reduce for optimisers that do not own a flat buffer (compat path, CPU/gloo tests)."""
+def _allreduce_dense_gradients(params: List[torch.nn.Parameter], world: int, weight: float = 1.0) -> None:
+    """Bucketed all-reduce for optimisers that do not own a flat buffer (compat path, CPU/gloo tests): every rank ends up
+    with ``sum_r(weight_r * grad_r) / world``."""
     import torch.distributed as tdist
 
     grads = [p.grad for p in params if p.grad is not None]
     if not grads:
         return
     flat = torch.cat([g.reshape(-1) for g in grads])
+    if weight != 1.0:
+        flat.mul_(weight)
     tdist.all_reduce(flat, op=tdist.ReduceOp.SUM)
     flat.div_(world)
     off = 0

@@ -80,24 +80,39 @@ def _uneven_worker(rank: int, world: int, port: int, out_dir: str):
             sys.path.insert(0, p)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     from buglab_b200 import distributed
-    from ptgnn.baseneuralmodel.trainer import _allreduce_dense_gradients, _while_all_ranks_have_data
+    from ptgnn.baseneuralmodel.trainer import _allreduce_dense_gradients, _RankSync
 
     distributed.init_from_env("gloo")
-    my_batches = list(range(5 if rank == 0 else 3))  # rank 0 has two more minibatches than rank 1
+    # rank 0 has two more minibatches than rank 1, and the ranks' minibatches hold different numbers of graphs
+    torch.manual_seed(0)
+    data = torch.randn(40, 3)                      # the union data set; y = mean over graphs of (w . x)^2
+    sizes = [[4, 2, 3, 4, 4], [1, 2, 3]][rank]
+    starts = [[0, 5, 9, 20, 30], [4, 7, 12]][rank]
+    my_batches = [(data[s: s + n], [None] * n) for s, n in zip(starts, sizes)]
+    w = torch.nn.Parameter(torch.tensor([0.5, -1.0, 2.0]))
+    sync = _RankSync("cpu")
     seen = []
-    w = torch.nn.Parameter(torch.zeros(2))
-    for b in _while_all_ranks_have_data(iter(my_batches), "cpu"):
-        w.grad = torch.full((2,), float(b + rank))
-        _allreduce_dense_gradients([w], world)  # the per-step collective that would dead-lock on uneven epochs
-        seen.append((b, w.grad.tolist()))
+    for x, raw in sync.batches(iter(my_batches)):
+        w.grad = None
+        ((x @ w) ** 2).mean().backward()           # local mean over the local graphs, like the model's losses
+        _allreduce_dense_gradients([w], world, sync.weight)   # the per-step collective that would dead-lock on uneven epochs
+        seen.append((len(raw), sync.weight, w.grad.clone()))
     torch.save(seen, os.path.join(out_dir, f"uneven{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_uneven_shards_end_the_epoch_together(tmp_path):
+def test_uneven_shards_end_the_epoch_together_and_weight_by_graphs(tmp_path):
     port = 31500 + (os.getpid() % 2000)
     mp.spawn(_uneven_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     a, b = torch.load(tmp_path / "uneven0.pt"), torch.load(tmp_path / "uneven1.pt")
-    assert [x[0] for x in a] == [0, 1, 2] and [x[0] for x in b] == [0, 1, 2]   # both stop after 3 steps, nobody hangs
-    assert a == b and a[1][1] == [1.5, 1.5]                                     # averaged gradient (1 + 2) / 2
+    assert [x[0] for x in a] == [4, 2, 3] and [x[0] for x in b] == [1, 2, 3]      # both stop after 3 steps, nobody hangs
+    assert [x[1] for x in a] == [1.6, 1.0, 1.0] and [x[1] for x in b] == [0.4, 1.0, 1.0]
+    torch.manual_seed(0)
+    data = torch.randn(40, 3)
+    w = torch.tensor([0.5, -1.0, 2.0], requires_grad=True)
+    union = torch.cat([data[0:4], data[4:5]])                                       # step 0: 4 graphs on rank 0, 1 on rank 1
+    expected, = torch.autograd.grad(((union @ w) ** 2).mean(), w)
+    for rank_result in (a, b):
+        assert torch.allclose(rank_result[0][2], expected, atol=1e-6)               # == single-device step on the union batch
+    assert torch.equal(a[1][2], b[1][2]) and torch.equal(a[2][2], b[2][2])
