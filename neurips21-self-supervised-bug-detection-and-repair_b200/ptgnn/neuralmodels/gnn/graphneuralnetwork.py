@@ -180,12 +180,14 @@ class GraphNeuralNetworkModel(AbstractNeuralModel[GraphData, TensorizedGraphData
 
     # ---- minibatch packing ----------------------------------------------------------------------
     def initialize_minibatch(self) -> Dict[str, Any]:
+        # Chunks are appended as they come (no per-graph arithmetic here); the node offset of every chunk is recorded and
+        # applied once, vectorised, when the minibatch is finalised.
         return {
             "node_ids": [], "node_lens": [],
-            "adjacency_lists": [([], []) for _ in range(self.num_edge_types)],
+            "adjacency_lists": [([], [], []) for _ in range(self.num_edge_types)],  # (sources, targets, node offset) chunks
             "num_nodes_per_graph": [],
-            "reference_node_ids": {},
-            "reference_node_graph_idx": {},
+            "reference_node_ids": {},        # name -> per-graph arrays (graph-local node ids)
+            "reference_node_graphs": {},     # name -> graph index of each of those arrays
             "num_nodes": 0,
         }
 
@@ -196,14 +198,14 @@ class GraphNeuralNetworkModel(AbstractNeuralModel[GraphData, TensorizedGraphData
         ids, lens = tensorized_datapoint.node_tensorized_data
         mb["node_ids"].append(ids)
         mb["node_lens"].append(lens)
-        for (srcs, tgts), (src, tgt) in zip(mb["adjacency_lists"], tensorized_datapoint.adjacency_lists):
+        for (srcs, tgts, offsets), (src, tgt) in zip(mb["adjacency_lists"], tensorized_datapoint.adjacency_lists):
             if src.shape[0]:
-                srcs.append(src + offset)
-                tgts.append(tgt + offset)
+                srcs.append(src)
+                tgts.append(tgt)
+                offsets.append(offset)
         for name, nodes in tensorized_datapoint.reference_nodes.items():
-            mb["reference_node_ids"].setdefault(name, []).append(nodes + offset)
-            n_refs = nodes.shape[0]
-            mb["reference_node_graph_idx"].setdefault(name, []).append(np.full(n_refs, graph_idx, dtype=np.int32))
+            mb["reference_node_ids"].setdefault(name, []).append(nodes)
+            mb["reference_node_graphs"].setdefault(name, []).append(graph_idx)
         mb["num_nodes_per_graph"].append(tensorized_datapoint.num_nodes)
         mb["num_nodes"] = offset + tensorized_datapoint.num_nodes
         return mb["num_nodes"] < self.stop_extending_minibatch_after_num_nodes
@@ -211,37 +213,67 @@ class GraphNeuralNetworkModel(AbstractNeuralModel[GraphData, TensorizedGraphData
     def finalize_minibatch(self, accumulated_minibatch_data: Dict[str, Any], device: Union[str, torch.device]) -> Dict[str, Any]:
         mb = accumulated_minibatch_data
         device = torch.device(device)
-        pieces: List[np.ndarray] = []
-        layout: List[Tuple[int, Tuple[int, ...]]] = []
+        num_graphs = len(mb["num_nodes_per_graph"])
+        nodes_per_graph = np.asarray(mb["num_nodes_per_graph"], dtype=np.int64)
+        node_offsets = np.zeros(num_graphs, dtype=np.int32)
+        if num_graphs > 1:
+            np.cumsum(nodes_per_graph[:-1], out=node_offsets[1:])
 
-        def add(arr: np.ndarray) -> int:
-            layout.append((sum(p.size for p in pieces), arr.shape))
-            pieces.append(arr.reshape(-1))
+        # Pass 1 lays every index table out in ONE staging buffer; pass 2 concatenates the chunks straight into it and adds
+        # the node offsets in place (one vectorised add per table instead of one small numpy call per graph and table).
+        layout: List[Tuple[int, Tuple[int, ...]]] = []
+        fillers: List[Tuple[int, int, Any]] = []
+        total = 0
+
+        def reserve(shape: Tuple[int, ...], fill) -> int:
+            nonlocal total
+            n = int(np.prod(shape)) if len(shape) else 1
+            layout.append((total, tuple(shape)))
+            fillers.append((total, n, fill))
+            total += n
             return len(layout) - 1
 
-        def cat(chunks: List[np.ndarray], trailing=()) -> np.ndarray:
-            if not chunks:
-                return np.zeros((0,) + tuple(trailing), dtype=np.int32)
-            return np.concatenate(chunks)
+        def table(chunks: List[np.ndarray], trailing: Tuple[int, ...] = (), chunk_offsets=None) -> int:
+            rows = sum(c.shape[0] for c in chunks)
+            shape = (rows,) + tuple(trailing)
+
+            def fill(flat: np.ndarray) -> None:
+                if rows == 0:
+                    return
+                out = flat.reshape(shape)
+                np.concatenate(chunks, out=out)
+                if chunk_offsets is not None:
+                    per_row = np.repeat(np.asarray(chunk_offsets, dtype=np.int32), [c.shape[0] for c in chunks])
+                    out += per_row.reshape((-1,) + (1,) * len(trailing))
+
+            return reserve(shape, fill)
+
+        def repeated(values: np.ndarray, counts) -> int:
+            counts = np.asarray(counts, dtype=np.int64)
+            n = int(counts.sum())
+
+            def fill(flat: np.ndarray) -> None:
+                if n:
+                    flat[:] = np.repeat(values, counts)
+
+            return reserve((n,), fill)
 
         T = self.__node_embedding_model.max_num_subtokens
-        h_ids = add(cat(mb["node_ids"], (T,)))
-        h_lens = add(cat(mb["node_lens"]))
-        h_adj = [(add(cat(srcs)), add(cat(tgts))) for srcs, tgts in mb["adjacency_lists"]]
-        num_graphs = len(mb["num_nodes_per_graph"])
-        h_n2g = add(np.repeat(np.arange(num_graphs, dtype=np.int32), mb["num_nodes_per_graph"]))
+        h_ids = table(mb["node_ids"], (T,))
+        h_lens = table(mb["node_lens"])
+        h_adj = [(table(srcs, (), offsets), table(tgts, (), offsets)) for srcs, tgts, offsets in mb["adjacency_lists"]]
+        h_n2g = repeated(np.arange(num_graphs, dtype=np.int32), nodes_per_graph)
         h_ref = {}
         for name, chunks in mb["reference_node_ids"].items():
+            graphs = np.asarray(mb["reference_node_graphs"][name], dtype=np.int32)
             trailing = chunks[0].shape[1:] if chunks else ()
-            h_ref[name] = (add(cat(chunks, trailing)), add(cat(mb["reference_node_graph_idx"][name])))
+            h_ref[name] = (table(chunks, trailing, node_offsets[graphs]),
+                           repeated(graphs, [c.shape[0] for c in chunks]))
 
-        total = sum(p.size for p in pieces)
         staging = torch.empty(max(total, 1), dtype=torch.int32, pin_memory=(device.type == "cuda"))
         host = staging.numpy()
-        off = 0
-        for p in pieces:
-            host[off: off + p.size] = p
-            off += p.size
+        for start, n, fill in fillers:
+            fill(host[start: start + n])
         on_device = staging.to(device, non_blocking=True)
 
         def view(handle: int) -> torch.Tensor:
