@@ -14,4 +14,6 @@ What it restates (plain PyTorch fp32 / fp64 and numpy, straightforward per-edge 
   * the in-repo pieces (heads, detector and selector/generator losses, rewrite bookkeeping, data schema) — restated with file:line
     citations and pinned against the REAL reference code imported from /root/reference
     (tests/golden/make_golden.py wrote the fixtures under tests/golden/).
+  * ``seq_ref.py`` — the relational-transformer layer of the seq-great / seq-rat models (torch-only
+    reference files, so fully pinned: outputs and gradients of the real classes in tests/golden/seq_layers.npz).
 """
