@@ -155,6 +155,190 @@ class SyntheticBugLabGenerator:
             yield self.sample()
 
 
+class SyntheticProgramGenerator:
+    """Samples whose graphs have the STRUCTURE the sequence models rely on (reference buglab/models/seqmodel.py:442-624):
+    a single ``NextToken`` chain over the leaf tokens in source order, a ``Child`` tree whose internal nodes are AST
+    labels (``Assign`` owns an ``=`` token, ``BinaryOperation`` an operator token, ``ComparisonTarget`` a comparison
+    token, ``Call`` its ``args``), symbol nodes outside the tree reached by ``OccurrenceOf`` edges, and data-/control-flow
+    relations between tokens and statements.  Node ids follow a pre-order walk, so tokens and AST nodes interleave as in
+    extracted graphs.  The same sample works for the graph models (it is schema-valid ``BugLabData``)."""
+
+    _BIN_OPS = ("+", "-", "*", "/", "//", "%", "**", "|", "&")
+    _CMP_OPS = ("<", "<=", "==", "!=", ">", ">=", "is", "in")
+
+    def __init__(self, seed: int = 0, statements: int = 12, vocabulary: int = 400, max_depth: int = 3):
+        self.rng = np.random.default_rng(seed)
+        self.statements, self.max_depth = statements, max_depth
+        self.identifiers = _identifier_vocabulary(self.rng, vocabulary)
+        self._sample_idx = 0
+
+    def sample(self, statements: Optional[int] = None) -> Dict[str, Any]:
+        rng = self.rng
+        nodes: List[str] = []
+        child: List[Any] = []
+        tokens: List[int] = []
+        sibling: List[Any] = []
+        occurrences: Dict[str, List[int]] = {}
+        calls: Dict[int, List[int]] = {}
+        binops: List[int] = []
+        statements_nodes: List[int] = []
+        local_names = [self.identifiers[int(i)] for i in rng.integers(0, len(self.identifiers), size=int(rng.integers(4, 10)))]
+
+        def new(label: str) -> int:
+            nodes.append(label)
+            return len(nodes) - 1
+
+        def token(label: str, parent: int, field: str) -> int:
+            t = new(label)
+            tokens.append(t)
+            child.append((parent, t, field))
+            return t
+
+        def name(parent: int, field: str) -> int:
+            n = new("Name")
+            child.append((parent, n, field))
+            ident = local_names[int(rng.integers(0, len(local_names)))]
+            occurrences.setdefault(ident, []).append(token(ident, n, "value"))
+            return n
+
+        def expression(parent: int, field: str, depth: int) -> int:
+            r = rng.random()
+            if depth >= self.max_depth or r < 0.4:
+                if r < 0.1:
+                    lit = new("Integer")
+                    child.append((parent, lit, field))
+                    token(str(int(rng.integers(0, 100))), lit, "value")
+                    return lit
+                return name(parent, field)
+            if r < 0.7:
+                b = new("BinaryOperation")
+                child.append((parent, b, field))
+                binops.append(b)
+                expression(b, "left", depth + 1)
+                token(self._BIN_OPS[int(rng.integers(0, len(self._BIN_OPS)))], b, "operator")
+                expression(b, "right", depth + 1)
+                return b
+            if r < 0.85:
+                c = new("Comparison")
+                child.append((parent, c, field))
+                expression(c, "left", depth + 1)
+                target = new("ComparisonTarget")
+                child.append((c, target, "comparisons"))
+                token(self._CMP_OPS[int(rng.integers(0, len(self._CMP_OPS)))], target, "operator")
+                expression(target, "comparator", depth + 1)
+                return c
+            call = new("Call")
+            child.append((parent, call, field))
+            name(call, "func")
+            token("(", call, "lpar")
+            args = []
+            for i in range(int(rng.integers(2, 5))):
+                if i:
+                    token(",", call, "comma")
+                before = len(nodes)
+                expression(call, "args", depth + 1)
+                args.append(before)          # the argument's root node was created first (pre-order ids)
+            token(")", call, "rpar")
+            calls[call] = args
+            return call
+
+        module = new("Module")
+        for _ in range(self.statements if statements is None else statements):
+            r = rng.random()
+            if r < 0.5:
+                st = new("Assign")
+                child.append((module, st, "body"))
+                name(st, "targets")
+                token("=", st, "equal")
+                expression(st, "value", 0)
+            elif r < 0.65:
+                st = new("AugAssign")
+                child.append((module, st, "body"))
+                name(st, "target")
+                token("+=", st, "operator")
+                expression(st, "value", 1)
+            elif r < 0.8:
+                st = new("Return")
+                child.append((module, st, "body"))
+                token("return", st, "keyword")
+                expression(st, "value", 0)
+            elif r < 0.9:
+                st = new("If")
+                child.append((module, st, "body"))
+                token("if", st, "keyword")
+                expression(st, "test", 1)
+                token(":", st, "colon")
+            else:
+                st = new("Expr")
+                child.append((module, st, "body"))
+                expression(st, "value", 1)
+            statements_nodes.append(st)
+        for parent in set(p for p, _, _ in child):
+            kids = [c for p, c, _ in child if p == parent]
+            sibling.extend((a, b) for a, b in zip(kids, kids[1:]))
+
+        symbol_of: Dict[str, int] = {ident: new(ident) for ident in occurrences}      # symbol nodes live outside the tree
+        occurrence_edges = [(t, symbol_of[ident]) for ident, toks in occurrences.items() for t in toks]
+        ident_tokens = [t for toks in occurrences.values() for t in toks]
+
+        def token_pairs(count: int):
+            if len(ident_tokens) < 2:
+                return []
+            picks = rng.integers(0, len(ident_tokens), size=(count, 2))
+            return [(int(ident_tokens[a]), int(ident_tokens[b])) for a, b in picks]
+
+        edges: Dict[str, List] = {
+            "Child": child,
+            "NextToken": [(a, b) for a, b in zip(tokens, tokens[1:])],
+            "Sibling": sibling,
+            "OccurrenceOf": occurrence_edges,
+            "NextMayUse": token_pairs(len(ident_tokens)),
+            "LastMayWrite": token_pairs(len(ident_tokens) // 2),
+            "ComputedFrom": token_pairs(len(ident_tokens) // 2),
+            "ControlFlowNext": [(a, b) for a, b in zip(statements_nodes, statements_nodes[1:])],
+        }
+
+        reference_nodes: List[int] = []
+        rewrites: List[Any] = []
+        metadata: List[Any] = []
+        symbols = list(symbol_of.values())
+        for b in binops:                                   # operator rewrites at every binary operation
+            for op in rng.choice(len(_TEXT_OPS), size=int(rng.integers(2, 5)), replace=False):
+                reference_nodes.append(b)
+                rewrites.append(("ReplaceText", _TEXT_OPS[int(op)]))
+                metadata.append(("BinaryOperatorRewriteScout", None))
+        for t in rng.permutation(ident_tokens)[: max(2, len(ident_tokens) // 3)].tolist():   # variable misuse at name tokens
+            for sym in rng.permutation(symbols)[: int(rng.integers(2, 5))].tolist():
+                reference_nodes.append(int(t))
+                rewrites.append(("ReplaceText", nodes[sym]))
+                metadata.append(("VariableMisuseRewriteScout", int(sym)))
+        for call, args in calls.items():                  # argument swaps at calls
+            for _ in range(int(rng.integers(1, 3))):
+                a, b = rng.choice(len(args), size=2, replace=False)
+                reference_nodes.append(call)
+                rewrites.append(("ArgSwap", (int(a), int(b))))
+                metadata.append(("ArgSwapRewriteScout", None))
+        if not reference_nodes:                            # degenerate tiny program: one harmless candidate
+            reference_nodes.append(tokens[0])
+            rewrites.append(("ReplaceText", "0"))
+            metadata.append(("LiteralRewriteScout", None))
+        target = None if rng.random() < 0.4 else int(rng.integers(0, len(reference_nodes)))
+        self._sample_idx += 1
+        return {
+            "graph": {"nodes": nodes, "edges": edges, "path": f"pkg/prog_{self._sample_idx}.py", "text": "",
+                      "reference_nodes": reference_nodes, "code_range": ((0, 0), (1, 0))},
+            "candidate_rewrites": rewrites,
+            "candidate_rewrite_metadata": metadata,
+            "candidate_rewrite_ranges": [((0, 0), (0, 1))] * len(rewrites),
+            "target_fix_action_idx": target,
+            "package_name": "synthetic",
+        }
+
+    def samples(self, count: int) -> Iterator[Dict[str, Any]]:
+        for _ in range(count):
+            yield self.sample()
+
+
 def write_shards(directory: str, num_shards: int, graphs_per_shard: int, seed: int = 0, **generator_kwargs) -> List[str]:
     """Writes ``num_shards`` files ``shard_XXXX.msgpack.l.gz`` in the reference wire format."""
     import os
