@@ -74,8 +74,20 @@ def gnn(*, mp_layer, add_self_edge: bool, use_all_gnn_layer_outputs: bool = Fals
     )
 
 
-def seq_transformer(**_):
-    raise NotImplementedError("the seq-* models are a SURVEY.md §8f 'next' row; only gnn-mlp is built on the B200 path")
+def seq_transformer(*, layer_type: str, hidden_state_size: int = 256, dropout_rate: float = 0.1, vocab_size: int = 15000,
+                    selector_loss_type: str = "classify-max-loss", num_layers: int = 5, num_heads: int = 8,
+                    max_seq_size: int = 400, intermediate_dimension_size: int = 1024,
+                    buggy_samples_weight_spec: Union[str, int, float] = 1.0, rezero_mode: str = "off",
+                    normalisation_mode: str = "postnorm", **__):
+    """Reference modelregistry.py:97-126.  Host side only for now: the model tensorises and packs, its
+    ``build_neural_module`` raises until the relational-transformer kernels exist."""
+    from buglab.models.seqmodel import SeqBugLabModel
+
+    return SeqBugLabModel(
+        hidden_state_size, max_subtoken_vocab_size=vocab_size, dropout_rate=dropout_rate, layer_type=layer_type,
+        generator_loss_type=selector_loss_type, intermediate_dimension_size=intermediate_dimension_size,
+        buggy_samples_weight_schedule=buggy_sample_weight_schedule(buggy_samples_weight_spec), max_seq_size=max_seq_size,
+        num_heads=num_heads, num_layers=num_layers, rezero_mode=rezero_mode, normalisation_mode=normalisation_mode)
 
 
 def construct_model_dict(gnn_constructor: Callable, seq_constructor: Callable) -> Dict[str, Callable]:

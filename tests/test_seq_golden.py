@@ -1,0 +1,142 @@
+"""Sequence models, host side: graph -> token-sequence projection, per-sample tensors and minibatch
+packing of this repo's ``buglab.models.seqmodel.SeqBugLabModel`` against the REAL reference's
+(tests/golden/seq_model.npz, written by tests/golden/make_seq_model_golden.py).  Integer bookkeeping: bit-exact."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "neurips21-self-supervised-bug-detection-and-repair_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+SPEC = {"modelName": "seq-great", "hidden_state_size": 32, "dropout_rate": 0.0, "num_layers": 2, "num_heads": 4,
+        "intermediate_dimension_size": 64, "max_seq_size": 200}
+
+
+def jsonable(x):
+    if isinstance(x, dict):
+        return {str(k): jsonable(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [jsonable(v) for v in x]
+    if isinstance(x, np.ndarray):
+        return x.tolist()
+    if isinstance(x, np.integer):
+        return int(x)
+    if isinstance(x, np.floating):
+        return float(x)
+    return x
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(GOLDEN_DIR, "seq_model.npz"), allow_pickle=True)
+
+
+@pytest.fixture(scope="module")
+def samples():
+    from buglab.utils.msgpackutils import load_msgpack_l_gz
+
+    return lambda: list(load_msgpack_l_gz(os.path.join(GOLDEN_DIR, "seq_samples.msgpack.l.gz")))
+
+
+@pytest.fixture(scope="module")
+def mirror(samples):
+    import logging
+    from pathlib import Path
+
+    from buglab.models.modelregistry import load_model
+
+    logging.getLogger("buglab.models.seqmodel").setLevel(logging.CRITICAL)  # two fixture samples are rejected on purpose
+    model, nn, needs_metadata = load_model(dict(SPEC), Path("/tmp/_seq_mirror.pkl.gz"))
+    assert nn is None and needs_metadata
+    model.compute_metadata(iter(samples()))
+    return model
+
+
+def test_metadata_matches_reference(golden, mirror):
+    assert list(mirror.token_embedder.vocabulary.id_to_token) == list(golden["meta/vocabulary"])
+    assert set(mirror.edge_types) == set(golden["meta/edge_types_in_reference_order"])
+    assert list(mirror.edge_types) == sorted(mirror.edge_types)      # deterministic numbering (the reference's is hash-seeded)
+
+
+def test_projection_and_sample_tensors_bit_exact(golden, mirror, samples):
+    tensorized = [mirror.tensorize(dp) for dp in samples()]
+    assert [t is None for t in tensorized] == golden["meta/dropped"].tolist() == [False] * 6 + [True, True]
+    for i, t in enumerate(tensorized):
+        if t is None:
+            continue
+        expected = json.loads(str(golden[f"sample/{i}"]))
+        mine = t._asdict()
+        mine["target_subtokens_ids"] = [np.asarray(x).tolist() for x in mine["target_subtokens_ids"]]
+        mine = json.loads(json.dumps(jsonable(mine)))
+        assert mine.keys() == expected.keys()
+        for key in expected:
+            assert mine[key] == expected[key], (i, key)
+        # dict ORDER matters too: relations are packed in this order, node mappings are handed to predict()
+        assert list(mine["intra_token_edges"]) == list(expected["intra_token_edges"])
+        assert list(mine["node_mappings"]) == list(expected["node_mappings"])
+
+
+def test_minibatch_tensors_bit_exact(golden, mirror, samples):
+    mb = mirror.initialize_minibatch()
+    for t in (mirror.tensorize(dp) for dp in samples()):
+        if t is not None:
+            assert mirror.extend_minibatch_with(t, mb) is True
+    mb = mirror.finalize_minibatch(mb, "cpu")
+    tensor_keys = sorted(k[3:] for k in golden.files if k.startswith("mb/") and k != "mb/edge_type_names")
+    assert sorted(k for k, v in mb.items() if isinstance(v, torch.Tensor)) == tensor_keys
+    for key in tensor_keys:
+        expected = golden[f"mb/{key}"]
+        got = mb[key]
+        assert got.dtype == torch.from_numpy(expected).dtype and tuple(got.shape) == expected.shape, key
+        if key == "edge_types":  # numbered differently (sorted here, set order there): compare by relation NAME
+            assert [mirror.edge_types[int(i)] for i in got] == list(golden["mb/edge_type_names"])
+        else:
+            assert np.array_equal(got.numpy(), expected), key
+    assert mb["input_sequence_ids"].shape[0] == 6 and mb["edges"].shape[1] == 3
+
+
+def test_projection_rejects_malformed_graphs(mirror, samples):
+    from buglab.models.seqmodel import TokenProjectionError, project_graph_to_tokens
+
+    good = samples()[1]
+    labels, position, relations, refs = project_graph_to_tokens(good["graph"])
+    chain = [a for a, _ in good["graph"]["edges"]["NextToken"]] + [good["graph"]["edges"]["NextToken"][-1][1]]
+    assert labels == [good["graph"]["nodes"][t] for t in chain]
+    assert all(position[t] == i for i, t in enumerate(chain))
+    assert set(relations) == {"NextMayUse", "LastMayWrite", "ComputedFrom", "ControlFlowNext"}
+    assert refs == [position[n] for n in good["graph"]["reference_nodes"]]
+    # symbols sit at their first occurrence
+    for token, symbol in good["graph"]["edges"]["OccurrenceOf"]:
+        assert position[symbol] <= position[token]
+
+    cyclic = samples()[1]
+    cyclic["graph"]["edges"]["NextToken"].append((chain[-1], chain[3]))
+    with pytest.raises(TokenProjectionError):
+        project_graph_to_tokens(cyclic["graph"])
+    assert mirror.tensorize(cyclic) is None
+
+    headless = samples()[1]
+    headless["graph"]["edges"]["NextToken"].append((chain[-1], chain[0]))
+    with pytest.raises(TokenProjectionError):
+        project_graph_to_tokens(headless["graph"])
+
+    no_operator = samples()[1]
+    g = no_operator["graph"]
+    binop = g["nodes"].index("BinaryOperation")
+    for i, e in enumerate(g["edges"]["Child"]):
+        if e[0] == binop and e[2] == "operator":
+            g["nodes"][e[1]] = "??"
+    assert mirror.tensorize(no_operator) is None
+
+
+def test_module_is_not_built_yet(mirror):
+    with pytest.raises(NotImplementedError):
+        mirror.build_neural_module()
