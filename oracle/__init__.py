@@ -15,5 +15,6 @@ What it restates (plain PyTorch fp32 / fp64 and numpy, straightforward per-edge 
     citations and pinned against the REAL reference code imported from /root/reference
     (tests/golden/make_golden.py wrote the fixtures under tests/golden/).
   * ``seq_ref.py`` — the relational-transformer layer of the seq-great / seq-rat models (torch-only
-    reference files, so fully pinned: outputs and gradients of the real classes in tests/golden/seq_layers.npz).
+    reference files, so fully pinned: outputs and gradients of the real classes in tests/golden/seq_layers.npz);
+    ``seq_model_ref.py`` — the whole sequence module on top of it, pinned by tests/golden/seq_model.npz.
 """

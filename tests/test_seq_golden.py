@@ -140,3 +140,82 @@ def test_projection_rejects_malformed_graphs(mirror, samples):
 def test_module_is_not_built_yet(mirror):
     with pytest.raises(NotImplementedError):
         mirror.build_neural_module()
+
+
+# ------------------------------------------------------------------------------------------------ the module (oracle)
+def _reference_minibatch(golden, mirror, layer_type):
+    mb = {k[3:]: torch.from_numpy(golden[k]) for k in golden.files if k.startswith("mb/") and k != "mb/edge_type_names"}
+    # relation ids in the numbering the reference module was built with
+    order = list(golden[f"{layer_type}/edge_types_in_reference_order"])
+    mb["edge_types"] = torch.tensor([order.index(n) for n in golden[f"{layer_type}/edge_type_names"]], dtype=torch.int64)
+    return mb, order
+
+
+@pytest.mark.parametrize("layer_type", ["great", "rat"])
+def test_oracle_module_matches_reference(golden, mirror, layer_type):
+    """Loss, token representations, every log-probability and every parameter gradient of the real SeqBugLabModule."""
+    from oracle.seq_model_ref import SeqBugLabModule
+
+    mb, order = _reference_minibatch(golden, mirror, layer_type)
+    prefix = f"{layer_type}/param/"
+    state = {k[len(prefix):]: torch.from_numpy(golden[k]) for k in golden.files if k.startswith(prefix)}
+    rows = state["_SeqBugLabModule__positional_encoding"].shape[1]
+    module = SeqBugLabModule(vocabulary_size=state["_SeqBugLabModule__token_embedder._SubtokenUnitEmbedder__embeddings.weight"].shape[0],
+                             embedding_dim=SPEC["hidden_state_size"], num_edge_types=len(order), num_layers=SPEC["num_layers"],
+                             num_heads=SPEC["num_heads"], intermediate_dimension=SPEC["intermediate_dimension_size"],
+                             rewrite_vocabulary_size=state["_text_repair_module._TextRepairModule__text_rewrite_embeddings.weight"].shape[0],
+                             layer_type=layer_type, positional_rows=rows)
+    missing, unexpected = module.load_state_dict(state, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    module.train()  # dropout is 0; train mode as in the fixture
+    loss, details = module(**mb, return_details=True)
+    assert abs(float(loss.detach()) - float(golden[f"{layer_type}/loss"])) < 2e-5
+    lengths = mb["token_sequence_lengths"]
+    valid = torch.arange(mb["input_sequence_ids"].shape[1])[None, :] < lengths[:, None]
+    rep_ref = torch.from_numpy(golden[f"{layer_type}/output_representation"])
+    assert float((details["output_representation"].detach() - rep_ref)[valid].abs().max()) < 1e-5
+    for mine, theirs in (("localization_logprobs", "localization_logprobs"), ("text_logprobs", "text_logprobs"),
+                         ("varmisuse_logprobs", "varmisuse_logprobs"), ("argswap_logprobs", "argswap_logprobs")):
+        ref = torch.from_numpy(golden[f"{layer_type}/{theirs}"])
+        assert details[mine].shape == ref.shape and ref.numel() > 0, mine
+        assert float((details[mine].detach() - ref).abs().max()) < 2e-5, mine
+    assert torch.equal(details["localization_groups"], torch.from_numpy(golden[f"{layer_type}/localization_groups"]))
+    loss.backward()
+    checked = 0
+    for name, p in module.named_parameters():
+        key = f"{layer_type}/grad/{name}"
+        if key not in golden.files:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name      # norm2 (unused in post-norm mode)
+            continue
+        ref = torch.from_numpy(golden[key])
+        tol = 2e-5 * (float(ref.abs().max()) + 1e-12) + 2e-6
+        assert float((p.grad - ref).abs().max()) <= tol, (name, float((p.grad - ref).abs().max()), tol)
+        checked += 1
+    assert checked >= 35
+
+
+def test_oracle_module_on_the_mirrors_own_minibatch(golden, mirror, samples):
+    """The mirror's packed minibatch (its own relation numbering) drives the oracle to the reference's loss once the
+    relation-indexed bias tables are permuted accordingly — numbering is the only difference between the two hosts."""
+    from oracle.seq_model_ref import SeqBugLabModule
+
+    packed = mirror.initialize_minibatch()
+    for t in (mirror.tensorize(dp) for dp in samples()):
+        if t is not None:
+            mirror.extend_minibatch_with(t, packed)
+    mb = mirror.finalize_minibatch(packed, "cpu")
+    order = list(golden["great/edge_types_in_reference_order"])
+    perm = torch.tensor([order.index(kind) for kind in mirror.edge_types])   # mirror id -> reference id
+    prefix = "great/param/"
+    state = {k[len(prefix):]: torch.from_numpy(golden[k]) for k in golden.files if k.startswith(prefix)}
+    for k in list(state):
+        if "edge_attention_biases" in k or "edge_value_biases" in k:
+            state[k] = state[k][perm]
+    module = SeqBugLabModule(vocabulary_size=len(mirror.token_embedder.vocabulary), embedding_dim=32, num_edge_types=len(order),
+                             num_layers=2, num_heads=4, intermediate_dimension=64,
+                             rewrite_vocabulary_size=len(mirror._target_rewrite_ops), layer_type="great",
+                             positional_rows=state["_SeqBugLabModule__positional_encoding"].shape[1])
+    module.load_state_dict(state)
+    tensors = {k: v for k, v in mb.items() if isinstance(v, torch.Tensor)}
+    loss = module(**tensors)
+    assert abs(float(loss.detach()) - float(golden["great/loss"])) < 2e-5
