@@ -62,6 +62,9 @@ _SIGNATURES = {
     "bl_subtoken_maxpool_bwd": (c_i32, [c_ptr] * 3 + [c_i64, c_i32, c_i32, c_f32, c_u64, c_ptr, c_ptr]),
     "bl_grad_sqnorm": (c_i32, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
     "bl_adam_step": (c_i32, [c_ptr] * 4 + [c_i64, c_f32, c_f32, c_f32, c_f32, c_i64, c_f32, c_ptr, c_f32, c_ptr]),
+    "bl_seq_attention_supported": (c_i32, [c_i32]),
+    "bl_seq_attention_fwd": (c_i32, [c_ptr] * 9 + [c_i32] * 5 + [c_ptr, c_ptr, c_ptr]),
+    "bl_seq_attention_bwd": (c_i32, [c_ptr] * 12 + [c_i32] * 5 + [c_ptr] * 9 + [c_ptr]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -106,7 +109,7 @@ KERNELS_PER_CALL = {
     "bl_subtoken_maxpool_bwd": 1, "bl_grad_sqnorm": 2, "bl_adam_step": 1,
     "bl_rows_split3_f16": 1, "bl_unscale_pow2": 1, "bl_weights_split3_f16": 2, "bl_pair_project_fwd": 0, "bl_pair_project_bwd_input": 0,
     "bl_pair_project_bwd_weight": 1, "bl_rows_split2_f16": 1, "bl_grouped_colsum": 1, "bl_absmax": 1, "bl_weight_parts_f16": 1,
-    "bl_pair_project_tc": 1, "bl_pair_weight_grad_tc": 1,
+    "bl_pair_project_tc": 1, "bl_pair_weight_grad_tc": 1, "bl_seq_attention_fwd": 1, "bl_seq_attention_bwd": 2,
 }
 launch_counter = {"kernels": 0, "calls": 0}
 

@@ -664,6 +664,113 @@ def subtoken_maxpool(emb, ids, lens, p_drop: float = 0.0, training: bool = False
 
 
 # ---------------------------------------------------------------------------------------------------
+# Edge-biased attention of the sequence models
+# ---------------------------------------------------------------------------------------------------
+class SeqAttentionPlan(NamedTuple):
+    """The typed edges of one minibatch as attention "entries" (see include/buglab_b200.h): both directions of every edge,
+    grouped by query row (``row_*``) and by key (``col_*``).  Built once per minibatch, shared by all layers."""
+
+    num_samples: int
+    max_len: int
+    num_tables: int          # 2 * relation kinds
+    lengths: torch.Tensor    # [B] int32
+    row_ptr: torch.Tensor    # [B*L+1] int32
+    row_key: torch.Tensor    # [entries] int32
+    row_tab: torch.Tensor
+    col_ptr: torch.Tensor
+    col_query: torch.Tensor
+    col_tab: torch.Tensor
+
+
+def build_seq_attention_plan(edges: torch.Tensor, edge_types: torch.Tensor, lengths: torch.Tensor, max_len: int,
+                             num_edge_types: int) -> SeqAttentionPlan:
+    """``edges`` [E, 3] = (sample, source position, target position), ``edge_types`` [E] (seqmodel.py:780-782).
+    Plain torch index arithmetic (runs where the tensors live); the kernels only read the result."""
+    B, L, T = int(lengths.shape[0]), int(max_len), int(num_edge_types)
+    sample, src, tgt = edges[:, 0].long(), edges[:, 1].long(), edges[:, 2].long()
+    kinds = edge_types.long()
+    query = torch.cat((sample * L + src, sample * L + tgt))      # global query row of each entry
+    key = torch.cat((tgt, src))
+    table = torch.cat((kinds, kinds + T))
+
+    def grouped(major: torch.Tensor, minor: torch.Tensor):
+        order = torch.argsort(major * L + minor, stable=True)
+        counts = torch.bincount(major, minlength=B * L)
+        ptr = torch.zeros(B * L + 1, dtype=torch.int64, device=edges.device)
+        torch.cumsum(counts, dim=0, out=ptr[1:])
+        return order, ptr.to(torch.int32)
+
+    row_order, row_ptr = grouped(query, key)
+    key_row = (query // L) * L + key                             # global key row of each entry
+    col_order, col_ptr = grouped(key_row, query % L)
+    i32 = lambda t: t.to(torch.int32).contiguous()  # noqa: E731
+    return SeqAttentionPlan(B, L, 2 * T, i32(lengths), row_ptr, i32(key[row_order]), i32(table[row_order]),
+                            col_ptr, i32((query % L)[col_order]), i32(table[col_order]))
+
+
+def _seq_attention_backend():
+    """(forward, backward) callables with the C-ABI argument order minus the stream.  The product has exactly one backend,
+    the CUDA library; tests substitute the host emulation of the same kernel source (tests/emul)."""
+    lib = _lib.load()
+
+    def fwd(*args):
+        check(lib.bl_seq_attention_fwd(*args, stream_ptr(None)), "bl_seq_attention_fwd")
+
+    def bwd(*args):
+        check(lib.bl_seq_attention_bwd(*args, stream_ptr(None)), "bl_seq_attention_bwd")
+
+    return fwd, bwd, f32, i32
+
+
+class SeqEdgeAttentionFn(torch.autograd.Function):
+    """out[b, h, i] = sum_j softmax_j(<q_i, k_j> + edge terms) (v_j + edge value terms); q, k, v: [B, H, L, D] fp32."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, bias, vbias, plan: SeqAttentionPlan):
+        fwd, _, fp, ip = _seq_attention_backend()
+        q, k, v, bias = q.contiguous(), k.contiguous(), v.contiguous(), bias.contiguous()
+        vbias = vbias.contiguous() if vbias is not None else None
+        B, H, L, D = q.shape
+        if (B, L) != (plan.num_samples, plan.max_len) or bias.shape != (plan.num_tables, H, D):
+            raise ValueError(f"shape mismatch: q {tuple(q.shape)}, bias {tuple(bias.shape)}, plan B={plan.num_samples} "
+                             f"L={plan.max_len} tables={plan.num_tables}")
+        out = torch.empty_like(q)
+        lse = torch.empty((B, H, L), device=q.device, dtype=torch.float32)
+        fwd(fp(q), fp(k), fp(v), ip(plan.lengths), fp(bias), fp(vbias) if vbias is not None else None, ip(plan.row_ptr),
+            ip(plan.row_key), ip(plan.row_tab), B, H, L, D, plan.num_tables, fp(out), fp(lse))
+        ctx.plan = plan
+        ctx.has_vbias = vbias is not None
+        ctx.save_for_backward(q, k, v, bias, vbias if vbias is not None else bias.new_zeros(0), out, lse)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        _, bwd, fp, ip = _seq_attention_backend()
+        q, k, v, bias, vbias, out, lse = ctx.saved_tensors
+        vbias = vbias if ctx.has_vbias else None
+        plan: SeqAttentionPlan = ctx.plan
+        B, H, L, D = q.shape
+        d_out = d_out.contiguous()
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        entries = int(plan.row_key.shape[0])
+        d_entry_bias = torch.empty((max(entries, 1), H, D), device=q.device, dtype=torch.float32)
+        d_entry_vbias = torch.empty_like(d_entry_bias) if vbias is not None else None
+        delta = torch.empty((B, H, L), device=q.device, dtype=torch.float32)
+        bwd(fp(q), fp(k), fp(v), ip(plan.lengths), fp(bias), fp(vbias) if vbias is not None else None, ip(plan.row_ptr),
+            ip(plan.row_key), ip(plan.row_tab), ip(plan.col_ptr), ip(plan.col_query), ip(plan.col_tab), B, H, L, D,
+            plan.num_tables, fp(out), fp(lse), fp(d_out), fp(dq), fp(dk), fp(dv), fp(d_entry_bias),
+            fp(d_entry_vbias) if d_entry_vbias is not None else None, fp(delta))
+        tabs = plan.row_tab.long()
+        d_bias = torch.zeros_like(bias).index_add_(0, tabs, d_entry_bias[:entries])
+        d_vbias = torch.zeros_like(vbias).index_add_(0, tabs, d_entry_vbias[:entries]) if vbias is not None else None
+        return dq, dk, dv, d_bias, d_vbias, None
+
+
+def seq_edge_attention(q, k, v, bias, vbias, plan: SeqAttentionPlan) -> torch.Tensor:
+    return SeqEdgeAttentionFn.apply(q, k, v, bias, vbias, plan)
+
+
+# ---------------------------------------------------------------------------------------------------
 # Flat-buffer optimiser (A12)
 # ---------------------------------------------------------------------------------------------------
 def grad_sqnorm(flat_grad: torch.Tensor, out: torch.Tensor, partial: torch.Tensor) -> None:

@@ -1,0 +1,170 @@
+"""The seq-attention CUDA kernels without a GPU: csrc/seq_attention_core.h (the per-row arithmetic the kernels execute, one
+thread per row) is compiled for the host and driven by loops (tests/emul/seq_attention_emul.cpp), then compared with the
+oracle (oracle/seq_ref.py, itself pinned to the real reference).  Covers the arithmetic, the entry (CSR) construction in
+``ops.build_seq_attention_plan`` and the autograd wiring of ``ops.SeqEdgeAttentionFn`` — everything except the CUDA launch."""
+import ctypes
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "neurips21-self-supervised-bug-detection-and-repair_b200")
+for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from buglab_b200 import ops  # noqa: E402
+from oracle import seq_ref  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def emulation(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    out = tmp_path_factory.mktemp("emul") / "libseq_attention_emul.so"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas", "-o", str(out),
+                    os.path.join(ROOT, "tests", "emul", "seq_attention_emul.cpp")], check=True)
+    lib = ctypes.CDLL(str(out))
+    c_i32, c_ptr = ctypes.c_int32, ctypes.c_void_p
+    lib.emul_seq_attention_fwd.restype, lib.emul_seq_attention_fwd.argtypes = c_i32, [c_ptr] * 9 + [c_i32] * 5 + [c_ptr] * 2
+    lib.emul_seq_attention_bwd.restype, lib.emul_seq_attention_bwd.argtypes = c_i32, [c_ptr] * 12 + [c_i32] * 5 + [c_ptr] * 9
+    return lib
+
+
+@pytest.fixture()
+def host_backend(emulation, monkeypatch):
+    """Routes ops.SeqEdgeAttentionFn to the host emulation (same argument order as the C ABI, no stream)."""
+    def pointer(dtype):
+        def get(t):
+            if t is None:
+                return None
+            assert t.dtype == dtype and t.is_contiguous() and not t.is_cuda
+            return t.data_ptr()
+        return get
+
+    def fwd(*args):
+        assert emulation.emul_seq_attention_fwd(*args) == 0
+
+    def bwd(*args):
+        assert emulation.emul_seq_attention_bwd(*args) == 0
+
+    monkeypatch.setattr(ops, "_seq_attention_backend", lambda: (fwd, bwd, pointer(torch.float32), pointer(torch.int32)))
+
+
+def attention_through_the_kernels(att, x, mask, edges, edge_types, num_edge_types):
+    """RelationalMultiheadAttention.forward with the score/softmax/value part done by the kernel source."""
+    B, L, _ = x.shape
+    lengths = (~mask).sum(dim=1) if mask is not None else torch.full((B,), L)
+    plan = ops.build_seq_attention_plan(edges, edge_types, lengths, L, num_edge_types)
+    q, k, v = att.project(x)
+    H, dk = att._num_heads, att._key_query_dim
+    bias = torch.cat((att._edge_attention_biases.weight, att._reverse_edge_attention_biases.weight)).view(-1, H, dk)
+    vbias = None
+    if att._use_edge_value_biases:
+        vbias = torch.cat((att._edge_value_biases.weight, att._reverse_edge_value_biases.weight)).view(-1, H, att._value_dim)
+    return att.merge(ops.seq_edge_attention(q, k, v, bias, vbias, plan))
+
+
+def random_case(seed, B, L, E, d_model, heads, types, value_biases):
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    att = seq_ref.RelationalMultiheadAttention(num_heads=heads, num_edge_types=types, input_state_dimension=d_model,
+                                               key_query_dimension=d_model // heads, value_dimension=d_model // heads,
+                                               output_dimension=d_model, dropout_rate=0.0,
+                                               use_edge_value_biases=value_biases).eval()
+    lengths = torch.randint(max(1, L // 2), L + 1, (B,), generator=g)
+    lengths[0] = L
+    mask = torch.arange(L)[None, :] >= lengths[:, None]
+    x = (torch.randn(B, L, d_model, generator=g) * (~mask)[..., None]).requires_grad_(True)
+    sample = torch.randint(0, B, (E,), generator=g)
+    hi = lengths[sample].float()
+    edges = torch.stack([sample, (torch.rand(E, generator=g) * hi).long(), (torch.rand(E, generator=g) * hi).long()], dim=1)
+    edge_types = torch.randint(0, types, (E,), generator=g)
+    weights = torch.randn(B, L, d_model, generator=g) * (~mask)[..., None]
+    return att, x, mask, edges, edge_types, weights
+
+
+CASES = [  # seed, B, L, E, d_model, heads, relation kinds, value biases
+    (1, 3, 12, 40, 32, 4, 5, False),      # seq-great shape (head dim 8)
+    (2, 3, 12, 40, 32, 4, 5, True),       # seq-rat
+    (3, 1, 6, 90, 16, 2, 3, True),        # dense duplicates: many entries on the same (i, j)
+    (4, 2, 9, 0, 32, 2, 4, True),         # no edges at all (head dim 16)
+    (5, 2, 33, 150, 64, 2, 6, True),      # head dim 32, length not a multiple of anything
+    (6, 2, 20, 60, 128, 2, 4, False),     # head dim 64 (config 4's)
+    (7, 4, 7, 25, 32, 4, 2, True),        # short sequences, heavy padding
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"seed{c[0]}")
+def test_kernel_source_matches_oracle(host_backend, case):
+    seed, B, L, E, d_model, heads, types, value_biases = case
+    att, x, mask, edges, edge_types, weights = random_case(*case)
+    keep = ~mask
+
+    expected = att(x, mask, edges, edge_types)
+    (expected * weights).sum().backward()
+    ref_grads = {n: p.grad.clone() for n, p in att.named_parameters()}
+    ref_dx = x.grad.clone()
+    x.grad = None
+    att.zero_grad()
+
+    got = attention_through_the_kernels(att, x, mask, edges, edge_types, types)
+    assert float((got - expected).detach()[keep].abs().max()) < 3e-6
+    (got * weights).sum().backward()
+    scale = float(ref_dx.abs().max()) + 1e-12
+    assert float((x.grad - ref_dx).abs().max()) <= 2e-5 * scale + 2e-6
+    for name, p in att.named_parameters():
+        ref = ref_grads[name]
+        tol = 2e-5 * (float(ref.abs().max()) + 1e-12) + 2e-6
+        assert float((p.grad - ref).abs().max()) <= tol, (name, float((p.grad - ref).abs().max()), tol)
+
+
+def test_plan_lists_both_directions_sorted():
+    edges = torch.tensor([[0, 2, 1], [0, 2, 1], [1, 0, 3], [0, 1, 1]])
+    types = torch.tensor([1, 0, 2, 1])
+    plan = ops.build_seq_attention_plan(edges, types, torch.tensor([3, 4]), 4, 3)
+    assert plan.num_tables == 6 and plan.row_key.shape[0] == 8
+    rp, rk, rt = plan.row_ptr.tolist(), plan.row_key.tolist(), plan.row_tab.tolist()
+    rows = {r: sorted(zip(rk[rp[r]: rp[r + 1]], rt[rp[r]: rp[r + 1]])) for r in range(8) if rp[r + 1] > rp[r]}
+    # sample 0: (2->1, kind 1), (2->1, kind 0), (1->1 self loop, kind 1); sample 1: (0->3, kind 2); reverse tables are 3 + kind
+    assert rows == {1: [(1, 1), (1, 4), (2, 3), (2, 4)], 2: [(1, 0), (1, 1)], 4: [(3, 2)], 7: [(0, 5)]}
+    for r in range(8):
+        assert rk[rp[r]: rp[r + 1]] == sorted(rk[rp[r]: rp[r + 1]])          # keys ascending within a row
+    cp, cq, ct = plan.col_ptr.tolist(), plan.col_query.tolist(), plan.col_tab.tolist()
+    cols = {c: sorted(zip(cq[cp[c]: cp[c + 1]], ct[cp[c]: cp[c + 1]])) for c in range(8) if cp[c + 1] > cp[c]}
+    assert cols == {1: [(1, 1), (1, 4), (2, 0), (2, 1)], 2: [(1, 3), (1, 4)], 4: [(3, 5)], 7: [(0, 2)]}
+    for c in range(8):
+        assert cq[cp[c]: cp[c + 1]] == sorted(cq[cp[c]: cp[c + 1]])
+    empty = ops.build_seq_attention_plan(torch.zeros((0, 3), dtype=torch.long), torch.zeros(0, dtype=torch.long),
+                                         torch.tensor([2]), 3, 2)
+    assert empty.row_ptr.tolist() == [0, 0, 0, 0] and empty.row_key.numel() == 0
+
+
+def test_golden_layer_cases_through_the_kernel_source(host_backend):
+    """The reference-generated layer fixtures (tests/golden/seq_layers.npz), attention computed by the kernel source."""
+    import numpy as np
+
+    import test_seq_oracle as layer_tests
+
+    golden = np.load(layer_tests.GOLDEN)
+    for name in ("great_postnorm", "rat_postnorm", "prenorm_gelu", "postnorm_rezero_vector", "medium"):
+        layer, src, mask, edges, edge_types = layer_tests.build(golden, name)
+        types = int(golden[f"{name}/dims"][5])
+        att = layer.self_attn
+        att.forward = lambda x, m, e, t, att=att, types=types: attention_through_the_kernels(att, x, m, e, t, types)
+        y = layer(src, mask, edges, edge_types)
+        keep = ~mask
+        expected = torch.from_numpy(golden[f"{name}/out"])
+        assert float((y.detach() - expected)[keep].abs().max()) < 5e-6, name
+        (y * torch.from_numpy(golden[f"{name}/weights"])).sum().backward()
+        g = torch.from_numpy(golden[f"{name}/grad_src"])
+        assert float((src.grad - g).abs().max()) <= 2e-5 * float(g.abs().max()) + 2e-6, name
+        for pname, p in layer.named_parameters():
+            key = f"{name}/grad/{pname}"
+            if key in golden.files:
+                ref = torch.from_numpy(golden[key])
+                assert float((p.grad - ref).abs().max()) <= 2e-5 * float(ref.abs().max()) + 2e-6, (name, pname)
