@@ -117,8 +117,6 @@ class AbstractBugLabModel:
                                  varmisuse_logprobs, node_mappings=None):
         """Splits minibatch-level predictions back into per-sample ``(datapoint, {node: logprob}, [rewrite logprob])``
         (reference basemodel.py:240-346).  Location groups are consumed in sample order, one per unique candidate node."""
-        if node_mappings is not None:
-            raise NotImplementedError("node_mappings belongs to the sequence models, outside this build")
         loc_sample = np.asarray(candidate_location_sample_idx)
         loc_logprobs = np.asarray(candidate_location_log_probs)
         order = np.argsort(loc_sample, kind="stable")
@@ -140,7 +138,10 @@ class AbstractBugLabModel:
             candidate_nodes = np.unique(point["graph"]["reference_nodes"])
             sample_logprobs = loc_logprobs[order[bounds[sample_idx]: bounds[sample_idx + 1]]]
             assert len(sample_logprobs) == len(candidate_nodes) + 1
-            location_logprobs = {int(n): lp for n, lp in zip(candidate_nodes, sample_logprobs)}
+            keys = candidate_nodes if node_mappings is None else [node_mappings[sample_idx][k] for k in candidate_nodes]
+            # sequence models: several graph nodes can share one token position; like the reference's dict
+            # comprehension, a repeated position keeps the LAST of its log-probabilities (basemodel.py:291-294)
+            location_logprobs = {int(n): lp for n, lp in zip(keys, sample_logprobs)}
             location_logprobs[-1] = sample_logprobs[-1]  # the NO_BUG slot comes last within a sample
 
             flat_swap, flat_text, flat_misuse = [], [], []
@@ -158,4 +159,16 @@ class AbstractBugLabModel:
                     assert rewrite_probs[i] is None
                     rewrite_probs[i] = lp
             assert None not in rewrite_probs
+            if node_mappings is not None:
+                # report per GRAPH node again: every reference node that was projected onto a position gets its log-prob
+                nodes_at: Dict[int, List[int]] = defaultdict(list)
+                reference_nodes = point["graph"]["reference_nodes"]
+                for graph_node, position in node_mappings[sample_idx].items():
+                    if graph_node in reference_nodes:
+                        nodes_at[position].append(graph_node)
+                per_node: Dict[int, float] = {}
+                for position, lp in location_logprobs.items():
+                    for node in (nodes_at[position] if position >= 0 else [position]):
+                        per_node[node] = lp
+                location_logprobs = per_node
             yield point, location_logprobs, rewrite_probs

@@ -4,8 +4,11 @@ code graph onto its token sequence, per-sample tensors and minibatch packing —
 Restates reference buglab/models/seqmodel.py:442-624 (graph -> tokens), :626-729 (``tensorize``), :731-975 (minibatch);
 integer bookkeeping is bit-exact against the real reference (tests/golden/seq_model.npz, tests/test_seq_golden.py).
 
-NOT built yet: the B200 kernels of the relational transformer encoder (edge-biased attention).  ``build_neural_module``
-therefore raises; the arithmetic those kernels must reproduce is pinned in oracle/seq_ref.py + oracle/seq_model_ref.py.
+The module (``SeqBugLabModule``, reference seqmodel.py:65-396) runs its attention core on the hand-written
+``bl_seq_attention_*`` kernels (first correct path; their source is pinned on the CPU through a host emulation, B200 parity
+tests are gated until they have run once), LayerNorm / subtoken embedding / segment ops on the kernels the graph model
+already uses, dense layers on library GEMMs.  Layer types ``great`` and ``rat``; ``transformer`` / ``gru`` are not built.
+The arithmetic is pinned in oracle/seq_ref.py + oracle/seq_model_ref.py.
 """
 import logging
 from collections import defaultdict
@@ -13,10 +16,16 @@ from typing import Any, Callable, Dict, Iterator, List, NamedTuple, Optional, Tu
 
 import numpy as np
 import torch
-from ptgnn.baseneuralmodel import AbstractNeuralModel
+from ptgnn.baseneuralmodel import AbstractNeuralModel, ModuleWithMetrics
 from ptgnn.neuralmodels.embeddings.strelementrepresentationmodel import StrElementRepresentationModel
+from torch import nn
 
 from buglab.models.basemodel import AbstractBugLabModel
+from buglab.models.layers.fixermodules import (CandidatePairSelectorModule, SingleCandidateNodeSelectorModule,
+                                                TextRepairModule)
+from buglab.models.layers.localizationmodule import LocalizationModule
+from buglab.models.layers.relational_transformer import RelationalTransformerEncoderLayer
+from buglab.models.utils import compute_generator_loss, scatter_log_softmax, scatter_max
 from buglab.representations.data import BugLabData, BugLabGraph
 
 LOGGER = logging.getLogger(__name__)
@@ -182,6 +191,162 @@ def project_graph_to_tokens(graph: BugLabGraph):
     return [proj.labels[t] for t in proj.tokens], position, relations, reference_positions
 
 
+
+def _const_one(_epoch: int) -> float:
+    return 1.0
+
+
+class SeqBugLabModule(ModuleWithMetrics):
+    """Subtoken embedding + positional table -> LayerNorm -> relational transformer layers -> localisation / repair heads."""
+
+    def __init__(self, token_embedder, embedding_dim: int, num_edge_types: int, num_layers: int, num_heads: int,
+                 intermediate_dimension: int, dropout_rate: float, rewrite_vocabulary_size: int, layer_type: str = "great",
+                 buggy_samples_weight_schedule: Callable[[int], float] = _const_one,
+                 generator_loss_type: Optional[str] = "norm-kl", rezero_mode: str = "off",
+                 normalisation_mode: str = "postnorm"):
+        super().__init__()
+        if layer_type not in ("great", "rat"):
+            raise NotImplementedError(f"layer type `{layer_type}`: only the relational layers (great, rat) are built")
+        self.__generator_loss_type = generator_loss_type
+        self.__token_embedder = token_embedder
+        self.__positional_encoding = nn.Parameter(torch.randn(1, 5000, embedding_dim), requires_grad=True)
+        self.__dropout_layer = nn.Dropout(dropout_rate)
+        self.__input_layer_norm = nn.LayerNorm(embedding_dim)
+        self.__layer_type = layer_type
+        self.__num_edge_types = num_edge_types
+        self.__seq_layers = nn.ModuleList([
+            RelationalTransformerEncoderLayer(
+                nhead=num_heads, num_edge_types=num_edge_types, d_model=embedding_dim,
+                key_query_dimension=embedding_dim // num_heads, value_dimension=embedding_dim // num_heads,
+                dim_feedforward=intermediate_dimension, dropout=dropout_rate,
+                use_edge_value_biases=layer_type == "rat", rezero_mode=rezero_mode, normalisation_mode=normalisation_mode)
+            for _ in range(num_layers)])
+        self.__localization_module = LocalizationModule(embedding_dim, buggy_samples_weight_schedule=buggy_samples_weight_schedule)
+        self._buggy_samples_weight_schedule = buggy_samples_weight_schedule
+        self._text_repair_module = TextRepairModule(embedding_dim, rewrite_vocabulary_size)
+        self._varmisuse_module = SingleCandidateNodeSelectorModule(embedding_dim)
+        self._argswap_module = CandidatePairSelectorModule(embedding_dim)
+
+    # ---- metrics (device-resident; one D2H when reported) ---------------------------------------
+    def _reset_module_metrics(self) -> None:
+        if not hasattr(self, "_epoch_idx"):
+            self._epoch_idx = 0
+        elif self.training and self.__num_batches > 0:
+            self._epoch_idx += 1
+        self.__sums = None
+        self.__num_batches = 0
+
+    def _module_metrics(self) -> Dict[str, Any]:
+        if self.__sums is None:
+            return {}
+        loss, repair_loss, samples = self.__sums.tolist()
+        metrics = {"Loss": loss / self.__num_batches}
+        if samples > 0:
+            metrics["Repair Loss"] = repair_loss / samples
+        return metrics
+
+    def __accumulate(self, loss, repair_loss, samples) -> None:
+        with torch.no_grad():
+            s = torch.stack((loss.detach().double(), repair_loss.detach().double(), samples.double()))
+            self.__sums = s if self.__sums is None else self.__sums + s
+            self.__num_batches += 1
+
+    # ---- encoder (seqmodel.py:351-396) -------------------------------------------------------------
+    def _compute_output_representation(self, input_sequence_ids, input_seq_num_subtokens, token_sequence_lengths, edges,
+                                       edge_types):
+        from buglab_b200 import ops
+
+        B, L, T = input_sequence_ids.shape
+        x = self.__token_embedder(token_idxs=input_sequence_ids.reshape(B * L, T),
+                                  lengths=input_seq_num_subtokens.reshape(B * L)).view(B, L, -1)
+        is_token = torch.arange(L, device=x.device)[None, :] < token_sequence_lengths[:, None]
+        x = x + self.__positional_encoding[:, :L]
+        norm = self.__input_layer_norm
+        x = self.__dropout_layer(ops.layer_norm(x.reshape(B * L, -1), norm.weight, norm.bias, norm.eps).view(B, L, -1))
+        x = x * is_token.unsqueeze(-1)
+        padding = ~is_token
+        plan = ops.build_seq_attention_plan(edges, edge_types, token_sequence_lengths, L, self.__num_edge_types)
+        for layer in self.__seq_layers:
+            x = layer(src=x, src_mask=padding, edges=plan)
+        return x
+
+    @staticmethod
+    def _at(rep: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+        return rep[idx[:, 0], idx[:, 1]]
+
+    def _compute_localization_logprobs(self, candidate_reprs, candidate_to_sample_idx, num_samples):
+        groups, logprobs, _ = self.__localization_module.compute_localization_logprobs(
+            candidate_reprs, candidate_to_sample_idx, num_samples)
+        return groups, logprobs
+
+    # ---- repair heads (seqmodel.py:164-225) --------------------------------------------------------
+    def _compute_repair_logprobs(self, output_representations, target_rewrite_node_ids, target_rewrites,
+                                 rewrite_to_location_group, varmisused_node_ids, candidate_symbol_node_ids,
+                                 candidate_symbol_to_location_group, call_node_ids, candidate_swapped_node_ids,
+                                 swapped_pair_to_call_location_group, return_selected: bool = False):
+        rep, dev = output_representations, output_representations.device
+        text = (self._text_repair_module.compute_rewrite_logits(self._at(rep, target_rewrite_node_ids), target_rewrites)
+                if target_rewrites.shape[0] > 0 else torch.zeros(0, device=dev))
+        misuse = (self._varmisuse_module.compute_per_slot_log_probability(
+            self._at(rep, varmisused_node_ids), self._at(rep, candidate_symbol_node_ids))
+            if varmisused_node_ids.shape[0] > 0 else torch.zeros(0, device=dev))
+        swap = (self._argswap_module.compute_per_pair_logits(
+            self._at(rep, call_node_ids), rep[candidate_swapped_node_ids[:, 0].unsqueeze(-1), candidate_swapped_node_ids[:, 1:]])
+            if call_node_ids.shape[0] > 0 else torch.zeros(0, device=dev))
+        sizes = [text.shape[0], misuse.shape[0], swap.shape[0]]
+        logits = torch.cat((text, misuse, swap))
+        groups = torch.cat((rewrite_to_location_group, candidate_symbol_to_location_group, swapped_pair_to_call_location_group))
+        if logits.shape[0] == 0:
+            empty = torch.zeros(0, dtype=torch.bool, device=dev)
+            return (swap, text, misuse, (empty, empty, empty)) if return_selected else (swap, text, misuse)
+        text_lp, misuse_lp, swap_lp = torch.split(scatter_log_softmax(logits, index=groups), sizes)
+        if not return_selected:
+            return swap_lp, text_lp, misuse_lp
+        with torch.no_grad():
+            group_max = scatter_max(logits, groups)[0]
+            text_sel, misuse_sel, swap_sel = torch.split(group_max[groups] == logits, sizes)
+        return swap_lp, text_lp, misuse_lp, (swap_sel, text_sel, misuse_sel)
+
+    # ---- loss (seqmodel.py:232-349) ----------------------------------------------------------------
+    def forward(self, *, input_sequence_ids, input_seq_num_subtokens, token_sequence_lengths, edges, edge_types, has_bug,
+                candidate_location_idxs, target_location_idxs, target_rewrite_node_ids, target_rewrites,
+                rewrite_to_location_group, correct_rewrite_idxs, text_rewrite_idxs, varmisused_node_ids,
+                candidate_symbol_node_ids, candidate_symbol_to_location_group, correct_candidate_symbols,
+                candidate_rewrite_idxs, call_node_ids, candidate_swapped_node_ids, swapped_pair_to_call_location_group,
+                correct_swapped_pair, pair_rewrite_idxs, rewrite_to_graph_id: Optional[torch.Tensor] = None,
+                rewrite_logprobs: Optional[torch.Tensor] = None, **_visualization_data):
+        rep = self._compute_output_representation(input_sequence_ids, input_seq_num_subtokens, token_sequence_lengths, edges,
+                                                  edge_types)
+        candidates = self._at(rep, candidate_location_idxs)
+        candidate_to_sample = candidate_location_idxs[:, 0]
+        swap_lp, text_lp, misuse_lp, (swap_sel, text_sel, misuse_sel) = self._compute_repair_logprobs(
+            rep, target_rewrite_node_ids, target_rewrites, rewrite_to_location_group, varmisused_node_ids,
+            candidate_symbol_node_ids, candidate_symbol_to_location_group, call_node_ids, candidate_swapped_node_ids,
+            swapped_pair_to_call_location_group, return_selected=True)
+
+        if rewrite_logprobs is not None:  # selector training
+            _, localization_logprobs, arange = self.__localization_module.compute_localization_logprobs(
+                candidate_reprs=candidates, candidate_to_sample_idx=candidate_to_sample, num_samples=has_bug.shape[0])
+            loss = compute_generator_loss(
+                swap_lp, arange, candidate_rewrite_idxs, candidate_symbol_to_location_group, localization_logprobs,
+                self.__generator_loss_type, pair_rewrite_idxs, rewrite_logprobs, rewrite_to_graph_id,
+                rewrite_to_location_group, swapped_pair_to_call_location_group, text_lp, text_rewrite_idxs, misuse_lp)
+            zero = torch.zeros((), device=loss.device)
+            self.__accumulate(loss, zero, zero)
+            return loss
+
+        localization_loss = self.__localization_module(
+            candidate_reprs=candidates, candidate_to_sample_idx=candidate_to_sample, has_bug=has_bug,
+            correct_candidate_idxs=target_location_idxs)
+        repair_loss = (self._text_repair_module(text_lp, correct_rewrite_idxs, selected_fixes=text_sel).sum()
+                       + self._varmisuse_module(misuse_lp, correct_candidate_symbols, selected_fixes=misuse_sel).sum()
+                       + self._argswap_module(swap_lp, correct_swapped_pair, selected_fixes=swap_sel).sum())
+        repair_loss = repair_loss * self._buggy_samples_weight_schedule(self._epoch_idx)
+        loss = localization_loss + repair_loss / has_bug.shape[0]
+        self.__accumulate(loss, repair_loss, has_bug.sum())
+        return loss
+
+
 _PAIR_KEYS = ("candidate_location_idxs", "target_rewrite_node_ids", "varmisused_node_ids", "candidate_symbol_node_ids",
               "call_node_ids")
 _FLAT_KEYS = ("target_location_idxs", "target_rewrites", "rewrite_to_location_group", "correct_rewrite_idxs",
@@ -246,10 +411,15 @@ class SeqBugLabModel(AbstractNeuralModel[BugLabData, SeqModelTensorizedSample, A
         self.__edge_type_to_idx = {kind: i for i, kind in enumerate(self.__edge_types)}
         self.__edge_types_seen = None
 
-    def build_neural_module(self):
-        raise NotImplementedError(
-            f"seq-{self.layer_type}: the B200 kernels of the relational transformer encoder are not built yet "
-            "(SURVEY.md §8(f) row 2); the host side (this class) and the oracle (oracle/seq_ref.py) are.")
+    def build_neural_module(self) -> SeqBugLabModule:
+        return SeqBugLabModule(
+            token_embedder=self.__token_embedder.build_neural_module(), embedding_dim=self.__token_embedder.embedding_size,
+            num_edge_types=len(self.__edge_types), num_layers=self.num_layers, num_heads=self.num_heads,
+            intermediate_dimension=self.intermediate_dimension_size, dropout_rate=self.dropout_rate,
+            rewrite_vocabulary_size=len(self._target_rewrite_ops), layer_type=self.layer_type,
+            buggy_samples_weight_schedule=self.buggy_samples_weight_schedule,
+            generator_loss_type=self.generator_loss_type, rezero_mode=self.rezero_mode,
+            normalisation_mode=self.normalisation_mode)
 
     # ---- one sample (seqmodel.py:646-729) --------------------------------------------------------
     def tensorize(self, datapoint: BugLabData) -> Optional[SeqModelTensorizedSample]:
@@ -410,5 +580,26 @@ class SeqBugLabModel(AbstractNeuralModel[BugLabData, SeqModelTensorizedSample, A
                                                          dtype=torch.float32, device=device)
         return minibatch
 
-    def predict(self, data: Iterator[BugLabData], trained_nn, device, parallelize: bool):
-        raise NotImplementedError("seq-* inference needs the relational transformer module (not built yet)")
+    def predict(self, data: Iterator[BugLabData], trained_nn: SeqBugLabModule, device, parallelize: bool
+                ) -> Iterator[Tuple[BugLabData, Dict[int, float], List[float]]]:
+        """Per sample: {graph node (or -1 = NO_BUG): log-prob} and one log-prob per candidate rewrite, scored at every
+        location (reference seqmodel.py:977-1031; minibatches of <= 50 samples)."""
+        trained_nn.eval()
+        with torch.no_grad(), self._tensorize_all_location_rewrites():
+            for mb, original_datapoints in self.minibatch_iterator(
+                    self.tensorize_dataset(data, return_input_data=True, parallelize=parallelize), device,
+                    max_minibatch_size=50, parallelize=parallelize):
+                num_samples = mb["input_sequence_ids"].shape[0]
+                rep = trained_nn._compute_output_representation(
+                    mb["input_sequence_ids"], mb["input_seq_num_subtokens"], mb["token_sequence_lengths"], mb["edges"],
+                    mb["edge_types"])
+                where = mb["candidate_location_idxs"]
+                groups, logprobs = trained_nn._compute_localization_logprobs(rep[where[:, 0], where[:, 1]], where[:, 0],
+                                                                             num_samples)
+                swap_lp, text_lp, misuse_lp = trained_nn._compute_repair_logprobs(
+                    rep, mb["target_rewrite_node_ids"], mb["target_rewrites"], mb["rewrite_to_location_group"],
+                    mb["varmisused_node_ids"], mb["candidate_symbol_node_ids"], mb["candidate_symbol_to_location_group"],
+                    mb["call_node_ids"], mb["candidate_swapped_node_ids"], mb["swapped_pair_to_call_location_group"])
+                yield from self._iter_per_sample_results(
+                    mb, groups.cpu().numpy(), logprobs.cpu().numpy(), swap_lp, num_samples, original_datapoints, text_lp,
+                    misuse_lp, node_mappings=mb["node_mappings"])

@@ -10,6 +10,7 @@ unpacked with ``msgpack`` and go through ``model.tensorize`` — the reference-s
 the same either way.  There is no silent degradation: a missing library raises at construction.
 """
 import ctypes
+import logging
 import os
 import threading
 from collections import defaultdict
@@ -18,6 +19,8 @@ from typing import Any, Dict, Iterable, Iterator, List, Optional, Sequence, Tupl
 
 import msgpack
 import numpy as np
+
+LOGGER = logging.getLogger(__name__)
 
 _LIB_NAME = "libbuglab_shards.so"
 _lib: Optional[ctypes.CDLL] = None
@@ -417,6 +420,12 @@ class ShardDataset:
     def tensorized(self, model) -> Iterator[Tuple[Any, None]]:
         from buglab.utils.msgpackutils import select_shard_files
 
+        if not hasattr(model, "gnn_model"):
+            # the native tensoriser produces the GRAPH models' per-sample tensors; other model families (the sequence
+            # models project graphs onto token sequences in host code) get the reference-shaped chain, said out loud
+            LOGGER.info("%s is not a graph model: shards are decoded and tensorised by the host-language path.",
+                        type(model).__name__)
+            return model.tensorize_dataset(iter(self), return_input_data=False, parallelize=(self._threads or 2) > 1)
         if self._tensorizer is None or self._tensorizer_model is not model:
             self._tensorizer, self._tensorizer_model = NativeShardTensorizer(model), model
         files, shard_elements = select_shard_files(self._path, self._shuffle, self._first_n, self._rank, self._world)

@@ -137,6 +137,13 @@ def main():
             out[pre + "argswap_logprobs"], out[pre + "text_logprobs"] = swap.numpy(), text.numpy()
             out[pre + "varmisuse_logprobs"] = misuse.numpy()
         out[pre + "metrics"] = np.array(json.dumps(jsonable(nn.report_metrics())))
+        # inference: per graph node log-probabilities and per rewrite log-probabilities (seqmodel.py:977-1031)
+        predictions = []
+        for dp, location_logprobs, rewrite_logprobs in model.predict(iter(load()), nn, "cpu", parallelize=False):
+            predictions.append({"path": dp["graph"]["path"],
+                                "locations": {str(int(k)): float(v) for k, v in location_logprobs.items()},
+                                "rewrites": [float(x) for x in rewrite_logprobs]})
+        out[pre + "predictions"] = np.array(json.dumps(predictions))
     path = os.path.join(HERE, "seq_model.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path} ({os.path.getsize(path) / 1e3:.0f} kB), dropped = {out['meta/dropped'].tolist()}")

@@ -2,10 +2,7 @@
 thread per row) is compiled for the host and driven by loops (tests/emul/seq_attention_emul.cpp), then compared with the
 oracle (oracle/seq_ref.py, itself pinned to the real reference).  Covers the arithmetic, the entry (CSR) construction in
 ``ops.build_seq_attention_plan`` and the autograd wiring of ``ops.SeqEdgeAttentionFn`` — everything except the CUDA launch."""
-import ctypes
 import os
-import shutil
-import subprocess
 import sys
 
 import pytest
@@ -19,40 +16,6 @@ for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
 
 from buglab_b200 import ops  # noqa: E402
 from oracle import seq_ref  # noqa: E402
-
-
-@pytest.fixture(scope="module")
-def emulation(tmp_path_factory):
-    if shutil.which("g++") is None:
-        pytest.skip("g++ not available")
-    out = tmp_path_factory.mktemp("emul") / "libseq_attention_emul.so"
-    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas", "-o", str(out),
-                    os.path.join(ROOT, "tests", "emul", "seq_attention_emul.cpp")], check=True)
-    lib = ctypes.CDLL(str(out))
-    c_i32, c_ptr = ctypes.c_int32, ctypes.c_void_p
-    lib.emul_seq_attention_fwd.restype, lib.emul_seq_attention_fwd.argtypes = c_i32, [c_ptr] * 9 + [c_i32] * 5 + [c_ptr] * 2
-    lib.emul_seq_attention_bwd.restype, lib.emul_seq_attention_bwd.argtypes = c_i32, [c_ptr] * 12 + [c_i32] * 5 + [c_ptr] * 9
-    return lib
-
-
-@pytest.fixture()
-def host_backend(emulation, monkeypatch):
-    """Routes ops.SeqEdgeAttentionFn to the host emulation (same argument order as the C ABI, no stream)."""
-    def pointer(dtype):
-        def get(t):
-            if t is None:
-                return None
-            assert t.dtype == dtype and t.is_contiguous() and not t.is_cuda
-            return t.data_ptr()
-        return get
-
-    def fwd(*args):
-        assert emulation.emul_seq_attention_fwd(*args) == 0
-
-    def bwd(*args):
-        assert emulation.emul_seq_attention_bwd(*args) == 0
-
-    monkeypatch.setattr(ops, "_seq_attention_backend", lambda: (fwd, bwd, pointer(torch.float32), pointer(torch.int32)))
 
 
 def attention_through_the_kernels(att, x, mask, edges, edge_types, num_edge_types):

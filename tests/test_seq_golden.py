@@ -137,9 +137,15 @@ def test_projection_rejects_malformed_graphs(mirror, samples):
     assert mirror.tensorize(no_operator) is None
 
 
-def test_module_is_not_built_yet(mirror):
+def test_unbuilt_layer_types_say_so(samples):
+    from pathlib import Path
+
+    from buglab.models.modelregistry import load_model
+
+    model, _, _ = load_model({"modelName": "seq-gru", "hidden_state_size": 32}, Path("/tmp/_seq_gru.pkl.gz"))
+    model.compute_metadata(iter(samples()))
     with pytest.raises(NotImplementedError):
-        mirror.build_neural_module()
+        model.build_neural_module()
 
 
 # ------------------------------------------------------------------------------------------------ the module (oracle)
@@ -219,3 +225,90 @@ def test_oracle_module_on_the_mirrors_own_minibatch(golden, mirror, samples):
     tensors = {k: v for k, v in mb.items() if isinstance(v, torch.Tensor)}
     loss = module(**tensors)
     assert abs(float(loss.detach()) - float(golden["great/loss"])) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ the module (mirror)
+@pytest.fixture()
+def cpu_kernels(monkeypatch, request):
+    """Runs the mirror's module on the CPU: every CUDA entry point it reaches is replaced by the oracle's restatement of
+    that one op (segment ops, LayerNorm, subtoken max-pool) or, for the new attention kernels, by the host emulation of
+    the kernel source.  What is under test is the WIRING — parameter names, shapes, op order, index handling."""
+    from buglab_b200 import ops
+    from oracle import mp_ref, scatter_ref
+
+    request.getfixturevalue("host_backend")  # attention -> host emulation of csrc/seq_attention_core.h
+    monkeypatch.setattr(ops, "layer_norm", lambda x, g, b, eps=1e-5: torch.nn.functional.layer_norm(x, (x.shape[-1],), g, b, eps))
+    monkeypatch.setattr(ops, "subtoken_maxpool", lambda emb, ids, lens, p_drop=0.0, training=False:
+                        mp_ref.subtoken_maxpool_ref(emb, ids.long(), lens.long()))
+    monkeypatch.setattr(ops, "segment_log_softmax", lambda src, index, eps=1e-12, num_segments=None:
+                        scatter_ref.scatter_log_softmax(src, index.long()))
+    monkeypatch.setattr(ops, "segment_minmax", lambda src, index, dim=-1, dim_size=None, is_min=False:
+                        (scatter_ref.scatter_min if is_min else scatter_ref.scatter_max)(src, index.long(), dim, dim_size))
+    monkeypatch.setattr(ops, "segment_sum", lambda src, index, dim=-1, dim_size=None:
+                        scatter_ref.scatter_sum(src, index.long(), dim, dim_size))
+
+
+@pytest.mark.parametrize("layer_type", ["great", "rat"])
+def test_mirror_module_reproduces_reference_on_cpu_kernels(golden, samples, cpu_kernels, layer_type):
+    import logging
+    from pathlib import Path
+
+    from buglab.models.modelregistry import load_model
+
+    logging.getLogger("buglab.models.seqmodel").setLevel(logging.CRITICAL)
+    model, _, _ = load_model(dict(SPEC, modelName=f"seq-{layer_type}"), Path("/tmp/_seq_mirror2.pkl.gz"))
+    model.compute_metadata(iter(samples()))
+    nn = model.build_neural_module()
+    nn._argswap_module._input_dim = SPEC["hidden_state_size"]
+    order = list(golden[f"{layer_type}/edge_types_in_reference_order"])
+    perm = torch.tensor([order.index(kind) for kind in model.edge_types])      # mirror id -> reference id
+    inverse = torch.argsort(perm)
+    prefix = f"{layer_type}/param/"
+    state = {k[len(prefix):]: torch.from_numpy(golden[k]) for k in golden.files if k.startswith(prefix)}
+    rows = state["_SeqBugLabModule__positional_encoding"].shape[1]
+    full = nn.state_dict()["_SeqBugLabModule__positional_encoding"].clone()
+    full[:, :rows] = state["_SeqBugLabModule__positional_encoding"]
+    state["_SeqBugLabModule__positional_encoding"] = full
+    for k in list(state):
+        if "edge_attention_biases" in k or "edge_value_biases" in k:
+            state[k] = state[k][perm]
+    missing, unexpected = nn.load_state_dict(state, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)      # same parameter names as the reference module
+    nn.train()
+
+    packed = model.initialize_minibatch()
+    for t in (model.tensorize(dp) for dp in samples()):
+        if t is not None:
+            model.extend_minibatch_with(t, packed)
+    mb = model.finalize_minibatch(packed, "cpu")
+    loss = nn(**mb)
+    assert abs(float(loss.detach()) - float(golden[f"{layer_type}/loss"])) < 3e-5
+    loss.backward()
+    checked = 0
+    for name, p in nn.named_parameters():
+        key = f"{layer_type}/grad/{name}"
+        if key not in golden.files:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+            continue
+        ref = torch.from_numpy(golden[key])
+        grad = p.grad
+        if "positional_encoding" in name:
+            grad = grad[:, :rows]
+        if "edge_attention_biases" in name or "edge_value_biases" in name:
+            grad = grad[inverse]
+        tol = 3e-5 * (float(ref.abs().max()) + 1e-12) + 3e-6
+        assert float((grad - ref).abs().max()) <= tol, (name, float((grad - ref).abs().max()), tol)
+        checked += 1
+    assert checked >= 35
+    metrics = nn.report_metrics()
+    assert abs(metrics["Loss"] - float(golden[f"{layer_type}/loss"])) < 3e-5
+
+    # inference through predict(): per graph node and per rewrite log-probabilities, in the reference's order
+    expected = json.loads(str(golden[f"{layer_type}/predictions"]))
+    got = list(model.predict(iter(samples()), nn, "cpu", parallelize=False))
+    assert [dp["graph"]["path"] for dp, _, _ in got] == [e["path"] for e in expected] and len(got) == 6
+    for (dp, locations, rewrites), e in zip(got, expected):
+        assert [str(k) for k in locations] == list(e["locations"])           # same nodes, same order, NO_BUG (-1) last
+        assert max(abs(float(locations[int(k)]) - v) for k, v in e["locations"].items()) < 3e-5
+        assert len(rewrites) == len(e["rewrites"]) == len(dp["candidate_rewrites"])
+        assert max(abs(float(a) - b) for a, b in zip(rewrites, e["rewrites"])) < 3e-5
