@@ -56,3 +56,58 @@ def test_kernels_match_oracle(cuda_device, case_index):
     for name, ref in ref_grads.items():
         err = float((params[name].grad.cpu() - ref).abs().max())
         assert err <= 5e-5 * float(ref.abs().max()) + 5e-6, (name, err)
+
+
+@pytest.mark.parametrize("layer_type", ["great", "rat"])
+def test_module_matches_reference_goldens(cuda_device, layer_type):
+    """The whole sequence module on the B200 path against the real reference's loss and gradients
+    (tests/golden/seq_model.npz) — the GPU twin of test_seq_golden.test_mirror_module_reproduces_reference_on_cpu_kernels."""
+    import logging
+    from pathlib import Path
+
+    import numpy as np
+
+    import test_seq_golden as sg
+    from buglab.models.modelregistry import load_model
+    from buglab.utils.msgpackutils import load_msgpack_l_gz
+
+    golden = np.load(os.path.join(sg.GOLDEN_DIR, "seq_model.npz"), allow_pickle=True)
+    samples = lambda: list(load_msgpack_l_gz(os.path.join(sg.GOLDEN_DIR, "seq_samples.msgpack.l.gz")))  # noqa: E731
+    logging.getLogger("buglab.models.seqmodel").setLevel(logging.CRITICAL)
+    model, _, _ = load_model(dict(sg.SPEC, modelName=f"seq-{layer_type}"), Path("/tmp/_seq_gpu.pkl.gz"))
+    model.compute_metadata(iter(samples()))
+    nn = model.build_neural_module()
+    nn._argswap_module._input_dim = sg.SPEC["hidden_state_size"]
+    order = list(golden[f"{layer_type}/edge_types_in_reference_order"])
+    perm = torch.tensor([order.index(kind) for kind in model.edge_types])
+    inverse = torch.argsort(perm)
+    prefix = f"{layer_type}/param/"
+    state = {k[len(prefix):]: torch.from_numpy(golden[k]) for k in golden.files if k.startswith(prefix)}
+    rows = state["_SeqBugLabModule__positional_encoding"].shape[1]
+    full = nn.state_dict()["_SeqBugLabModule__positional_encoding"].clone()
+    full[:, :rows] = state["_SeqBugLabModule__positional_encoding"]
+    state["_SeqBugLabModule__positional_encoding"] = full
+    for k in list(state):
+        if "edge_attention_biases" in k or "edge_value_biases" in k:
+            state[k] = state[k][perm]
+    nn.load_state_dict(state)
+    nn.to(cuda_device).train()
+    packed = model.initialize_minibatch()
+    for t in (model.tensorize(dp) for dp in samples()):
+        if t is not None:
+            model.extend_minibatch_with(t, packed)
+    mb = model.finalize_minibatch(packed, cuda_device)
+    loss = nn(**mb)
+    assert abs(float(loss.detach()) - float(golden[f"{layer_type}/loss"])) < 1e-4      # north_star's fp32 tolerance
+    loss.backward()
+    for name, p in nn.named_parameters():
+        key = f"{layer_type}/grad/{name}"
+        if key not in golden.files:
+            continue
+        ref = torch.from_numpy(golden[key])
+        grad = p.grad.cpu()
+        if "positional_encoding" in name:
+            grad = grad[:, :rows]
+        if "edge_attention_biases" in name or "edge_value_biases" in name:
+            grad = grad[inverse]
+        assert float((grad - ref).abs().max()) <= 1e-4 * (float(ref.abs().max()) + 1e-12) + 1e-5, name
