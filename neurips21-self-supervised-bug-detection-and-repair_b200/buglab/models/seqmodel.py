@@ -7,7 +7,8 @@ integer bookkeeping is bit-exact against the real reference (tests/golden/seq_mo
 The module (``SeqBugLabModule``, reference seqmodel.py:65-396) runs its attention core on the hand-written
 ``bl_seq_attention_*`` kernels (first correct path; their source is pinned on the CPU through a host emulation, B200 parity
 tests are gated until they have run once), LayerNorm / subtoken embedding / segment ops on the kernels the graph model
-already uses, dense layers on library GEMMs.  Layer types ``great`` and ``rat``; ``transformer`` / ``gru`` are not built.
+already uses, dense layers on library GEMMs.  The edge-free baselines ``transformer`` / ``gru`` are torch's own layers,
+as they are in the reference.
 The arithmetic is pinned in oracle/seq_ref.py + oracle/seq_model_ref.py.
 """
 import logging
@@ -205,8 +206,8 @@ class SeqBugLabModule(ModuleWithMetrics):
                  generator_loss_type: Optional[str] = "norm-kl", rezero_mode: str = "off",
                  normalisation_mode: str = "postnorm"):
         super().__init__()
-        if layer_type not in ("great", "rat"):
-            raise NotImplementedError(f"layer type `{layer_type}`: only the relational layers (great, rat) are built")
+        if layer_type not in ("great", "rat", "transformer", "gru"):
+            raise ValueError(f"Unrecognized layer type `{layer_type}`.")
         self.__generator_loss_type = generator_loss_type
         self.__token_embedder = token_embedder
         self.__positional_encoding = nn.Parameter(torch.randn(1, 5000, embedding_dim), requires_grad=True)
@@ -214,13 +215,23 @@ class SeqBugLabModule(ModuleWithMetrics):
         self.__input_layer_norm = nn.LayerNorm(embedding_dim)
         self.__layer_type = layer_type
         self.__num_edge_types = num_edge_types
-        self.__seq_layers = nn.ModuleList([
-            RelationalTransformerEncoderLayer(
-                nhead=num_heads, num_edge_types=num_edge_types, d_model=embedding_dim,
-                key_query_dimension=embedding_dim // num_heads, value_dimension=embedding_dim // num_heads,
-                dim_feedforward=intermediate_dimension, dropout=dropout_rate,
-                use_edge_value_biases=layer_type == "rat", rezero_mode=rezero_mode, normalisation_mode=normalisation_mode)
-            for _ in range(num_layers)])
+        if layer_type in ("great", "rat"):
+            self.__seq_layers = nn.ModuleList([
+                RelationalTransformerEncoderLayer(
+                    nhead=num_heads, num_edge_types=num_edge_types, d_model=embedding_dim,
+                    key_query_dimension=embedding_dim // num_heads, value_dimension=embedding_dim // num_heads,
+                    dim_feedforward=intermediate_dimension, dropout=dropout_rate,
+                    use_edge_value_biases=layer_type == "rat", rezero_mode=rezero_mode,
+                    normalisation_mode=normalisation_mode)
+                for _ in range(num_layers)])
+        elif layer_type == "transformer":
+            # the two edge-free baselines are torch's own layers in the reference too (seqmodel.py:110-131): library code
+            self.__seq_layers = nn.ModuleList([
+                nn.TransformerEncoderLayer(d_model=embedding_dim, nhead=num_heads, dim_feedforward=intermediate_dimension,
+                                           dropout=dropout_rate) for _ in range(num_layers)])
+        else:
+            self.__seq_layers = nn.GRU(input_size=embedding_dim, hidden_size=embedding_dim // 2, num_layers=num_layers,
+                                       bidirectional=True, batch_first=True)
         self.__localization_module = LocalizationModule(embedding_dim, buggy_samples_weight_schedule=buggy_samples_weight_schedule)
         self._buggy_samples_weight_schedule = buggy_samples_weight_schedule
         self._text_repair_module = TextRepairModule(embedding_dim, rewrite_vocabulary_size)
@@ -260,14 +271,23 @@ class SeqBugLabModule(ModuleWithMetrics):
         x = self.__token_embedder(token_idxs=input_sequence_ids.reshape(B * L, T),
                                   lengths=input_seq_num_subtokens.reshape(B * L)).view(B, L, -1)
         is_token = torch.arange(L, device=x.device)[None, :] < token_sequence_lengths[:, None]
-        x = x + self.__positional_encoding[:, :L]
-        norm = self.__input_layer_norm
-        x = self.__dropout_layer(ops.layer_norm(x.reshape(B * L, -1), norm.weight, norm.bias, norm.eps).view(B, L, -1))
+        if self.__layer_type != "gru":  # positions and the BERT-style input LayerNorm are for the attention variants only
+            x = x + self.__positional_encoding[:, :L]
+            norm = self.__input_layer_norm
+            x = self.__dropout_layer(ops.layer_norm(x.reshape(B * L, -1), norm.weight, norm.bias, norm.eps).view(B, L, -1))
         x = x * is_token.unsqueeze(-1)
         padding = ~is_token
-        plan = ops.build_seq_attention_plan(edges, edge_types, token_sequence_lengths, L, self.__num_edge_types)
-        for layer in self.__seq_layers:
-            x = layer(src=x, src_mask=padding, edges=plan)
+        if self.__layer_type in ("great", "rat"):
+            plan = ops.build_seq_attention_plan(edges, edge_types, token_sequence_lengths, L, self.__num_edge_types)
+            for layer in self.__seq_layers:
+                x = layer(src=x, src_mask=padding, edges=plan)
+        elif self.__layer_type == "transformer":
+            for layer in self.__seq_layers:
+                x = layer(x.transpose(0, 1), src_key_padding_mask=padding).transpose(0, 1)
+        else:
+            packed = nn.utils.rnn.pack_padded_sequence(x, lengths=token_sequence_lengths.cpu(), batch_first=True,
+                                                       enforce_sorted=False)
+            x, _ = nn.utils.rnn.pad_packed_sequence(self.__seq_layers(packed)[0], batch_first=True)
         return x
 
     @staticmethod

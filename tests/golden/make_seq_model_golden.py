@@ -69,7 +69,7 @@ def main():
     load = lambda: list(load_msgpack_l_gz(shard))  # noqa: E731
 
     out = {}
-    for layer_type in ("great", "rat"):
+    for layer_type in ("great", "rat", "transformer", "gru"):
         torch.manual_seed(SEED)
         model, _, _ = load_model({"modelName": f"seq-{layer_type}", "hidden_state_size": HIDDEN, "dropout_rate": 0.0,
                                   "num_layers": LAYERS, "num_heads": HEADS, "intermediate_dimension_size": FF,

@@ -58,7 +58,7 @@ def test_kernels_match_oracle(cuda_device, case_index):
         assert err <= 5e-5 * float(ref.abs().max()) + 5e-6, (name, err)
 
 
-@pytest.mark.parametrize("layer_type", ["great", "rat"])
+@pytest.mark.parametrize("layer_type", ["great", "rat", "transformer", "gru"])
 def test_module_matches_reference_goldens(cuda_device, layer_type):
     """The whole sequence module on the B200 path against the real reference's loss and gradients
     (tests/golden/seq_model.npz) — the GPU twin of test_seq_golden.test_mirror_module_reproduces_reference_on_cpu_kernels."""

@@ -137,15 +137,11 @@ def test_projection_rejects_malformed_graphs(mirror, samples):
     assert mirror.tensorize(no_operator) is None
 
 
-def test_unbuilt_layer_types_say_so(samples):
-    from pathlib import Path
+def test_unknown_layer_type_is_rejected():
+    from buglab.models.seqmodel import SeqBugLabModel
 
-    from buglab.models.modelregistry import load_model
-
-    model, _, _ = load_model({"modelName": "seq-gru", "hidden_state_size": 32}, Path("/tmp/_seq_gru.pkl.gz"))
-    model.compute_metadata(iter(samples()))
-    with pytest.raises(NotImplementedError):
-        model.build_neural_module()
+    with pytest.raises(ValueError):
+        SeqBugLabModel(32, 100, 0.0, layer_type="lstm")
 
 
 # ------------------------------------------------------------------------------------------------ the module (oracle)
@@ -248,7 +244,7 @@ def cpu_kernels(monkeypatch, request):
                         scatter_ref.scatter_sum(src, index.long(), dim, dim_size))
 
 
-@pytest.mark.parametrize("layer_type", ["great", "rat"])
+@pytest.mark.parametrize("layer_type", ["great", "rat", "transformer", "gru"])
 def test_mirror_module_reproduces_reference_on_cpu_kernels(golden, samples, cpu_kernels, layer_type):
     import logging
     from pathlib import Path
