@@ -43,12 +43,50 @@ struct Problem {
     const int32_t* col_tab;
 };
 
+// Rows are D * 4 bytes with D a multiple of 4 and come from 256-byte aligned allocations, so every row can be read in
+// 16-byte pieces (LDG.128 on the device; the row pointers are uniform across a warp -> one broadcast transaction).
+struct alignas(16) F4 { float x, y, z, w; };
+BL_HD F4 load4(const float* p) { return *reinterpret_cast<const F4*>(p); }
+
+// <a, b> with `a` in registers (or anywhere) and `b` a row in memory
 template <int D>
 BL_HD float dot(const float* a, const float* b) {
     float s = 0.f;
 #pragma unroll
-    for (int d = 0; d < D; ++d) s = fmaf(a[d], b[d], s);
+    for (int d = 0; d < D; d += 4) {
+        const F4 v = load4(b + d);
+        s = fmaf(a[d], v.x, s);
+        s = fmaf(a[d + 1], v.y, s);
+        s = fmaf(a[d + 2], v.z, s);
+        s = fmaf(a[d + 3], v.w, s);
+    }
     return s;
+}
+
+// acc = acc * keep + w * row
+template <int D>
+BL_HD void scale_add(float* acc, float keep, float w, const float* row) {
+#pragma unroll
+    for (int d = 0; d < D; d += 4) {
+        const F4 v = load4(row + d);
+        acc[d] = fmaf(w, v.x, acc[d] * keep);
+        acc[d + 1] = fmaf(w, v.y, acc[d + 1] * keep);
+        acc[d + 2] = fmaf(w, v.z, acc[d + 2] * keep);
+        acc[d + 3] = fmaf(w, v.w, acc[d + 3] * keep);
+    }
+}
+
+// acc += w * row
+template <int D>
+BL_HD void axpy(float* acc, float w, const float* row) {
+#pragma unroll
+    for (int d = 0; d < D; d += 4) {
+        const F4 v = load4(row + d);
+        acc[d] = fmaf(w, v.x, acc[d]);
+        acc[d + 1] = fmaf(w, v.y, acc[d + 1]);
+        acc[d + 2] = fmaf(w, v.z, acc[d + 2]);
+        acc[d + 3] = fmaf(w, v.w, acc[d + 3]);
+    }
 }
 
 // ---- forward: out[b, h, i, :], lse[b, h, i] ------------------------------------------------------------------------
@@ -81,15 +119,9 @@ BL_HD void forward_row(const Problem& p, int b, int h, int i, float* out, float*
         const float rescale = expf(m - m_new);   // 0 on the first key (m = -inf)
         const float w = expf(s - m_new);
         l = l * rescale + w;
-        const float* vrow = p.v + (head + j) * D;
-#pragma unroll
-        for (int d = 0; d < D; ++d) acc[d] = acc[d] * rescale + w * vrow[d];
+        scale_add<D>(acc, rescale, w, p.v + (head + j) * D);
         if (p.vbias != nullptr) {
-            for (int f = e_first; f < e; ++f) {
-                const float* vb = p.vbias + ((size_t)p.row_tab[f] * p.H + h) * D;
-#pragma unroll
-                for (int d = 0; d < D; ++d) acc[d] = fmaf(w, vb[d], acc[d]);
-            }
+            for (int f = e_first; f < e; ++f) axpy<D>(acc, w, p.vbias + ((size_t)p.row_tab[f] * p.H + h) * D);
         }
         m = m_new;
     }
@@ -142,14 +174,12 @@ BL_HD void backward_row(const Problem& p, const float* out, const float* lse, co
         }
         const float prob = expf(s - row_lse);
         const float ds = prob * (dp - delta);
-        const float* krow = p.k + (head + j) * D;
-#pragma unroll
-        for (int d = 0; d < D; ++d) acc[d] = fmaf(ds, krow[d], acc[d]);
+        axpy<D>(acc, ds, p.k + (head + j) * D);
         for (int f = e_first; f < e; ++f) {
-            const float* brow = p.bias + ((size_t)p.row_tab[f] * p.H + h) * D;
+            axpy<D>(acc, ds, p.bias + ((size_t)p.row_tab[f] * p.H + h) * D);
             float* db = d_entry_bias + ((size_t)f * p.H + h) * D;
 #pragma unroll
-            for (int d = 0; d < D; ++d) { acc[d] = fmaf(ds, brow[d], acc[d]); db[d] = ds * q[d]; }
+            for (int d = 0; d < D; ++d) db[d] = ds * q[d];
             if (d_entry_vbias != nullptr) {
                 float* dvb = d_entry_vbias + ((size_t)f * p.H + h) * D;
 #pragma unroll
@@ -191,17 +221,27 @@ BL_HD void backward_col(const Problem& p, const float* lse, const float* delta, 
     for (int i = 0; i < len; ++i) {
         const float* qrow = p.q + (head + i) * D;
         const float* grow = d_out + (head + i) * D;
-        float s = dot<D>(qrow, kk);
-        float dp = dot<D>(grow, vv);
+        float s = dot<D>(kk, qrow);
+        float dp = dot<D>(vv, grow);
         while (e < e_end && p.col_query[e] == i) {
-            s += dot<D>(qrow, p.bias + ((size_t)p.col_tab[e] * p.H + h) * D);
-            if (p.vbias != nullptr) dp += dot<D>(grow, p.vbias + ((size_t)p.col_tab[e] * p.H + h) * D);
+            // two rows in memory: stage the table row in registers once per entry (entries are rare)
+            float tab[D];
+            const float* brow = p.bias + ((size_t)p.col_tab[e] * p.H + h) * D;
+#pragma unroll
+            for (int d = 0; d < D; ++d) tab[d] = brow[d];
+            s += dot<D>(tab, qrow);
+            if (p.vbias != nullptr) {
+                const float* vbrow = p.vbias + ((size_t)p.col_tab[e] * p.H + h) * D;
+#pragma unroll
+                for (int d = 0; d < D; ++d) tab[d] = vbrow[d];
+                dp += dot<D>(tab, grow);
+            }
             ++e;
         }
         const float prob = expf(s - lse[head + i]);
         const float ds = prob * (dp - delta[head + i]);
-#pragma unroll
-        for (int d = 0; d < D; ++d) { acc_k[d] = fmaf(ds, qrow[d], acc_k[d]); acc_v[d] = fmaf(prob, grow[d], acc_v[d]); }
+        axpy<D>(acc_k, ds, qrow);
+        axpy<D>(acc_v, prob, grow);
     }
 #pragma unroll
     for (int d = 0; d < D; ++d) { dkrow[d] = acc_k[d]; dvrow[d] = acc_v[d]; }
