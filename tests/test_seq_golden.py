@@ -308,3 +308,21 @@ def test_mirror_module_reproduces_reference_on_cpu_kernels(golden, samples, cpu_
         assert max(abs(float(locations[int(k)]) - v) for k, v in e["locations"].items()) < 3e-5
         assert len(rewrites) == len(e["rewrites"]) == len(dp["candidate_rewrites"])
         assert max(abs(float(a) - b) for a, b in zip(rewrites, e["rewrites"])) < 3e-5
+
+
+def test_shard_dataset_serves_sequence_models_through_the_host_path(mirror, samples, tmp_path):
+    """The native shard tensoriser is for the graph models; a sequence model asking a ShardDataset for tensors gets the
+    reference-shaped chain (explicitly, with a log line), and the trainer-facing output shape is the same."""
+    from buglab.utils.msgpackutils import save_msgpack_l_gz
+    from buglab_b200.shards import ShardDataset
+    from dpu_utils.utils import RichPath
+
+    save_msgpack_l_gz(samples(), str(tmp_path / "a.msgpack.l.gz"))
+    dataset = ShardDataset(RichPath.create(str(tmp_path)), num_threads=1)
+    got = list(dataset.tensorized(mirror))
+    expected = [t for t in (mirror.tensorize(dp) for dp in samples()) if t is not None]
+    assert len(got) == len(expected) == 6 and all(raw is None for _, raw in got)
+    for (t, _), e in zip(got, expected):
+        assert t.candidate_location_idxs.tolist() == e.candidate_location_idxs.tolist()
+        assert t.intra_token_edges == e.intra_token_edges and t.node_mappings == e.node_mappings
+    assert dataset.tensorizer is None      # no native tensoriser was built for this model family
