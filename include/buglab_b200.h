@@ -278,19 +278,22 @@ int bl_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
  *   "entries" = the two directions of every typed edge (b, s, t, type): (row s, key t, table type), (row t, key s, table
  *   T + type).  row_ptr[B*L+1] / row_key / row_tab list them grouped by (b, query row) with ascending keys; col_ptr /
  *   col_query / col_tab list the same entries grouped by (b, key) with ascending query rows.  Duplicates add up.
+ *   p_drop / seed: dropout on the attention probabilities (multihead_attention.py:77), counter-based mask over
+ *   (seed, b, h, query, key) as in the other kernels; pass the same pair to the backward call.
  * STATUS: first correct path (fp32 CUDA cores, one thread per row).  The arithmetic is pinned against the oracle through
  * the host emulation of the same source (csrc/seq_attention_core.h); B200 parity tests are gated until they have run.
  * ------------------------------------------------------------------------------------------------ */
 int bl_seq_attention_supported(int32_t head_dim);
 int bl_seq_attention_fwd(const float* q, const float* k, const float* v, const int32_t* lengths, const float* bias,
                          const float* vbias, const int32_t* row_ptr, const int32_t* row_key, const int32_t* row_tab,
-                         int32_t B, int32_t H, int32_t L, int32_t D, int32_t T2, float* out, float* lse, bl_stream_t stream);
+                         int32_t B, int32_t H, int32_t L, int32_t D, int32_t T2, float p_drop, uint64_t seed,
+                         float* out, float* lse, bl_stream_t stream);
 /* dq, dk, dv: [B, H, L, D];  d_entry_bias (and d_entry_vbias when vbias != NULL): [entries, H, D] in row order — the caller
  * sums them into the tables by row_tab;  delta[B, H, L] is scratch. */
 int bl_seq_attention_bwd(const float* q, const float* k, const float* v, const int32_t* lengths, const float* bias,
                          const float* vbias, const int32_t* row_ptr, const int32_t* row_key, const int32_t* row_tab,
                          const int32_t* col_ptr, const int32_t* col_query, const int32_t* col_tab,
-                         int32_t B, int32_t H, int32_t L, int32_t D, int32_t T2,
+                         int32_t B, int32_t H, int32_t L, int32_t D, int32_t T2, float p_drop, uint64_t seed,
                          const float* out, const float* lse, const float* d_out, float* dq, float* dk, float* dv,
                          float* d_entry_bias, float* d_entry_vbias, float* delta, bl_stream_t stream);
 

@@ -24,9 +24,7 @@ class MultiheadAttention(nn.Module):
     def __init__(self, *, num_heads: int, input_state_dimension: int, key_query_dimension: int, value_dimension: int,
                  output_dimension: int, dropout_rate: float):
         super().__init__()
-        if dropout_rate > 0:
-            raise NotImplementedError("attention-probability dropout is not fused into the B200 attention kernel yet; "
-                                      "run the sequence models with dropout_rate=0")
+        self._dropout_rate = float(dropout_rate)  # on the attention probabilities, inside the attention kernel
         self._num_heads, self._key_query_dim, self._value_dim = num_heads, key_query_dimension, value_dimension
         self._selfatt_head_transforms = nn.Linear(input_state_dimension,
                                                   num_heads * (2 * key_query_dimension + value_dimension), bias=False)
@@ -81,7 +79,7 @@ class RelationalMultiheadAttention(MultiheadAttention):
         if self._use_edge_value_biases:
             vbias = torch.cat((self._edge_value_biases.weight, self._reverse_edge_value_biases.weight)
                               ).view(-1, H, self._value_dim)
-        return self._merge(ops.seq_edge_attention(q, k, v, bias, vbias, plan))
+        return self._merge(ops.seq_edge_attention(q, k, v, bias, vbias, plan, self._dropout_rate, self.training))
 
 
 class RelationalTransformerEncoderLayer(nn.Module):

@@ -63,8 +63,8 @@ _SIGNATURES = {
     "bl_grad_sqnorm": (c_i32, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
     "bl_adam_step": (c_i32, [c_ptr] * 4 + [c_i64, c_f32, c_f32, c_f32, c_f32, c_i64, c_f32, c_ptr, c_f32, c_ptr]),
     "bl_seq_attention_supported": (c_i32, [c_i32]),
-    "bl_seq_attention_fwd": (c_i32, [c_ptr] * 9 + [c_i32] * 5 + [c_ptr, c_ptr, c_ptr]),
-    "bl_seq_attention_bwd": (c_i32, [c_ptr] * 12 + [c_i32] * 5 + [c_ptr] * 9 + [c_ptr]),
+    "bl_seq_attention_fwd": (c_i32, [c_ptr] * 9 + [c_i32] * 5 + [c_f32, c_u64] + [c_ptr, c_ptr, c_ptr]),
+    "bl_seq_attention_bwd": (c_i32, [c_ptr] * 12 + [c_i32] * 5 + [c_f32, c_u64] + [c_ptr] * 9 + [c_ptr]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -726,7 +726,7 @@ class SeqEdgeAttentionFn(torch.autograd.Function):
     """out[b, h, i] = sum_j softmax_j(<q_i, k_j> + edge terms) (v_j + edge value terms); q, k, v: [B, H, L, D] fp32."""
 
     @staticmethod
-    def forward(ctx, q, k, v, bias, vbias, plan: SeqAttentionPlan):
+    def forward(ctx, q, k, v, bias, vbias, plan: SeqAttentionPlan, p_drop: float = 0.0, seed: int = 0):
         fwd, _, fp, ip = _seq_attention_backend()
         q, k, v, bias = q.contiguous(), k.contiguous(), v.contiguous(), bias.contiguous()
         vbias = vbias.contiguous() if vbias is not None else None
@@ -737,8 +737,9 @@ class SeqEdgeAttentionFn(torch.autograd.Function):
         out = torch.empty_like(q)
         lse = torch.empty((B, H, L), device=q.device, dtype=torch.float32)
         fwd(fp(q), fp(k), fp(v), ip(plan.lengths), fp(bias), fp(vbias) if vbias is not None else None, ip(plan.row_ptr),
-            ip(plan.row_key), ip(plan.row_tab), B, H, L, D, plan.num_tables, fp(out), fp(lse))
+            ip(plan.row_key), ip(plan.row_tab), B, H, L, D, plan.num_tables, float(p_drop), int(seed), fp(out), fp(lse))
         ctx.plan = plan
+        ctx.dropout = (float(p_drop), int(seed))
         ctx.has_vbias = vbias is not None
         ctx.save_for_backward(q, k, v, bias, vbias if vbias is not None else bias.new_zeros(0), out, lse)
         return out
@@ -758,16 +759,20 @@ class SeqEdgeAttentionFn(torch.autograd.Function):
         delta = torch.empty((B, H, L), device=q.device, dtype=torch.float32)
         bwd(fp(q), fp(k), fp(v), ip(plan.lengths), fp(bias), fp(vbias) if vbias is not None else None, ip(plan.row_ptr),
             ip(plan.row_key), ip(plan.row_tab), ip(plan.col_ptr), ip(plan.col_query), ip(plan.col_tab), B, H, L, D,
-            plan.num_tables, fp(out), fp(lse), fp(d_out), fp(dq), fp(dk), fp(dv), fp(d_entry_bias),
+            plan.num_tables, ctx.dropout[0], ctx.dropout[1], fp(out), fp(lse), fp(d_out), fp(dq), fp(dk), fp(dv),
+            fp(d_entry_bias),
             fp(d_entry_vbias) if d_entry_vbias is not None else None, fp(delta))
         tabs = plan.row_tab.long()
         d_bias = torch.zeros_like(bias).index_add_(0, tabs, d_entry_bias[:entries])
         d_vbias = torch.zeros_like(vbias).index_add_(0, tabs, d_entry_vbias[:entries]) if vbias is not None else None
-        return dq, dk, dv, d_bias, d_vbias, None
+        return dq, dk, dv, d_bias, d_vbias, None, None, None
 
 
-def seq_edge_attention(q, k, v, bias, vbias, plan: SeqAttentionPlan) -> torch.Tensor:
-    return SeqEdgeAttentionFn.apply(q, k, v, bias, vbias, plan)
+def seq_edge_attention(q, k, v, bias, vbias, plan: SeqAttentionPlan, p_drop: float = 0.0, training: bool = False) -> torch.Tensor:
+    """``p_drop``: dropout on the attention probabilities (active when ``training``); the mask is a pure function of a fresh
+    seed and the (sample, head, query, key) index, recomputed in backward."""
+    p = float(p_drop) if training else 0.0
+    return SeqEdgeAttentionFn.apply(q, k, v, bias, vbias, plan, p, fresh_seed() if p > 0 else 0)
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -51,8 +51,9 @@ static bool supported_head_dim(int D) { return D == 8 || D == 16 || D == 32 || D
 static seqatt::Problem make_problem(const float* q, const float* k, const float* v, const int32_t* lengths, const float* bias,
                                     const float* vbias, const int32_t* row_ptr, const int32_t* row_key, const int32_t* row_tab,
                                     const int32_t* col_ptr, const int32_t* col_query, const int32_t* col_tab, int B, int H, int L,
-                                    int T2) {
+                                    int T2, float p_drop, uint64_t seed) {
     seqatt::Problem p;
+    p.p_drop = p_drop; p.seed = seed;
     p.B = B; p.H = H; p.L = L; p.T2 = T2;
     p.q = q; p.k = k; p.v = v; p.lengths = lengths; p.bias = bias; p.vbias = vbias;
     p.row_ptr = row_ptr; p.row_key = row_key; p.row_tab = row_tab;
@@ -66,16 +67,17 @@ extern "C" int bl_seq_attention_supported(int32_t head_dim) { return bl::support
 
 extern "C" int bl_seq_attention_fwd(const float* q, const float* k, const float* v, const int32_t* lengths, const float* bias,
                                     const float* vbias, const int32_t* row_ptr, const int32_t* row_key,
-                                    const int32_t* row_tab, int32_t B, int32_t H, int32_t L, int32_t D, int32_t T2, float* out,
-                                    float* lse, bl_stream_t stream_) {
+                                    const int32_t* row_tab, int32_t B, int32_t H, int32_t L, int32_t D, int32_t T2, float p_drop,
+                                    uint64_t seed, float* out, float* lse, bl_stream_t stream_) {
     using namespace bl;
     if (!q || !k || !v || !lengths || !bias || !row_ptr || !out || !lse) return BL_ERR_INVALID_ARGUMENT;
     if (B < 0 || H <= 0 || L <= 0 || T2 <= 0 || !supported_head_dim(D)) return BL_ERR_UNSUPPORTED;
+    if (!(p_drop >= 0.f && p_drop < 1.f)) return BL_ERR_INVALID_ARGUMENT;
     const int64_t rows = (int64_t)B * H * L;
     if (rows == 0) return BL_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     const seqatt::Problem p = make_problem(q, k, v, lengths, bias, vbias, row_ptr, row_key, row_tab, nullptr, nullptr, nullptr,
-                                           B, H, L, T2);
+                                           B, H, L, T2, p_drop, seed);
     const unsigned grid = grid_for(rows, 128);
     switch (D) {
         case 8: seq_attention_fwd_kernel<8><<<grid, 128, 0, stream>>>(p, out, lse); break;
@@ -90,8 +92,9 @@ extern "C" int bl_seq_attention_bwd(const float* q, const float* k, const float*
                                     const float* vbias, const int32_t* row_ptr, const int32_t* row_key,
                                     const int32_t* row_tab, const int32_t* col_ptr, const int32_t* col_query,
                                     const int32_t* col_tab, int32_t B, int32_t H, int32_t L, int32_t D, int32_t T2,
-                                    const float* out, const float* lse, const float* d_out, float* dq, float* dk, float* dv,
-                                    float* d_entry_bias, float* d_entry_vbias, float* delta, bl_stream_t stream_) {
+                                    float p_drop, uint64_t seed, const float* out, const float* lse, const float* d_out,
+                                    float* dq, float* dk, float* dv, float* d_entry_bias, float* d_entry_vbias, float* delta,
+                                    bl_stream_t stream_) {
     using namespace bl;
     if (!q || !k || !v || !lengths || !bias || !row_ptr || !col_ptr || !out || !lse || !d_out || !dq || !dk || !dv || !delta)
         return BL_ERR_INVALID_ARGUMENT;
@@ -100,8 +103,9 @@ extern "C" int bl_seq_attention_bwd(const float* q, const float* k, const float*
     const int64_t rows = (int64_t)B * H * L;
     if (rows == 0) return BL_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (!(p_drop >= 0.f && p_drop < 1.f)) return BL_ERR_INVALID_ARGUMENT;
     const seqatt::Problem p = make_problem(q, k, v, lengths, bias, vbias, row_ptr, row_key, row_tab, col_ptr, col_query, col_tab,
-                                           B, H, L, T2);
+                                           B, H, L, T2, p_drop, seed);
     const unsigned grid = grid_for(rows, 128);
 #define BL_LAUNCH_BWD(DD)                                                                                                   \
     seq_attention_bwd_row_kernel<DD><<<grid, 128, 0, stream>>>(p, out, lse, d_out, dq, d_entry_bias, d_entry_vbias, delta);  \

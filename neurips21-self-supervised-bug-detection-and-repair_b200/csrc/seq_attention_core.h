@@ -4,7 +4,8 @@
 // edge_attention_bias_is_scalar == False (the only mode the registry builds, seqmodel.py:93-107):
 //     s[i, j]  = <q_i, k_j> + sum over entries e of row i with key j of <q_i, bias[tab_e]>          (q is pre-scaled)
 //     p[i, :]  = softmax over the unmasked keys j < len
-//     o_i      = sum_j p[i, j] * (v_j + sum over entries e of (i, j) of vbias[tab_e])                (vbias: "rat" only)
+//     p'[i, j] = p[i, j] * keep(seed, b, h, i, j) / (1 - p_drop)      (dropout on the probabilities, multihead_attention.py:77)
+//     o_i      = sum_j p'[i, j] * (v_j + sum over entries e of (i, j) of vbias[tab_e])               (vbias: "rat" only)
 // An "entry" is one direction of one typed edge: edge (b, s, t, type) gives (row s, key t, table type) and
 // (row t, key s, table T + type); repeated entries add up (index_put_(accumulate=True), :105-109, :172-176).
 //
@@ -41,7 +42,21 @@ struct Problem {
     const int32_t* col_ptr;
     const int32_t* col_query;
     const int32_t* col_tab;
+    float p_drop;               // dropout probability on the attention probabilities (0 = off)
+    uint64_t seed;              // counter-based mask: element (b, h, i, j) is kept iff u(seed, index) >= p_drop
 };
+
+// Same counter-based generator as the other kernels (common.cuh hash_u32 / keep_element): splitmix64 finaliser.
+BL_HD float dropout_scale(const Problem& p, int b, int h, int i, int j) {
+    if (p.p_drop <= 0.f) return 1.f;
+    const uint64_t idx = (((uint64_t)b * p.H + h) * p.L + i) * p.L + j;
+    uint64_t z = p.seed + idx * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    const float u = (float)((uint32_t)(z >> 32) >> 8) * (1.0f / 16777216.0f);
+    return u >= p.p_drop ? 1.f / (1.f - p.p_drop) : 0.f;
+}
 
 // Rows are D * 4 bytes with D a multiple of 4 and come from 256-byte aligned allocations, so every row can be read in
 // 16-byte pieces (LDG.128 on the device; the row pointers are uniform across a warp -> one broadcast transaction).
@@ -119,9 +134,10 @@ BL_HD void forward_row(const Problem& p, int b, int h, int i, float* out, float*
         const float rescale = expf(m - m_new);   // 0 on the first key (m = -inf)
         const float w = expf(s - m_new);
         l = l * rescale + w;
-        scale_add<D>(acc, rescale, w, p.v + (head + j) * D);
+        const float wm = w * dropout_scale(p, b, h, i, j);   // the normaliser l sees the undropped weight
+        scale_add<D>(acc, rescale, wm, p.v + (head + j) * D);
         if (p.vbias != nullptr) {
-            for (int f = e_first; f < e; ++f) axpy<D>(acc, w, p.vbias + ((size_t)p.row_tab[f] * p.H + h) * D);
+            for (int f = e_first; f < e; ++f) axpy<D>(acc, wm, p.vbias + ((size_t)p.row_tab[f] * p.H + h) * D);
         }
         m = m_new;
     }
@@ -173,7 +189,8 @@ BL_HD void backward_row(const Problem& p, const float* out, const float* lse, co
             ++e;
         }
         const float prob = expf(s - row_lse);
-        const float ds = prob * (dp - delta);
+        const float mask = dropout_scale(p, b, h, i, j);
+        const float ds = prob * (mask * dp - delta);
         axpy<D>(acc, ds, p.k + (head + j) * D);
         for (int f = e_first; f < e; ++f) {
             axpy<D>(acc, ds, p.bias + ((size_t)p.row_tab[f] * p.H + h) * D);
@@ -183,7 +200,7 @@ BL_HD void backward_row(const Problem& p, const float* out, const float* lse, co
             if (d_entry_vbias != nullptr) {
                 float* dvb = d_entry_vbias + ((size_t)f * p.H + h) * D;
 #pragma unroll
-                for (int d = 0; d < D; ++d) dvb[d] = prob * g[d];
+                for (int d = 0; d < D; ++d) dvb[d] = prob * mask * g[d];
             }
         }
     }
@@ -239,9 +256,10 @@ BL_HD void backward_col(const Problem& p, const float* lse, const float* delta, 
             ++e;
         }
         const float prob = expf(s - lse[head + i]);
-        const float ds = prob * (dp - delta[head + i]);
+        const float mask = dropout_scale(p, b, h, i, j);
+        const float ds = prob * (mask * dp - delta[head + i]);
         axpy<D>(acc_k, ds, qrow);
-        axpy<D>(acc_v, prob, grow);
+        axpy<D>(acc_v, prob * mask, grow);
     }
 #pragma unroll
     for (int d = 0; d < D; ++d) { dkrow[d] = acc_k[d]; dvrow[d] = acc_v[d]; }

@@ -38,8 +38,8 @@ def emulation(tmp_path_factory):
                     os.path.join(ROOT, "tests", "emul", "seq_attention_emul.cpp")], check=True)
     lib = ctypes.CDLL(str(out))
     c_i32, c_ptr = ctypes.c_int32, ctypes.c_void_p
-    lib.emul_seq_attention_fwd.restype, lib.emul_seq_attention_fwd.argtypes = c_i32, [c_ptr] * 9 + [c_i32] * 5 + [c_ptr] * 2
-    lib.emul_seq_attention_bwd.restype, lib.emul_seq_attention_bwd.argtypes = c_i32, [c_ptr] * 12 + [c_i32] * 5 + [c_ptr] * 9
+    lib.emul_seq_attention_fwd.restype, lib.emul_seq_attention_fwd.argtypes = c_i32, [c_ptr] * 9 + [c_i32] * 5 + [ctypes.c_float, ctypes.c_uint64] + [c_ptr] * 2
+    lib.emul_seq_attention_bwd.restype, lib.emul_seq_attention_bwd.argtypes = c_i32, [c_ptr] * 12 + [c_i32] * 5 + [ctypes.c_float, ctypes.c_uint64] + [c_ptr] * 9
     return lib
 
 

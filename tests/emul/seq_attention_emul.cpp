@@ -7,8 +7,10 @@ namespace {
 
 seqatt::Problem make(const float* q, const float* k, const float* v, const int32_t* lengths, const float* bias,
                      const float* vbias, const int32_t* row_ptr, const int32_t* row_key, const int32_t* row_tab,
-                     const int32_t* col_ptr, const int32_t* col_query, const int32_t* col_tab, int B, int H, int L, int T2) {
+                     const int32_t* col_ptr, const int32_t* col_query, const int32_t* col_tab, int B, int H, int L, int T2,
+                     float p_drop, uint64_t seed) {
     seqatt::Problem p;
+    p.p_drop = p_drop; p.seed = seed;
     p.B = B; p.H = H; p.L = L; p.T2 = T2;
     p.q = q; p.k = k; p.v = v; p.lengths = lengths; p.bias = bias; p.vbias = vbias;
     p.row_ptr = row_ptr; p.row_key = row_key; p.row_tab = row_tab;
@@ -39,9 +41,10 @@ void bwd(const seqatt::Problem& p, const float* out, const float* lse, const flo
 
 extern "C" int emul_seq_attention_fwd(const float* q, const float* k, const float* v, const int32_t* lengths, const float* bias,
                                       const float* vbias, const int32_t* row_ptr, const int32_t* row_key,
-                                      const int32_t* row_tab, int32_t B, int32_t H, int32_t L, int32_t D, int32_t T2, float* out,
-                                      float* lse) {
-    const seqatt::Problem p = make(q, k, v, lengths, bias, vbias, row_ptr, row_key, row_tab, nullptr, nullptr, nullptr, B, H, L, T2);
+                                      const int32_t* row_tab, int32_t B, int32_t H, int32_t L, int32_t D, int32_t T2, float p_drop,
+                                      uint64_t seed, float* out, float* lse) {
+    const seqatt::Problem p = make(q, k, v, lengths, bias, vbias, row_ptr, row_key, row_tab, nullptr, nullptr, nullptr, B, H, L, T2,
+                                   p_drop, seed);
     switch (D) {
         case 8: fwd<8>(p, out, lse); return 0;
         case 16: fwd<16>(p, out, lse); return 0;
@@ -55,9 +58,10 @@ extern "C" int emul_seq_attention_bwd(const float* q, const float* k, const floa
                                       const float* vbias, const int32_t* row_ptr, const int32_t* row_key,
                                       const int32_t* row_tab, const int32_t* col_ptr, const int32_t* col_query,
                                       const int32_t* col_tab, int32_t B, int32_t H, int32_t L, int32_t D, int32_t T2,
-                                      const float* out, const float* lse, const float* d_out, float* dq, float* dk, float* dv,
-                                      float* d_entry_bias, float* d_entry_vbias, float* delta) {
-    const seqatt::Problem p = make(q, k, v, lengths, bias, vbias, row_ptr, row_key, row_tab, col_ptr, col_query, col_tab, B, H, L, T2);
+                                      float p_drop, uint64_t seed, const float* out, const float* lse, const float* d_out,
+                                      float* dq, float* dk, float* dv, float* d_entry_bias, float* d_entry_vbias, float* delta) {
+    const seqatt::Problem p = make(q, k, v, lengths, bias, vbias, row_ptr, row_key, row_tab, col_ptr, col_query, col_tab, B, H, L, T2,
+                                   p_drop, seed);
     switch (D) {
         case 8: bwd<8>(p, out, lse, d_out, dq, dk, dv, d_entry_bias, d_entry_vbias, delta); return 0;
         case 16: bwd<16>(p, out, lse, d_out, dq, dk, dv, d_entry_bias, d_entry_vbias, delta); return 0;

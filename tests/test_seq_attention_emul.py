@@ -131,3 +131,79 @@ def test_golden_layer_cases_through_the_kernel_source(host_backend):
             if key in golden.files:
                 ref = torch.from_numpy(golden[key])
                 assert float((p.grad - ref).abs().max()) <= 2e-5 * float(ref.abs().max()) + 2e-6, (name, pname)
+
+
+def dropout_scale_table(seed: int, B: int, H: int, L: int, p_drop: float) -> torch.Tensor:
+    """The kernels' counter-based mask (csrc/seq_attention_core.h::dropout_scale) restated with numpy uint64 arithmetic."""
+    import numpy as np
+
+    idx = np.arange(B * H * L * L, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + idx * np.uint64(0x9E3779B97F4A7C15) + np.uint64(0x632BE59BD9B4E019)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    u = ((z >> np.uint64(32)).astype(np.uint32) >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    scale = np.where(u >= np.float32(p_drop), np.float32(1.0) / (np.float32(1.0) - np.float32(p_drop)), np.float32(0.0))
+    return torch.from_numpy(scale.reshape(B, H, L, L).astype(np.float32))
+
+
+@pytest.mark.parametrize("value_biases", [False, True])
+def test_attention_probability_dropout(host_backend, value_biases):
+    """Dropout on the probabilities (multihead_attention.py:77), fused into the kernels with a counter-based mask: same
+    result as masking the oracle's probabilities with that mask, forward and backward; about p_drop of the mass is dropped."""
+    seed, p_drop = 123456789012345, 0.3
+    att, x, mask, edges, edge_types, weights = random_case(11, 2, 10, 30, 32, 4, 3, value_biases)
+    B, L, _ = x.shape
+    H, dk = att._num_heads, att._key_query_dim
+    keep = ~mask
+    lengths = keep.sum(dim=1)
+    plan = ops.build_seq_attention_plan(edges, edge_types, lengths, L, 3)
+    scale = dropout_scale_table(seed, B, H, L, p_drop)
+    assert 0.2 < float((scale == 0).float().mean()) < 0.4
+
+    def tables():
+        bias = torch.cat((att._edge_attention_biases.weight, att._reverse_edge_attention_biases.weight)).view(-1, H, dk)
+        vbias = (torch.cat((att._edge_value_biases.weight, att._reverse_edge_value_biases.weight)).view(-1, H, dk)
+                 if value_biases else None)
+        return bias, vbias
+
+    # oracle arithmetic with the explicit mask
+    q, k, v = att.project(x)
+    sample, src, tgt = edges[:, 0], edges[:, 1], edges[:, 2]
+    fwd, rev = att.edge_score_terms(sample, src, tgt, edge_types, q, k)
+    scores = seq_ref._accumulate_scores(q @ k.transpose(-1, -2), sample, src, tgt, fwd, rev)
+    probs = torch.softmax(scores.masked_fill(mask[:, None, None, :], float("-inf")), dim=-1) * scale
+    out = probs @ v
+    if value_biases:
+        _, vbias = tables()
+        T = 3
+        out = seq_ref._accumulate_rows(out, sample, src, tgt, probs[sample, :, src, tgt].unsqueeze(-1) * vbias[edge_types],
+                                       probs[sample, :, tgt, src].unsqueeze(-1) * vbias[T + edge_types])
+    expected = att.merge(out)
+    (expected * weights).sum().backward()
+    ref_dx = x.grad.clone()
+    ref_grads = {n: p.grad.clone() for n, p in att.named_parameters()}
+    x.grad = None
+    att.zero_grad()
+
+    q, k, v = att.project(x)
+    bias, vbias = tables()
+    got = att.merge(ops.SeqEdgeAttentionFn.apply(q, k, v, bias, vbias, plan, p_drop, seed))
+    assert float((got - expected).detach()[keep].abs().max()) < 3e-6
+    (got * weights).sum().backward()
+    assert float((x.grad - ref_dx).abs().max()) <= 2e-5 * float(ref_dx.abs().max()) + 2e-6
+    for name, p in att.named_parameters():
+        ref = ref_grads[name]
+        assert float((p.grad - ref).abs().max()) <= 2e-5 * float(ref.abs().max()) + 2e-6, name
+
+    # eval mode / p = 0 is the undropped attention; training mode draws a fresh seed per call
+    plain = ops.seq_edge_attention(q.detach(), k.detach(), v.detach(), bias.detach(), None if vbias is None else vbias.detach(),
+                                   plan, p_drop, training=False)
+    again = ops.seq_edge_attention(q.detach(), k.detach(), v.detach(), bias.detach(), None if vbias is None else vbias.detach(),
+                                   plan, 0.0, training=True)
+    assert torch.equal(plain, again)
+    torch.manual_seed(1)
+    a = ops.seq_edge_attention(q.detach(), k.detach(), v.detach(), bias.detach(), None, plan, p_drop, training=True)
+    b = ops.seq_edge_attention(q.detach(), k.detach(), v.detach(), bias.detach(), None, plan, p_drop, training=True)
+    assert not torch.equal(a, b)
