@@ -326,3 +326,31 @@ def test_shard_dataset_serves_sequence_models_through_the_host_path(mirror, samp
         assert t.candidate_location_idxs.tolist() == e.candidate_location_idxs.tolist()
         assert t.intra_token_edges == e.intra_token_edges and t.node_mappings == e.node_mappings
     assert dataset.tensorizer is None      # no native tensoriser was built for this model family
+
+
+def test_registry_defaults_build_and_checkpoints_round_trip(tmp_path):
+    """Every sequence model name builds with the registry's default spec (dropout 0.1 included) and survives the reference's
+    checkpoint format (gzip(torch.save((model, nn))), modelregistry.py:147-156)."""
+    import copy
+    import logging
+    from pathlib import Path
+
+    from buglab.models.modelregistry import load_model
+    from buglab.models.seqmodel import SeqBugLabModel
+    from buglab_b200.synthetic import SyntheticProgramGenerator
+
+    logging.getLogger("buglab.models.seqmodel").setLevel(logging.CRITICAL)
+    for name in ("seq-great", "seq-rat", "seq-transformer", "seq-gru"):
+        model, _, _ = load_model({"modelName": name, "hidden_state_size": 64, "num_layers": 1}, Path(str(tmp_path / "m.pkl.gz")))
+        model.compute_metadata(SyntheticProgramGenerator(seed=0).samples(6))
+        assert sum(p.numel() for p in model.build_neural_module().parameters()) > 0
+    model, _, _ = load_model({"modelName": "seq-rat", "hidden_state_size": 32, "num_heads": 4, "num_layers": 2,
+                              "buggy_samples_weight_spec": "warmdown(3, 0.5)"}, Path(str(tmp_path / "m.pkl.gz")))
+    model.compute_metadata(SyntheticProgramGenerator(seed=0).samples(6))
+    nn = model.build_neural_module()
+    model.save(Path(str(tmp_path / "m.pkl.gz")), nn)
+    restored, restored_nn = SeqBugLabModel.restore_model(Path(str(tmp_path / "m.pkl.gz")), torch.device("cpu"))
+    assert restored.edge_types == model.edge_types
+    assert all(torch.equal(a, b) for a, b in zip(nn.state_dict().values(), restored_nn.state_dict().values()))
+    sample = SyntheticProgramGenerator(seed=3).sample()
+    assert model.tensorize(copy.deepcopy(sample)).node_mappings == restored.tensorize(copy.deepcopy(sample)).node_mappings
