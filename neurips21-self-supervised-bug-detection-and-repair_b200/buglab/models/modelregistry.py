@@ -1,5 +1,5 @@
-"""Model name -> constructor (reference: buglab/models/modelregistry.py:18-166).  Only the gnn-mlp family is built on
-the B200 kernels; the other registry names are kept so callers get a clear error instead of a KeyError."""
+"""Model name -> constructor (reference: buglab/models/modelregistry.py:18-166): the graph family (``gnn-mlp`` on the B200
+kernels; ``ggnn`` is named but its gated layer is not built) and the sequence family (``seq-*``)."""
 import logging
 import re
 from functools import partial
@@ -38,7 +38,7 @@ def buggy_sample_weight_schedule(weight_spec: Union[str, int, float]) -> Callabl
 
 
 class _LayerStack:
-    """Picklable ``n_edges -> layer list`` closure (the reference uses a lambda, modelregistry.py:85-87)."""
+    """Picklable ``number of edge kinds -> layer list`` (upstream uses a lambda here)."""
 
     def __init__(self, mp_layer, hidden_state_size, dropout_rate, edge_feature_size):
         self.mp_layer, self.hidden, self.dropout, self.features = mp_layer, hidden_state_size, dropout_rate, edge_feature_size
@@ -47,31 +47,31 @@ class _LayerStack:
         return self.mp_layer(self.hidden, self.dropout, n_edges, features_dimension=self.features)
 
 
+# defaults of the node-label embedder when the spec does not override them (subtoken vocabulary, <= 6 parts, max-pooled)
+_NODE_REPRESENTATION_DEFAULTS = {"token_splitting": "subtoken", "max_num_subtokens": 6, "subtoken_combination": "max",
+                                 "vocabulary_size": 15000}
+
+
 def gnn(*, mp_layer, add_self_edge: bool, use_all_gnn_layer_outputs: bool = False, hidden_state_size: int = 128,
         dropout_rate: float = 0.2, node_representations: Optional[Dict[str, Any]] = None,
         selector_loss_type="classify-max-loss", stop_extending_minibatch_after_num_nodes: int = 30000,
         max_nodes_per_graph: int = 35000, buggy_samples_weight_spec: Union[str, int, float] = 1.0,
         edge_feature_size: int = 0, **kwargs):
-    node_representations = dict(node_representations or {})
-    node_representations.setdefault("token_splitting", "subtoken")
-    node_representations.setdefault("max_num_subtokens", 6)
-    node_representations.setdefault("subtoken_combination", "max")
-    node_representations.setdefault("vocabulary_size", 15000)
+    """The graph family: a subtoken node embedder feeding ``mp_layer``'s message-passing stack (keyword surface of the
+    reference's ``gnn``, modelregistry.py:44-94, because model specs are JSON dicts splatted into it)."""
     if edge_feature_size > 0:
         raise NotImplementedError("edge_feature_size > 0 is outside the gnn-mlp default path built here")
-    return GnnBugLabModel(
-        GraphNeuralNetworkModel(
-            node_representation_model=StrElementRepresentationModel(embedding_size=hidden_state_size, **node_representations),
-            edge_representation_model=None,
-            add_self_edges=add_self_edge,
-            message_passing_layer_creator=_LayerStack(mp_layer, hidden_state_size, dropout_rate, edge_feature_size),
-            stop_extending_minibatch_after_num_nodes=stop_extending_minibatch_after_num_nodes,
-            max_nodes_per_graph=max_nodes_per_graph,
-        ),
-        use_all_gnn_layer_outputs=use_all_gnn_layer_outputs,
-        generator_loss_type=selector_loss_type,
-        buggy_samples_weight_schedule=buggy_sample_weight_schedule(buggy_samples_weight_spec),
-    )
+    embedder_spec = {**_NODE_REPRESENTATION_DEFAULTS, **(node_representations or {})}
+    graph_model = GraphNeuralNetworkModel(
+        node_representation_model=StrElementRepresentationModel(embedding_size=hidden_state_size, **embedder_spec),
+        edge_representation_model=None,
+        message_passing_layer_creator=_LayerStack(mp_layer, hidden_state_size, dropout_rate, edge_feature_size),
+        add_self_edges=add_self_edge,
+        max_nodes_per_graph=max_nodes_per_graph,
+        stop_extending_minibatch_after_num_nodes=stop_extending_minibatch_after_num_nodes)
+    return GnnBugLabModel(graph_model, use_all_gnn_layer_outputs=use_all_gnn_layer_outputs,
+                          generator_loss_type=selector_loss_type,
+                          buggy_samples_weight_schedule=buggy_sample_weight_schedule(buggy_samples_weight_spec))
 
 
 def seq_transformer(*, layer_type: str, hidden_state_size: int = 256, dropout_rate: float = 0.1, vocab_size: int = 15000,
@@ -79,42 +79,60 @@ def seq_transformer(*, layer_type: str, hidden_state_size: int = 256, dropout_ra
                     max_seq_size: int = 400, intermediate_dimension_size: int = 1024,
                     buggy_samples_weight_spec: Union[str, int, float] = 1.0, rezero_mode: str = "off",
                     normalisation_mode: str = "postnorm", **__):
-    """Reference modelregistry.py:97-126.  Host side only for now: the model tensorises and packs, its
-    ``build_neural_module`` raises until the relational-transformer kernels exist."""
+    """The sequence family (keyword surface of the reference's ``seq_transformer``, modelregistry.py:97-126)."""
     from buglab.models.seqmodel import SeqBugLabModel
 
-    return SeqBugLabModel(
-        hidden_state_size, max_subtoken_vocab_size=vocab_size, dropout_rate=dropout_rate, layer_type=layer_type,
-        generator_loss_type=selector_loss_type, intermediate_dimension_size=intermediate_dimension_size,
-        buggy_samples_weight_schedule=buggy_sample_weight_schedule(buggy_samples_weight_spec), max_seq_size=max_seq_size,
-        num_heads=num_heads, num_layers=num_layers, rezero_mode=rezero_mode, normalisation_mode=normalisation_mode)
+    encoder = dict(layer_type=layer_type, num_layers=num_layers, num_heads=num_heads, max_seq_size=max_seq_size,
+                   intermediate_dimension_size=intermediate_dimension_size, rezero_mode=rezero_mode,
+                   normalisation_mode=normalisation_mode)
+    return SeqBugLabModel(hidden_state_size, max_subtoken_vocab_size=vocab_size, dropout_rate=dropout_rate,
+                          generator_loss_type=selector_loss_type,
+                          buggy_samples_weight_schedule=buggy_sample_weight_schedule(buggy_samples_weight_spec), **encoder)
+
+
+# model name -> (family, keyword arguments the name fixes)
+_MODEL_TABLE = {
+    "gnn-mlp": ("graph", dict(mp_layer=create_mlp_mp_layers, add_self_edge=True)),
+    "ggnn": ("graph", dict(mp_layer=create_ggnn_mp_layers, add_self_edge=False)),
+    "seq-great": ("sequence", dict(layer_type="great")),
+    "seq-rat": ("sequence", dict(layer_type="rat")),
+    "seq-transformer": ("sequence", dict(layer_type="transformer")),
+    "seq-gru": ("sequence", dict(layer_type="gru")),
+}
+
+
+class _ModelEntry:
+    """``spec dict -> model`` for one registry name."""
+
+    def __init__(self, constructor: Callable, fixed: Dict[str, Any]):
+        self._constructor, self._fixed = constructor, fixed
+
+    def __call__(self, spec: Dict[str, Any]):
+        return self._constructor(**self._fixed, **spec)
 
 
 def construct_model_dict(gnn_constructor: Callable, seq_constructor: Callable) -> Dict[str, Callable]:
-    return {
-        "gnn-mlp": lambda kwargs: gnn_constructor(mp_layer=create_mlp_mp_layers, add_self_edge=True, **kwargs),
-        "ggnn": lambda kwargs: gnn_constructor(mp_layer=create_ggnn_mp_layers, add_self_edge=False, **kwargs),
-        "seq-great": lambda kwargs: seq_constructor(layer_type="great", **kwargs),
-        "seq-rat": lambda kwargs: seq_constructor(layer_type="rat", **kwargs),
-        "seq-transformer": lambda kwargs: seq_constructor(layer_type="transformer", **kwargs),
-        "seq-gru": lambda kwargs: seq_constructor(layer_type="gru", **kwargs),
-    }
+    """Name -> ``callable(spec)``; the two constructors are parameters because the controllers wrap them upstream."""
+    family = {"graph": gnn_constructor, "sequence": seq_constructor}
+    return {name: _ModelEntry(family[kind], fixed) for name, (kind, fixed) in _MODEL_TABLE.items()}
 
 
 def load_model(model_spec: Dict[str, Any], model_path: Path, restore_path: Optional[str] = None,
                restore_if_model_exists: bool = False, type_model: bool = False
                ) -> Tuple[AbstractNeuralModel, Optional[ModuleWithMetrics], bool]:
-    """(model, restored nn or None, whether metadata still has to be computed)."""
+    """``(model, restored module or None, metadata still to be computed?)`` — a checkpoint (explicit ``restore_path``, or
+    ``model_path`` itself when it exists and ``restore_if_model_exists``) wins over building from the spec."""
     assert model_path.name.endswith(".pkl.gz"), "MODEL_FILENAME must have a `.pkl.gz` suffix."
-    if restore_path is not None or (restore_if_model_exists and model_path.exists()):
+    checkpoint = Path(restore_path) if restore_path is not None else (
+        model_path if restore_if_model_exists and model_path.exists() else None)
+    if checkpoint is not None:
         import torch
 
-        source = Path(restore_path) if restore_path is not None else model_path
-        LOGGER.info("Resuming training from %s." % source)
-        model, nn = AbstractNeuralModel.restore_model(source, torch.device("cuda:0" if torch.cuda.is_available() else "cpu"))
-        return model, nn, False
-    models = construct_model_dict(gnn, seq_transformer)
-    if model_spec["modelName"] not in models:
-        raise ValueError("Unknown model `%s`. Known models: %s" % (model_spec["modelName"], list(models.keys())))
-    spec = {k: v for k, v in model_spec.items() if k != "modelName"}
-    return models[model_spec["modelName"]](spec), None, True
+        LOGGER.info("Resuming training from %s." % checkpoint)
+        device = torch.device("cuda:0" if torch.cuda.is_available() else "cpu")
+        return (*AbstractNeuralModel.restore_model(checkpoint, device), False)
+    registry = construct_model_dict(gnn, seq_transformer)
+    name = model_spec["modelName"]
+    if name not in registry:
+        raise ValueError("Unknown model `%s`. Known models: %s" % (name, list(registry.keys())))
+    return registry[name]({k: v for k, v in model_spec.items() if k != "modelName"}), None, True

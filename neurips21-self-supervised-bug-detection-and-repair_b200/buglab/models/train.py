@@ -4,20 +4,20 @@ Usage:
     train.py [options] MODEL_NAME TRAIN_DATA_PATH VALID_DATA_PATH MODEL_FILENAME
 
 Options:
-    --aml                         Run this in Azure ML
-    --amp                         Use AMP
-    --azure-info=<path>           Azure authentication information file (JSON). Used to load data from Azure storage.
-    --max-num-epochs=<epochs>     The maximum number of epochs to run training for. [default: 100]
-    --max-files-per-fold=<n>      The maximum number of files to include in each fold.
-    --minibatch-size=<size>       The minibatch size. [default: 300]
-    --validate-after=<n_samples>  Run the validation after seen n_samples. [default: 1000000]
-    --restore-path=<path>         The path to previous model file for starting from previous checkpoint.
+    --aml                         Azure ML run (not available in this build).
+    --amp                         Accepted for compatibility; the B200 path computes in fp32.
+    --azure-info=<path>           JSON file with Azure storage credentials, for data paths that live there.
+    --max-num-epochs=<epochs>     Stop after this many epochs at the latest. [default: 100]
+    --max-files-per-fold=<n>      Read at most n shard files from each of the two data directories.
+    --minibatch-size=<size>       Graphs per minibatch (a node budget may close a minibatch earlier). [default: 300]
+    --validate-after=<n_samples>  Length of a training "epoch" in samples: validate after this many. [default: 1000000]
+    --restore-path=<path>         Continue from this checkpoint instead of starting from the model spec.
     --model-spec=<json>           Extra registry keyword arguments as JSON, e.g. '{"hidden_state_size": 256}'.
-    --sequential                  Do not parallelize data loading. Makes debugging easier.
+    --sequential                  Load and tensorise data in the calling thread (easier to debug).
     --host-loader                 Decode shards with the Python msgpack path instead of the native shard decoder.
-    --quiet                       Do not show progress bar.
-    -h --help                     Show this screen.
-    --debug                       Enable debug routines. [default: False]
+    --quiet                       No progress output.
+    -h --help                     Print this text.
+    --debug                       Drop into the debugger on an exception. [default: False]
 """
 # Entry point with the reference's command line (buglab/models/train.py:2-19,54-144).  Under ``torchrun`` every
 # rank runs this script: shard files are split round-robin across ranks and gradients are all-reduced over NCCL.
@@ -48,68 +48,65 @@ def construct_data_loading_callable(data_path: RichPath, shuffle: bool = False, 
                                          world_size=world_size)
 
 
+def _optional_int(value) -> Optional[int]:
+    return None if value is None else int(value)
+
+
+def _data_sources(arguments, rank: int, world: int):
+    """(training data, validation data, a loader for the metadata pass).  The native shard path and the host path select
+    the same files, shard them over ranks the same way and stop after the same number of elements."""
+    credentials = arguments.get("--azure-info", None)
+    files_cap = _optional_int(arguments["--max-files-per-fold"])
+    epoch_length = int(arguments["--validate-after"])
+    folds = {name: RichPath.create(arguments[key], credentials)
+             for name, key in (("train", "TRAIN_DATA_PATH"), ("valid", "VALID_DATA_PATH"))}
+    if arguments.get("--host-loader"):
+        def source(fold, **kw):
+            return LazyDataIterable(construct_data_loading_callable(folds[fold], max_files_per_fold=files_cap, rank=rank,
+                                                                    world_size=world, **kw))
+        training = source("train", shuffle=True, limit_num_yielded_elements=epoch_length)
+        validation = source("valid")
+    else:
+        from buglab_b200.shards import ShardDataset  # file -> packed arrays in native code (include/buglab_shards.h)
+
+        threads = 1 if arguments["--sequential"] else None
+        common = dict(take_only_first_n_files=files_cap, rank=rank, world_size=world, num_threads=threads)
+        training = ShardDataset(folds["train"], shuffle=True, limit_num_yielded_elements=epoch_length, **common)
+        validation = ShardDataset(folds["valid"], **common)
+    # Every rank computes metadata from the SAME unsharded, unshuffled prefix of the training fold, so vocabularies and the
+    # relation layout agree everywhere without a broadcast (the reference, single-process, samples a shuffled prefix).
+    metadata = LazyDataIterable(construct_data_loading_callable(folds["train"], shuffle=False,
+                                                                limit_num_yielded_elements=250_000))
+    return training, validation, metadata
+
+
 def run(arguments):
     from buglab_b200 import distributed
 
     if arguments["--aml"]:
         raise NotImplementedError("Azure ML runs are outside the scope of this build")
     distributed.init_from_env()
-    rank, world = distributed.rank(), distributed.world_size()
     configure_logging(None)
-    azure_info_path = arguments.get("--azure-info", None)
-    max_files_per_fold = arguments["--max-files-per-fold"]
-    max_files_per_fold = None if max_files_per_fold is None else int(max_files_per_fold)
+    training_data, validation_data, metadata_data = _data_sources(arguments, distributed.rank(), distributed.world_size())
 
-    train_path = RichPath.create(arguments["TRAIN_DATA_PATH"], azure_info_path)
-    valid_path = RichPath.create(arguments["VALID_DATA_PATH"], azure_info_path)
-    validate_after = int(arguments["--validate-after"])
-    if arguments.get("--host-loader"):
-        training_data = LazyDataIterable(construct_data_loading_callable(
-            train_path, shuffle=True, max_files_per_fold=max_files_per_fold, limit_num_yielded_elements=validate_after,
-            rank=rank, world_size=world))
-        validation_data = LazyDataIterable(construct_data_loading_callable(
-            valid_path, max_files_per_fold=max_files_per_fold, rank=rank, world_size=world))
-    else:
-        # same file selection / sharding / limits; samples go file -> packed arrays in native code (include/buglab_shards.h)
-        from buglab_b200.shards import ShardDataset
+    spec = {"modelName": arguments["MODEL_NAME"], **json.loads(arguments.get("--model-spec") or "{}")}
+    checkpoint_path = Path(arguments["MODEL_FILENAME"])
+    model, restored_module, needs_metadata = load_model(spec, checkpoint_path, arguments.get("--restore-path", None))
 
-        threads = 1 if arguments["--sequential"] else None
-        training_data = ShardDataset(train_path, shuffle=True, take_only_first_n_files=max_files_per_fold,
-                                     limit_num_yielded_elements=validate_after, rank=rank, world_size=world,
-                                     num_threads=threads)
-        validation_data = ShardDataset(valid_path, take_only_first_n_files=max_files_per_fold, rank=rank,
-                                       world_size=world, num_threads=threads)
-
-    model_path = Path(arguments["MODEL_FILENAME"])
-    model_spec = {"modelName": arguments["MODEL_NAME"]}
-    if arguments.get("--model-spec"):
-        model_spec.update(json.loads(arguments["--model-spec"]))
-    model, nn, initialize_metadata = load_model(model_spec, model_path, arguments.get("--restore-path", None))
-
-    trainer = ModelTrainer(
-        model, model_path,
-        max_num_epochs=int(arguments["--max-num-epochs"]),
-        minibatch_size=int(arguments["--minibatch-size"]),
-        optimizer_creator=optimizer,
-        clip_gradient_norm=0.5,
-        scheduler_creator=lambda o: LinearWarmupScheduler(o),
-        enable_amp=arguments["--amp"],
-    )
-    if nn is not None:
-        trainer.neural_module = nn
-    trainer.register_train_epoch_end_hook(lambda model, nn, epoch, metrics: log_run(None, "train", model, epoch, metrics))
-    trainer.register_validation_epoch_end_hook(lambda model, nn, epoch, metrics: log_run(None, "valid", model, epoch, metrics))
-
-    if initialize_metadata:
-        # every rank reads the SAME (unsharded, unshuffled-order-independent) metadata sample so that vocabularies
-        # and the edge-type layout are identical everywhere
-        data_for_metadata = LazyDataIterable(construct_data_loading_callable(
-            RichPath.create(arguments["TRAIN_DATA_PATH"], azure_info_path), shuffle=False,
-            limit_num_yielded_elements=250_000))
-        trainer.load_metadata_and_create_network(data_for_metadata, not arguments["--sequential"], not arguments["--quiet"])
-
-    trainer.train(training_data, validation_data, show_progress_bar=not arguments["--quiet"],
-                  initialize_metadata=False, parallelize=not arguments["--sequential"], patience=10)
+    in_background = not arguments["--sequential"]
+    verbose = not arguments["--quiet"]
+    trainer = ModelTrainer(model, checkpoint_path, optimizer_creator=optimizer, scheduler_creator=LinearWarmupScheduler,
+                           clip_gradient_norm=0.5, minibatch_size=int(arguments["--minibatch-size"]),
+                           max_num_epochs=int(arguments["--max-num-epochs"]), enable_amp=arguments["--amp"])
+    if restored_module is not None:
+        trainer.neural_module = restored_module
+    for phase, register in (("train", trainer.register_train_epoch_end_hook),
+                            ("valid", trainer.register_validation_epoch_end_hook)):
+        register(lambda model, nn, epoch, metrics, phase=phase: log_run(None, phase, model, epoch, metrics))
+    if needs_metadata:
+        trainer.load_metadata_and_create_network(metadata_data, in_background, verbose)
+    trainer.train(training_data, validation_data, initialize_metadata=False, parallelize=in_background,
+                  show_progress_bar=verbose, patience=10)
 
 
 def main(argv=None):
