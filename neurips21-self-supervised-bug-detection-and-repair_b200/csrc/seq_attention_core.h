@@ -24,6 +24,11 @@
 #define BL_HD inline
 #endif
 
+// Compiler-only barrier: rows read for a dot product are read AGAIN (cache hits) when they are needed for an update a few
+// lines later, instead of being kept in 64 more registers across the exp / dropout code — at head size 64 the three
+// per-thread vectors already take 192 registers.
+#define BL_REREAD_ROWS() asm volatile("" ::: "memory")
+
 namespace seqatt {
 
 struct Problem {
@@ -74,6 +79,21 @@ BL_HD float dot(const float* a, const float* b) {
         s = fmaf(a[d + 1], v.y, s);
         s = fmaf(a[d + 2], v.z, s);
         s = fmaf(a[d + 3], v.w, s);
+    }
+    return s;
+}
+
+// <a, b> with both rows in memory
+template <int D>
+BL_HD float dot_rows(const float* a, const float* b) {
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; d += 4) {
+        const F4 u = load4(a + d), v = load4(b + d);
+        s = fmaf(u.x, v.x, s);
+        s = fmaf(u.y, v.y, s);
+        s = fmaf(u.z, v.z, s);
+        s = fmaf(u.w, v.w, s);
     }
     return s;
 }
@@ -191,6 +211,7 @@ BL_HD void backward_row(const Problem& p, const float* out, const float* lse, co
         const float prob = expf(s - row_lse);
         const float mask = dropout_scale(p, b, h, i, j);
         const float ds = prob * (mask * dp - delta);
+        BL_REREAD_ROWS();
         axpy<D>(acc, ds, p.k + (head + j) * D);
         for (int f = e_first; f < e; ++f) {
             axpy<D>(acc, ds, p.bias + ((size_t)p.row_tab[f] * p.H + h) * D);
@@ -228,41 +249,54 @@ BL_HD void backward_col(const Problem& p, const float* lse, const float* delta, 
         for (int d = 0; d < D; ++d) { dkrow[d] = 0.f; dvrow[d] = 0.f; }
         return;
     }
-    float kk[D], vv[D], acc_k[D], acc_v[D];
+    // Two sweeps over the queries, one per output, so that each holds only k_j and ONE accumulator in registers (at head
+    // size 64 a single sweep with both accumulators spills); the score is recomputed in the second sweep.
+    float kk[D], acc[D];
     const float* krow = p.k + (head + j) * D;
     const float* vrow = p.v + (head + j) * D;
 #pragma unroll
-    for (int d = 0; d < D; ++d) { kk[d] = krow[d]; vv[d] = vrow[d]; acc_k[d] = 0.f; acc_v[d] = 0.f; }
-    int e = p.col_ptr[b * p.L + j];
+    for (int d = 0; d < D; ++d) kk[d] = krow[d];
+    const int e_begin = p.col_ptr[b * p.L + j];
     const int e_end = p.col_ptr[b * p.L + j + 1];
+
+    // sweep 1: dK_j = sum_i dS_ij q_i
+#pragma unroll
+    for (int d = 0; d < D; ++d) acc[d] = 0.f;
+    int e = e_begin;
     for (int i = 0; i < len; ++i) {
         const float* qrow = p.q + (head + i) * D;
         const float* grow = d_out + (head + i) * D;
         float s = dot<D>(kk, qrow);
-        float dp = dot<D>(vv, grow);
+        float dp = dot_rows<D>(vrow, grow);
         while (e < e_end && p.col_query[e] == i) {
-            // two rows in memory: stage the table row in registers once per entry (entries are rare)
-            float tab[D];
-            const float* brow = p.bias + ((size_t)p.col_tab[e] * p.H + h) * D;
-#pragma unroll
-            for (int d = 0; d < D; ++d) tab[d] = brow[d];
-            s += dot<D>(tab, qrow);
-            if (p.vbias != nullptr) {
-                const float* vbrow = p.vbias + ((size_t)p.col_tab[e] * p.H + h) * D;
-#pragma unroll
-                for (int d = 0; d < D; ++d) tab[d] = vbrow[d];
-                dp += dot<D>(tab, grow);
-            }
+            s += dot_rows<D>(p.bias + ((size_t)p.col_tab[e] * p.H + h) * D, qrow);
+            if (p.vbias != nullptr) dp += dot_rows<D>(p.vbias + ((size_t)p.col_tab[e] * p.H + h) * D, grow);
             ++e;
         }
         const float prob = expf(s - lse[head + i]);
-        const float mask = dropout_scale(p, b, h, i, j);
-        const float ds = prob * (mask * dp - delta[head + i]);
-        axpy<D>(acc_k, ds, qrow);
-        axpy<D>(acc_v, prob * mask, grow);
+        const float ds = prob * (dropout_scale(p, b, h, i, j) * dp - delta[head + i]);
+        BL_REREAD_ROWS();
+        axpy<D>(acc, ds, qrow);
     }
 #pragma unroll
-    for (int d = 0; d < D; ++d) { dkrow[d] = acc_k[d]; dvrow[d] = acc_v[d]; }
+    for (int d = 0; d < D; ++d) dkrow[d] = acc[d];
+
+    // sweep 2: dV_j = sum_i p'_ij dO_i
+#pragma unroll
+    for (int d = 0; d < D; ++d) acc[d] = 0.f;
+    e = e_begin;
+    for (int i = 0; i < len; ++i) {
+        const float* qrow = p.q + (head + i) * D;
+        float s = dot<D>(kk, qrow);
+        while (e < e_end && p.col_query[e] == i) {
+            s += dot_rows<D>(p.bias + ((size_t)p.col_tab[e] * p.H + h) * D, qrow);
+            ++e;
+        }
+        const float weight = expf(s - lse[head + i]) * dropout_scale(p, b, h, i, j);
+        axpy<D>(acc, weight, d_out + (head + i) * D);
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) dvrow[d] = acc[d];
 }
 
 }  // namespace seqatt
