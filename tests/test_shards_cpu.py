@@ -136,6 +136,32 @@ def test_tokenizer_matches_host_ids(kind):
     assert needs_host == 5
 
 
+def test_tokenizer_matches_host_on_random_identifiers():
+    """20 000 random labels over an alphabet that stresses the splitter (case runs, digits, underscores, punctuation,
+    lower-invariant and case-variant non-ASCII): native ids == host ids, or the native side declines (case-variant only)."""
+    from ptgnn.neuralmodels.embeddings.strelementrepresentationmodel import StrElementRepresentationModel
+
+    rng = random.Random(99)
+    alphabet = list("abcxyzABCXYZ019__--+.( ") + ["é", "ß", "日", "Σ", "É", "ǅ", "😀"]
+    labels = ["".join(rng.choice(alphabet) for _ in range(rng.randrange(0, 14))) for _ in range(20000)]
+    node_model = StrElementRepresentationModel(token_splitting="subtoken", embedding_size=8, vocabulary_size=3000,
+                                               min_freq_threshold=2, max_num_subtokens=5, subtoken_combination="max")
+    for label in labels[:6000]:
+        node_model.update_metadata_from(label)
+    node_model.finalize_metadata()
+    tok = shards.Tokenizer(node_model.vocabulary, "subtoken", node_model.max_num_subtokens)
+    declined = 0
+    for label in labels:
+        got = tok.ids(label)
+        if got is None:
+            declined += 1
+            assert any(ord(c) >= 0x80 and c.lower() != c for c in label), repr(label)
+        else:
+            assert got == tuple(node_model._ids_of(label)), repr(label)
+            assert not any(ord(c) >= 0x80 and c.lower() != c for c in label), repr(label)   # never handles what it should decline
+    assert 2000 < declined < 12000
+
+
 def test_vocabulary_without_unk_routes_misses_to_host():
     from dpu_utils.mlutils import Vocabulary
 
