@@ -207,3 +207,31 @@ def test_attention_probability_dropout(host_backend, value_biases):
     a = ops.seq_edge_attention(q.detach(), k.detach(), v.detach(), bias.detach(), None, plan, p_drop, training=True)
     b = ops.seq_edge_attention(q.detach(), k.detach(), v.detach(), bias.detach(), None, plan, p_drop, training=True)
     assert not torch.equal(a, b)
+
+
+def test_plan_against_brute_force_on_random_edge_sets():
+    g = torch.Generator().manual_seed(5)
+    for trial in range(20):
+        B, L, T = int(torch.randint(1, 5, (1,), generator=g)), int(torch.randint(2, 40, (1,), generator=g)), int(torch.randint(1, 6, (1,), generator=g))
+        E = int(torch.randint(0, 300, (1,), generator=g))
+        edges = torch.stack([torch.randint(0, B, (E,), generator=g), torch.randint(0, L, (E,), generator=g),
+                             torch.randint(0, L, (E,), generator=g)], dim=1)
+        kinds = torch.randint(0, T, (E,), generator=g)
+        plan = ops.build_seq_attention_plan(edges, kinds, torch.full((B,), L), L, T)
+        expected_rows = {}
+        for (b, s, t), kind in zip(edges.tolist(), kinds.tolist()):
+            expected_rows.setdefault(b * L + s, []).append((t, kind))
+            expected_rows.setdefault(b * L + t, []).append((s, T + kind))
+        rp, rk, rt = plan.row_ptr.tolist(), plan.row_key.tolist(), plan.row_tab.tolist()
+        cp, cq, ct = plan.col_ptr.tolist(), plan.col_query.tolist(), plan.col_tab.tolist()
+        assert rp[-1] == cp[-1] == 2 * E
+        expected_cols = {}
+        for row, entries in expected_rows.items():
+            b, i = divmod(row, L)
+            for key, tab in entries:
+                expected_cols.setdefault(b * L + key, []).append((i, tab))
+        for r in range(B * L):
+            got = list(zip(rk[rp[r]: rp[r + 1]], rt[rp[r]: rp[r + 1]]))
+            assert sorted(got) == sorted(expected_rows.get(r, [])) and [k for k, _ in got] == sorted(k for k, _ in got)
+            got = list(zip(cq[cp[r]: cp[r + 1]], ct[cp[r]: cp[r + 1]]))
+            assert sorted(got) == sorted(expected_cols.get(r, [])) and [q for q, _ in got] == sorted(q for q, _ in got)
