@@ -33,6 +33,7 @@ extern "C" {
 #define BL_SHARDS_ERR_GZIP 2      /* not a gzip stream / corrupt deflate data */
 #define BL_SHARDS_ERR_ARG 3       /* bad argument (null handle, index out of range) */
 #define BL_SHARDS_ERR_MSGPACK 4   /* malformed msgpack inside an object */
+#define BL_SHARDS_ERR_NOMEM 5     /* allocation failed (no C++ exception ever crosses this boundary) */
 
 #define BL_SAMPLE_OK 0            /* arrays below are valid */
 #define BL_SAMPLE_NIL 1           /* the object is msgpack nil: skipped by the loader (msgpackutils.py:38) */

@@ -743,15 +743,22 @@ const char* bl_shards_error_string(int32_t code) {
     case BL_SHARDS_ERR_GZIP: return "corrupt or truncated gzip stream";
     case BL_SHARDS_ERR_ARG: return "bad argument";
     case BL_SHARDS_ERR_MSGPACK: return "malformed msgpack object";
+    case BL_SHARDS_ERR_NOMEM: return "out of memory";
     default: return "unknown error";
   }
 }
 
 int32_t bl_shard_open_buffer(const uint8_t* gz, int64_t gz_len, bl_shard** out) {
   if (out == nullptr || (gz == nullptr && gz_len != 0) || gz_len < 0) return BL_SHARDS_ERR_ARG;
-  bl_shard* shard = new bl_shard();
-  shard->status = inflate_all(gz, (size_t)gz_len, shard->raw);
-  index_objects(*shard);
+  bl_shard* shard = nullptr;
+  try {
+    shard = new bl_shard();
+    shard->status = inflate_all(gz, (size_t)gz_len, shard->raw);
+    index_objects(*shard);
+  } catch (...) {  // std::bad_alloc / length_error on absurd sizes
+    delete shard;
+    return BL_SHARDS_ERR_NOMEM;
+  }
   *out = shard;
   return BL_SHARDS_OK;
 }
@@ -763,8 +770,14 @@ int32_t bl_shard_open(const char* path, bl_shard** out) {
   std::vector<uint8_t> gz;
   uint8_t buf[1 << 16];
   size_t got;
-  while ((got = fread(buf, 1, sizeof(buf), f)) > 0) gz.insert(gz.end(), buf, buf + got);
-  bool failed = ferror(f) != 0;
+  bool failed = false;
+  try {
+    while ((got = fread(buf, 1, sizeof(buf), f)) > 0) gz.insert(gz.end(), buf, buf + got);
+  } catch (...) {
+    fclose(f);
+    return BL_SHARDS_ERR_NOMEM;
+  }
+  failed = ferror(f) != 0;
   fclose(f);
   if (failed) return BL_SHARDS_ERR_IO;
   return bl_shard_open_buffer(gz.data(), (int64_t)gz.size(), out);
@@ -790,7 +803,9 @@ int32_t bl_tokenizer_create(const uint8_t* blob, const int64_t* offsets, const i
       (splitting_kind != BL_SPLIT_TOKEN && splitting_kind != BL_SPLIT_SUBTOKEN) || num_lower_variant < 0 ||
       (num_lower_variant > 0 && !lower_variant_codepoints))
     return BL_SHARDS_ERR_ARG;
-  bl_tokenizer* tok = new bl_tokenizer();
+  bl_tokenizer* tok = nullptr;
+  try {
+  tok = new bl_tokenizer();
   if (num_tokens > 0) tok->blob.assign(reinterpret_cast<const char*>(blob), (size_t)offsets[num_tokens]);
   size_t capacity = 16;
   while (capacity < (size_t)num_tokens * 2 + 2) capacity <<= 1;
@@ -818,6 +833,10 @@ int32_t bl_tokenizer_create(const uint8_t* blob, const int64_t* offsets, const i
   tok->max_subtokens = splitting_kind == BL_SPLIT_TOKEN ? 1 : max_subtokens;
   tok->lower_variant.assign(lower_variant_codepoints, lower_variant_codepoints + num_lower_variant);
   std::sort(tok->lower_variant.begin(), tok->lower_variant.end());
+  } catch (...) {
+    delete tok;
+    return BL_SHARDS_ERR_NOMEM;
+  }
   *out = tok;
   return BL_SHARDS_OK;
 }
@@ -834,7 +853,11 @@ int32_t bl_tokenizer_ids(const bl_tokenizer* tok, const uint8_t* label, int64_t 
 
 int32_t bl_sample_create(bl_sample** out) {
   if (!out) return BL_SHARDS_ERR_ARG;
-  *out = new bl_sample();
+  try {
+    *out = new bl_sample();
+  } catch (...) {
+    return BL_SHARDS_ERR_NOMEM;
+  }
   return BL_SHARDS_OK;
 }
 
@@ -846,19 +869,27 @@ int32_t bl_sample_decode(const bl_shard* shard, int64_t index, const bl_tokenize
   if (!shard || !tok || !sample || !view || num_edge_types < 0 || (num_edge_types > 0 && !edge_type_names) || index < 0 ||
       index >= bl_shard_num_objects(shard))
     return BL_SHARDS_ERR_ARG;
-  return decode_sample(*shard, index, *tok, edge_type_names, num_edge_types, *sample, *view);
+  try {
+    return decode_sample(*shard, index, *tok, edge_type_names, num_edge_types, *sample, *view);
+  } catch (...) {  // decode_sample handles its own control-flow exceptions; what is left is allocation failure
+    return BL_SHARDS_ERR_NOMEM;
+  }
 }
 
 int64_t bl_pyset_iteration_order(const int64_t* values, int64_t n, int64_t* out) {
   if (n < 0 || (n > 0 && (!values || !out))) return -1;
-  PySetOrder set;
-  for (int64_t i = 0; i < n; ++i) {
-    if (values[i] < 0 || values[i] >= ((int64_t)1 << 61) - 1) return -1;
-    set.add(values[i]);
+  try {
+    PySetOrder set;
+    for (int64_t i = 0; i < n; ++i) {
+      if (values[i] < 0 || values[i] >= ((int64_t)1 << 61) - 1) return -1;
+      set.add(values[i]);
+    }
+    int64_t k = 0;
+    set.for_each([&](int64_t v) { out[k++] = v; });
+    return k;
+  } catch (...) {
+    return -1;
   }
-  int64_t k = 0;
-  set.for_each([&](int64_t v) { out[k++] = v; });
-  return k;
 }
 
 }  // extern "C"
