@@ -129,8 +129,9 @@ def load_model(model_spec: Dict[str, Any], model_path: Path, restore_path: Optio
         import torch
 
         LOGGER.info("Resuming training from %s." % checkpoint)
-        device = torch.device("cuda:0" if torch.cuda.is_available() else "cpu")
-        return (*AbstractNeuralModel.restore_model(checkpoint, device), False)
+        # restored on the host: ModelTrainer.train moves the module to this rank's device (restoring on cuda:0 would make
+        # every torchrun rank materialise the model — and a CUDA context — on GPU 0 first)
+        return (*AbstractNeuralModel.restore_model(checkpoint, torch.device("cpu")), False)
     registry = construct_model_dict(gnn, seq_transformer)
     name = model_spec["modelName"]
     if name not in registry:

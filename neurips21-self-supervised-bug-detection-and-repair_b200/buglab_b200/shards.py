@@ -124,11 +124,14 @@ def _check_set_order(handle: ctypes.CDLL) -> None:
 
 
 def lower_variant_codepoints() -> np.ndarray:
-    """Non-ASCII code points that ``str.lower()`` changes, from THIS interpreter's Unicode tables (labels containing one
-    are left to the host path, so native and host case folding cannot disagree)."""
+    """Non-ASCII code points that the native splitter (ASCII character classes, ASCII lower-casing) would treat
+    differently from the host: those ``str.lower()`` changes and those that are letters or digits for
+    ``str.isalnum()`` (the identifier splitter's classes), from THIS interpreter's Unicode tables.  Labels containing
+    one are left to the host path, so native and host tokenisation cannot disagree."""
     global _LOWER_VARIANT
     if _LOWER_VARIANT is None:
-        cps = [c for c in range(0x80, 0x110000) if not (0xD800 <= c <= 0xDFFF) and chr(c).lower() != chr(c)]
+        cps = [c for c in range(0x80, 0x110000) if not (0xD800 <= c <= 0xDFFF)
+               and (chr(c).lower() != chr(c) or chr(c).isalnum())]
         _LOWER_VARIANT = np.array(cps, dtype=np.int32)
     return _LOWER_VARIANT
 

@@ -41,22 +41,40 @@ def _distributed():
     return distributed
 
 
-def _record_stream(obj, stream, _depth: int = 0) -> None:
-    """Tell the caching allocator that every tensor reachable from ``obj`` is also used on ``stream`` (they were
-    allocated on the producer's side stream; without this their blocks could be recycled while still in use)."""
+def _reachable_cuda_tensors(obj, out: List[torch.Tensor], _depth: int = 0, any_device: bool = False) -> List[torch.Tensor]:
+    """Every CUDA tensor reachable from a finalised minibatch: dict values, list/tuple items, ALL fields of named
+    tuples (an ``EdgePlan`` starts with plain ints, so no first-element shortcut) and the ``plan`` attribute that
+    ``PlannedAdjacency`` carries."""
     if isinstance(obj, torch.Tensor):
-        if obj.is_cuda:
-            obj.record_stream(stream)
-    elif isinstance(obj, dict):
+        if obj.is_cuda or any_device:  # any_device: host-side tests of the traversal itself
+            out.append(obj)
+        return out
+    if _depth > 8:
+        return out
+    if isinstance(obj, dict):
         for v in obj.values():
-            _record_stream(v, stream, _depth + 1)
+            _reachable_cuda_tensors(v, out, _depth + 1, any_device)
     elif isinstance(obj, (list, tuple)):
-        if _depth < 6 and (not obj or not isinstance(obj[0], (int, float, str))):
+        is_named = hasattr(obj, "_fields")
+        # long homogeneous lists of Python scalars (e.g. per-graph counts) are skipped after a look at the first item
+        if is_named or not obj or not isinstance(obj[0], (int, float, str)):
             for v in obj:
-                _record_stream(v, stream, _depth + 1)
-        plan = getattr(obj, "plan", None)  # PlannedAdjacency carries the device plan as an attribute
+                if not isinstance(v, (int, float, str, type(None))):
+                    _reachable_cuda_tensors(v, out, _depth + 1, any_device)
+        plan = getattr(obj, "plan", None)
         if plan is not None:
-            _record_stream(tuple(plan), stream, _depth + 1)
+            _reachable_cuda_tensors(plan, out, _depth + 1, any_device)
+    return out
+
+
+def _record_stream(obj, stream) -> int:
+    """Tell the caching allocator that every tensor reachable from ``obj`` is also used on ``stream`` (they were
+    allocated on the producer's side stream; without this their blocks could be recycled while still in use).
+    Returns the number of tensors recorded."""
+    tensors = _reachable_cuda_tensors(obj, [])
+    for t in tensors:
+        t.record_stream(stream)
+    return len(tensors)
 
 
 class _Prefetcher:
@@ -336,24 +354,28 @@ class ModelTrainer:
         nn = self.neural_module
         nn.eval()
         nn.reset_metrics()
+        # Each minibatch loss is a mean over its graphs (gnn.py:251); weighting by the graph count makes the reported
+        # validation loss — and, across data-parallel ranks holding different numbers of samples, the target metric —
+        # the value over the union of the validation set, so the improved / patience decision matches a one-device run.
         loss_sum = torch.zeros((), device=device, dtype=torch.float64)
-        num_steps = 0
+        num_samples = 0
         with torch.no_grad():
-            for mb_data, _raw in self._minibatches(validation_tensors, device, parallelize):
-                loss_sum += nn(**mb_data).double()
-                num_steps += 1
-        total, steps = float(loss_sum), float(num_steps)
+            for mb_data, raw_points in self._minibatches(validation_tensors, device, parallelize):
+                n = len(raw_points)
+                loss_sum += nn(**mb_data).double() * n
+                num_samples += n
+        total, samples = float(loss_sum), float(num_samples)
         if dist.is_distributed():
-            total, steps = dist.all_ranks_sum(total, device), dist.all_ranks_sum(steps, device)
-        if steps == 0:
+            total, samples = dist.all_ranks_sum(total, device), dist.all_ranks_sum(samples, device)
+        if samples == 0:
             raise RuntimeError("No validation minibatches were produced.")
-        validation_loss = total / steps
+        validation_loss = total / samples
         metrics = dict(nn.report_metrics())
         if self._target_metric is not None:
             target_metric = metrics[self._target_metric]
             if dist.is_distributed():
-                # every rank must take the same improved / early-stopping decision: use the mean over the ranks' shards
-                target_metric = dist.all_ranks_sum(float(target_metric), device) / dist.world_size()
+                # per-sample ratios: sum(metric_r * n_r) / sum(n_r) is the metric over the union of the ranks' shards
+                target_metric = dist.all_ranks_sum(float(target_metric) * num_samples, device) / samples
             improved = target_metric > best_target_metric if self._target_metric_higher_is_better \
                 else target_metric < best_target_metric
         else:

@@ -315,3 +315,52 @@ def test_buffered_shuffle_is_a_permutation_and_streams():
     assert max(abs(pos - x) for pos, x in enumerate(out)) < 600      # local mixing: nothing travels arbitrarily far ...
     assert sum(1 for pos, x in enumerate(out) if abs(pos - x) > 16) > 500   # ... but most samples do move
     assert list(_buffered_shuffle(iter([]), 8)) == [] and sorted(_buffered_shuffle(iter([3, 1, 2]), 8)) == [1, 2, 3]
+
+
+def test_record_stream_traversal_reaches_every_plan_tensor():
+    """the device plan is a NamedTuple whose first fields are ints; every tensor field of it (and of
+    the adjacency carrying it) must be visited so the caching allocator learns about the cross-stream use."""
+    import torch
+    from buglab_b200.ops import EdgePlan
+    from ptgnn.baseneuralmodel.trainer import _reachable_cuda_tensors
+    from ptgnn.neuralmodels.gnn.messagepassing.abstractmessagepassing import PlannedAdjacency
+
+    t = lambda: torch.zeros(3, dtype=torch.int32)  # noqa: E731
+    fields = {}
+    for name, kind in EdgePlan.__annotations__.items():
+        fields[name] = t() if kind is torch.Tensor else ((0, 1) if "host" in name else 5)
+    plan = EdgePlan(**fields)
+    adjacency = PlannedAdjacency([(t(), t()), (t(), t())])
+    adjacency.plan = plan
+    minibatch = {"graph_data": {"adjacency_lists": adjacency, "node_data": {"token_idxs": t(), "lengths": t()},
+                                "reference_node_ids": {"a": t()}, "num_graphs": 4, "counts": [1, 2, 3]},
+                 "correct_idxs": t(), "names": ["x", "y"], "nested": [(t(), None, 3)]}
+    found = _reachable_cuda_tensors(minibatch, [], any_device=True)
+    ids = {id(x) for x in found}
+    n_plan_tensors = sum(1 for v in plan if isinstance(v, torch.Tensor))
+    assert n_plan_tensors >= 14
+    for v in plan:
+        if isinstance(v, torch.Tensor):
+            assert id(v) in ids
+    assert len(found) == n_plan_tensors + 4 + 3 + 1 + 1
+
+
+def test_identifier_splitting_follows_the_unicode_state_machine():
+    """upstream dpu_utils classifies characters with str.isupper/isdigit/isalnum.  The ASCII regex fast path must
+    equal that state machine on ASCII input, and non-ASCII letters must not be treated as separators."""
+    import random
+
+    from dpu_utils.codeutils.identifiersplitting import (split_camelcase, split_camelcase_unicode,
+                                                         split_identifier_into_parts)
+
+    rng = random.Random(5)
+    alphabet = "abXYZq019-+.( $A"
+    for _ in range(20000):
+        s = "".join(rng.choice(alphabet) for _ in range(rng.randrange(0, 12)))
+        assert split_camelcase(s) == split_camelcase_unicode(s), repr(s)
+    assert split_identifier_into_parts("naïve") == ["naïve"]
+    assert split_identifier_into_parts("Größe") == ["größe"]
+    assert split_identifier_into_parts("fooΣigma") == ["foo", "σigma"]
+    assert split_identifier_into_parts("x٣y") == ["x", "٣", "y"]          # ARABIC-INDIC DIGIT THREE is a digit
+    assert split_identifier_into_parts("a→b") == ["a", "→", "b"]
+    assert split_identifier_into_parts("__") == ["__"]
