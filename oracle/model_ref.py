@@ -85,6 +85,10 @@ class GraphNeuralNetwork(nn.Module):
         for layer, winners in zip(mp_layers, per_layer_winners):
             layer.forced_winners = winners
 
+    def routing_audits(self):
+        """Per message-passing layer: the audit of the last forced routing (see mp_ref.MlpMessagePassingLayer)."""
+        return [l.routing_audit for l in self.__message_passing_layers if not isinstance(l, _NoParams)]
+
     def forward(self, node_data, adjacency_lists, return_all_states: bool = False):
         state = self.__node_embedder(**node_data)
         states, remembered = [state], None

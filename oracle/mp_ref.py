@@ -59,6 +59,9 @@ class MlpMessagePassingLayer(nn.Module):
         # set, the max-aggregation uses THIS routing instead of its own argmax, which makes gradients comparable
         # elementwise with an implementation whose near-tied winners differ (see oracle/parity.py).
         self.forced_winners = None
+        # routing audit (filled whenever forced_winners is used): how the forced routing compares with THIS evaluation's
+        # own exact segment max — lets a test verify another implementation's winners without trusting them
+        self.routing_audit = None
 
     @property
     def output_state_dimension(self) -> int:
@@ -78,7 +81,20 @@ class MlpMessagePassingLayer(nn.Module):
             arg = self.forced_winners
             E = messages.shape[0]
             picked = messages.gather(0, arg.clamp(max=E - 1))
-            return torch.where(arg >= E, torch.zeros_like(picked), picked)
+            forced = torch.where(arg >= E, torch.zeros_like(picked), picked)
+            with torch.no_grad():
+                own_max, own_arg = scatter_max(messages, targets, dim=0, dim_size=N)
+                valid = arg < E
+                node_of_winner = targets[arg.clamp(max=E - 1)]
+                wrong_segment = valid & (node_of_winner != torch.arange(N).view(-1, 1))
+                deficit = (own_max - forced) / (1.0 + own_max.abs())     # >= 0 up to rounding: the forced edge's message
+                later_on_tie = valid & (own_arg < E) & (arg > own_arg) & (forced == own_max)
+                self.routing_audit = dict(
+                    decisions=int(arg.numel()), differing=int((arg != own_arg).sum()),
+                    wrong_segment=int(wrong_segment.sum()), empty_mismatch=int(((arg >= E) != (own_arg >= E)).sum()),
+                    max_relative_deficit=float(deficit.max()) if deficit.numel() else 0.0,
+                    later_edge_on_exact_tie=int(later_on_tie.sum()))
+            return forced
         if self.__aggregation == "max":
             return scatter_max(messages, targets, dim=0, dim_size=N)[0]
         if self.__aggregation == "min":

@@ -11,6 +11,10 @@ early layer's dW by ~1 %.  Gradient parity is therefore established in two ways:
   * ROUTING-CONDITIONED (model tests, smoke): the GPU path exports its winning edge per (node, channel)
     (`ops.WINNER_TRACE`), the oracle re-runs with that routing forced (`force_winners`) and every gradient tensor must
     then agree elementwise to 1e-4 (abs + rel) — this checks every backward kernel exactly;
+    and the routing itself is verified independently: the fp64 oracle, run with the forced routing, audits every
+    forced winner against its own exact segment max (`assert_routing_is_valid`): the edge must end in that node, empty
+    segments must agree, and the winner's exact message must attain the exact maximum to within 1e-5 relative — so a
+    wrong-edge bug cannot hide behind the conditioning, only genuine near-ties may differ;
   * UNCONDITIONED (goldens from the real reference, where routing cannot be forced): relative Frobenius error of every
     gradient tensor below 5e-2, which a routing bug (wrong edge, wrong type, missing term) fails by orders of
     magnitude while winner flips stay below it (CPU fp32 vs CPU fp64 reach ~1e-2).
@@ -72,3 +76,22 @@ def assert_grad_close(actual: torch.Tensor, expected: torch.Tensor, what: str = 
     assert frac_bad <= max_frac_bad, (
         f"{what}: {frac_bad:.3%} of entries off by more than 1e-4 (allowed {max_frac_bad:.2%}), "
         f"relative L2 error {rel_l2:.2e}, max abs diff {max_abs:.2e}")
+
+
+def assert_routing_is_valid(audits, what: str = "", max_relative_deficit: float = 1e-5, max_differing_frac: float = 1e-3) -> dict:
+    """``audits``: per layer dicts from the fp64 oracle run with another implementation's max-routing forced.
+    Every forced winner must be an in-edge of its node, agree on empty segments, and its exact (fp64) message must attain
+    the exact segment maximum up to ``max_relative_deficit`` (near-ties between two fp32 evaluations are ~1e-7); the
+    share of decisions that differ from the exact argmax must stay below ``max_differing_frac``."""
+    worst = dict(differing_frac=0.0, max_relative_deficit=0.0)
+    for i, a in enumerate(audits):
+        assert a is not None, f"{what}: layer {i} was not audited"
+        assert a["wrong_segment"] == 0, f"{what}: layer {i}: {a['wrong_segment']} winners are not in-edges of their node"
+        assert a["empty_mismatch"] == 0, f"{what}: layer {i}: {a['empty_mismatch']} empty-segment disagreements"
+        assert a["max_relative_deficit"] <= max_relative_deficit, (
+            f"{what}: layer {i}: a forced winner falls short of the exact maximum by {a['max_relative_deficit']:.2e} (relative)")
+        frac = a["differing"] / max(a["decisions"], 1)
+        assert frac <= max_differing_frac, f"{what}: layer {i}: {frac:.2e} of the winners differ from the exact argmax"
+        worst["differing_frac"] = max(worst["differing_frac"], frac)
+        worst["max_relative_deficit"] = max(worst["max_relative_deficit"], a["max_relative_deficit"])
+    return worst

@@ -95,3 +95,54 @@ def test_layer_module_matches_functional_and_isolated_nodes():
     dense = sd["_MlpMessagePassingLayer__state_update.1.weight"]
     expect = torch.tanh(torch.nn.functional.layer_norm(agg, (10,), ln_w, ln_b) @ dense.t())
     torch.testing.assert_close(out, expect)
+
+
+def test_routing_audit_accepts_the_exact_argmax_and_rejects_wrong_edges():
+    """The audit used by the GPU whole-model tests (oracle/parity.py::assert_routing_is_valid): forcing the layer's own
+    first-max-wins routing audits clean; a winner from another node's segment, a non-maximal edge of the right segment
+    and a wrong claim about an empty segment are each caught."""
+    import pytest
+    import torch
+
+    from oracle import parity
+    from oracle.mp_ref import MlpMessagePassingLayer, edge_messages_ref
+    from oracle.scatter_ref import scatter_max
+
+    torch.manual_seed(0)
+    N, D, K = 7, 8, 3
+    layer = MlpMessagePassingLayer(D, D, D, K).double()
+    h = torch.randn(N, D, dtype=torch.float64)
+    adjacency = [(torch.randint(0, N - 1, (9,)), torch.randint(0, N - 1, (9,))) for _ in range(K)]  # node N-1: no in-edges
+    layers = layer._MlpMessagePassingLayer__edge_message_transformation_layers
+    weight, bias = torch.stack([l.weight for l in layers]), torch.stack([l.bias for l in layers])
+    messages, targets = edge_messages_ref(h, adjacency, weight, bias)
+    E = messages.shape[0]
+    own_max, own_arg = scatter_max(messages, targets, dim=0, dim_size=N)
+    assert (own_arg[N - 1] == E).all()
+
+    def audit(arg):
+        layer.forced_winners = arg
+        out = layer.aggregated_messages(h, adjacency)
+        return out, [layer.routing_audit]
+
+    out, audits = audit(own_arg)
+    assert torch.equal(out, own_max)
+    worst = parity.assert_routing_is_valid(audits, "own routing")
+    assert worst["differing_frac"] == 0.0 and worst["max_relative_deficit"] == 0.0
+
+    node = int(targets[0])
+    other = next(e for e in range(E) if int(targets[e]) != node)
+    bad = own_arg.clone(); bad[node, 0] = other
+    with pytest.raises(AssertionError, match="not in-edges"):
+        parity.assert_routing_is_valid(audit(bad)[1], "foreign edge")
+
+    seg = [e for e in range(E) if int(targets[e]) == node]
+    if len(seg) > 1:
+        loser = next(e for e in seg if e != int(own_arg[node, 1]))
+        bad = own_arg.clone(); bad[node, 1] = loser
+        with pytest.raises(AssertionError, match="falls short"):
+            parity.assert_routing_is_valid(audit(bad)[1], "non-maximal edge")
+
+    bad = own_arg.clone(); bad[N - 1, 0] = 0
+    with pytest.raises(AssertionError):
+        parity.assert_routing_is_valid(audit(bad)[1], "edge claimed for an empty segment")
