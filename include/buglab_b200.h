@@ -164,6 +164,41 @@ int bl_pair_weight_grad_tc(const float* g, const float* x, const int32_t* idx, c
                            float* d_weight, int32_t ld, int32_t col0, bl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Second-generation projection GEMMs: TMA-fed tcgen05 (csrc/gemm_tma.cu).  Same reference call sites as
+ * bl_pair_project_tc / bl_pair_weight_grad_tc (per-type Linear_k of ptgnn's MlpMessagePassingLayer hoisted
+ * to unique (type, node) pairs, buglab/models/gnnlayerdefs.py:6-23; its two backward products; the layer's
+ * node-update Linear(M -> D_out)).  Operands are split into fp16 hi/lo parts ONCE per table
+ * (bl_rows_split_f16) and moved by the TMA engine (row gathers: tile::gather4); CTA pairs run
+ * tcgen05.mma.cta_group::2 on 256-row tiles unless BUGLAB_B200_TMA_CG=1.
+ *
+ * Split table layout: fp16 [2][rows + 1][dim] — part 0 = fp16(s*x), part 1 = fp16(s*x - part 0); the extra
+ * last row of each part is zero (the padding row the kernels read for rows past a segment end).
+ * s = pow2 pre-scale derived from *amax (NULL: 1).
+ *
+ * Segments: pair rows are grouped in num_segs ranges [seg_ptr[s], seg_ptr[s+1]) that share weight matrix
+ * seg_type[s] (NULL: s).  tile_ptr / slab_ptr = bl_segment_unit_prefix(seg_ptr, unit) with unit =
+ * bl_tma_tile_rows() / bl_tma_slab_rows(); max_tiles / max_slabs = any upper bound of their last entry
+ * (sizes the persistent grid without a device->host copy). */
+int bl_rows_split_f16(const float* x, const int32_t* idx, int64_t rows, int32_t dim, const float* amax, void* out,
+                      bl_stream_t stream);
+int bl_segment_unit_prefix(const int32_t* seg_ptr, int32_t num_segs, int32_t unit, int32_t* prefix, bl_stream_t stream);
+int bl_tma_tile_rows(void);
+int bl_tma_slab_rows(void);
+int bl_tma_gemm_supported(int32_t n_out, int32_t k_in);
+/* out[p, 0:n_out] = (1/s) * A[row(p), :] . W_type[0:n_out, 0:k_in]^T (+ bias_type);  row(p) = idx[p] or p (idx NULL);
+ * a_rows = rows per part of a_split (incl. the zero row); wparts as written by bl_weight_parts_f16; s from *amax. */
+int bl_tma_project(const void* a_split, int64_t a_rows, const int32_t* idx, const void* wparts, const float* bias,
+                   const float* amax, const int32_t* seg_ptr, const int32_t* seg_type, const int32_t* tile_ptr,
+                   int32_t num_segs, int32_t num_types, int64_t num_rows, int64_t max_tiles, int32_t n_out, int32_t k_in,
+                   float* out, bl_stream_t stream);
+int bl_tma_weight_grad_supported(int32_t m_out, int32_t n_in);
+/* d_weight[type, 0:m_out, col0:col0+n_in] = (1/s) * sum over pair rows of G[p, :]^T X[idx[p], :]  (block zeroed first) */
+int bl_tma_weight_grad(const void* g_split, int64_t g_rows, const void* x_split, int64_t x_rows, const int32_t* idx,
+                       const float* amax, const int32_t* seg_ptr, const int32_t* seg_type, const int32_t* slab_ptr,
+                       int32_t num_segs, int32_t num_types, int64_t num_rows, int64_t max_slabs, int32_t m_out,
+                       int32_t n_in, float* d_weight, int32_t ld, int32_t col0, bl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Fused typed-edge message + aggregate (THE hot kernel).
  *
  * Replaces, per layer, ptgnn MlpMessagePassingLayer.forward's

@@ -46,6 +46,11 @@ class EdgePlan(NamedTuple):
     num_t_pairs: int
     s_type_ptr_host: Tuple[int, ...]
     t_type_ptr_host: Tuple[int, ...]
+    # tile / slab prefix tables of the TMA GEMMs over the S- and T-pair segments (device, int32 [K+1])
+    s_tile_ptr: Optional[torch.Tensor] = None
+    t_tile_ptr: Optional[torch.Tensor] = None
+    s_slab_ptr: Optional[torch.Tensor] = None
+    t_slab_ptr: Optional[torch.Tensor] = None
 
 
 def build_edge_plan(
@@ -102,6 +107,11 @@ def build_edge_plan_from_flat(
         ),
         "bl_plan_build",
     )
+    tables = [None] * 4
+    if USE_TMA:
+        tile_rows, slab_rows = tma_tile_rows(), tma_slab_rows()
+        tables = [unit_prefix(s_type_ptr, tile_rows), unit_prefix(t_type_ptr, tile_rows),
+                  unit_prefix(s_type_ptr, slab_rows), unit_prefix(t_type_ptr, slab_rows)]
     meta_host = meta.cpu().tolist()  # the one host sync of the plan
     s_tp, t_tp = tuple(meta_host[: K + 1]), tuple(meta_host[K + 1 : 2 * (K + 1)])
     P_s, P_t = meta_host[-2], meta_host[-1]
@@ -109,7 +119,7 @@ def build_edge_plan_from_flat(
         N, E, K, e_perm[:E], e_src[:E], e_type[:E], row_ptr, urow[:E], vrow[:E],
         s_node[:P_s], s_type_ptr, s_by_node_ptr, s_by_node_idx[:P_s],
         t_node[:P_t], t_type_ptr, t_by_node_ptr, t_by_node_idx[:P_t],
-        P_s, P_t, s_tp, t_tp,
+        P_s, P_t, s_tp, t_tp, *tables,
     )
 
 
@@ -152,6 +162,17 @@ USE_TCGEN05 = os.environ.get("BUGLAB_B200_TCGEN05", "1") != "0"
 # Largest width that goes through the tcgen05 kernels; the 512-wide post-residual layers stay on split + cuBLAS by default
 # (measured parity there: 12.6 vs 12.1 ms per table), BUGLAB_B200_TC_MAX_WIDTH=512 switches them over.
 TC_MAX_WIDTH = int(os.environ.get("BUGLAB_B200_TC_MAX_WIDTH", "256"))
+# Second-generation GEMMs (csrc/gemm_tma.cu: node-level fp16 split, TMA-fed tcgen05, CTA pairs) for every shape they
+# support (all widths that are multiples of 256, and 128-wide projections); BUGLAB_B200_TMA=0 restores round 1's kernels.
+USE_TMA = os.environ.get("BUGLAB_B200_TMA", "1") != "0"
+
+
+def _tma_proj_ok(n_out: int, k_in: int) -> bool:
+    return USE_TMA and PROJECTION_MODE == "f16x3" and bool(_lib.load().bl_tma_gemm_supported(n_out, k_in))
+
+
+def _tma_wgrad_ok(m_out: int, n_in: int) -> bool:
+    return USE_TMA and PROJECTION_MODE == "f16x3" and bool(_lib.load().bl_tma_weight_grad_supported(m_out, n_in))
 
 
 def _host_i32(values: Tuple[int, ...]):
@@ -217,6 +238,75 @@ def pair_weight_grad_tc(g: torch.Tensor, x: torch.Tensor, idx: torch.Tensor, ama
                                              stream_ptr(g.device)), "bl_pair_weight_grad_tc")
 
 
+# ---------------------------------------------------------------------------------------------------
+# Second-generation GEMMs (csrc/gemm_tma.cu): split once per table, TMA-fed tcgen05, CTA pairs
+# ---------------------------------------------------------------------------------------------------
+def rows_split(x: torch.Tensor, idx: Optional[torch.Tensor] = None, amax: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp16 hi/lo split table ``[2, rows + 1, dim]`` of ``x`` (or of ``x[idx]``), pre-scaled by the power of two derived
+    from ``amax``; the extra last row of each part is zero."""
+    rows = int(idx.shape[0]) if idx is not None else int(x.shape[0])
+    dim = int(x.shape[1])
+    out = torch.empty((2, rows + 1, dim), device=x.device, dtype=torch.float16)
+    check(_lib.load().bl_rows_split_f16(f32(x), i32(idx) if idx is not None else None, rows, dim,
+                                        f32(amax) if amax is not None else None, out.data_ptr(), stream_ptr(x.device)),
+          "bl_rows_split_f16")
+    return out
+
+
+def unit_prefix(seg_ptr: torch.Tensor, unit: int) -> torch.Tensor:
+    """``prefix[s] = sum_{s' < s} ceil(rows(s') / unit)`` on the device (tile / slab tables of the TMA GEMMs)."""
+    num_segs = int(seg_ptr.shape[0]) - 1
+    out = torch.empty(num_segs + 1, device=seg_ptr.device, dtype=torch.int32)
+    check(_lib.load().bl_segment_unit_prefix(i32(seg_ptr), num_segs, int(unit), i32(out), stream_ptr(seg_ptr.device)),
+          "bl_segment_unit_prefix")
+    return out
+
+
+def tma_tile_rows() -> int:
+    return int(_lib.load().bl_tma_tile_rows())
+
+
+def tma_slab_rows() -> int:
+    return int(_lib.load().bl_tma_slab_rows())
+
+
+def tma_project(a_split: torch.Tensor, idx: Optional[torch.Tensor], parts: torch.Tensor, bias: Optional[torch.Tensor],
+                amax: Optional[torch.Tensor], seg_ptr: torch.Tensor, seg_type: Optional[torch.Tensor], num_rows: int,
+                tile_ptr: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``out[p] = (1/s) * A[row(p)] @ W_type.T (+ bias_type)`` on the TMA-fed tcgen05 kernel; ``a_split`` from
+    :func:`rows_split`, ``parts`` from :func:`weight_parts`."""
+    num_types, _, n_out, k_in = parts.shape
+    num_segs = int(seg_ptr.shape[0]) - 1
+    if tile_ptr is None:
+        tile_ptr = unit_prefix(seg_ptr, tma_tile_rows())
+    out = torch.empty((num_rows, n_out), device=a_split.device, dtype=torch.float32)
+    max_tiles = num_rows // tma_tile_rows() + num_segs
+    check(_lib.load().bl_tma_project(a_split.data_ptr(), int(a_split.shape[1]), i32(idx) if idx is not None else None,
+                                     parts.data_ptr(), f32(bias) if bias is not None else None,
+                                     f32(amax) if amax is not None else None, i32(seg_ptr),
+                                     i32(seg_type) if seg_type is not None else None, i32(tile_ptr), num_segs, num_types,
+                                     num_rows, max_tiles, n_out, k_in, f32(out), stream_ptr(a_split.device)), "bl_tma_project")
+    return out
+
+
+def tma_weight_grad(g_split: torch.Tensor, x_split: torch.Tensor, idx: torch.Tensor, amax: Optional[torch.Tensor],
+                    seg_ptr: torch.Tensor, seg_type: Optional[torch.Tensor], d_weight: torch.Tensor, col0: int,
+                    slab_ptr: Optional[torch.Tensor] = None) -> None:
+    """``d_weight[type, :, col0:col0+n] = (1/s) * sum_p G[p]^T X[idx[p]]`` (block zeroed first) on the TMA-fed tcgen05 kernel."""
+    num_types, m_out, ld = d_weight.shape
+    n_in = int(x_split.shape[2])
+    num_segs = int(seg_ptr.shape[0]) - 1
+    num_rows = int(idx.shape[0])
+    if slab_ptr is None:
+        slab_ptr = unit_prefix(seg_ptr, tma_slab_rows())
+    max_slabs = num_rows // tma_slab_rows() + num_segs
+    check(_lib.load().bl_tma_weight_grad(g_split.data_ptr(), int(g_split.shape[1]), x_split.data_ptr(), int(x_split.shape[1]),
+                                         i32(idx), f32(amax) if amax is not None else None, i32(seg_ptr),
+                                         i32(seg_type) if seg_type is not None else None, i32(slab_ptr), num_segs, num_types,
+                                         num_rows, max_slabs, m_out, n_in, f32(d_weight), ld, col0,
+                                         stream_ptr(g_split.device)), "bl_tma_weight_grad")
+
+
 def _project_pairs_f16x3(h: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor, col0: int,
                           type_ptr: Tuple[int, ...], bias: Optional[torch.Tensor],
                           type_ptr_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -256,8 +346,16 @@ class TypedEdgeMessageMax(torch.autograd.Function):
         if twoD != 2 * D or K != plan.num_edge_types or N != plan.num_nodes:
             raise ValueError(f"shape mismatch: h {tuple(h.shape)}, weight {tuple(weight.shape)}, plan K={plan.num_edge_types} N={plan.num_nodes}")
         bias_c = bias.contiguous() if bias is not None else None
+        h_split = None
         with torch.no_grad():
-            if PROJECTION_MODE == "f16x3":
+            if _tma_proj_ok(M, D) and plan.s_tile_ptr is not None:
+                # split h ONCE per layer at node granularity; both projections gather its rows by TMA
+                h_split = rows_split(h)
+                u_rows = tma_project(h_split, plan.s_node, weight_parts(weight, M, D, 0, False), None, None,
+                                     plan.s_type_ptr, None, plan.num_s_pairs, plan.s_tile_ptr)
+                v_rows = tma_project(h_split, plan.t_node, weight_parts(weight, M, D, D, False), bias_c, None,
+                                     plan.t_type_ptr, None, plan.num_t_pairs, plan.t_tile_ptr)
+            elif PROJECTION_MODE == "f16x3":
                 u_rows = _project_pairs_f16x3(h, plan.s_node, weight, 0, plan.s_type_ptr_host, None, plan.s_type_ptr)
                 v_rows = _project_pairs_f16x3(h, plan.t_node, weight, D, plan.t_type_ptr_host, bias_c, plan.t_type_ptr)
             else:
@@ -281,6 +379,7 @@ class TypedEdgeMessageMax(torch.autograd.Function):
         ctx.plan = plan
         ctx.has_bias = bias is not None
         ctx.mode = PROJECTION_MODE
+        ctx.h_split = h_split if (h_split is not None and _tma_wgrad_ok(M, D)) else None  # x operand of the weight gradient
         ctx.save_for_backward(h, weight, xwin, ewin)
         return agg
 
@@ -304,7 +403,34 @@ class TypedEdgeMessageMax(torch.autograd.Function):
         )
         d_bias = torch.zeros((K, M), device=dev, dtype=torch.float32) if ctx.has_bias else None
         d_rows = []
-        if ctx.mode == "f16x3":
+        unscaled = False
+        if ctx.mode == "f16x3" and _tma_proj_ok(D, M) and plan.s_tile_ptr is not None:
+            # second-generation path: split each gradient table once (pre-scaled), then TMA-fed tcgen05 for both products
+            unscaled = True  # the projection epilogue undoes the pre-scale
+            d_weight = torch.empty_like(weight)
+            if d_bias is not None:
+                check(lib.bl_grouped_colsum(f32(dv), i32(plan.t_type_ptr), K, M, f32(d_bias), stream_ptr(dev)), "bl_grouped_colsum")
+            wg_ok = _tma_wgrad_ok(M, D)
+            h_split = ctx.h_split if ctx.h_split is not None else (rows_split(h) if wg_ok else None)
+            for rows_idx, d_tab, col0, type_ptr, type_ptr_dev, tile_ptr, slab_ptr in (
+                    (plan.s_node, du, 0, plan.s_type_ptr_host, plan.s_type_ptr, plan.s_tile_ptr, plan.s_slab_ptr),
+                    (plan.t_node, dv, D, plan.t_type_ptr_host, plan.t_type_ptr, plan.t_tile_ptr, plan.t_slab_ptr)):
+                g_split = rows_split(d_tab, None, amax)
+                d_rows.append(tma_project(g_split, None, weight_parts(weight, D, M, col0, True), None, amax, type_ptr_dev, None,
+                                          int(rows_idx.shape[0]), tile_ptr))
+                if wg_ok:
+                    tma_weight_grad(g_split, h_split, rows_idx, amax, type_ptr_dev, None, d_weight, col0, slab_ptr)
+                else:  # widths the weight-gradient kernel does not cover (e.g. 128): round 1's split + library GEMM
+                    g2 = _split2_rows(d_tab, None, amax)
+                    a2 = _split2_rows(h, rows_idx)
+                    tmp = torch.empty((K, 2 * M, 2 * D), device=dev, dtype=torch.float32)
+                    check(lib.bl_pair_project_bwd_weight(g2.data_ptr(), 2 * M, 0, a2.data_ptr(), _host_i32(type_ptr), K, M, D,
+                                                         f32(amax), f32(tmp), f32(d_weight), 2 * D, col0, stream_ptr(dev)),
+                          "bl_pair_project_bwd_weight")
+                    del g2, a2, tmp
+                del g_split
+            del du, dv
+        elif ctx.mode == "f16x3":
             d_weight = torch.empty_like(weight)
             if d_bias is not None:
                 check(lib.bl_grouped_colsum(f32(dv), i32(plan.t_type_ptr), K, M, f32(d_bias), stream_ptr(dev)), "bl_grouped_colsum")
@@ -368,7 +494,7 @@ class TypedEdgeMessageMax(torch.autograd.Function):
         check(
             lib.bl_rows_segment_sum(f32(d_rows[0]), i32(plan.s_by_node_ptr), i32(plan.s_by_node_idx),
                                     f32(d_rows[1]), i32(plan.t_by_node_ptr), i32(plan.t_by_node_idx),
-                                    N, D, 0, f32(amax) if amax is not None else None, f32(d_h), stream_ptr(dev)),
+                                    N, D, 0, f32(amax) if (amax is not None and not unscaled) else None, f32(d_h), stream_ptr(dev)),
             "bl_rows_segment_sum",
         )
         return d_h, d_weight, d_bias, None
@@ -435,8 +561,53 @@ class DenseLinearF16x3(torch.autograd.Function):
         return dx, dw
 
 
+def _single_segment(rows: int, device) -> torch.Tensor:
+    """Device tensor ``[0, rows]`` (one segment covering the whole table) built without a host->device copy."""
+    seg = torch.full((2,), int(rows), dtype=torch.int32, device=device)
+    seg[0].zero_()
+    return seg
+
+
+class DenseLinearTma(torch.autograd.Function):
+    """y = x @ weight.T (no bias) for x [R, K_in], weight [N_out, K_in] on the TMA-fed tcgen05 kernels: the node-update
+    ``Linear(M -> D_out)`` of the message-passing layer.  Same split-fp16 arithmetic as the projections (fp32-class
+    accuracy), forward and both backward products; nothing runs on a library GEMM."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, weight: torch.Tensor):
+        x = x.contiguous()
+        weight = weight.contiguous()
+        R, K_in = x.shape
+        N_out = weight.shape[0]
+        seg = _single_segment(R, x.device)
+        x_split = rows_split(x)
+        y = tma_project(x_split, None, weight_parts(weight.view(1, N_out, K_in), N_out, K_in, 0, False), None, None, seg, None, R)
+        ctx.save_for_backward(x_split, weight, seg)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: torch.Tensor):
+        lib = _lib.load()
+        x_split, weight, seg = ctx.saved_tensors
+        dy = dy.contiguous()
+        R, N_out = dy.shape
+        K_in = weight.shape[1]
+        dev = dy.device
+        amax = torch.empty(1, device=dev, dtype=torch.float32)
+        check(lib.bl_absmax(f32(dy), dy.numel(), f32(amax), stream_ptr(dev)), "bl_absmax")
+        g_split = rows_split(dy, None, amax)
+        dx = tma_project(g_split, None, weight_parts(weight.view(1, N_out, K_in), K_in, N_out, 0, True), None, amax, seg, None, R)
+        dw = torch.empty_like(weight)
+        identity = torch.arange(R, device=dev, dtype=torch.int32)
+        tma_weight_grad(g_split, x_split, identity, amax, seg, None, dw.view(1, N_out, K_in), 0)
+        return dx, dw
+
+
 def dense_linear(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     """Bias-free Linear: split-fp16 tensor-core GEMMs by default, plain fp32 library GEMM in "fp32" mode or for odd widths."""
+    n_out, k_in = int(weight.shape[0]), int(x.shape[1])
+    if _tma_proj_ok(n_out, k_in) and _tma_proj_ok(k_in, n_out) and _tma_wgrad_ok(n_out, k_in):
+        return DenseLinearTma.apply(x, weight)
     if PROJECTION_MODE == "f16x3" and x.shape[1] % 4 == 0 and weight.shape[0] % 4 == 0:
         return DenseLinearF16x3.apply(x, weight)
     return torch.nn.functional.linear(x, weight)

@@ -10,7 +10,20 @@
 namespace bl {
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
-constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs (compile-time sizing of partial buffers; launches use num_sms())
+
+// SM count of the CURRENT device, queried once per device (persistent-kernel grid size).
+inline int num_sms() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return kNumSMs;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSMs;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
 
 // Records the last CUDA error text for bl_error_string(BL_ERR_CUDA).
 void set_cuda_error(cudaError_t e, const char* where);

@@ -13,7 +13,7 @@ early layer's dW by ~1 %.  Gradient parity is therefore established in two ways:
     then agree elementwise to 1e-4 (abs + rel) — this checks every backward kernel exactly;
     and the routing itself is verified independently: the fp64 oracle, run with the forced routing, audits every
     forced winner against its own exact segment max (`assert_routing_is_valid`): the edge must end in that node, empty
-    segments must agree, and the winner's exact message must attain the exact maximum to within 1e-5 relative — so a
+    segments must agree, and the winner's exact message must attain the exact maximum to within 1e-4 relative (the forward tolerance) — so a
     wrong-edge bug cannot hide behind the conditioning, only genuine near-ties may differ;
   * UNCONDITIONED (goldens from the real reference, where routing cannot be forced): relative Frobenius error of every
     gradient tensor below 5e-2, which a routing bug (wrong edge, wrong type, missing term) fails by orders of
@@ -78,11 +78,14 @@ def assert_grad_close(actual: torch.Tensor, expected: torch.Tensor, what: str = 
         f"relative L2 error {rel_l2:.2e}, max abs diff {max_abs:.2e}")
 
 
-def assert_routing_is_valid(audits, what: str = "", max_relative_deficit: float = 1e-5, max_differing_frac: float = 1e-3) -> dict:
+def assert_routing_is_valid(audits, what: str = "", max_relative_deficit: float = 1e-4, max_differing_frac: float = 1e-3) -> dict:
     """``audits``: per layer dicts from the fp64 oracle run with another implementation's max-routing forced.
     Every forced winner must be an in-edge of its node, agree on empty segments, and its exact (fp64) message must attain
-    the exact segment maximum up to ``max_relative_deficit`` (near-ties between two fp32 evaluations are ~1e-7); the
-    share of decisions that differ from the exact argmax must stay below ``max_differing_frac``."""
+    the exact segment maximum up to ``max_relative_deficit``; the share of decisions that differ from the exact argmax
+    must stay below ``max_differing_frac``.  The deficit bound is the forward tolerance (1e-4): the audited layer's input
+    states are the implementation's own, which may sit up to 1e-4 from the exact ones after several layers, so two messages
+    closer than that can legitimately swap (measured on B200: worst 1.3e-5 at H=128 / 30 000 nodes in layer 8, ~1e-7 in
+    the first layers); a wrong edge misses by O(1)."""
     worst = dict(differing_frac=0.0, max_relative_deficit=0.0)
     for i, a in enumerate(audits):
         assert a is not None, f"{what}: layer {i} was not audited"

@@ -1,9 +1,7 @@
 """B200 parity of the seq-attention kernels through the C ABI, against the CPU oracle.
 
-GATED: these tests have not run on a B200 yet (the kernels were written after round 1's GPU budget was spent; their
-arithmetic is pinned on the CPU by tests/test_seq_attention_emul.py, which executes the same source).  They run only when
-BUGLAB_B200_SEQ_GPU=1, so that an unverified launch path cannot take down the round-end GPU suite; flip the default once
-they have passed."""
+First B200 run: round 2, 11/11 passed (gpurun_out/r2c1_seq_tests.txt); part of the default ``-m gpu`` suite since then
+(BUGLAB_B200_SEQ_GPU=0 skips them)."""
 import os
 import sys
 
@@ -17,8 +15,8 @@ for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("BUGLAB_B200_SEQ_GPU", "0") != "1",
-                                 reason="seq-attention GPU parity is opt-in until it has run once (BUGLAB_B200_SEQ_GPU=1)")]
+              pytest.mark.skipif(os.environ.get("BUGLAB_B200_SEQ_GPU", "1") == "0",
+                                 reason="seq-attention GPU parity switched off by BUGLAB_B200_SEQ_GPU=0")]
 
 
 @pytest.mark.parametrize("case_index", range(7))
