@@ -7,8 +7,17 @@ step and GPU (~2k nodes each, 8 forward edge kinds -> 17 kinds per layer), fp32,
   value      graphs/s with the packed minibatch already resident in HBM (plan build + step inside the timed region)
   e2e        graphs/s through the public API from HOST (tensorised numpy) samples: pack -> pinned -> H2D -> plan ->
              step -> D2H of the loss, every step
-  roofline   the fused typed-edge message+aggregate kernel, timed alone with CUDA events on its launch stream
-  cpu_baseline / --impl reference   the CPU oracle (port of the reference semantics) on the host cores
+  roofline        the DOMINANT kernel of the step (the TMA-fed tcgen05 projection, tensor-bound), timed alone
+  roofline_edge   the fused typed-edge message+aggregate kernel (north_star's HBM-bound kernel), timed alone
+  roofline_layer  SURVEY §8(d)'s object: one H->H message+aggregate layer forward (split + 2 projections + edge kernel),
+                  §8(d) algorithmic bytes / CUDA-event time, at this workload's shape; roofline_c3 = the same at
+                  BASELINE configs[2] (1 M nodes / 10 M edges / 14 edge kinds)
+  e2e_shards      graphs/s from .msgpack.l.gz files on disk (native decode -> tensorise -> pack -> H2D -> step)
+  config1         BASELINE configs[0] (hidden 128, one ~500-graph shard, the reference's 30 000-node minibatch budget)
+                  through the kept buglab.models.train entry point: this GPU vs the host cores
+  cpu_baseline / --impl reference   the kept train entry point on the host cores with the CPU oracle underneath
+                  (oracle/cpu_backend.py), on this arm's model config, minibatches cut by the reference's own
+                  30 000-node budget (its real batch size) — the bounded sample
 """
 import argparse
 import copy
@@ -45,6 +54,8 @@ def parse_args():
     ap.add_argument("--hidden", type=int, default=HIDDEN)
     ap.add_argument("--mean-nodes", type=int, default=MEAN_NODES)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-extras", action="store_true", help="only value / e2e / clocks (no rooflines, shards, config 1)")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="host threads of the CPU arm (0: min(32, affinity))")
     ap.add_argument("--profile", action="store_true",
                     help="profiling run for ncu: one minibatch, resident steps only (numbers printed under a profiler are not bench values)")
     return ap.parse_args()
@@ -251,127 +262,339 @@ def run_ours(args):
     }
 
     if rank == 0:
-        result["roofline"] = edge_kernel_roofline(resident[0], nn, args.hidden, device)
+        if not args.skip_extras:
+            del resident
+            torch.cuda.empty_cache()
+            result.update(rooflines(model, host_batches[0], args.hidden, device))
+            if world == 1:
+                result["e2e_shards"] = e2e_from_shards(args, device, result["value"])
+                result["config1"] = config1_gpu(device)
         if world == 1 and not args.skip_cpu_baseline:
-            result["cpu_baseline"] = cpu_baseline(args, steps=1, warmup=0)
+            result["cpu_baseline"] = cpu_arm_subprocess(args.hidden, steps=2, warmup=1, threads=args.cpu_threads)
+            if "config1" in result:
+                result["config1"]["cpu"] = cpu_arm_subprocess(CONFIG1_HIDDEN, steps=10, warmup=2, threads=args.cpu_threads)
         print(json.dumps(result), flush=True)
     if distributed.is_distributed():
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
 
 
-def edge_kernel_roofline(mb, nn, hidden, device):
-    """The fused typed-edge message+aggregate kernel (bl_edge_segmax_fwd) of one H->H layer, timed alone with CUDA
-    events on the stream it is launched on.  Algorithmic bytes per launch (reference formulation):
-    E*(2*D_in*4 + 12) + N*M*4."""
+# ---------------------------------------------------------------------------------------------------------------
+# rooflines
+# ---------------------------------------------------------------------------------------------------------------
+def ncu_traffic(kernel: str, key: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ``ncu --set full`` captures
+    (profiles/ncu_traffic.json, keyed by kernel and shape); None when that shape was never captured."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(kernel, {}).get(key)
+    except (OSError, ValueError):
+        return None
+
+
+def _time_on_stream(fn, device, reps=10, warm=3):
+    import torch
+
+    stream = torch.cuda.current_stream(device)
+    for _ in range(warm):
+        fn()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(device)
+    s.record(stream)
+    for _ in range(reps):
+        fn()
+    e.record(stream)
+    e.synchronize()
+    return s.elapsed_time(e) / reps
+
+
+def layer_rooflines(plan, hidden, device, label, seed=0):
+    """One H->H typed-edge message+aggregate layer forward at the shape of ``plan``: the whole layer (SURVEY §8(d) bytes
+    over the CUDA-event time of split + both projections + edge kernel), the edge kernel alone and one projection alone."""
     import torch
 
     from buglab_b200 import _lib, ops
 
     peaks, peak_kind = measured_peaks()
-    graph = mb["graph_data"]
-    adj = graph["adjacency_lists"]
-    plan = ops.build_edge_plan(adj, int(graph["node_to_graph_idx"].shape[0]))
-    N, E, M = plan.num_nodes, plan.num_edges, hidden
+    N, E, K, D, M = plan.num_nodes, plan.num_edges, plan.num_edge_types, hidden, hidden
     lib = _lib.load()
-    g = torch.Generator(device=device).manual_seed(0)
+    g = torch.Generator(device=device).manual_seed(seed)
+    h = torch.randn(N, D, device=device, generator=g)
+    weight = torch.randn(K, M, 2 * D, device=device, generator=g) / (2 * D) ** 0.5
+    bias = torch.randn(K, M, device=device, generator=g) * 0.1
+    shape_key = f"{N}x{E}x{M}"
+    algo_bytes = E * (2 * D * 4 + 12) + N * M * 4            # SURVEY.md §8(d), reference formulation
+    out = {}
+
+    # (1) the whole layer forward
+    def layer():
+        with torch.no_grad():
+            return ops.typed_edge_message_max(h, weight, bias, plan)
+
+    ms_layer = _time_on_stream(layer, device, reps=6, warm=2)
+    flops_layer = 2.0 * (plan.num_s_pairs + plan.num_t_pairs) * D * M * 3   # split-fp16: three MMAs per product
+    out["layer"] = {"bound": "hbm", "what": f"{label}: H->H message+aggregate layer forward (node split + U and V projections + "
+                    "fused edge kernel)", "achieved": algo_bytes / ms_layer / 1e6, "peak": peaks["hbm_gbs"], "peak_kind": peak_kind,
+                    "unit": "GB/s", "frac": algo_bytes / ms_layer / 1e6 / peaks["hbm_gbs"], "traffic": None,
+                    "algorithmic_bytes": algo_bytes, "ms": ms_layer, "nodes": N, "edges": E, "edge_kinds": K,
+                    "s_pairs": plan.num_s_pairs, "t_pairs": plan.num_t_pairs,
+                    "tensor_view": {"tflop_issued": flops_layer / 1e12, "achieved_tflops": flops_layer / ms_layer / 1e9,
+                                    "peak_tflops": peaks["bf16_tflops"],
+                                    "frac": flops_layer / ms_layer / 1e9 / peaks["bf16_tflops"],
+                                    "note": "fp32-exact projections need 3 fp16 MMAs per product: at the tensor peak alone they take "
+                                            f"{flops_layer / peaks['bf16_tflops'] / 1e9:.2f} ms, the HBM floor of the §8(d) bytes is "
+                                            f"{algo_bytes / peaks['hbm_gbs'] / 1e6:.2f} ms"}}
+
+    # (2) the fused edge kernel alone
     u = torch.randn(plan.num_s_pairs, M, device=device, generator=g)
     v = torch.randn(plan.num_t_pairs, M, device=device, generator=g)
     agg = torch.empty(N, M, device=device); xwin = torch.empty_like(agg)
     ewin = torch.empty(N, M, device=device, dtype=torch.int32)
     stream = torch.cuda.current_stream(device)
 
-    def launch():
+    def edge():
         _lib.check(lib.bl_edge_segmax_fwd(u.data_ptr(), v.data_ptr(), plan.row_ptr.data_ptr(), plan.urow.data_ptr(),
                                           plan.vrow.data_ptr(), N, M, agg.data_ptr(), xwin.data_ptr(), ewin.data_ptr(),
                                           stream.cuda_stream), "bl_edge_segmax_fwd")
 
-    for _ in range(3):
-        launch()
-    reps = 10
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(device)
-    s.record(stream)
-    for _ in range(reps):
-        launch()
-    e.record(stream)
-    e.synchronize()
-    ms = s.elapsed_time(e) / reps
-    algo_bytes = E * (2 * M * 4 + 12) + N * M * 4
-    achieved = algo_bytes / (ms / 1e3) / 1e9
-    return {"bound": "hbm", "kernel": "edge_segmax_fwd_warp (bl_edge_segmax_fwd), H->H layer", "achieved": achieved,
-            "peak": peaks["hbm_gbs"], "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-            # dram__bytes_read+write of this kernel on this exact workload, from the committed ncu --set full capture
-            # (profiles/r1_edge_segmax_fwd_ncu.md); null for any other shape
-            "traffic": 10253209000 if (N, E, M) == (564508, 6410926, 256) else None, "algorithmic_bytes": algo_bytes, "ms_per_launch": ms, "nodes": N, "edges": E,
-            "working_set_bytes": int((u.numel() + v.numel()) * 4)}
+    ms_edge = _time_on_stream(edge, device)
+    out["edge"] = {"bound": "hbm", "kernel": "edge_segmax_fwd_warp (bl_edge_segmax_fwd), H->H layer",
+                   "achieved": algo_bytes / ms_edge / 1e6, "peak": peaks["hbm_gbs"], "peak_kind": peak_kind, "unit": "GB/s",
+                   "frac": algo_bytes / ms_edge / 1e6 / peaks["hbm_gbs"], "traffic": ncu_traffic("edge_segmax_fwd_warp", shape_key),
+                   "algorithmic_bytes": algo_bytes, "ms_per_launch": ms_edge, "nodes": N, "edges": E,
+                   "working_set_bytes": int((u.numel() + v.numel()) * 4)}
+    del u, v, agg, xwin, ewin
+
+    # (3) the dominant kernel: one projection (U table) on the TMA-fed tcgen05 kernel
+    if ops.USE_TMA and plan.s_tile_ptr is not None and lib.bl_tma_gemm_supported(M, D):
+        h_split = ops.rows_split(h)
+        parts = ops.weight_parts(weight, M, D, 0, False)
+        P = plan.num_s_pairs
+
+        def proj():
+            return ops.tma_project(h_split, plan.s_node, parts, None, None, plan.s_type_ptr, None, P, plan.s_tile_ptr)
+
+        ms_proj = _time_on_stream(proj, device)
+        flops = 2.0 * P * D * M * 3
+        out["projection"] = {"bound": "tensor", "kernel": "tg::proj_kernel<256, 2, gather> (bl_tma_project), U table of an H->H layer",
+                             "achieved": flops / ms_proj / 1e9, "peak": peaks["bf16_tflops"], "peak_kind": peak_kind + " (cuBLAS bf16 burst)",
+                             "unit": "TFLOP/s", "frac": flops / ms_proj / 1e9 / peaks["bf16_tflops"],
+                             "traffic": ncu_traffic("proj_kernel", f"{P}x{D}x{M}"), "flops_per_launch": flops,
+                             "flops_note": "2*P*D*M*3: hi.hi + hi.lo + lo.hi MMAs actually issued (fp32-equivalent work is a third)",
+                             "ms_per_launch": ms_proj, "pair_rows": P,
+                             "hbm_view": {"algorithmic_bytes": P * (D * 4 + 4) + P * M * 4,
+                                          "achieved_GBs": (P * (D * 4 + 4) + P * M * 4) / ms_proj / 1e6}}
+    return out
 
 
-def best_cpu_thread_count() -> int:
-    """All host threads the process can actually use: os.cpu_count() over-reports inside CPU-limited containers (the
-    first B200 box reported 128 and ran the oracle 30x slower with 128 threads than 8 cores do), so a 1-second SGEMM
-    probe picks the fastest of {8, 16, 32, ..., affinity}."""
+def rooflines(model, tensorized_batch, hidden, device):
     import torch
 
+    from buglab_b200 import ops
+    from buglab_b200.synthetic import packed_edge_batch
+
+    mb = pack(model, tensorized_batch, device)
+    graph = mb["graph_data"]
+    plan = ops.build_edge_plan(graph["adjacency_lists"], int(graph["node_to_graph_idx"].shape[0]))
+    del mb, graph
+    here = layer_rooflines(plan, hidden, device, "this workload (configs[1])")
+    del plan
+    torch.cuda.empty_cache()
+    result = {"roofline": here.get("projection", here["edge"]), "roofline_edge": here["edge"], "roofline_layer": here["layer"]}
+    # BASELINE configs[2]: 1 M nodes / 10 M edges / 14 edge kinds, directly synthesised packed batch
+    src, tgt, etype = packed_edge_batch(1_000_000, 10_000_000, 14, 0)
+    plan = ops.build_edge_plan_from_flat(*(torch.from_numpy(a).to(device) for a in (src, tgt, etype)), 1_000_000, 14)
+    c3 = layer_rooflines(plan, 256, device, "configs[2] (1M nodes / 10M edges / 14 kinds)")
+    result["roofline_c3"] = {"layer": c3["layer"], "edge": c3["edge"], "projection": c3.get("projection")}
+    del plan
+    torch.cuda.empty_cache()
+    return result
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# end to end from shard files; BASELINE configs[0] through the train entry point
+# ---------------------------------------------------------------------------------------------------------------
+def e2e_from_shards(args, device, resident_value):
+    """The c2 train step fed from ``.msgpack.l.gz`` files: native decode + tensorise (include/buglab_shards.h) -> packing ->
+    pinned staging -> H2D -> device plan (producer thread) -> step -> loss D2H, through ModelTrainer's own prefetcher."""
+    import torch
+    from pathlib import Path
+
+    from buglab.models.modelregistry import load_model
+    from buglab.models.utils import LinearWarmupScheduler, optimizer
+    from buglab_b200.shards import ShardDataset
+    from buglab_b200.synthetic import SyntheticBugLabGenerator, write_shards
+    from dpu_utils.utils import RichPath
+    from ptgnn.baseneuralmodel.trainer import _Prefetcher
+
+    steps, warm = max(2, min(args.steps, 4)), 1
+    work = tempfile.mkdtemp(prefix="buglab_bench_shards_")
+    per_shard = 32
+    t0 = time.perf_counter()
+    write_shards(os.path.join(work, "train"), (steps + warm) * args.graphs // per_shard, per_shard, seed=1, mean_nodes=args.mean_nodes)
+    write_s = time.perf_counter() - t0
+    rich = RichPath.create(os.path.join(work, "train"))
+    model, _, _ = load_model({"modelName": "gnn-mlp", "hidden_state_size": args.hidden, "dropout_rate": DROPOUT,
+                              "stop_extending_minibatch_after_num_nodes": 10 ** 9, "max_nodes_per_graph": 10 ** 9},
+                             Path("/tmp/buglab_b200_bench_shards.pkl.gz"))
+    model.compute_metadata(SyntheticBugLabGenerator(seed=12345, mean_nodes=args.mean_nodes).samples(64))
+    torch.manual_seed(0)
+    nn = model.build_neural_module().to(device)
+    opt = optimizer(nn.parameters())
+    opt.max_grad_norm = 0.5
+    sched = LinearWarmupScheduler(opt)
+    nn.train()
+
+    def make():
+        it = model.minibatch_iterator(ShardDataset(rich).tensorized(model), device=device, max_minibatch_size=args.graphs,
+                                      yield_partial_minibatches=False)
+        for i, item in enumerate(it):
+            if i >= steps + warm:
+                return
+            yield item
+
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    graphs = 0
+    for i, (mb, raw) in enumerate(_Prefetcher(make, device)):
+        if i == warm:
+            torch.cuda.synchronize(device)
+            start.record()
+        opt.zero_grad()
+        loss = nn(**mb)
+        loss.backward()
+        opt.step()
+        sched.step(0, 0)
+        float(loss.detach())
+        if i >= warm:
+            graphs += len(raw)
+    end.record()
+    torch.cuda.synchronize(device)
+    value = graphs / (start.elapsed_time(end) / 1e3)
+    del nn, opt
+    torch.cuda.empty_cache()
+    return {"value": value, "unit": "graphs/s", "steps": steps, "fraction_of_resident_value": value / resident_value,
+            "from": "gzip+msgpack shard files -> native decode/tensorise (libbuglab_shards.so, worker threads) -> packing -> pinned "
+                    "staging -> H2D -> device plan -> step -> loss D2H", "shard_write_seconds": round(write_s, 1),
+            "host_cores": os.cpu_count()}
+
+
+CONFIG1_HIDDEN = 128
+CONFIG1_GRAPHS = 500
+
+
+def _config1_arguments(work, hidden, epochs, epoch_samples):
+    """docopt-style arguments of ``python -m buglab.models.train gnn-mlp TRAIN VALID MODEL`` for BASELINE configs[0]:
+    one shard of ~500 graphs (~2 000 nodes each), hidden 128 (or this arm's width for the reference arm), reference
+    defaults otherwise (``--minibatch-size 300``: the 30 000-node budget of modelregistry.py:53-54 ends the minibatches)."""
+    from buglab_b200.synthetic import write_shards
+
+    if not os.path.exists(os.path.join(work, "train")):
+        write_shards(os.path.join(work, "train"), 1, CONFIG1_GRAPHS, seed=11, mean_nodes=MEAN_NODES)
+        write_shards(os.path.join(work, "valid"), 1, 16, seed=12, mean_nodes=MEAN_NODES)
+    return {"MODEL_NAME": "gnn-mlp", "TRAIN_DATA_PATH": os.path.join(work, "train"), "VALID_DATA_PATH": os.path.join(work, "valid"),
+            "MODEL_FILENAME": os.path.join(work, "model.pkl.gz"), "--aml": False, "--azure-info": None, "--amp": False,
+            "--sequential": True, "--quiet": True, "--debug": False, "--host-loader": False, "--restore-path": None,
+            "--max-num-epochs": str(epochs), "--minibatch-size": "300", "--validate-after": str(epoch_samples),
+            "--limit-num-elements": None, "--max-files-per-fold": None,
+            "--model-spec": json.dumps({"hidden_state_size": hidden, "dropout_rate": DROPOUT})}
+
+
+def _train_entry_rate(arguments):
+    """Runs the kept train entry point and returns (graphs/s, steps, graphs) of its LAST training epoch (the epochs
+    before it are the warm-up), as ModelTrainer itself measures them."""
+    from buglab.models import train
+
+    trainer = train.run(arguments)
+    stats = trainer.last_epoch_stats
+    return stats["samples_per_second"], stats["train_steps"], stats["train_samples"], stats["train_seconds"]
+
+
+def config1_gpu(device):
+    import torch
+
+    work = tempfile.mkdtemp(prefix="buglab_bench_config1_")
+    # ~15 graphs (30 000 nodes) per step: epoch 1 = 2 warm-up steps' worth is too short to settle the allocator, so the
+    # warm-up epoch has 10 steps too; epoch 2 is the timed one
+    rate, steps, graphs, seconds = _train_entry_rate(_config1_arguments(work, CONFIG1_HIDDEN, epochs=2, epoch_samples=150))
+    torch.cuda.synchronize(device)
+    torch.cuda.empty_cache()
+    return {"workload": "BASELINE configs[0]: gnn-mlp hidden=128, one shard of 500 synthetic graphs (~2 000 nodes each), "
+                        "python -m buglab.models.train defaults (minibatches cut at 30 000 nodes), --sequential",
+            "gpu": {"value": rate, "unit": "graphs/s", "steps": steps, "graphs": graphs, "ms_per_step": 1e3 * seconds / max(steps, 1),
+                    "includes": "shard decode + tensorise + packing + H2D + plan + step, as the entry point runs them"}}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_thread_count(requested: int = 0) -> int:
+    """Fixed thread count of the CPU arm: min(32, usable CPUs).  (os.cpu_count() over-reports inside CPU-limited
+    containers: round 1's box reported 128 and ran the oracle 30x slower with 128 threads than with 32.)"""
+    if requested > 0:
+        return requested
     try:
         avail = len(os.sched_getaffinity(0))
     except AttributeError:
         avail = os.cpu_count() or 1
-    candidates = sorted({min(avail, c) for c in (8, 16, 32, 64, 128, avail)})
-    a = torch.randn(1536, 1536)
-    best, best_t = candidates[0], float("inf")
-    for c in candidates:
-        torch.set_num_threads(c)
-        a @ a
-        t0 = time.perf_counter()
-        for _ in range(3):
-            a @ a
-        dt = time.perf_counter() - t0
-        if dt < best_t * 0.9:
-            best, best_t = c, dt
-    return best
+    return max(1, min(32, avail))
 
 
-def cpu_baseline(args, steps: int, warmup: int):
-    """The CPU oracle (kind "port": the reference's arithmetic restated in PyTorch, see oracle/) running the same
-    train step on a bounded sample: CPU_GRAPHS_PER_STEP graphs of the same distribution per step."""
+def cpu_arm_subprocess(hidden, steps, warmup, threads):
+    """Runs the CPU arm in a fresh process (its oracle/cpu_backend.py patches are process-wide) and returns its
+    ``cpu_baseline`` object."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--hidden", str(hidden), "--steps", str(steps),
+           "--warmup", str(warmup), "--cpu-threads", str(threads)]
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1", CUDA_VISIBLE_DEVICES="")
+    for k in ("LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    proc = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=1500)
+    for line in reversed(proc.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            return json.loads(line)["cpu_baseline"]
+    return {"error": (proc.stderr or proc.stdout)[-400:]}
+
+
+def cpu_train_entry(hidden, steps, warmup, threads):
+    """``buglab.models.train`` on the host cores with the CPU oracle underneath (oracle/cpu_backend.py): warm-up epoch(s)
+    then one timed epoch of ``steps`` minibatches, each cut by the reference's 30 000-node budget (~15 graphs)."""
     import torch
 
-    from oracle import model_ref
+    from oracle import cpu_backend
 
-    cores = best_cpu_thread_count()
+    cores = cpu_thread_count(threads)
     torch.set_num_threads(cores)
-    model, host_batches = make_workload(777, CPU_GRAPHS_PER_STEP, args.hidden, args.mean_nodes, max(1, min(2, steps + warmup)), DROPOUT)
-    ref = model_ref.GnnBugLabModule(args.hidden, model.gnn_model.num_edge_types,
-                                    len(model.gnn_model.node_representation_model.vocabulary),
-                                    len(model._target_rewrite_ops), dropout_rate=DROPOUT, embedding_dropout_rate=DROPOUT)
-    opt = torch.optim.Adam(ref.parameters(), lr=1e-4)
-    ref.train()
-    mbs = [model_ref.minibatch_to_cpu(pack(model, tb, "cpu")) for tb in host_batches]
-    for i in range(warmup):
-        model_ref.train_step_ref(ref, opt, mbs[i % len(mbs)])
-    t0 = time.perf_counter()
-    for i in range(steps):
-        model_ref.train_step_ref(ref, opt, mbs[i % len(mbs)])
-    dt = time.perf_counter() - t0
-    return {"value": CPU_GRAPHS_PER_STEP * steps / dt, "unit": "graphs/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} train step(s) of {CPU_GRAPHS_PER_STEP} graphs (same generator, hidden={args.hidden}), "
-                      f"PyTorch CPU oracle with {cores} threads", "seconds": dt}
+    cpu_backend.install()
+    work = tempfile.mkdtemp(prefix="buglab_bench_cpu_")
+    graphs_per_step = 15  # 30 000 nodes / ~2 000 nodes per graph; the entry point counts epochs in samples
+    epochs = 2 if warmup > 0 else 1
+    arguments = _config1_arguments(work, hidden, epochs=epochs, epoch_samples=graphs_per_step * steps)
+    if warmup > 0 and warmup != steps:
+        # a shorter warm-up epoch: run it as its own call (epoch lengths are per call), then the timed call
+        _train_entry_rate(_config1_arguments(work, hidden, epochs=1, epoch_samples=graphs_per_step * warmup))
+        arguments = _config1_arguments(work, hidden, epochs=1, epoch_samples=graphs_per_step * steps)
+    rate, nsteps, graphs, seconds = _train_entry_rate(arguments)
+    return {"value": rate, "unit": "graphs/s", "cores": cores, "kind": "port",
+            "sample": f"{nsteps} minibatches ({graphs} graphs, <= 30 000 nodes each: the reference's own minibatch budget) of the "
+                      f"gnn-mlp hidden={hidden} train step through python -m buglab.models.train --sequential on {cores} host "
+                      f"threads, after {warmup} warm-up minibatches; arithmetic = oracle/ (PyTorch CPU restatement of ptgnn / "
+                      "torch_scatter, the same substitution that generates tests/golden)",
+            "seconds": seconds, "ms_per_step": 1e3 * seconds / max(nsteps, 1)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base = cpu_baseline(args, steps=args.steps, warmup=min(args.warmup, 1))
-    ms = base["seconds"] * 1e3
+    base = cpu_train_entry(args.hidden, steps=args.steps, warmup=min(args.warmup, 2), threads=args.cpu_threads)
     print(json.dumps({
         "impl": "reference",
         "metric": "code-graphs/sec (train step, device-timed)", "value": base["value"], "unit": "graphs/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms / max(args.steps, 1),
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 2), "ms_per_step": base["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"gnn-mlp hidden={args.hidden}, 8 MP layers, train step on the host CPU; bounded sample of "
-                               f"{CPU_GRAPHS_PER_STEP} graphs/step (~{args.mean_nodes} nodes each)", "parallelism": "cpu"},
+        "config": {"workload": f"gnn-mlp hidden={args.hidden}, 8 MP layers, train step (fwd+bwd+clip+Adam, dropout {DROPOUT}) on the "
+                               f"host CPU through buglab.models.train; bounded sample: minibatches of <= 30 000 nodes (~15 graphs of "
+                               f"~{MEAN_NODES} nodes), the reference's own minibatch budget", "parallelism": "cpu"},
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -107,6 +107,7 @@ def run(arguments):
         trainer.load_metadata_and_create_network(metadata_data, in_background, verbose)
     trainer.train(training_data, validation_data, initialize_metadata=False, parallelize=in_background,
                   show_progress_bar=verbose, patience=10)
+    return trainer  # callers that time the entry point (bench.py) read trainer.last_epoch_stats
 
 
 def main(argv=None):

@@ -18,4 +18,4 @@ fi
 echo "== model parity tests"; timeout 1500 python -m pytest tests/test_model_gpu.py -q -s > ${O}_model_tests.txt 2>&1; echo "rc=$?"; grep -E "batch 0|passed|failed|FAILED|Error" ${O}_model_tests.txt | tail -30
 echo "== rest of the gpu suite"; timeout 1500 python -m pytest tests -q -m gpu --deselect tests/test_model_gpu.py --deselect tests/test_tma_gemm_gpu.py > ${O}_gpu_suite.txt 2>&1; echo "rc=$?"; tail -15 ${O}_gpu_suite.txt
 echo "== bench"; timeout 900 python bench.py --steps 10 --warmup 3 > ${O}_bench.json 2> ${O}_bench.err; echo "rc=$?"; cat ${O}_bench.json; tail -3 ${O}_bench.err
-echo "== launch list of one bench step"; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file ${O}_launches.csv python bench.py --steps 1 --warmup 1 --skip-cpu-baseline > ${O}_ncu_bench.log 2>&1; echo "rc=$?"; wc -l ${O}_launches.csv
+echo "== launch list of one bench step"; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file ${O}_launches.csv python bench.py --steps 1 --warmup 1 --profile > ${O}_ncu_bench.log 2>&1; echo "rc=$?"; wc -l ${O}_launches.csv
