@@ -57,6 +57,117 @@ def allreduce_flat_gradient(flat_grad: torch.Tensor) -> float:
     return 1.0 / dist.get_world_size()
 
 
+class OverlappedGradientReducer:
+    """All-reduces a flat gradient buffer bucket by bucket WHILE backward is still running.
+
+    The parameters' ``.grad`` are views into one flat buffer (``FlatAdam``); buckets are contiguous slices of it, formed
+    over the parameters in reverse registration order (the order backward produces them: last layers first).  A
+    post-accumulate hook on every parameter counts its bucket down; a bucket is reduced on a side stream as soon as it
+    AND every earlier bucket are complete, so all ranks issue the same collectives in the same order no matter which
+    parameters a rank's minibatch leaves unused (their buckets are flushed, in order, by :meth:`finish`).  The global-norm
+    clip and the Adam step run after :meth:`finish`, on identical buffers on all ranks.
+
+    ``weight`` (see trainer._RankSync) scales this rank's gradient before the reduction, on the side stream."""
+
+    def __init__(self, flat_grad: torch.Tensor, params, offsets, bucket_bytes: int = 32 << 20):
+        self.flat = flat_grad
+        self._cuda = flat_grad.is_cuda
+        order = sorted(range(len(params)), key=lambda i: -offsets[i])  # reverse registration order
+        self._buckets = []  # (lo, hi) element ranges, in launch order
+        self._bucket_of = {}
+        lo = hi = None
+        count = 0
+        for i in order:
+            start, end = offsets[i], offsets[i] + params[i].numel()
+            lo = start if lo is None else min(lo, start)
+            hi = end if hi is None else max(hi, end)
+            self._bucket_of[i] = len(self._buckets)
+            count += 1
+            if (hi - lo) * 4 >= bucket_bytes:
+                self._buckets.append((lo, hi, count))
+                lo = hi = None
+                count = 0
+        if count:
+            self._buckets.append((lo, hi, count))
+        # the padding between parameter views belongs to no parameter: extend the buckets so they tile the buffer
+        edges = sorted(b[0] for b in self._buckets)
+        self._buckets = [(b[0], min([e for e in edges if e > b[0]], default=flat_grad.numel()), b[2]) for b in self._buckets]
+        self._stream = torch.cuda.Stream(flat_grad.device) if self._cuda else None
+        self._handles = [p.register_post_accumulate_grad_hook(lambda _p, i=i: self._on_grad(self._bucket_of[i]))
+                         for i, p in enumerate(params)]
+        self._pending, self._next, self._weight, self._active = [], 0, 1.0, False
+        self.exposed_ms_events = None
+
+    @property
+    def num_buckets(self) -> int:
+        return len(self._buckets)
+
+    def begin(self, weight: float = 1.0) -> None:
+        """Call before ``loss.backward()``."""
+        self._pending = [b[2] for b in self._buckets]
+        self._next, self._weight, self._active = 0, float(weight), is_distributed()
+
+    def _on_grad(self, bucket: int) -> None:
+        if not self._active:
+            return
+        self._pending[bucket] -= 1
+        while self._next < len(self._buckets) and self._pending[self._next] <= 0:
+            self._launch(self._next)
+            self._next += 1
+
+    def _launch(self, bucket: int) -> None:
+        lo, hi, _ = self._buckets[bucket]
+        chunk = self.flat[lo:hi]
+        if self._cuda:
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(self.flat.device))
+            with torch.cuda.stream(self._stream):
+                self._stream.wait_event(ready)
+                if self._weight != 1.0:
+                    chunk.mul_(self._weight)
+                dist.all_reduce(chunk, op=dist.ReduceOp.SUM)
+        else:
+            if self._weight != 1.0:
+                chunk.mul_(self._weight)
+            dist.all_reduce(chunk, op=dist.ReduceOp.SUM)
+
+    def finish(self) -> float:
+        """Call after ``loss.backward()``: flushes the remaining buckets, makes the compute stream wait for the reductions
+        and returns the scale (1/world) the optimiser applies.  A no-op (scale 1) outside data-parallel runs."""
+        if not self._active:
+            if self._weight != 1.0:
+                self.flat.mul_(self._weight)
+            return 1.0
+        compute = torch.cuda.current_stream(self.flat.device) if self._cuda else None
+        if self._cuda:
+            backward_done = torch.cuda.Event(enable_timing=True)
+            backward_done.record(compute)
+        while self._next < len(self._buckets):
+            self._launch(self._next)
+            self._next += 1
+        if self._cuda:
+            compute.wait_stream(self._stream)
+            reduced = torch.cuda.Event(enable_timing=True)
+            reduced.record(compute)
+            self.exposed_ms_events = (backward_done, reduced)
+        self._active = False
+        return 1.0 / dist.get_world_size()
+
+    def exposed_ms(self) -> Optional[float]:
+        """Time the compute stream spent waiting for the reductions after the last backward kernel of the latest step
+        (synchronises on two events; for reporting, not for the training loop)."""
+        if self.exposed_ms_events is None:
+            return None
+        a, b = self.exposed_ms_events
+        b.synchronize()
+        return a.elapsed_time(b)
+
+    def close(self) -> None:
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+
 def broadcast_module(module: torch.nn.Module, src: int = 0) -> None:
     """Make every rank start from rank ``src``'s parameters and buffers."""
     if not is_distributed():

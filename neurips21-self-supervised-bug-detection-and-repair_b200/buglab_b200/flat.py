@@ -69,6 +69,14 @@ class FlatAdam(torch.optim.Optimizer):
     def num_steps(self) -> int:
         return self._step
 
+    def gradient_reducer(self, bucket_bytes: int = 32 << 20):
+        """The bucketed all-reduce of this optimiser's flat gradient, overlapped with backward (created once)."""
+        if getattr(self, "_reducer", None) is None:
+            from .distributed import OverlappedGradientReducer
+
+            self._reducer = OverlappedGradientReducer(self.flat_grad, self._params, self._offsets, bucket_bytes)
+        return self._reducer
+
     def grad_norm(self) -> torch.Tensor:
         """Global L2 norm of the current flat gradient (device scalar; no sync)."""
         ops.grad_sqnorm(self.flat_grad, self._sqnorm, self._partial)

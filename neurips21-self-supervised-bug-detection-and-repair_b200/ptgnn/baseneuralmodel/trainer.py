@@ -309,15 +309,20 @@ class ModelTrainer:
             start_evt.record()
         t0 = time.perf_counter()
         sync = _RankSync(device)
+        reducer = optimizer.gradient_reducer() if (fused and dist.is_distributed()) else None
         for step_idx, (mb_data, raw_points) in enumerate(sync.batches(self._minibatches(training_tensors, device, parallelize))):
             optimizer.zero_grad()
             loss = nn(**mb_data)
-            loss.backward()
-            if fused:
+            if reducer is not None:
+                # bucketed all-reduce on a side stream while backward runs; sync.weight != 1 only for uneven minibatches
+                reducer.begin(sync.weight)
+                loss.backward()
+                optimizer.step(grad_scale=reducer.finish())
+            elif fused:
+                loss.backward()
                 if sync.weight != 1.0:
-                    optimizer.flat_grad.mul_(sync.weight)  # uneven minibatches only (typically the last step of an epoch)
-                scale = dist.allreduce_flat_gradient(optimizer.flat_grad)
-                optimizer.step(grad_scale=scale)
+                    optimizer.flat_grad.mul_(sync.weight)
+                optimizer.step(grad_scale=1.0)
             else:
                 if dist.is_distributed():
                     _allreduce_dense_gradients(params, dist.world_size(), sync.weight)

@@ -116,3 +116,65 @@ def test_uneven_shards_end_the_epoch_together_and_weight_by_graphs(tmp_path):
     for rank_result in (a, b):
         assert torch.allclose(rank_result[0][2], expected, atol=1e-6)               # == single-device step on the union batch
     assert torch.equal(a[1][2], b[1][2]) and torch.equal(a[2][2], b[2][2])
+
+
+def _reducer_worker(rank: int, world: int, port: int, out_dir: str):
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from buglab_b200 import distributed
+
+    distributed.init_from_env("gloo")
+    torch.manual_seed(5)
+    # three "layers" + a head that only rank 1's minibatch uses: bucket completion order differs between the ranks
+    layers = torch.nn.ModuleList([torch.nn.Linear(6, 6) for _ in range(3)])
+    rare_head = torch.nn.Linear(6, 1)
+    head = torch.nn.Linear(6, 1)
+    params = [p for m in (layers, rare_head, head) for p in m.parameters()]
+    offsets, total = [], 0
+    for p in params:
+        offsets.append(total)
+        total += (p.numel() + 3) // 4 * 4          # 16-byte aligned views, like FlatAdam
+    flat = torch.zeros(total)
+    for p, off in zip(params, offsets):
+        p.grad = flat[off: off + p.numel()].view_as(p)
+    reducer = distributed.OverlappedGradientReducer(flat, params, offsets, bucket_bytes=160)
+    assert reducer.num_buckets >= 3
+    x = torch.randn(5, 6, generator=torch.Generator().manual_seed(100 + rank))
+    weight = 0.5 if rank == 0 else 1.5            # uneven-minibatch weights (trainer._RankSync)
+    results = []
+    for step in range(2):
+        flat.zero_()
+        h = x
+        for layer in layers:
+            h = torch.tanh(layer(h))
+        loss = head(h).sum() + (rare_head(h).sum() if rank == 1 else 0.0)
+        reducer.begin(weight)
+        loss.backward()
+        assert all(p.grad.data_ptr() == flat.data_ptr() + 4 * off for p, off in zip(params, offsets))  # accumulated in place
+        scale = reducer.finish()
+        assert scale == 1.0 / world
+        results.append(flat.clone())
+    # the same step without the reducer: local gradient, scaled, summed in one piece
+    flat.zero_()
+    h = x
+    for layer in layers:
+        h = torch.tanh(layer(h))
+    (head(h).sum() + (rare_head(h).sum() if rank == 1 else 0.0)).backward()
+    expected = flat.clone() * weight
+    dist.all_reduce(expected)
+    torch.testing.assert_close(results[0], expected)
+    torch.testing.assert_close(results[1], expected)
+    reducer.close()
+    torch.save(results[1], os.path.join(out_dir, f"reduced{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_overlapped_bucket_reducer_matches_one_piece_allreduce(tmp_path):
+    """The bucketed reducer (hooks fire in backward order, buckets launch in a fixed order even when a rank leaves a
+    module unused) gives exactly the weighted sum a single all-reduce of the flat buffer gives, on both ranks."""
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_reducer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert torch.equal(torch.load(tmp_path / "reduced0.pt"), torch.load(tmp_path / "reduced1.pt"))
