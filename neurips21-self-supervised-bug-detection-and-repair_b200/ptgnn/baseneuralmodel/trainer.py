@@ -324,6 +324,7 @@ class ModelTrainer:
                     optimizer.flat_grad.mul_(sync.weight)
                 optimizer.step(grad_scale=1.0)
             else:
+                loss.backward()
                 if dist.is_distributed():
                     _allreduce_dense_gradients(params, dist.world_size(), sync.weight)
                 if self._clip_gradient_norm is not None:
