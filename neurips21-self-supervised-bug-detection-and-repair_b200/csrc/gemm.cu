@@ -384,7 +384,7 @@ extern "C" int bl_grouped_colsum(const float* rows, const int32_t* type_ptr, int
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc = check_cuda(cudaMemsetAsync(out, 0, (size_t)num_types * dim * sizeof(float), stream), "bl_grouped_colsum memset");
     if (rc) return rc;
-    grouped_colsum_kernel<<<4 * kNumSMs, 256, 0, stream>>>((const float4*)rows, type_ptr, num_types, dim / 4, out);
+    grouped_colsum_kernel<<<4 * num_sms(), 256, 0, stream>>>((const float4*)rows, type_ptr, num_types, dim / 4, out);
     return check_launch("bl_grouped_colsum");
 }
 
@@ -393,6 +393,6 @@ extern "C" int bl_absmax(const float* x, int64_t n, float* amax, bl_stream_t str
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc = check_cuda(cudaMemsetAsync(amax, 0, sizeof(float), stream), "bl_absmax memset");
     if (rc || n == 0) return rc;
-    absmax_kernel<<<4 * kNumSMs, 256, 0, stream>>>((const float4*)x, n / 4, (unsigned*)amax);
+    absmax_kernel<<<4 * num_sms(), 256, 0, stream>>>((const float4*)x, n / 4, (unsigned*)amax);
     return check_launch("bl_absmax");
 }

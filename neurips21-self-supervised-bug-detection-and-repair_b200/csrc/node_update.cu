@@ -205,10 +205,10 @@ extern "C" int bl_layernorm_bwd(const float* dy, const float* x, const float* ga
     if (rows < 0 || dim <= 0 || (dim & 3) || dim > LN_MAX_CHUNKS * 128) return BL_ERR_INVALID_ARGUMENT;
     cudaStream_t stream = (cudaStream_t)stream_;
     const size_t smem = (size_t)2 * 8 * dim * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {  // only the 1024-wide instantiation needs more than the default 48 KB of dynamic shared memory
-        cudaFuncSetAttribute(layernorm_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * 1024 * 4);
-        attr_set = true;
+    if (smem > 48 * 1024) {  // only the 1024-wide instantiation needs the opt-in; per-device attribute, set per call
+        int rc = check_cuda(cudaFuncSetAttribute(layernorm_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * 1024 * 4),
+                            "bl_layernorm_bwd attribute");
+        if (rc) return rc;
     }
 #define BL_LAUNCH_LN_BWD(C)                                                                                         \
     layernorm_bwd_kernel<C><<<BL_LN_PARTIALS, 256, smem, stream>>>((const float4*)dy, (const float4*)x,            \

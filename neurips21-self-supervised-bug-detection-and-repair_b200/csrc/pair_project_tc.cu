@@ -9,13 +9,10 @@
 // 128-byte-swizzled K-major smem tiles the UMMA descriptors expect; one gathered 128x64 fp32 chunk feeds 12 MMAs
 // (hi.w1, hi.w2, lo.w1 for 4 k-steps of 16), all accumulating into one fp32 TMEM tile of 128 lanes x N columns.
 //
-// CTA = 256 threads, persistent over (type, 128-row tile[, 256-column half]) work items; per 64-wide K chunk:
-//   all threads : wait until the MMAs that last read this smem stage committed (mbarrier), gather+split A (8 float4
-//                 each), cp.async the w1/w2 chunk rows (K-major, 128 B per row, 16-byte units XOR-swizzled by row&7),
-//                 fence.proxy.async, bar.sync
-//   thread 0    : 12 x tcgen05.mma.cta_group::1.kind::f16 (M=128, N=128|256, K=16), tcgen05.commit -> mbarrier[stage]
-// so the tensor core works on chunk i while the threads load chunk i+1 into the other stage.  Epilogue: tcgen05.ld
-// (32 lanes x 32 columns per warp and step) -> + bias -> 128-byte row segments to global.
+// First-generation kernels (round 1).  Since round 2 the projections run on csrc/gemm_tma.cu (operands split once per
+// table, TMA-fed, CTA pairs); these remain the path for BUGLAB_B200_TMA=0 and the referee the TMA kernels are checked
+// against.  Persistent warp-specialised CTA (see pair_project_tc_v2_kernel); epilogue: tcgen05.ld (32 lanes x 32 columns
+// per warp and step) -> + bias -> 128-byte row segments to global.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -149,168 +146,8 @@ struct Params {
     int num_types, N, Kin;
 };
 
-// NT = columns handled per work item (128 or 256); N is a multiple of NT.
-template <int NT>
-__global__ void __launch_bounds__(THREADS, 1) pair_project_tc_kernel(const Params p) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // stage layout: A_hi [128x128B] | A_lo [128x128B] | B_hi [NT x 128B] | B_lo [NT x 128B]
-    constexpr uint32_t A_BYTES = TILE_M * 128;
-    constexpr uint32_t B_BYTES = NT * 128;
-    constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-
-    __shared__ uint64_t mbar[2];       // stage free (MMAs that read it have completed)
-    __shared__ uint64_t mbar_acc;      // accumulator complete
-    __shared__ uint32_t tmem_base_smem;
-    __shared__ int tile_prefix[MAX_TYPES + 1];
-    __shared__ int row_index[TILE_M];
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_splits = p.N / NT;
-
-    if (tid == 0) {
-        mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
-        mbar_init(&mbar_acc, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        int acc = 0;
-        for (int k = 0; k < p.num_types; ++k) {
-            tile_prefix[k] = acc;
-            acc += (p.type_ptr[k + 1] - p.type_ptr[k] + TILE_M - 1) / TILE_M;
-        }
-        tile_prefix[p.num_types] = acc;
-    }
-    if (warp == 0) {  // TMEM: NT fp32 columns x 128 lanes
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(NT));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_base_smem;
-    const int total_tiles = tile_prefix[p.num_types] * n_splits;
-    const float scale = (p.amax != nullptr) ? pow2_scale_for(__ldg(p.amax)) : 1.0f;
-    const uint32_t idesc = umma_idesc_f16_f32(TILE_M, NT);
-    const int num_chunks = p.Kin / CHUNK_K;
-
-    uint32_t commits[2] = {0, 0};  // commits issued so far per stage (identical in all threads)
-    uint32_t acc_commits = 0;
-
-    for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
-        const int tile = work / n_splits, split = work - tile * n_splits;
-        int k = 0;
-        while (tile >= tile_prefix[k + 1]) ++k;  // num_types is small
-        const int row0 = p.type_ptr[k] + (tile - tile_prefix[k]) * TILE_M;
-        const int row_end = p.type_ptr[k + 1];
-        const int col0 = split * NT;
-
-        if (tid < TILE_M) {
-            const int r = row0 + tid;
-            row_index[tid] = (r < row_end) ? (p.idx ? __ldg(p.idx + r) : r) : -1;
-        }
-        __syncthreads();
-        int my_rows[(TILE_M * CHUNK_K / 4) / THREADS];
-#pragma unroll
-        for (int i = 0; i < (TILE_M * CHUNK_K / 4) / THREADS; ++i) my_rows[i] = row_index[(i * THREADS + tid) >> 4];
-        const __half* w_hi = p.wparts + ((size_t)(k * 2 + 0) * p.N + col0) * p.Kin;
-        const __half* w_lo = p.wparts + ((size_t)(k * 2 + 1) * p.N + col0) * p.Kin;
-
-        for (int c = 0; c < num_chunks; ++c) {
-            const int s = c & 1;
-            uint8_t* stage = smem + (size_t)s * STAGE_BYTES;
-            if (commits[s] > 0) mbar_wait(&mbar[s], (commits[s] - 1) & 1);  // MMAs of the previous use of this stage are done
-            // ---- B: NT rows x 128 B of w_hi and w_lo (K-major rows of Kin halfs), asynchronous ----
-#pragma unroll
-            for (int i = 0; i < (NT * 8) / THREADS; ++i) {
-                const int f = i * THREADS + tid;
-                const int r = f >> 3, u = f & 7;
-                const size_t goff = (size_t)r * p.Kin + c * CHUNK_K + u * 8;
-                cp_async16(smem_u32(stage + 2 * A_BYTES + sw128(r, u)), w_hi + goff);
-                cp_async16(smem_u32(stage + 2 * A_BYTES + B_BYTES + sw128(r, u)), w_lo + goff);
-            }
-            // ---- A: gather 128 rows x 64 fp32 (all loads in flight first), split, write hi / lo tiles ----
-            constexpr int A_ITERS = (TILE_M * CHUNK_K / 4) / THREADS;  // 8 float4 per thread
-            float4 av[A_ITERS];
-#pragma unroll
-            for (int i = 0; i < A_ITERS; ++i) {
-                const int f = i * THREADS + tid;
-                const int src_row = my_rows[i];  // row_index[f >> 4], hoisted per tile
-                av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (src_row >= 0)
-                    av[i] = __ldg(reinterpret_cast<const float4*>(p.src + (size_t)src_row * p.Kin + c * CHUNK_K) + (f & 15));
-            }
-#pragma unroll
-            for (int i = 0; i < A_ITERS; ++i) {
-                const int f = i * THREADS + tid;
-                const int r = f >> 4, c4 = f & 15;  // 16 float4 per row chunk
-                uint2 hp, lp;
-                if (p.amax != nullptr) split_f32x4<true>(av[i], scale, hp, lp); else split_f32x4<false>(av[i], 1.f, hp, lp);
-                const uint32_t off = sw128(r, c4 >> 1) + ((c4 & 1) << 3);  // 4 halfs = 8 bytes inside a 16-byte unit
-                *reinterpret_cast<uint2*>(stage + off) = hp;
-                *reinterpret_cast<uint2*>(stage + A_BYTES + off) = lp;
-            }
-            cp_async_wait_all();
-            fence_async_proxy();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after();
-                const uint32_t a_hi = smem_u32(stage), a_lo = a_hi + A_BYTES;
-                const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
-#pragma unroll
-                for (int kk = 0; kk < CHUNK_K / 16; ++kk) {
-                    const uint32_t koff = kk * 32;  // 16 halfs = 32 bytes along K inside the swizzle atom
-                    umma_f16(tmem_base, umma_desc_sw128(a_hi + koff), umma_desc_sw128(b_hi + koff), idesc, (c | kk) ? 1u : 0u);
-                    umma_f16(tmem_base, umma_desc_sw128(a_hi + koff), umma_desc_sw128(b_lo + koff), idesc, 1u);
-                    umma_f16(tmem_base, umma_desc_sw128(a_lo + koff), umma_desc_sw128(b_hi + koff), idesc, 1u);
-                }
-                tc_commit(&mbar[s]);                       // frees this stage when the 12 MMAs have read it
-                if (c == num_chunks - 1) tc_commit(&mbar_acc);  // accumulator complete
-            }
-            commits[s] += 1;
-        }
-        // ---- epilogue: TMEM -> registers -> (+bias) -> global ----
-        mbar_wait(&mbar_acc, acc_commits & 1);
-        acc_commits += 1;
-        tc_fence_after();
-        {
-            const int lane_base = (warp & 3) * 32;           // a warp may only touch its own quarter of the 128 lanes
-            const int r = lane_base + lane;
-            const bool valid = (row0 + r) < row_end;
-            float* orow = p.out + (size_t)(row0 + r) * p.N + col0;
-            const float* brow = p.bias ? p.bias + (size_t)k * p.N + col0 : nullptr;
-            constexpr int COLS_PER_GROUP = NT / 2;           // warps 0-3 take the first half of the columns, 4-7 the second
-            const int cbase = (warp >> 2) * COLS_PER_GROUP;
-#pragma unroll 1
-            for (int j = 0; j < COLS_PER_GROUP / 32; ++j) {
-                float v[32];
-                const int col = cbase + j * 32;
-                tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)col, v);
-                if (valid) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                        if (brow) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(brow + col) + q);
-                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                        }
-                        reinterpret_cast<float4*>(orow + col)[q] = o;
-                    }
-                }
-            }
-        }
-        tc_fence_before();
-        __syncthreads();  // accumulator drained (and row_index free) before the next tile's first MMA / index load
-    }
-
-    // all MMAs this CTA issued have completed (every accumulator was waited for); release TMEM
-    __syncthreads();
-    if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(NT));
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
-// v2: warp-specialised pipeline.  Same arithmetic and smem/TMEM layouts as pair_project_tc_kernel, different schedule:
+// Warp-specialised pipeline ("v2"; the single-role first version was removed in round 2):
 //   warps 0-7   PRODUCERS  two groups of 4 warps; group g owns smem stage g and loads every chunk with
 //                          (running chunk index & 1) == g: gather + split A, cp.async B, then arrive on full[g] (128
 //                          arrivals) — while one group waits for its loads the other converts and stores
@@ -720,48 +557,19 @@ extern "C" int bl_pair_project_tc(const float* src, const int32_t* idx, const fl
     cudaStream_t stream = (cudaStream_t)stream_;
     tc::Params p{src, idx, amax, (const __half*)parts, bias, type_ptr, out, num_types, n_out, k_in};
     const int64_t max_tiles = (num_rows + tc::TILE_M - 1) / tc::TILE_M + num_types;
-    static const bool use_v2 = []() {
-        const char* e = getenv("BUGLAB_B200_TC_V1");
-        return !(e && e[0] == '1');
-    }();
-    if (use_v2) {
-        if (n_out == 128) {
-            constexpr uint32_t smem = 2 * (2 * 128 * 128 + 2 * 128 * 128) + 1024;
-            static bool attr_set = false;
-            if (!attr_set) {
-                cudaFuncSetAttribute(tc::pair_project_tc_v2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-                attr_set = true;
-            }
-            tc::pair_project_tc_v2_kernel<128><<<(int)std::min<int64_t>(kNumSMs, max_tiles), tc::THREADS_V2, smem, stream>>>(p);
-        } else {
-            constexpr uint32_t smem = 2 * (2 * 128 * 128 + 2 * 256 * 128) + 1024;
-            static bool attr_set = false;
-            if (!attr_set) {
-                cudaFuncSetAttribute(tc::pair_project_tc_v2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-                attr_set = true;
-            }
-            tc::pair_project_tc_v2_kernel<256><<<(int)std::min<int64_t>(kNumSMs, max_tiles * (n_out / 256)), tc::THREADS_V2, smem, stream>>>(p);
-        }
-        return check_launch("bl_pair_project_tc(v2)");
-    }
+    // the opt-in to > 48 KB of dynamic shared memory is a per-device attribute: set it on every call (cheap) and check it
     if (n_out == 128) {
         constexpr uint32_t smem = 2 * (2 * 128 * 128 + 2 * 128 * 128) + 1024;
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(tc::pair_project_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            attr_set = true;
-        }
-        const int grid = (int)std::min<int64_t>(kNumSMs, max_tiles);
-        tc::pair_project_tc_kernel<128><<<grid, tc::THREADS, smem, stream>>>(p);
+        int rc = check_cuda(cudaFuncSetAttribute(tc::pair_project_tc_v2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                            "bl_pair_project_tc attribute");
+        if (rc) return rc;
+        tc::pair_project_tc_v2_kernel<128><<<(int)std::min<int64_t>(num_sms(), max_tiles), tc::THREADS_V2, smem, stream>>>(p);
     } else {
         constexpr uint32_t smem = 2 * (2 * 128 * 128 + 2 * 256 * 128) + 1024;
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(tc::pair_project_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            attr_set = true;
-        }
-        const int grid = (int)std::min<int64_t>(kNumSMs, max_tiles * (n_out / 256));
-        tc::pair_project_tc_kernel<256><<<grid, tc::THREADS, smem, stream>>>(p);
+        int rc = check_cuda(cudaFuncSetAttribute(tc::pair_project_tc_v2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                            "bl_pair_project_tc attribute");
+        if (rc) return rc;
+        tc::pair_project_tc_v2_kernel<256><<<(int)std::min<int64_t>(num_sms(), max_tiles * (n_out / 256)), tc::THREADS_V2, smem, stream>>>(p);
     }
     return check_launch("bl_pair_project_tc");
 }
@@ -784,13 +592,11 @@ extern "C" int bl_pair_weight_grad_tc(const float* g, const float* x, const int3
     if (num_rows == 0) return BL_OK;
     tc::WgParams p{g, x, idx, amax, type_ptr, d_weight, num_types, m_out, n_in, ld, col0};
     constexpr uint32_t smem = 2 * (2 * 128 * 128 + 2 * 256 * 128) + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(tc::pair_weight_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set = true;
-    }
+    rc = check_cuda(cudaFuncSetAttribute(tc::pair_weight_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                    "bl_pair_weight_grad_tc attribute");
+    if (rc) return rc;
     const int64_t items = ((num_rows + tc::WG_ROWS_PER_ITEM - 1) / tc::WG_ROWS_PER_ITEM + num_types) * (m_out / tc::TILE_M) * (n_in / 256);
-    const int grid = (int)std::min<int64_t>(kNumSMs, items);
+    const int grid = (int)std::min<int64_t>(num_sms(), items);
     tc::pair_weight_grad_tc_kernel<<<grid, tc::THREADS, smem, stream>>>(p);
     return check_launch("bl_pair_weight_grad_tc");
 }
