@@ -61,6 +61,9 @@ const char* bl_error_string(int code);
  *   s_by_node_ptr[N+1], s_by_node_idx[E]   CSR node -> S-pair ids (ascending pair id per node)
  *   t_*            same four tables for the T-pairs (type, tgt)
  *   counts[2]      {P_s, P_t}
+ *   s_edge_ptr[E+1], s_edge_idx[E]  (nullable) CSR S-pair -> its sorted edges (ascending): the edges whose U row
+ *                  is that pair; e_tgt[E] (nullable) target node of every sorted edge.  Both feed the by-source half
+ *                  of the edge kernel's backward (bl_edge_bwd_sources).
  * ------------------------------------------------------------------------------------------------ */
 size_t bl_plan_workspace_bytes(int64_t num_edges, int64_t num_nodes, int32_t num_edge_types);
 
@@ -70,7 +73,7 @@ int bl_plan_build(const int32_t* src, const int32_t* tgt, const int32_t* etype,
                   int32_t* urow, int32_t* vrow,
                   int32_t* s_node, int32_t* s_type_ptr, int32_t* s_by_node_ptr, int32_t* s_by_node_idx,
                   int32_t* t_node, int32_t* t_type_ptr, int32_t* t_by_node_ptr, int32_t* t_by_node_idx,
-                  int32_t* counts,
+                  int32_t* counts, int32_t* s_edge_ptr, int32_t* s_edge_idx, int32_t* e_tgt,
                   void* workspace, size_t workspace_bytes, bl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -162,6 +165,24 @@ int bl_pair_weight_grad_tc_supported(int32_t m_out, int32_t n_in);
 int bl_pair_weight_grad_tc(const float* g, const float* x, const int32_t* idx, const float* amax,
                            const int32_t* type_ptr, int32_t num_types, int64_t num_rows, int32_t m_out, int32_t n_in,
                            float* d_weight, int32_t ld, int32_t col0, bl_stream_t stream);
+
+/* Backward of the fused edge kernel in the form the second-generation GEMMs consume (deterministic: every output row
+ * has one writer, no memset, no atomics on the tables).  g[n,c] = d_agg[n,c] * GELU'(xwin[n,c]) belongs to the winning
+ * edge ewin[n,c] only (arg-routed backward of scatter_max).
+ *   bl_edge_bwd_targets: one warp per target node.  Writes g_rows[N, M] (fp32) and dV as an fp16 hi/lo split table
+ *     [2][P_t + 1][M] (pre-scaled by the power of two derived from amax_eff, last row of each part zero); adds the
+ *     per-type column sums of dV (= d bias_k) into d_bias[K, M] (zero-initialised by the caller; NULL: skipped).
+ *     amax_in = device scalar max|d_agg| (bl_absmax); the kernel publishes amax_eff = amax_in * 1.13 (bound of GELU') *
+ *     256 (fan-in headroom of the dU sums) for the consumers' 1/scale.
+ *   bl_edge_bwd_sources: one warp per S-pair row.  dU[p] = sum over the pair's edges e (ascending) of g masked to the
+ *     channels e won, written as the split table [2][P_s + 1][M] with the same scale. */
+int bl_edge_bwd_targets(const float* d_agg, const float* xwin, const int32_t* ewin, const int32_t* row_ptr,
+                        const int32_t* vrow, const int32_t* e_type, int64_t num_nodes, int32_t msg_dim,
+                        int32_t num_edge_types, int64_t num_t_pairs, const float* amax_in, float* amax_eff, float* g_rows,
+                        void* dv_split, float* d_bias, bl_stream_t stream);
+int bl_edge_bwd_sources(const float* g_rows, const int32_t* ewin, const int32_t* s_edge_ptr, const int32_t* s_edge_idx,
+                        const int32_t* e_tgt, int64_t num_s_pairs, int32_t msg_dim, const float* amax_eff, void* du_split,
+                        bl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Second-generation projection GEMMs: TMA-fed tcgen05 (csrc/gemm_tma.cu).  Same reference call sites as

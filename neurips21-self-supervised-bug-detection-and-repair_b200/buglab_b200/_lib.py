@@ -30,7 +30,7 @@ _SIGNATURES = {
     "bl_version": (c_i32, []),
     "bl_error_string": (ctypes.c_char_p, [c_i32]),
     "bl_plan_workspace_bytes": (c_size, [c_i64, c_i64, c_i32]),
-    "bl_plan_build": (c_i32, [c_ptr] * 3 + [c_i64, c_i64, c_i32] + [c_ptr] * 15 + [c_ptr, c_size, c_ptr]),
+    "bl_plan_build": (c_i32, [c_ptr] * 3 + [c_i64, c_i64, c_i32] + [c_ptr] * 18 + [c_ptr, c_size, c_ptr]),
     "bl_rows_gather": (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_ptr, c_ptr]),
     "bl_rows_segment_sum": (c_i32, [c_ptr] * 6 + [c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
     "bl_rows_split3_f16": (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_ptr, c_ptr, c_ptr]),
@@ -58,6 +58,8 @@ _SIGNATURES = {
                                    c_ptr, c_i32, c_i32, c_ptr]),
     "bl_edge_segmax_fwd": (c_i32, [c_ptr] * 5 + [c_i64, c_i32] + [c_ptr] * 3 + [c_ptr]),
     "bl_edge_segmax_bwd": (c_i32, [c_ptr] * 6 + [c_i64, c_i32, c_i64, c_i64] + [c_ptr] * 3 + [c_ptr]),
+    "bl_edge_bwd_targets": (c_i32, [c_ptr] * 6 + [c_i64, c_i32, c_i32, c_i64] + [c_ptr] * 5 + [c_ptr]),
+    "bl_edge_bwd_sources": (c_i32, [c_ptr] * 5 + [c_i64, c_i32, c_ptr, c_ptr, c_ptr]),
     "bl_layernorm_fwd": (c_i32, [c_ptr] * 3 + [c_i64, c_i32, c_f32] + [c_ptr] * 3 + [c_ptr]),
     "bl_layernorm_bwd": (c_i32, [c_ptr] * 5 + [c_i64, c_i32] + [c_ptr] * 4 + [c_ptr]),
     "bl_tanh_dropout_fwd": (c_i32, [c_ptr, c_i64, c_f32, c_u64, c_ptr, c_ptr, c_ptr]),
@@ -112,7 +114,7 @@ class BuglabB200Error(RuntimeError):
 # hand-written kernels launched per successful C-ABI call (CUB sorts/scans, memsets and cuBLAS GEMMs not counted)
 KERNELS_PER_CALL = {
     "bl_plan_build": 19, "bl_rows_gather": 1, "bl_rows_segment_sum": 1, "bl_edge_segmax_fwd": 1,
-    "bl_edge_segmax_bwd": 1, "bl_layernorm_fwd": 1, "bl_layernorm_bwd": 2, "bl_tanh_dropout_fwd": 1,
+    "bl_edge_segmax_bwd": 1, "bl_edge_bwd_targets": 1, "bl_edge_bwd_sources": 1, "bl_layernorm_fwd": 1, "bl_layernorm_bwd": 2, "bl_tanh_dropout_fwd": 1,
     "bl_tanh_dropout_bwd": 1, "bl_segment_minmax": 5, "bl_segment_minmax_bwd": 1, "bl_segment_sum": 1,
     "bl_segment_log_softmax_fwd": 5, "bl_segment_log_softmax_bwd": 2, "bl_subtoken_maxpool_fwd": 1,
     "bl_subtoken_maxpool_bwd": 1, "bl_grad_sqnorm": 2, "bl_adam_step": 1,

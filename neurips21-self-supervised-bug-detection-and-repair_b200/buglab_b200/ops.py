@@ -51,6 +51,10 @@ class EdgePlan(NamedTuple):
     t_tile_ptr: Optional[torch.Tensor] = None
     s_slab_ptr: Optional[torch.Tensor] = None
     t_slab_ptr: Optional[torch.Tensor] = None
+    # S-pair -> its sorted edges (CSR) and the target node of every sorted edge: by-source half of the edge backward
+    s_edge_ptr: Optional[torch.Tensor] = None
+    s_edge_idx: Optional[torch.Tensor] = None
+    e_tgt: Optional[torch.Tensor] = None
 
 
 def build_edge_plan(
@@ -95,6 +99,7 @@ def build_edge_plan_from_flat(
     # [s_type_ptr (K+1) | t_type_ptr (K+1) | counts (2)] in one buffer -> one D2H copy
     meta = torch.empty(2 * (K + 1) + 2, **opts)
     s_type_ptr, t_type_ptr, counts = meta[: K + 1], meta[K + 1 : 2 * (K + 1)], meta[2 * (K + 1) :]
+    s_edge_ptr, s_edge_idx, e_tgt = (torch.empty(Ea + 1, **opts), torch.empty(Ea, **opts), torch.empty(Ea, **opts))
     ws_bytes = lib.bl_plan_workspace_bytes(E, N, K)
     workspace = torch.empty(ws_bytes, device=device, dtype=torch.uint8)
     check(
@@ -103,7 +108,7 @@ def build_edge_plan_from_flat(
             i32(e_perm), i32(e_src), i32(e_type), i32(row_ptr), i32(urow), i32(vrow),
             i32(s_node), s_type_ptr.data_ptr(), i32(s_by_node_ptr), i32(s_by_node_idx),
             i32(t_node), t_type_ptr.data_ptr(), i32(t_by_node_ptr), i32(t_by_node_idx),
-            counts.data_ptr(), workspace.data_ptr(), ws_bytes, stream_ptr(device),
+            counts.data_ptr(), i32(s_edge_ptr), i32(s_edge_idx), i32(e_tgt), workspace.data_ptr(), ws_bytes, stream_ptr(device),
         ),
         "bl_plan_build",
     )
@@ -119,7 +124,7 @@ def build_edge_plan_from_flat(
         N, E, K, e_perm[:E], e_src[:E], e_type[:E], row_ptr, urow[:E], vrow[:E],
         s_node[:P_s], s_type_ptr, s_by_node_ptr, s_by_node_idx[:P_s],
         t_node[:P_t], t_type_ptr, t_by_node_ptr, t_by_node_idx[:P_t],
-        P_s, P_t, s_tp, t_tp, *tables,
+        P_s, P_t, s_tp, t_tp, *tables, s_edge_ptr[: P_s + 1], s_edge_idx[:E], e_tgt[:E],
     )
 
 
@@ -165,6 +170,9 @@ TC_MAX_WIDTH = int(os.environ.get("BUGLAB_B200_TC_MAX_WIDTH", "256"))
 # Second-generation GEMMs (csrc/gemm_tma.cu: node-level fp16 split, TMA-fed tcgen05, CTA pairs) for every shape they
 # support (all widths that are multiples of 256, and 128-wide projections); BUGLAB_B200_TMA=0 restores round 1's kernels.
 USE_TMA = os.environ.get("BUGLAB_B200_TMA", "1") != "0"
+# Edge backward that writes the gradient tables as fp16 split tables with one writer per row (bl_edge_bwd_targets/_sources)
+# instead of fp32 tables + REDs + a split pass; BUGLAB_B200_SPLIT_EDGE_BWD=0 keeps round 1's bl_edge_segmax_bwd.
+USE_SPLIT_EDGE_BACKWARD = os.environ.get("BUGLAB_B200_SPLIT_EDGE_BWD", "1") != "0"
 
 
 def _tma_proj_ok(n_out: int, k_in: int) -> bool:
@@ -392,6 +400,40 @@ class TypedEdgeMessageMax(torch.autograd.Function):
         K, M, _ = weight.shape
         d_agg = d_agg.contiguous()
         dev = h.device
+        d_bias = torch.zeros((K, M), device=dev, dtype=torch.float32) if ctx.has_bias else None
+        if (ctx.mode == "f16x3" and USE_SPLIT_EDGE_BACKWARD and M in (128, 256, 512) and _tma_proj_ok(D, M) and _tma_wgrad_ok(M, D)
+                and plan.s_tile_ptr is not None and plan.s_edge_ptr is not None):
+            # Second-generation backward, end to end: the edge kernels write both gradient tables directly as pre-scaled
+            # fp16 hi/lo split tables (one writer per row, no memset, no atomics on the tables) and fold the bias column
+            # sums in; the TMA-fed tcgen05 kernels take it from there.
+            amax_in = torch.empty(1, device=dev, dtype=torch.float32)
+            check(lib.bl_absmax(f32(d_agg), d_agg.numel(), f32(amax_in), stream_ptr(dev)), "bl_absmax")
+            amax = torch.empty(1, device=dev, dtype=torch.float32)
+            g_rows = torch.empty((N, M), device=dev, dtype=torch.float32)
+            dv_split = torch.empty((2, plan.num_t_pairs + 1, M), device=dev, dtype=torch.float16)
+            check(lib.bl_edge_bwd_targets(f32(d_agg), f32(xwin), i32(ewin), i32(plan.row_ptr), i32(plan.vrow), i32(plan.e_type),
+                                          N, M, K, plan.num_t_pairs, f32(amax_in), f32(amax), f32(g_rows), dv_split.data_ptr(),
+                                          f32(d_bias) if d_bias is not None else None, stream_ptr(dev)), "bl_edge_bwd_targets")
+            du_split = torch.empty((2, plan.num_s_pairs + 1, M), device=dev, dtype=torch.float16)
+            check(lib.bl_edge_bwd_sources(f32(g_rows), i32(ewin), i32(plan.s_edge_ptr), i32(plan.s_edge_idx), i32(plan.e_tgt),
+                                          plan.num_s_pairs, M, f32(amax), du_split.data_ptr(), stream_ptr(dev)), "bl_edge_bwd_sources")
+            del g_rows
+            h_split = ctx.h_split if ctx.h_split is not None else rows_split(h)
+            d_weight = torch.empty_like(weight)
+            d_rows = []
+            for rows_idx, g_split, col0, type_ptr_dev, tile_ptr, slab_ptr in (
+                    (plan.s_node, du_split, 0, plan.s_type_ptr, plan.s_tile_ptr, plan.s_slab_ptr),
+                    (plan.t_node, dv_split, D, plan.t_type_ptr, plan.t_tile_ptr, plan.t_slab_ptr)):
+                d_rows.append(tma_project(g_split, None, weight_parts(weight, D, M, col0, True), None, amax, type_ptr_dev, None,
+                                          int(rows_idx.shape[0]), tile_ptr))
+                tma_weight_grad(g_split, h_split, rows_idx, amax, type_ptr_dev, None, d_weight, col0, slab_ptr)
+            del du_split, dv_split
+            d_h = torch.empty_like(h)
+            check(lib.bl_rows_segment_sum(f32(d_rows[0]), i32(plan.s_by_node_ptr), i32(plan.s_by_node_idx),
+                                          f32(d_rows[1]), i32(plan.t_by_node_ptr), i32(plan.t_by_node_idx),
+                                          N, D, 0, None, f32(d_h), stream_ptr(dev)), "bl_rows_segment_sum")
+            return d_h, d_weight, d_bias, None
+
         du = torch.empty((plan.num_s_pairs, M), device=dev, dtype=torch.float32)
         dv = torch.empty((plan.num_t_pairs, M), device=dev, dtype=torch.float32)
         amax = torch.empty(1, device=dev, dtype=torch.float32) if ctx.mode == "f16x3" else None
@@ -401,7 +443,6 @@ class TypedEdgeMessageMax(torch.autograd.Function):
                                    f32(amax) if amax is not None else None, stream_ptr(dev)),
             "bl_edge_segmax_bwd",
         )
-        d_bias = torch.zeros((K, M), device=dev, dtype=torch.float32) if ctx.has_bias else None
         d_rows = []
         unscaled = False
         if ctx.mode == "f16x3" and _tma_proj_ok(D, M) and plan.s_tile_ptr is not None:

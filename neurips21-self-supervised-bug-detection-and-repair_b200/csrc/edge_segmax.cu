@@ -6,6 +6,10 @@
 // in flight per warp) plus 8 bytes of indices, and does 1 add + 4 compare/selects per channel.
 // One warp owns one target node (its CSR segment), so the segmented max needs no atomics; the
 // per-channel running extremes live in registers.
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace bl {
@@ -243,6 +247,155 @@ edge_segmax_bwd_generic(const float* __restrict__ d_agg, const float* __restrict
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Second-generation backward (feeds csrc/gemm_tma.cu): gradient tables leave the kernels as fp16 hi/lo split tables
+// [2][rows + 1][M] (pre-scaled by a power of two, last row of each part zero), every row written by exactly one warp.
+//   targets kernel: warp per target node  -> g rows (fp32), dV split rows, per-type column sums of dV (d bias)
+//   sources kernel: warp per S-pair row   -> dU split rows = sum over the pair's edges of g masked to the channels won
+// ---------------------------------------------------------------------------------------------
+constexpr float kGeluGradBound = 1.13f;  // max |GELU'(x)| = 1.1289...
+
+__device__ __forceinline__ void split_store_f16x4(const float4 v, float scale, __half* __restrict__ hi_row, __half* __restrict__ lo_row,
+                                                  int chunk) {
+    const float x0 = fminf(fmaxf(v.x * scale, -65000.f), 65000.f), x1 = fminf(fmaxf(v.y * scale, -65000.f), 65000.f);
+    const float x2 = fminf(fmaxf(v.z * scale, -65000.f), 65000.f), x3 = fminf(fmaxf(v.w * scale, -65000.f), 65000.f);
+    const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+    const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn(x0 - b01.x, x1 - b01.y), l23 = __floats2half2_rn(x2 - b23.x, x3 - b23.y);
+    uint2 hv, lv;
+    hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+    lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+    reinterpret_cast<uint2*>(hi_row)[chunk] = hv;
+    reinterpret_cast<uint2*>(lo_row)[chunk] = lv;
+}
+
+template <int ITER>
+__global__ void __launch_bounds__(256)
+edge_bwd_targets_warp(const float* __restrict__ d_agg, const float* __restrict__ xwin, const int* __restrict__ ewin,
+                      const int* __restrict__ row_ptr, const int* __restrict__ vrow, const int* __restrict__ e_type,
+                      int num_nodes, int num_types, int64_t num_t_pairs, const float* __restrict__ amax_in,
+                      float* __restrict__ amax_eff, float* __restrict__ g_rows, __half* __restrict__ dv_split,
+                      float* __restrict__ d_bias) {
+    constexpr int M4 = 32 * ITER;
+    constexpr int M = 128 * ITER;
+    extern __shared__ float bias_acc[];  // [num_types][M] when d_bias != nullptr
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const float amax = __ldg(amax_in) * (kGeluGradBound * kFanInHeadroom);
+    const float scale = pow2_scale_for(amax);
+    __half* const hi_base = dv_split;
+    __half* const lo_base = dv_split + (size_t)(num_t_pairs + 1) * M;
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        if (lane == 0) *amax_eff = amax;
+        // the zero (padding) row of both parts
+        for (int i = lane; i < M4; i += 32) {
+            reinterpret_cast<uint2*>(hi_base + (size_t)num_t_pairs * M)[i] = make_uint2(0u, 0u);
+            reinterpret_cast<uint2*>(lo_base + (size_t)num_t_pairs * M)[i] = make_uint2(0u, 0u);
+        }
+    }
+    if (d_bias != nullptr) {
+        for (int i = threadIdx.x; i < num_types * M; i += blockDim.x) bias_acc[i] = 0.f;
+        __syncthreads();
+    }
+    for (int node = blockIdx.x * warps_per_block + (threadIdx.x >> 5); node < num_nodes; node += gridDim.x * warps_per_block) {
+        const int beg = __ldg(row_ptr + node);
+        const int end = __ldg(row_ptr + node + 1);
+        float4 g[ITER];
+        int4 wv[ITER];
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) {
+            const size_t off = (size_t)node * M4 + lane + 32 * i;
+            g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            wv[i] = make_int4(-1, -1, -1, -1);
+            if (beg != end) {  // a non-empty segment always has a winner (ewin >= 0)
+                const float4 d = __ldg(reinterpret_cast<const float4*>(d_agg) + off);
+                const float4 x = __ldg(reinterpret_cast<const float4*>(xwin) + off);
+                const int4 e = __ldg(reinterpret_cast<const int4*>(ewin) + off);
+                g[i] = make_float4(d.x * gelu_grad(x.x), d.y * gelu_grad(x.y), d.z * gelu_grad(x.z), d.w * gelu_grad(x.w));
+                wv[i] = make_int4(__ldg(vrow + e.x), __ldg(vrow + e.y), __ldg(vrow + e.z), __ldg(vrow + e.w));
+            }
+            reinterpret_cast<float4*>(g_rows)[off] = g[i];  // isolated nodes: zeros
+        }
+        // every V row of this segment is written exactly once (runs of equal vrow are contiguous and share one type)
+        int prev_v = -1;
+        for (int base = beg; base < end; base += 32) {
+            const int cnt = min(32, end - base);
+            const int my_v = __ldg(vrow + base + min(lane, cnt - 1));
+            const int my_t = __ldg(e_type + base + min(lane, cnt - 1));
+            for (int t = 0; t < cnt; ++t) {
+                const int v = __shfl_sync(FULL_MASK, my_v, t);
+                const int type = __shfl_sync(FULL_MASK, my_t, t);
+                if (v == prev_v) continue;  // warp-uniform
+                prev_v = v;
+                __half* hi_row = hi_base + (size_t)v * M;
+                __half* lo_row = lo_base + (size_t)v * M;
+#pragma unroll
+                for (int i = 0; i < ITER; ++i) {
+                    float4 o;
+                    o.x = (wv[i].x == v) ? g[i].x : 0.f;
+                    o.y = (wv[i].y == v) ? g[i].y : 0.f;
+                    o.z = (wv[i].z == v) ? g[i].z : 0.f;
+                    o.w = (wv[i].w == v) ? g[i].w : 0.f;
+                    split_store_f16x4(o, scale, hi_row, lo_row, lane + 32 * i);
+                    if (d_bias != nullptr) {
+                        float* acc = bias_acc + (size_t)type * M + 4 * (lane + 32 * i);
+                        if (o.x != 0.f) atomicAdd(acc + 0, o.x);
+                        if (o.y != 0.f) atomicAdd(acc + 1, o.y);
+                        if (o.z != 0.f) atomicAdd(acc + 2, o.z);
+                        if (o.w != 0.f) atomicAdd(acc + 3, o.w);
+                    }
+                }
+            }
+        }
+    }
+    if (d_bias != nullptr) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < num_types * M; i += blockDim.x) {
+            const float v = bias_acc[i];
+            if (v != 0.f) atomicAdd(d_bias + i, v);
+        }
+    }
+}
+
+template <int ITER>
+__global__ void __launch_bounds__(256)
+edge_bwd_sources_warp(const float* __restrict__ g_rows, const int* __restrict__ ewin, const int* __restrict__ s_edge_ptr,
+                      const int* __restrict__ s_edge_idx, const int* __restrict__ e_tgt, int64_t num_s_pairs,
+                      const float* __restrict__ amax_eff, __half* __restrict__ du_split) {
+    constexpr int M4 = 32 * ITER;
+    constexpr int M = 128 * ITER;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row > num_s_pairs) return;
+    __half* hi_row = du_split + (size_t)row * M;
+    __half* lo_row = du_split + (size_t)(num_s_pairs + 1 + row) * M;
+    float4 acc[ITER];
+#pragma unroll
+    for (int i = 0; i < ITER; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < num_s_pairs) {  // row == num_s_pairs: the zero (padding) row
+        const int beg = __ldg(s_edge_ptr + row), end = __ldg(s_edge_ptr + row + 1);
+        for (int j = beg; j < end; ++j) {  // ascending sorted-edge id: a fixed summation order
+            const int e = __ldg(s_edge_idx + j);
+            const int t = __ldg(e_tgt + e);
+#pragma unroll
+            for (int i = 0; i < ITER; ++i) {
+                const size_t off = (size_t)t * M4 + lane + 32 * i;
+                const int4 w = __ldg(reinterpret_cast<const int4*>(ewin) + off);
+                if (w.x == e || w.y == e || w.z == e || w.w == e) {
+                    const float4 gv = __ldg(reinterpret_cast<const float4*>(g_rows) + off);
+                    if (w.x == e) acc[i].x += gv.x;
+                    if (w.y == e) acc[i].y += gv.y;
+                    if (w.z == e) acc[i].z += gv.z;
+                    if (w.w == e) acc[i].w += gv.w;
+                }
+            }
+        }
+    }
+    const float scale = pow2_scale_for(__ldg(amax_eff));
+#pragma unroll
+    for (int i = 0; i < ITER; ++i) split_store_f16x4(acc[i], scale, hi_row, lo_row, lane + 32 * i);
+}
+
 }  // namespace bl
 
 using namespace bl;
@@ -303,4 +456,51 @@ extern "C" int bl_edge_segmax_bwd(const float* d_agg, const float* xwin, const i
             d_agg, xwin, ewin, row_ptr, urow, vrow, num_nodes, msg_dim, d_u_rows, d_v_rows, amax_bits);
     }
     return check_launch("bl_edge_segmax_bwd");
+}
+
+extern "C" int bl_edge_bwd_targets(const float* d_agg, const float* xwin, const int32_t* ewin, const int32_t* row_ptr,
+                                   const int32_t* vrow, const int32_t* e_type, int64_t num_nodes, int32_t msg_dim,
+                                   int32_t num_edge_types, int64_t num_t_pairs, const float* amax_in, float* amax_eff,
+                                   float* g_rows, void* dv_split, float* d_bias, bl_stream_t stream_) {
+    if (num_nodes <= 0 || num_nodes > 0x7fffffffLL || num_edge_types <= 0 || num_t_pairs < 0 || amax_in == nullptr || amax_eff == nullptr)
+        return BL_ERR_INVALID_ARGUMENT;
+    if (msg_dim != 128 && msg_dim != 256 && msg_dim != 512) return BL_ERR_UNSUPPORTED;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t smem = d_bias ? (size_t)num_edge_types * msg_dim * sizeof(float) : 0;
+    if (smem > 200 * 1024) return BL_ERR_UNSUPPORTED;
+    const int threads = 256;
+    const int grid = (int)std::min<int64_t>((num_nodes * 32 + threads - 1) / threads, (int64_t)num_sms() * 8);
+    const int n = (int)num_nodes;
+#define BL_LAUNCH_EBT(ITER)                                                                                            \
+    do {                                                                                                               \
+        if (smem > 48 * 1024) {                                                                                        \
+            int rc = check_cuda(cudaFuncSetAttribute(edge_bwd_targets_warp<ITER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), \
+                                "bl_edge_bwd_targets attribute");                                                      \
+            if (rc) return rc;                                                                                         \
+        }                                                                                                              \
+        edge_bwd_targets_warp<ITER><<<grid, threads, smem, stream>>>(d_agg, xwin, ewin, row_ptr, vrow, e_type, n, num_edge_types, \
+                                                                     num_t_pairs, amax_in, amax_eff, g_rows, (__half*)dv_split, d_bias); \
+    } while (0)
+    if (msg_dim == 128) BL_LAUNCH_EBT(1);
+    else if (msg_dim == 256) BL_LAUNCH_EBT(2);
+    else BL_LAUNCH_EBT(4);
+#undef BL_LAUNCH_EBT
+    return check_launch("bl_edge_bwd_targets");
+}
+
+extern "C" int bl_edge_bwd_sources(const float* g_rows, const int32_t* ewin, const int32_t* s_edge_ptr, const int32_t* s_edge_idx,
+                                   const int32_t* e_tgt, int64_t num_s_pairs, int32_t msg_dim, const float* amax_eff,
+                                   void* du_split, bl_stream_t stream_) {
+    if (num_s_pairs < 0 || amax_eff == nullptr) return BL_ERR_INVALID_ARGUMENT;
+    if (msg_dim != 128 && msg_dim != 256 && msg_dim != 512) return BL_ERR_UNSUPPORTED;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int threads = 256;
+    const unsigned grid = grid_for((num_s_pairs + 1) * 32, threads);
+    if (msg_dim == 128)
+        edge_bwd_sources_warp<1><<<grid, threads, 0, stream>>>(g_rows, ewin, s_edge_ptr, s_edge_idx, e_tgt, num_s_pairs, amax_eff, (__half*)du_split);
+    else if (msg_dim == 256)
+        edge_bwd_sources_warp<2><<<grid, threads, 0, stream>>>(g_rows, ewin, s_edge_ptr, s_edge_idx, e_tgt, num_s_pairs, amax_eff, (__half*)du_split);
+    else
+        edge_bwd_sources_warp<4><<<grid, threads, 0, stream>>>(g_rows, ewin, s_edge_ptr, s_edge_idx, e_tgt, num_s_pairs, amax_eff, (__half*)du_split);
+    return check_launch("bl_edge_bwd_sources");
 }

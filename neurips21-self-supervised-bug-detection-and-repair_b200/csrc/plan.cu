@@ -73,18 +73,23 @@ __global__ void scatter_pairs(const unsigned long long* __restrict__ keys_sorted
                               const int* __restrict__ pid_incl, int64_t E, int64_t N,
                               int* __restrict__ row_of_edge, int* __restrict__ pair_node,
                               unsigned* __restrict__ pair_node_key, unsigned long long* __restrict__ ukeys,
-                              int* __restrict__ count_out) {
+                              int* __restrict__ count_out, int* __restrict__ edge_ptr, int* __restrict__ edge_idx) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= E) return;
     const int pid = pid_incl[i] - 1;
     row_of_edge[edge_of[i]] = pid;
+    if (edge_idx != nullptr) edge_idx[i] = edge_of[i];  // sorted-edge ids grouped by pair, ascending inside a pair (stable sort)
     if (flags[i]) {
         const int node = (int)(keys_sorted[i] % (unsigned long long)N);
         pair_node[pid] = node;
         pair_node_key[pid] = (unsigned)node;
         ukeys[pid] = keys_sorted[i];
+        if (edge_ptr != nullptr) edge_ptr[pid] = (int)i;
     }
-    if (i == E - 1) *count_out = pid + 1;
+    if (i == E - 1) {
+        *count_out = pid + 1;
+        if (edge_ptr != nullptr) edge_ptr[pid + 1] = (int)E;
+    }
 }
 
 // pad pair tables beyond the pair count with sentinels (node key N sorts last)
@@ -165,7 +170,8 @@ static size_t carve(Workspace* ws, void* base, int64_t E) {
 // of sorted edge i.
 static int build_pairs(const Workspace& ws, const int* e_type, const int* node_of_edge, int64_t E,
                        int64_t N, int K, int* row_of_edge, int* pair_node, int* type_ptr,
-                       int* by_node_ptr, int* by_node_idx, int* count_out, cudaStream_t stream) {
+                       int* by_node_ptr, int* by_node_idx, int* count_out, int* edge_ptr, int* edge_idx,
+                       cudaStream_t stream) {
     const int T = 256;
     const unsigned g = grid_for(E, T);
     size_t tb = ws.cub_bytes;
@@ -178,7 +184,7 @@ static int build_pairs(const Workspace& ws, const int* e_type, const int* node_o
     tb = ws.cub_bytes;
     cub::DeviceScan::InclusiveSum(ws.cub_temp, tb, ws.flags, ws.scan, (int)E, stream);
     scatter_pairs<<<g, T, 0, stream>>>(ws.k64_b, ws.v32_b, ws.flags, ws.scan, E, N, row_of_edge, pair_node,
-                                       ws.k32_a, ws.ukeys, count_out);
+                                       ws.k32_a, ws.ukeys, count_out, edge_ptr, edge_idx);
     pad_pairs<<<g, T, 0, stream>>>(count_out, E, N, pair_node, ws.k32_a);
     type_ptr_kernel<<<grid_for(K + 1, 64), 64, 0, stream>>>(ws.ukeys, count_out, N, K, type_ptr);
     // node -> pairs CSR: stable sort of pair ids by node (padding has key N and sorts last)
@@ -206,8 +212,8 @@ extern "C" int bl_plan_build(const int32_t* src, const int32_t* tgt, const int32
                              int32_t* row_ptr, int32_t* urow, int32_t* vrow, int32_t* s_node,
                              int32_t* s_type_ptr, int32_t* s_by_node_ptr, int32_t* s_by_node_idx,
                              int32_t* t_node, int32_t* t_type_ptr, int32_t* t_by_node_ptr,
-                             int32_t* t_by_node_idx, int32_t* counts, void* workspace,
-                             size_t workspace_bytes, bl_stream_t stream_) {
+                             int32_t* t_by_node_idx, int32_t* counts, int32_t* s_edge_ptr, int32_t* s_edge_idx,
+                             int32_t* e_tgt, void* workspace, size_t workspace_bytes, bl_stream_t stream_) {
     if (E < 0 || N <= 0 || K <= 0 || E > 0x7ffffff0LL || N > 0x7ffffff0LL) return BL_ERR_INVALID_ARGUMENT;
     cudaStream_t stream = (cudaStream_t)stream_;
     Workspace ws;
@@ -222,6 +228,7 @@ extern "C" int bl_plan_build(const int32_t* src, const int32_t* tgt, const int32
         cudaMemsetAsync(t_by_node_ptr, 0, (size_t)(N + 1) * 4, stream);
         cudaMemsetAsync(s_type_ptr, 0, (size_t)(K + 1) * 4, stream);
         cudaMemsetAsync(t_type_ptr, 0, (size_t)(K + 1) * 4, stream);
+        if (s_edge_ptr != nullptr) cudaMemsetAsync(s_edge_ptr, 0, 4, stream);
         return check_cuda(cudaMemsetAsync(counts, 0, 8, stream), "plan memset");
     }
     const unsigned g = grid_for(E, T);
@@ -240,13 +247,17 @@ extern "C" int bl_plan_build(const int32_t* src, const int32_t* tgt, const int32
     rc = check_cuda(cudaMemcpyAsync(e_tgt_sorted, ws.k32_b, (size_t)E * 4, cudaMemcpyDeviceToDevice, stream),
                     "plan copy");
     if (rc) return rc;
+    if (e_tgt != nullptr) {  // target node of every sorted edge (for the by-source backward of the edge kernel)
+        rc = check_cuda(cudaMemcpyAsync(e_tgt, ws.k32_b, (size_t)E * 4, cudaMemcpyDeviceToDevice, stream), "plan copy");
+        if (rc) return rc;
+    }
     // 2. S-pairs (type, src)
     rc = build_pairs(ws, e_type, e_src, E, N, K, urow, s_node, s_type_ptr, s_by_node_ptr, s_by_node_idx,
-                     counts + 0, stream);
+                     counts + 0, s_edge_ptr, s_edge_idx, stream);
     if (rc) return rc;
     // 3. T-pairs (type, tgt).  e_tgt_sorted aliases t_by_node_idx, which build_pairs writes only in
     // its final sort, after every read of node_of_edge (make_pair_keys) has been issued in stream order.
     rc = build_pairs(ws, e_type, e_tgt_sorted, E, N, K, vrow, t_node, t_type_ptr, t_by_node_ptr,
-                     t_by_node_idx, counts + 1, stream);
+                     t_by_node_idx, counts + 1, nullptr, nullptr, stream);
     return rc;
 }

@@ -32,6 +32,11 @@ def build_plan_ref(src: np.ndarray, tgt: np.ndarray, etype: np.ndarray, num_node
         s_node=s_node, s_type_ptr=s_type_ptr, s_by_node_ptr=s_by_node_ptr, s_by_node_idx=s_by_node_idx,
         t_node=t_node, t_type_ptr=t_type_ptr, t_by_node_ptr=t_by_node_ptr, t_by_node_idx=t_by_node_idx,
     )
+    # S-pair -> its sorted edges (ascending) and the target of every sorted edge (by-source half of the edge backward)
+    by_pair = np.argsort(urow, kind="stable")
+    out["s_edge_idx"] = by_pair
+    out["s_edge_ptr"] = np.searchsorted(urow[by_pair], np.arange(s_node.shape[0] + 1), side="left")
+    out["e_tgt"] = e_tgt
     out = {k: np.asarray(v, dtype=np.int32) for k, v in out.items()}
     out["num_s_pairs"], out["num_t_pairs"] = int(s_node.shape[0]), int(t_node.shape[0])
     return out

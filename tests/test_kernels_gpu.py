@@ -32,7 +32,8 @@ def test_plan_bit_exact(cuda_device, N, K, epk, self_edges):
     plan = _plan(adj, N, cuda_device)
     assert plan.num_s_pairs == ref["num_s_pairs"] and plan.num_t_pairs == ref["num_t_pairs"]
     for name in ("e_perm", "e_src", "e_type", "row_ptr", "urow", "vrow", "s_node", "s_type_ptr", "s_by_node_ptr",
-                 "s_by_node_idx", "t_node", "t_type_ptr", "t_by_node_ptr", "t_by_node_idx"):
+                 "s_by_node_idx", "t_node", "t_type_ptr", "t_by_node_ptr", "t_by_node_idx", "s_edge_ptr", "s_edge_idx",
+                 "e_tgt"):
         got = getattr(plan, name).cpu().numpy()
         assert got.dtype == np.int32
         np.testing.assert_array_equal(got, ref[name], err_msg=name)
