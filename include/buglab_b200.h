@@ -61,6 +61,10 @@ const char* bl_error_string(int code);
  *   s_by_node_ptr[N+1], s_by_node_idx[E]   CSR node -> S-pair ids (ascending pair id per node)
  *   t_*            same four tables for the T-pairs (type, tgt)
  *   counts[2]      {P_s, P_t}
+ *   block_nodes    0: pairs ordered by (type, node) — s_type_ptr / t_type_ptr have K+1 entries, one segment per type.
+ *                  B > 0: pairs ordered by (node / B, type, node) — the two pointer arrays have ceil(N/B)*K + 1 entries,
+ *                  segment s = (node block s / K, type s % K); only the segment-aware GEMMs (bl_tma_*) accept this
+ *                  layout (they then sweep the node states once per layer instead of once per type).
  *   s_edge_ptr[E+1], s_edge_idx[E]  (nullable) CSR S-pair -> its sorted edges (ascending): the edges whose U row
  *                  is that pair; e_tgt[E] (nullable) target node of every sorted edge.  Both feed the by-source half
  *                  of the edge kernel's backward (bl_edge_bwd_sources).
@@ -73,7 +77,7 @@ int bl_plan_build(const int32_t* src, const int32_t* tgt, const int32_t* etype,
                   int32_t* urow, int32_t* vrow,
                   int32_t* s_node, int32_t* s_type_ptr, int32_t* s_by_node_ptr, int32_t* s_by_node_idx,
                   int32_t* t_node, int32_t* t_type_ptr, int32_t* t_by_node_ptr, int32_t* t_by_node_idx,
-                  int32_t* counts, int32_t* s_edge_ptr, int32_t* s_edge_idx, int32_t* e_tgt,
+                  int32_t* counts, int32_t* s_edge_ptr, int32_t* s_edge_idx, int32_t* e_tgt, int32_t block_nodes,
                   void* workspace, size_t workspace_bytes, bl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -55,10 +55,15 @@ class EdgePlan(NamedTuple):
     s_edge_ptr: Optional[torch.Tensor] = None
     s_edge_idx: Optional[torch.Tensor] = None
     e_tgt: Optional[torch.Tensor] = None
+    # pair layout: 0 = type-major (one segment per type); B > 0 = node-blocked, segments (node block, type) with
+    # seg_type[s] = s % K (then s_type_ptr / t_type_ptr hold num_segs + 1 segment pointers and the *_host tuples are empty)
+    block_nodes: int = 0
+    num_segs: int = 0
+    seg_type: Optional[torch.Tensor] = None
 
 
 def build_edge_plan(
-    adjacency_lists: Sequence[Tuple[torch.Tensor, torch.Tensor]], num_nodes: int
+    adjacency_lists: Sequence[Tuple[torch.Tensor, torch.Tensor]], num_nodes: int, block_nodes: int = 0
 ) -> EdgePlan:
     """Build the plan from ptgnn-style adjacency lists ``[(src_k, tgt_k)]`` (one per edge type, any int dtype).
 
@@ -78,16 +83,20 @@ def build_edge_plan(
     etype = torch.repeat_interleave(
         torch.arange(K, device=device, dtype=torch.int32), torch.tensor(sizes, device=device), output_size=E
     ) if E > 0 else torch.zeros(0, device=device, dtype=torch.int32)
-    return build_edge_plan_from_flat(src, tgt, etype, num_nodes, K)
+    return build_edge_plan_from_flat(src, tgt, etype, num_nodes, K, block_nodes)
 
 
 def build_edge_plan_from_flat(
-    src: torch.Tensor, tgt: torch.Tensor, etype: torch.Tensor, num_nodes: int, num_edge_types: int
+    src: torch.Tensor, tgt: torch.Tensor, etype: torch.Tensor, num_nodes: int, num_edge_types: int, block_nodes: int = 0
 ) -> EdgePlan:
-    """Same, from the type-major concatenation (int32 CUDA tensors)."""
+    """Same, from the type-major concatenation (int32 CUDA tensors).  ``block_nodes`` > 0 orders the pair tables by
+    (node block, type, node) — only for models whose every layer runs on the segment-aware TMA GEMMs
+    (:func:`plan_block_nodes_for`)."""
     lib = _lib.load()
     device = src.device
     E, N, K = int(src.shape[0]), int(num_nodes), int(num_edge_types)
+    B = int(block_nodes) if USE_TMA else 0
+    S = ((N + B - 1) // B) * K if B > 0 else K
     opts = dict(device=device, dtype=torch.int32)
     Ea = max(E, 1)
     e_perm, e_src, e_type = (torch.empty(Ea, **opts) for _ in range(3))
@@ -96,9 +105,9 @@ def build_edge_plan_from_flat(
     s_node, s_by_node_idx = torch.empty(Ea, **opts), torch.empty(Ea, **opts)
     t_node, t_by_node_idx = torch.empty(Ea, **opts), torch.empty(Ea, **opts)
     s_by_node_ptr, t_by_node_ptr = torch.empty(N + 1, **opts), torch.empty(N + 1, **opts)
-    # [s_type_ptr (K+1) | t_type_ptr (K+1) | counts (2)] in one buffer -> one D2H copy
-    meta = torch.empty(2 * (K + 1) + 2, **opts)
-    s_type_ptr, t_type_ptr, counts = meta[: K + 1], meta[K + 1 : 2 * (K + 1)], meta[2 * (K + 1) :]
+    # [counts (2) | s_type_ptr (S+1) | t_type_ptr (S+1)] in one buffer -> one D2H copy (of the counts only when blocked)
+    meta = torch.empty(2 + 2 * (S + 1), **opts)
+    counts, s_type_ptr, t_type_ptr = meta[:2], meta[2 : S + 3], meta[S + 3 :]
     s_edge_ptr, s_edge_idx, e_tgt = (torch.empty(Ea + 1, **opts), torch.empty(Ea, **opts), torch.empty(Ea, **opts))
     ws_bytes = lib.bl_plan_workspace_bytes(E, N, K)
     workspace = torch.empty(ws_bytes, device=device, dtype=torch.uint8)
@@ -108,7 +117,7 @@ def build_edge_plan_from_flat(
             i32(e_perm), i32(e_src), i32(e_type), i32(row_ptr), i32(urow), i32(vrow),
             i32(s_node), s_type_ptr.data_ptr(), i32(s_by_node_ptr), i32(s_by_node_idx),
             i32(t_node), t_type_ptr.data_ptr(), i32(t_by_node_ptr), i32(t_by_node_idx),
-            counts.data_ptr(), i32(s_edge_ptr), i32(s_edge_idx), i32(e_tgt), workspace.data_ptr(), ws_bytes, stream_ptr(device),
+            counts.data_ptr(), i32(s_edge_ptr), i32(s_edge_idx), i32(e_tgt), B, workspace.data_ptr(), ws_bytes, stream_ptr(device),
         ),
         "bl_plan_build",
     )
@@ -117,15 +126,37 @@ def build_edge_plan_from_flat(
         tile_rows, slab_rows = tma_tile_rows(), tma_slab_rows()
         tables = [unit_prefix(s_type_ptr, tile_rows), unit_prefix(t_type_ptr, tile_rows),
                   unit_prefix(s_type_ptr, slab_rows), unit_prefix(t_type_ptr, slab_rows)]
-    meta_host = meta.cpu().tolist()  # the one host sync of the plan
-    s_tp, t_tp = tuple(meta_host[: K + 1]), tuple(meta_host[K + 1 : 2 * (K + 1)])
-    P_s, P_t = meta_host[-2], meta_host[-1]
+    seg_type = None
+    if B > 0:
+        seg_type = torch.arange(S, device=device, dtype=torch.int32).remainder_(K)
+        P_s, P_t = meta[:2].cpu().tolist()  # the one host sync of the plan
+        s_tp = t_tp = ()
+    else:
+        meta_host = meta.cpu().tolist()  # the one host sync of the plan
+        P_s, P_t = meta_host[0], meta_host[1]
+        s_tp, t_tp = tuple(meta_host[2 : K + 3]), tuple(meta_host[K + 3 :])
     return EdgePlan(
         N, E, K, e_perm[:E], e_src[:E], e_type[:E], row_ptr, urow[:E], vrow[:E],
         s_node[:P_s], s_type_ptr, s_by_node_ptr, s_by_node_idx[:P_s],
         t_node[:P_t], t_type_ptr, t_by_node_ptr, t_by_node_idx[:P_t],
-        P_s, P_t, s_tp, t_tp, *tables, s_edge_ptr[: P_s + 1], s_edge_idx[:E], e_tgt[:E],
+        P_s, P_t, s_tp, t_tp, *tables, s_edge_ptr[: P_s + 1], s_edge_idx[:E], e_tgt[:E], B, S, seg_type,
     )
+
+
+PLAN_BLOCK_NODES = int(os.environ.get("BUGLAB_B200_PLAN_BLOCK", "8192"))
+
+
+def plan_block_nodes_for(layer_dims: Sequence[Tuple[int, int]]) -> int:
+    """Node-block size of the pair tables for a model whose message-passing layers have the given (D_in, M) shapes:
+    ``PLAN_BLOCK_NODES`` when EVERY layer runs forward, backward and weight gradient on the segment-aware TMA GEMMs and the
+    split-table edge backward, else 0 (type-major tables, which the first-generation and library paths need)."""
+    if not (USE_TMA and USE_SPLIT_EDGE_BACKWARD and PROJECTION_MODE == "f16x3" and PLAN_BLOCK_NODES > 0):
+        return 0
+    try:
+        ok = all(M in (128, 256, 512) and _tma_proj_ok(M, D) and _tma_proj_ok(D, M) and _tma_wgrad_ok(M, D) for D, M in layer_dims)
+    except Exception:  # library not built / no driver: host-only use of the model classes
+        return 0
+    return PLAN_BLOCK_NODES if ok and len(layer_dims) > 0 else 0
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -360,9 +391,11 @@ class TypedEdgeMessageMax(torch.autograd.Function):
                 # split h ONCE per layer at node granularity; both projections gather its rows by TMA
                 h_split = rows_split(h)
                 u_rows = tma_project(h_split, plan.s_node, weight_parts(weight, M, D, 0, False), None, None,
-                                     plan.s_type_ptr, None, plan.num_s_pairs, plan.s_tile_ptr)
+                                     plan.s_type_ptr, plan.seg_type, plan.num_s_pairs, plan.s_tile_ptr)
                 v_rows = tma_project(h_split, plan.t_node, weight_parts(weight, M, D, D, False), bias_c, None,
-                                     plan.t_type_ptr, None, plan.num_t_pairs, plan.t_tile_ptr)
+                                     plan.t_type_ptr, plan.seg_type, plan.num_t_pairs, plan.t_tile_ptr)
+            elif plan.block_nodes > 0:
+                raise _lib.BuglabB200Error(f"a node-blocked plan needs the TMA GEMMs, which do not cover (D={D}, M={M})")
             elif PROJECTION_MODE == "f16x3":
                 u_rows = _project_pairs_f16x3(h, plan.s_node, weight, 0, plan.s_type_ptr_host, None, plan.s_type_ptr)
                 v_rows = _project_pairs_f16x3(h, plan.t_node, weight, D, plan.t_type_ptr_host, bias_c, plan.t_type_ptr)
@@ -424,9 +457,9 @@ class TypedEdgeMessageMax(torch.autograd.Function):
             for rows_idx, g_split, col0, type_ptr_dev, tile_ptr, slab_ptr in (
                     (plan.s_node, du_split, 0, plan.s_type_ptr, plan.s_tile_ptr, plan.s_slab_ptr),
                     (plan.t_node, dv_split, D, plan.t_type_ptr, plan.t_tile_ptr, plan.t_slab_ptr)):
-                d_rows.append(tma_project(g_split, None, weight_parts(weight, D, M, col0, True), None, amax, type_ptr_dev, None,
-                                          int(rows_idx.shape[0]), tile_ptr))
-                tma_weight_grad(g_split, h_split, rows_idx, amax, type_ptr_dev, None, d_weight, col0, slab_ptr)
+                d_rows.append(tma_project(g_split, None, weight_parts(weight, D, M, col0, True), None, amax, type_ptr_dev,
+                                          plan.seg_type, int(rows_idx.shape[0]), tile_ptr))
+                tma_weight_grad(g_split, h_split, rows_idx, amax, type_ptr_dev, plan.seg_type, d_weight, col0, slab_ptr)
             del du_split, dv_split
             d_h = torch.empty_like(h)
             check(lib.bl_rows_segment_sum(f32(d_rows[0]), i32(plan.s_by_node_ptr), i32(plan.s_by_node_idx),
@@ -434,6 +467,8 @@ class TypedEdgeMessageMax(torch.autograd.Function):
                                           N, D, 0, None, f32(d_h), stream_ptr(dev)), "bl_rows_segment_sum")
             return d_h, d_weight, d_bias, None
 
+        if plan.block_nodes > 0:
+            raise _lib.BuglabB200Error(f"a node-blocked plan needs the TMA backward, which does not cover (D={D}, M={M})")
         du = torch.empty((plan.num_s_pairs, M), device=dev, dtype=torch.float32)
         dv = torch.empty((plan.num_t_pairs, M), device=dev, dtype=torch.float32)
         amax = torch.empty(1, device=dev, dtype=torch.float32) if ctx.mode == "f16x3" else None

@@ -7,8 +7,9 @@
 //
 // All sorts are stable LSD radix sorts (cub::DeviceRadixSort), so the result is deterministic:
 //   1. sort edges by tgt; the input is type-major, stability => order (tgt, type, original index)
-//   2. S-pairs: sort sorted-edge ids by key type*N+src, flag key changes, scan -> urow, s_node
-//   3. T-pairs: same with key type*N+tgt -> vrow, t_node
+//   2. S-pairs: sort sorted-edge ids by the pair key of (type, src) — type-major, or node-blocked (block, type, node) —
+//      flag key changes, scan -> urow, s_node, segment pointers
+//   3. T-pairs: same with (type, tgt) -> vrow, t_node
 //   4. node -> pair CSRs (for the segmented-sum backward of the row gathers)
 // Pair counts are only known on device; tables are sized by the upper bound E and padded entries
 // carry sentinel keys, so no host synchronisation happens here.
@@ -53,11 +54,24 @@ __global__ void fill_ptr_kernel(const unsigned* __restrict__ keys, int64_t n_ite
     for (int64_t t = lo; t <= hi; ++t) ptr[t] = (int)i;
 }
 
-// key[i] = type[i]*N + node[i]  (node taken through an optional indirection-free array)
+// Pair key.  Type-major layout (block == 0): key = type*N + node, pairs ordered by (type, node), one segment per type.
+// Node-blocked layout (block = B > 0): key = ((node / B)*K + type)*B + node % B, pairs ordered by (node block, type, node):
+// one segment per (block, type), so that the GEMMs and the by-source edge backward sweep the node states ONCE (all
+// types of a block while its rows are L2-resident) instead of once per type.
+__device__ __forceinline__ unsigned long long pair_key(int type, int node, int64_t N, int K, int block) {
+    if (block <= 0) return (unsigned long long)type * (unsigned long long)N + (unsigned long long)node;
+    const unsigned long long seg = (unsigned long long)(node / block) * (unsigned long long)K + (unsigned long long)type;
+    return seg * (unsigned long long)block + (unsigned long long)(node % block);
+}
+__device__ __forceinline__ int node_of_key(unsigned long long key, int64_t N, int K, int block) {
+    if (block <= 0) return (int)(key % (unsigned long long)N);
+    const unsigned long long seg = key / (unsigned long long)block;
+    return (int)((seg / (unsigned long long)K) * (unsigned long long)block + key % (unsigned long long)block);
+}
 __global__ void make_pair_keys(const int* __restrict__ e_type, const int* __restrict__ node, int64_t E,
-                               int64_t N, unsigned long long* __restrict__ keys) {
+                               int64_t N, int K, int block, unsigned long long* __restrict__ keys) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < E) keys[i] = (unsigned long long)e_type[i] * (unsigned long long)N + (unsigned long long)node[i];
+    if (i < E) keys[i] = pair_key(e_type[i], node[i], N, K, block);
 }
 
 __global__ void flag_changes(const unsigned long long* __restrict__ keys_sorted, int64_t E,
@@ -70,7 +84,7 @@ __global__ void flag_changes(const unsigned long long* __restrict__ keys_sorted,
 // unique keys, and (last thread) the pair count.
 __global__ void scatter_pairs(const unsigned long long* __restrict__ keys_sorted,
                               const int* __restrict__ edge_of, const int* __restrict__ flags,
-                              const int* __restrict__ pid_incl, int64_t E, int64_t N,
+                              const int* __restrict__ pid_incl, int64_t E, int64_t N, int K, int block,
                               int* __restrict__ row_of_edge, int* __restrict__ pair_node,
                               unsigned* __restrict__ pair_node_key, unsigned long long* __restrict__ ukeys,
                               int* __restrict__ count_out, int* __restrict__ edge_ptr, int* __restrict__ edge_idx) {
@@ -80,7 +94,7 @@ __global__ void scatter_pairs(const unsigned long long* __restrict__ keys_sorted
     row_of_edge[edge_of[i]] = pid;
     if (edge_idx != nullptr) edge_idx[i] = edge_of[i];  // sorted-edge ids grouped by pair, ascending inside a pair (stable sort)
     if (flags[i]) {
-        const int node = (int)(keys_sorted[i] % (unsigned long long)N);
+        const int node = node_of_key(keys_sorted[i], N, K, block);
         pair_node[pid] = node;
         pair_node_key[pid] = (unsigned)node;
         ukeys[pid] = keys_sorted[i];
@@ -103,12 +117,12 @@ __global__ void pad_pairs(const int* __restrict__ count, int64_t E, int64_t N, i
     }
 }
 
-// type_ptr[k] = lower_bound(ukeys[0:P], k*N), k in [0,K]
+// seg_ptr[s] = lower_bound(ukeys[0:P], s*unit), s in [0, S]   (type-major: unit = N, S = K; blocked: unit = B, S = blocks*K)
 __global__ void type_ptr_kernel(const unsigned long long* __restrict__ ukeys, const int* __restrict__ count,
-                                int64_t N, int K, int* __restrict__ type_ptr) {
+                                int64_t unit, int S, int* __restrict__ type_ptr) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k > K) return;
-    const unsigned long long target = (unsigned long long)k * (unsigned long long)N;
+    if (k > S) return;
+    const unsigned long long target = (unsigned long long)k * (unsigned long long)unit;
     int lo = 0, hi = *count;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
@@ -169,24 +183,26 @@ static size_t carve(Workspace* ws, void* base, int64_t E) {
 // Builds one (type,node) pair table + node->pair CSR.  `node_of_edge[i]` is the node (src or tgt)
 // of sorted edge i.
 static int build_pairs(const Workspace& ws, const int* e_type, const int* node_of_edge, int64_t E,
-                       int64_t N, int K, int* row_of_edge, int* pair_node, int* type_ptr,
+                       int64_t N, int K, int block, int* row_of_edge, int* pair_node, int* type_ptr,
                        int* by_node_ptr, int* by_node_idx, int* count_out, int* edge_ptr, int* edge_idx,
                        cudaStream_t stream) {
     const int T = 256;
     const unsigned g = grid_for(E, T);
     size_t tb = ws.cub_bytes;
-    make_pair_keys<<<g, T, 0, stream>>>(e_type, node_of_edge, E, N, ws.k64_a);
+    make_pair_keys<<<g, T, 0, stream>>>(e_type, node_of_edge, E, N, K, block, ws.k64_a);
     iota_kernel<<<g, T, 0, stream>>>(ws.v32_a, E);
-    const int key_bits = bits_for((uint64_t)K * (uint64_t)N);
+    const int64_t unit = block > 0 ? block : N;
+    const int num_segs = block > 0 ? (int)((N + block - 1) / block) * K : K;
+    const int key_bits = bits_for((uint64_t)num_segs * (uint64_t)unit);
     cub::DeviceRadixSort::SortPairs(ws.cub_temp, tb, ws.k64_a, ws.k64_b, ws.v32_a, ws.v32_b, (int)E, 0,
                                     key_bits, stream);
     flag_changes<<<g, T, 0, stream>>>(ws.k64_b, E, ws.flags);
     tb = ws.cub_bytes;
     cub::DeviceScan::InclusiveSum(ws.cub_temp, tb, ws.flags, ws.scan, (int)E, stream);
-    scatter_pairs<<<g, T, 0, stream>>>(ws.k64_b, ws.v32_b, ws.flags, ws.scan, E, N, row_of_edge, pair_node,
+    scatter_pairs<<<g, T, 0, stream>>>(ws.k64_b, ws.v32_b, ws.flags, ws.scan, E, N, K, block, row_of_edge, pair_node,
                                        ws.k32_a, ws.ukeys, count_out, edge_ptr, edge_idx);
     pad_pairs<<<g, T, 0, stream>>>(count_out, E, N, pair_node, ws.k32_a);
-    type_ptr_kernel<<<grid_for(K + 1, 64), 64, 0, stream>>>(ws.ukeys, count_out, N, K, type_ptr);
+    type_ptr_kernel<<<grid_for(num_segs + 1, 64), 64, 0, stream>>>(ws.ukeys, count_out, unit, num_segs, type_ptr);
     // node -> pairs CSR: stable sort of pair ids by node (padding has key N and sorts last)
     iota_kernel<<<g, T, 0, stream>>>(ws.v32_a, E);
     tb = ws.cub_bytes;
@@ -213,8 +229,9 @@ extern "C" int bl_plan_build(const int32_t* src, const int32_t* tgt, const int32
                              int32_t* s_type_ptr, int32_t* s_by_node_ptr, int32_t* s_by_node_idx,
                              int32_t* t_node, int32_t* t_type_ptr, int32_t* t_by_node_ptr,
                              int32_t* t_by_node_idx, int32_t* counts, int32_t* s_edge_ptr, int32_t* s_edge_idx,
-                             int32_t* e_tgt, void* workspace, size_t workspace_bytes, bl_stream_t stream_) {
-    if (E < 0 || N <= 0 || K <= 0 || E > 0x7ffffff0LL || N > 0x7ffffff0LL) return BL_ERR_INVALID_ARGUMENT;
+                             int32_t* e_tgt, int32_t block_nodes, void* workspace, size_t workspace_bytes, bl_stream_t stream_) {
+    if (E < 0 || N <= 0 || K <= 0 || E > 0x7ffffff0LL || N > 0x7ffffff0LL || block_nodes < 0) return BL_ERR_INVALID_ARGUMENT;
+    const int num_segs = block_nodes > 0 ? (int)((N + block_nodes - 1) / block_nodes) * K : K;
     cudaStream_t stream = (cudaStream_t)stream_;
     Workspace ws;
     const size_t need = carve(&ws, workspace, E);
@@ -226,8 +243,8 @@ extern "C" int bl_plan_build(const int32_t* src, const int32_t* tgt, const int32
         if (rc) return rc;
         cudaMemsetAsync(s_by_node_ptr, 0, (size_t)(N + 1) * 4, stream);
         cudaMemsetAsync(t_by_node_ptr, 0, (size_t)(N + 1) * 4, stream);
-        cudaMemsetAsync(s_type_ptr, 0, (size_t)(K + 1) * 4, stream);
-        cudaMemsetAsync(t_type_ptr, 0, (size_t)(K + 1) * 4, stream);
+        cudaMemsetAsync(s_type_ptr, 0, (size_t)(num_segs + 1) * 4, stream);
+        cudaMemsetAsync(t_type_ptr, 0, (size_t)(num_segs + 1) * 4, stream);
         if (s_edge_ptr != nullptr) cudaMemsetAsync(s_edge_ptr, 0, 4, stream);
         return check_cuda(cudaMemsetAsync(counts, 0, 8, stream), "plan memset");
     }
@@ -252,12 +269,12 @@ extern "C" int bl_plan_build(const int32_t* src, const int32_t* tgt, const int32
         if (rc) return rc;
     }
     // 2. S-pairs (type, src)
-    rc = build_pairs(ws, e_type, e_src, E, N, K, urow, s_node, s_type_ptr, s_by_node_ptr, s_by_node_idx,
+    rc = build_pairs(ws, e_type, e_src, E, N, K, block_nodes, urow, s_node, s_type_ptr, s_by_node_ptr, s_by_node_idx,
                      counts + 0, s_edge_ptr, s_edge_idx, stream);
     if (rc) return rc;
     // 3. T-pairs (type, tgt).  e_tgt_sorted aliases t_by_node_idx, which build_pairs writes only in
     // its final sort, after every read of node_of_edge (make_pair_keys) has been issued in stream order.
-    rc = build_pairs(ws, e_type, e_tgt_sorted, E, N, K, vrow, t_node, t_type_ptr, t_by_node_ptr,
+    rc = build_pairs(ws, e_type, e_tgt_sorted, E, N, K, block_nodes, vrow, t_node, t_type_ptr, t_by_node_ptr,
                      t_by_node_idx, counts + 1, nullptr, nullptr, stream);
     return rc;
 }

@@ -32,6 +32,14 @@ class GraphNeuralNetwork(ModuleWithMetrics):
         self.__node_embedder = node_embedder
         self.__edge_embedder = edge_embedder
 
+    def plan_block_nodes(self) -> int:
+        """Pair-table layout every layer of this network can consume (0 = type-major), see ops.plan_block_nodes_for."""
+        from buglab_b200 import ops
+
+        dims = [(l.input_state_dimension, l.message_dimension) for l in self.__message_passing_layers
+                if hasattr(l, "message_dimension")]
+        return ops.plan_block_nodes_for(dims)
+
     @property
     def message_passing_layers(self) -> List[AbstractMessagePassingLayer]:
         return list(self.__message_passing_layers)
@@ -55,10 +63,10 @@ class GraphNeuralNetwork(ModuleWithMetrics):
         num_nodes = initial_node_states.shape[0]
         if not isinstance(adjacency_lists, PlannedAdjacency):
             planned = PlannedAdjacency(adjacency_lists)
-            planned.plan = plan_for(adjacency_lists, num_nodes)
+            planned.plan = plan_for(adjacency_lists, num_nodes, self.plan_block_nodes())
             adjacency_lists = planned
         elif adjacency_lists.plan is None:
-            adjacency_lists.plan = plan_for(adjacency_lists, num_nodes)
+            adjacency_lists.plan = plan_for(adjacency_lists, num_nodes, self.plan_block_nodes())
         states = [initial_node_states]
         for layer in self.__message_passing_layers:
             states.append(layer(node_states=states[-1], adjacency_lists=adjacency_lists,
@@ -131,6 +139,10 @@ class GraphNeuralNetworkModel(AbstractNeuralModel[GraphData, TensorizedGraphData
 
     def build_neural_module(self) -> GraphNeuralNetwork:
         layers = self.__message_passing_layers_creator(self.num_edge_types)
+        # (D_in, M) of every message-passing layer: finalize_minibatch picks the pair-table layout of the device plan from
+        # them (it runs on the producer thread, without the module)
+        self._mp_layer_dims = tuple((l.input_state_dimension, l.message_dimension) for l in layers
+                                    if hasattr(l, "message_dimension"))
         return GraphNeuralNetwork(layers, node_embedder=self.__node_embedding_model.build_neural_module())
 
     # ---- tensorise one graph --------------------------------------------------------------------
@@ -284,6 +296,9 @@ class GraphNeuralNetworkModel(AbstractNeuralModel[GraphData, TensorizedGraphData
         adjacency = PlannedAdjacency((view(s), view(t)) for s, t in h_adj)
         adjacency.num_nodes = mb["num_nodes"]
         if device.type == "cuda":
+            from buglab_b200 import ops
+
+            adjacency.block_nodes = ops.plan_block_nodes_for(getattr(self, "_mp_layer_dims", ()))
             adjacency.plan = plan_for(adjacency, mb["num_nodes"])
         return {
             "node_data": {"token_idxs": view(h_ids), "lengths": view(h_lens)},

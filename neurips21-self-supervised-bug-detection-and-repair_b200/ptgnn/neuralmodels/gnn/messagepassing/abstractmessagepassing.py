@@ -11,14 +11,17 @@ class PlannedAdjacency(list):
 
     plan = None
     num_nodes = None
+    block_nodes = 0  # pair-table layout the model's layers can consume (ops.plan_block_nodes_for); 0 = type-major
 
 
-def plan_for(adjacency_lists, num_nodes: int):
+def plan_for(adjacency_lists, num_nodes: int, block_nodes=None):
     from buglab_b200 import ops
 
     plan = getattr(adjacency_lists, "plan", None)
     if plan is None or plan.num_nodes != num_nodes:
-        plan = ops.build_edge_plan(adjacency_lists, num_nodes)
+        if block_nodes is None:
+            block_nodes = getattr(adjacency_lists, "block_nodes", 0)
+        plan = ops.build_edge_plan(adjacency_lists, num_nodes, block_nodes)
         if isinstance(adjacency_lists, PlannedAdjacency):
             adjacency_lists.plan = plan
     return plan

@@ -52,6 +52,10 @@ class MlpMessagePassingLayer(AbstractMessagePassingLayer):
     def output_state_dimension(self) -> int:
         return self.__output_state_dim
 
+    @property
+    def message_dimension(self) -> int:
+        return self.__message_dim
+
     def stacked_message_parameters(self) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
         layers = self.__edge_message_transformation_layers
         weight = torch.stack([l.weight for l in layers])  # [K, M, 2*D_in]

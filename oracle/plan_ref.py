@@ -8,7 +8,9 @@ are the ones ptgnn's MlpMessagePassingLayer implies: edges are concatenated type
 import numpy as np
 
 
-def build_plan_ref(src: np.ndarray, tgt: np.ndarray, etype: np.ndarray, num_nodes: int, num_edge_types: int) -> dict:
+def build_plan_ref(src: np.ndarray, tgt: np.ndarray, etype: np.ndarray, num_nodes: int, num_edge_types: int,
+                   block_nodes: int = 0) -> dict:
+    """``block_nodes`` = B > 0: pair tables ordered by (node // B, type, node), segment s = (block s // K, type s % K)."""
     src, tgt, etype = (np.asarray(a, dtype=np.int64) for a in (src, tgt, etype))
     E, N, K = src.shape[0], int(num_nodes), int(num_edge_types)
     assert np.all(np.diff(etype) >= 0), "input must be the type-major concatenation"
@@ -16,11 +18,20 @@ def build_plan_ref(src: np.ndarray, tgt: np.ndarray, etype: np.ndarray, num_node
     e_src, e_tgt, e_type = src[perm], tgt[perm], etype[perm]
     row_ptr = np.searchsorted(e_tgt, np.arange(N + 1), side="left")
 
+    B = int(block_nodes)
+    S = ((N + B - 1) // B) * K if B > 0 else K
+
     def pairs(node_of_edge):
-        keys = e_type * N + node_of_edge
-        ukeys, inv = np.unique(keys, return_inverse=True)  # sorted unique keys: (type, node) order
-        pair_node = ukeys % N
-        type_ptr = np.searchsorted(ukeys, np.arange(K + 1) * N, side="left")
+        if B > 0:
+            keys = ((node_of_edge // B) * K + e_type) * B + node_of_edge % B
+            ukeys, inv = np.unique(keys, return_inverse=True)  # (node block, type, node) order
+            pair_node = (ukeys // B // K) * B + ukeys % B
+            type_ptr = np.searchsorted(ukeys, np.arange(S + 1) * B, side="left")
+        else:
+            keys = e_type * N + node_of_edge
+            ukeys, inv = np.unique(keys, return_inverse=True)  # sorted unique keys: (type, node) order
+            pair_node = ukeys % N
+            type_ptr = np.searchsorted(ukeys, np.arange(K + 1) * N, side="left")
         order = np.argsort(pair_node, kind="stable")
         by_node_ptr = np.searchsorted(pair_node[order], np.arange(N + 1), side="left")
         return inv.reshape(-1), pair_node, type_ptr, by_node_ptr, order

@@ -38,6 +38,21 @@ def test_plan_bit_exact(cuda_device, N, K, epk, self_edges):
         assert got.dtype == np.int32
         np.testing.assert_array_equal(got, ref[name], err_msg=name)
     assert plan.s_type_ptr_host == tuple(ref["s_type_ptr"].tolist())
+    # node-blocked layout: same edges, pair tables ordered by (node block, type, node)
+    from buglab_b200 import ops
+
+    for block in (64, 1 << 20):
+        ref = build_plan_ref(src.numpy(), tgt.numpy(), et.numpy(), N, K, block_nodes=block)
+        plan = ops.build_edge_plan([(s.to(cuda_device), t.to(cuda_device)) for s, t in adj], N, block_nodes=block)
+        assert plan.block_nodes == (block if ops.USE_TMA else 0)
+        if plan.block_nodes == 0:
+            break
+        assert plan.num_segs == int(ref["s_type_ptr"].shape[0]) - 1 and plan.num_s_pairs == ref["num_s_pairs"]
+        for name in ("e_perm", "e_src", "e_type", "row_ptr", "urow", "vrow", "s_node", "s_type_ptr", "s_by_node_ptr",
+                     "s_by_node_idx", "t_node", "t_type_ptr", "t_by_node_ptr", "t_by_node_idx", "s_edge_ptr", "s_edge_idx",
+                     "e_tgt"):
+            np.testing.assert_array_equal(getattr(plan, name).cpu().numpy(), ref[name], err_msg=f"{name} (block {block})")
+        np.testing.assert_array_equal(plan.seg_type.cpu().numpy(), np.arange(plan.num_segs) % K)
 
 
 def test_plan_no_edges(cuda_device):
@@ -55,13 +70,21 @@ def test_plan_no_edges(cuda_device):
     (1500, 64, 128, 6, [4000, 2500, 0, 800], True, True),   # warp kernel ITER=1
     (2000, 128, 256, 5, [9000, 3000, 50], False, True),     # ITER=2, isolated nodes
     (1200, 256, 512, 7, [5000, 2000, 700], True, True),     # ITER=4 (the wide post-residual layer)
+    (3000, 256, 256, 9, [9000, 6000, 0, 2500, 40], True, True),   # the bench's H->H layer shape
+    (1500, 512, 512, 4, [6000, 3000, 900], True, False),          # the bench's wide layer shape
 ])
-@pytest.mark.parametrize("mode", ["f16x3", "fp32"])
+@pytest.mark.parametrize("mode", ["f16x3", "fp32", "f16x3-blocked"])
 def test_typed_edge_message_max_fwd_bwd(cuda_device, monkeypatch, mode, N, D, M, K, epk, self_edges, use_bias):
     from buglab_b200 import ops
     from oracle.mp_ref import typed_edge_message_max_ref
 
-    monkeypatch.setattr(ops, "PROJECTION_MODE", mode)  # split-bf16 tensor-core GEMMs (default) or fp32 SGEMM
+    block_nodes = 0
+    if mode == "f16x3-blocked":  # node-blocked pair tables (many small segments): only where every product runs on the TMA GEMMs
+        mode = "f16x3"
+        if ops.plan_block_nodes_for([(D, M)]) == 0:
+            pytest.skip("shape not covered by the segment-aware TMA path")
+        block_nodes = 192
+    monkeypatch.setattr(ops, "PROJECTION_MODE", mode)  # split-fp16 tensor-core GEMMs (default) or fp32 SGEMM
 
     adj = random_adjacency(N, K, epk, seed=3 * N + M, self_edges=self_edges)
     g = torch.Generator().manual_seed(N + D)
@@ -75,7 +98,8 @@ def test_typed_edge_message_max_fwd_bwd(cuda_device, monkeypatch, mode, N, D, M,
     agg_ref, arg_ref = typed_edge_message_max_ref(h_ref, adj, w_ref, b_ref)
     agg_ref.backward(d_out.double())
 
-    plan = _plan(adj, N, cuda_device)
+    plan = ops.build_edge_plan([(s.to(cuda_device), t.to(cuda_device)) for s, t in adj], N, block_nodes=block_nodes)
+    assert plan.block_nodes == block_nodes
     h_g, w_g = h.to(cuda_device).requires_grad_(), w.to(cuda_device).requires_grad_()
     b_g = b.to(cuda_device).requires_grad_() if use_bias else None
     agg = ops.typed_edge_message_max(h_g, w_g, b_g, plan)
