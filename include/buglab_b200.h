@@ -216,6 +216,14 @@ int bl_tma_project(const void* a_split, int64_t a_rows, const int32_t* idx, cons
                    const float* amax, const int32_t* seg_ptr, const int32_t* seg_type, const int32_t* tile_ptr,
                    int32_t num_segs, int32_t num_types, int64_t num_rows, int64_t max_tiles, int32_t n_out, int32_t k_in,
                    float* out, bl_stream_t stream);
+/* Weight-stationary variant for the 256 x 256 products (CTA pairs): the pair keeps a slab's weight matrix (hi and lo, its
+ * 128 output columns per CTA: 128 KB) in shared memory and streams only A.  slab_ptr = bl_segment_unit_prefix(seg_ptr,
+ * bl_tma_slab_rows()).  BUGLAB_B200_TMA_BSTAT=0 switches it off (the streaming kernel is used instead). */
+int bl_tma_project_stationary_supported(int32_t n_out, int32_t k_in);
+int bl_tma_project_stationary(const void* a_split, int64_t a_rows, const int32_t* idx, const void* wparts, const float* bias,
+                              const float* amax, const int32_t* seg_ptr, const int32_t* seg_type, const int32_t* slab_ptr,
+                              int32_t num_segs, int32_t num_types, int64_t num_rows, int64_t max_slabs, int32_t n_out,
+                              int32_t k_in, float* out, bl_stream_t stream);
 int bl_tma_weight_grad_supported(int32_t m_out, int32_t n_in);
 /* d_weight[type, 0:m_out, col0:col0+n_in] = (1/s) * sum over pair rows of G[p, :]^T X[idx[p], :]  (block zeroed first) */
 int bl_tma_weight_grad(const void* g_split, int64_t g_rows, const void* x_split, int64_t x_rows, const int32_t* idx,

@@ -311,14 +311,25 @@ def tma_slab_rows() -> int:
 
 def tma_project(a_split: torch.Tensor, idx: Optional[torch.Tensor], parts: torch.Tensor, bias: Optional[torch.Tensor],
                 amax: Optional[torch.Tensor], seg_ptr: torch.Tensor, seg_type: Optional[torch.Tensor], num_rows: int,
-                tile_ptr: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """``out[p] = (1/s) * A[row(p)] @ W_type.T (+ bias_type)`` on the TMA-fed tcgen05 kernel; ``a_split`` from
-    :func:`rows_split`, ``parts`` from :func:`weight_parts`."""
+                tile_ptr: Optional[torch.Tensor] = None, slab_ptr: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``out[p] = (1/s) * A[row(p)] @ W_type.T (+ bias_type)`` on the TMA-fed tcgen05 kernels; ``a_split`` from
+    :func:`rows_split`, ``parts`` from :func:`weight_parts`.  256 x 256 products run on the weight-stationary variant
+    (one weight load per slab of pair rows) when ``slab_ptr`` is given."""
     num_types, _, n_out, k_in = parts.shape
     num_segs = int(seg_ptr.shape[0]) - 1
+    out = torch.empty((num_rows, n_out), device=a_split.device, dtype=torch.float32)
+    lib = _lib.load()
+    if slab_ptr is not None and lib.bl_tma_project_stationary_supported(n_out, k_in):
+        max_slabs = num_rows // tma_slab_rows() + num_segs
+        check(lib.bl_tma_project_stationary(a_split.data_ptr(), int(a_split.shape[1]), i32(idx) if idx is not None else None,
+                                            parts.data_ptr(), f32(bias) if bias is not None else None,
+                                            f32(amax) if amax is not None else None, i32(seg_ptr),
+                                            i32(seg_type) if seg_type is not None else None, i32(slab_ptr), num_segs, num_types,
+                                            num_rows, max_slabs, n_out, k_in, f32(out), stream_ptr(a_split.device)),
+              "bl_tma_project_stationary")
+        return out
     if tile_ptr is None:
         tile_ptr = unit_prefix(seg_ptr, tma_tile_rows())
-    out = torch.empty((num_rows, n_out), device=a_split.device, dtype=torch.float32)
     max_tiles = num_rows // tma_tile_rows() + num_segs
     check(_lib.load().bl_tma_project(a_split.data_ptr(), int(a_split.shape[1]), i32(idx) if idx is not None else None,
                                      parts.data_ptr(), f32(bias) if bias is not None else None,
@@ -391,9 +402,9 @@ class TypedEdgeMessageMax(torch.autograd.Function):
                 # split h ONCE per layer at node granularity; both projections gather its rows by TMA
                 h_split = rows_split(h)
                 u_rows = tma_project(h_split, plan.s_node, weight_parts(weight, M, D, 0, False), None, None,
-                                     plan.s_type_ptr, plan.seg_type, plan.num_s_pairs, plan.s_tile_ptr)
+                                     plan.s_type_ptr, plan.seg_type, plan.num_s_pairs, plan.s_tile_ptr, plan.s_slab_ptr)
                 v_rows = tma_project(h_split, plan.t_node, weight_parts(weight, M, D, D, False), bias_c, None,
-                                     plan.t_type_ptr, plan.seg_type, plan.num_t_pairs, plan.t_tile_ptr)
+                                     plan.t_type_ptr, plan.seg_type, plan.num_t_pairs, plan.t_tile_ptr, plan.t_slab_ptr)
             elif plan.block_nodes > 0:
                 raise _lib.BuglabB200Error(f"a node-blocked plan needs the TMA GEMMs, which do not cover (D={D}, M={M})")
             elif PROJECTION_MODE == "f16x3":
@@ -458,7 +469,7 @@ class TypedEdgeMessageMax(torch.autograd.Function):
                     (plan.s_node, du_split, 0, plan.s_type_ptr, plan.s_tile_ptr, plan.s_slab_ptr),
                     (plan.t_node, dv_split, D, plan.t_type_ptr, plan.t_tile_ptr, plan.t_slab_ptr)):
                 d_rows.append(tma_project(g_split, None, weight_parts(weight, D, M, col0, True), None, amax, type_ptr_dev,
-                                          plan.seg_type, int(rows_idx.shape[0]), tile_ptr))
+                                          plan.seg_type, int(rows_idx.shape[0]), tile_ptr, slab_ptr))
                 tma_weight_grad(g_split, h_split, rows_idx, amax, type_ptr_dev, plan.seg_type, d_weight, col0, slab_ptr)
             del du_split, dv_split
             d_h = torch.empty_like(h)
@@ -493,7 +504,7 @@ class TypedEdgeMessageMax(torch.autograd.Function):
                     (plan.t_node, dv, D, plan.t_type_ptr_host, plan.t_type_ptr, plan.t_tile_ptr, plan.t_slab_ptr)):
                 g_split = rows_split(d_tab, None, amax)
                 d_rows.append(tma_project(g_split, None, weight_parts(weight, D, M, col0, True), None, amax, type_ptr_dev, None,
-                                          int(rows_idx.shape[0]), tile_ptr))
+                                          int(rows_idx.shape[0]), tile_ptr, slab_ptr))
                 if wg_ok:
                     tma_weight_grad(g_split, h_split, rows_idx, amax, type_ptr_dev, None, d_weight, col0, slab_ptr)
                 else:  # widths the weight-gradient kernel does not cover (e.g. 128): round 1's split + library GEMM
@@ -657,14 +668,16 @@ class DenseLinearTma(torch.autograd.Function):
         N_out = weight.shape[0]
         seg = _single_segment(R, x.device)
         x_split = rows_split(x)
-        y = tma_project(x_split, None, weight_parts(weight.view(1, N_out, K_in), N_out, K_in, 0, False), None, None, seg, None, R)
-        ctx.save_for_backward(x_split, weight, seg)
+        slabs = unit_prefix(seg, tma_slab_rows())
+        y = tma_project(x_split, None, weight_parts(weight.view(1, N_out, K_in), N_out, K_in, 0, False), None, None, seg, None, R,
+                        None, slabs)
+        ctx.save_for_backward(x_split, weight, seg, slabs)
         return y
 
     @staticmethod
     def backward(ctx, dy: torch.Tensor):
         lib = _lib.load()
-        x_split, weight, seg = ctx.saved_tensors
+        x_split, weight, seg, slabs = ctx.saved_tensors
         dy = dy.contiguous()
         R, N_out = dy.shape
         K_in = weight.shape[1]
@@ -672,10 +685,11 @@ class DenseLinearTma(torch.autograd.Function):
         amax = torch.empty(1, device=dev, dtype=torch.float32)
         check(lib.bl_absmax(f32(dy), dy.numel(), f32(amax), stream_ptr(dev)), "bl_absmax")
         g_split = rows_split(dy, None, amax)
-        dx = tma_project(g_split, None, weight_parts(weight.view(1, N_out, K_in), K_in, N_out, 0, True), None, amax, seg, None, R)
+        dx = tma_project(g_split, None, weight_parts(weight.view(1, N_out, K_in), K_in, N_out, 0, True), None, amax, seg, None, R,
+                         None, slabs)
         dw = torch.empty_like(weight)
         identity = torch.arange(R, device=dev, dtype=torch.int32)
-        tma_weight_grad(g_split, x_split, identity, amax, seg, None, dw.view(1, N_out, K_in), 0)
+        tma_weight_grad(g_split, x_split, identity, amax, seg, None, dw.view(1, N_out, K_in), 0, slabs)
         return dx, dw
 
 

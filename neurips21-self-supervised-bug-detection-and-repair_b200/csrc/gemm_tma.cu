@@ -34,6 +34,9 @@ constexpr int TILE_M = 128;   // rows per CTA = TMEM lanes
 constexpr int CHUNK_K = 64;   // fp16 elements per smem row = 128 bytes = one swizzle atom
 constexpr int THREADS = 288;  // warps 0-3 producers, 4 MMA + TMEM alloc, 5-8 epilogue
 constexpr int MMA_WARP = 4, FIRST_EPI_WARP = 5;
+// slab = unit of the weight gradient's pair-row reduction (also bounds the truncating tensor-core accumulation chain:
+// 768 MMAs) and of the weight-stationary projection (one weight load per slab)
+constexpr int SLAB_ROWS = 4096;
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address (pair leader)
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -404,6 +407,220 @@ proj_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 }
 
 // =====================================================================================================================
+// Projection, weight-stationary variant (CTA pairs, N = 256, Kin = 256: the H -> H layers' forward and backward-input).
+// Work unit = one slab (<= SLAB_ROWS consecutive pair rows of one segment): the pair loads the slab's weight matrix ONCE
+// (hi and lo parts, each CTA its 128 output columns: 128 KB of shared memory) and streams only the A tiles (three
+// 32 KB stages) for the slab's <= 16 row tiles.  Streaming the weights per tile costs as many L2->SM bytes as A itself
+// (at the tensor peak the two together meet the chip's L2 throughput); here they are read once per 4 096 rows.
+// =====================================================================================================================
+struct ProjBsCfg {
+    static constexpr int NT = 256, CG = 2, NTL = 128, KIN = 256, CHUNKS = KIN / CHUNK_K;
+    static constexpr uint32_t A_BYTES = TILE_M * 128;
+    static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES;               // A hi + lo of one 64-wide chunk
+    static constexpr uint32_t B_CHUNK_BYTES = NTL * 128;               // one part of one chunk of the weights
+    static constexpr uint32_t B_BYTES = CHUNKS * 2 * B_CHUNK_BYTES;    // 128 KB
+    static constexpr int STAGES = 3;
+    static constexpr uint32_t SMEM_BYTES = B_BYTES + STAGES * STAGE_BYTES + 1024;
+};
+
+template <bool GATHER>
+__global__ void __launch_bounds__(THREADS, 1)
+proj_bs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ProjParams p) {
+    using Cfg = ProjBsCfg;
+    constexpr int CG = Cfg::CG, NT = Cfg::NT, STAGES = Cfg::STAGES, CHUNKS = Cfg::CHUNKS;
+    constexpr uint32_t A_BYTES = Cfg::A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES, B_CHUNK_BYTES = Cfg::B_CHUNK_BYTES;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem_b = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // resident weights
+    uint8_t* smem_a = smem_b + Cfg::B_BYTES;                                        // A stage ring
+
+    __shared__ uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2], b_full, b_empty;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t cta_rank = cluster_ctarank();
+    const bool leader = cta_rank == 0;
+    const int num_clusters = gridDim.x / CG, cluster_id = blockIdx.x / CG;
+
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full[i], CG);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], CG * 4);
+        }
+        mbar_init(&b_full, CG);
+        mbar_init(&b_empty, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&map_a);
+        prefetch_tensormap(&map_b);
+    }
+    cluster_sync_all();
+    if (warp == MMA_WARP) tmem_alloc<CG>(&tmem_base_smem, 2 * NT);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    // p.tile_ptr holds the SLAB prefix here (unit SLAB_ROWS); a slab has <= SLAB_ROWS / 256 row tiles
+    const int total_slabs = __ldg(p.tile_ptr + p.num_segs);
+    auto locate = [&](int slab, int& type, int& row_begin, int& row_end) {
+        const int s = find_segment(p.tile_ptr, p.num_segs, slab);
+        type = p.seg_type ? __ldg(p.seg_type + s) : s;
+        row_begin = __ldg(p.seg_ptr + s) + (slab - __ldg(p.tile_ptr + s)) * SLAB_ROWS;
+        row_end = min(row_begin + SLAB_ROWS, __ldg(p.seg_ptr + s + 1));
+    };
+
+    if (warp < 4) {
+        // ============================== TMA PRODUCERS ==============================
+        const int part = warp & 1, parity = warp >> 1;
+        int stage = 0;
+        uint32_t phase = 0, chunk_counter = 0, slab_counter = 0;
+        for (int slab = cluster_id; slab < total_slabs; slab += num_clusters, ++slab_counter) {
+            int type, row_begin, row_end;
+            locate(slab, type, row_begin, row_end);
+            if (parity == 0) {  // warps 0 (hi) and 1 (lo) bring the slab's weights in once the previous slab's MMAs are done
+                mbar_wait(&b_empty, (slab_counter & 1u) ^ 1u, 4);
+                if (lane == 0) {
+                    if (part == 0) {
+                        if (leader) mbar_arrive_expect_tx(&b_full, Cfg::B_BYTES * CG);
+                        else mbar_arrive_cluster(&b_full, 0);
+                    }
+                    const int b_row = (type * 2 + part) * p.N + (int)cta_rank * Cfg::NTL;
+#pragma unroll
+                    for (int c = 0; c < CHUNKS; ++c)
+                        tma_load_2d<CG>(&map_b, &b_full, smem_b + (c * 2 + part) * B_CHUNK_BYTES, c * CHUNK_K, b_row);
+                }
+                __syncwarp();
+            }
+            const int num_tiles = (row_end - row_begin + TILE_M * CG - 1) / (TILE_M * CG);
+            for (int t = 0; t < num_tiles; ++t) {
+                const int row0 = row_begin + t * (TILE_M * CG) + (int)cta_rank * TILE_M;
+                int rows[4];
+                if (GATHER) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = row0 + lane * 4 + j;
+                        rows[j] = ((r < row_end) ? __ldg(p.idx + r) : (p.a_rows - 1)) + part * p.a_rows;
+                    }
+                }
+                for (int c = 0; c < CHUNKS; ++c, ++chunk_counter) {
+                    if ((int)(chunk_counter & 1u) == parity) {
+                        mbar_wait(&empty[stage], phase ^ 1u, 0);
+                        uint8_t* st = smem_a + (size_t)stage * STAGE_BYTES;
+                        if (lane == 0) {
+                            if (part == 0) {
+                                if (leader) mbar_arrive_expect_tx(&full[stage], STAGE_BYTES * CG);
+                                else mbar_arrive_cluster(&full[stage], 0);
+                            }
+                            if (!GATHER) tma_load_2d<CG>(&map_a, &full[stage], st + part * A_BYTES, c * CHUNK_K, part * p.a_rows + row0);
+                        }
+                        __syncwarp();
+                        if (GATHER)
+                            tma_gather4<CG>(&map_a, &full[stage], st + part * A_BYTES + lane * 512, c * CHUNK_K, rows[0], rows[1],
+                                            rows[2], rows[3]);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        // ============================== MMA ISSUER (pair leader only) ==============================
+        if (leader) {
+            const uint32_t idesc = idesc_f16_f32(TILE_M * CG, NT, false);
+            const uint32_t b_base = smem_u32(smem_b);
+            int stage = 0;
+            uint32_t phase = 0, tile_counter = 0, slab_counter = 0;
+            for (int slab = cluster_id; slab < total_slabs; slab += num_clusters, ++slab_counter) {
+                int type, row_begin, row_end;
+                locate(slab, type, row_begin, row_end);
+                const int num_tiles = (row_end - row_begin + TILE_M * CG - 1) / (TILE_M * CG);
+                mbar_wait(&b_full, slab_counter & 1u, 5);
+                tc_fence_after();
+                for (int t = 0; t < num_tiles; ++t, ++tile_counter) {
+                    const uint32_t a = tile_counter & 1u, ause = tile_counter >> 1;
+                    mbar_wait(&acc_empty[a], (ause & 1u) ^ 1u, 1);
+                    tc_fence_after();
+                    const uint32_t tmem_acc = tmem_base + a * NT;
+                    for (int c = 0; c < CHUNKS; ++c) {
+                        mbar_wait(&full[stage], phase, 2);
+                        tc_fence_after();
+                        if (lane == 0) {
+                            const uint32_t a_hi = smem_u32(smem_a + (size_t)stage * STAGE_BYTES), a_lo = a_hi + A_BYTES;
+                            const uint32_t b_hi = b_base + (c * 2) * B_CHUNK_BYTES, b_lo = b_hi + B_CHUNK_BYTES;
+#pragma unroll
+                            for (int kk = 0; kk < CHUNK_K / 16; ++kk) {
+                                const uint32_t koff = kk * 32;
+                                umma_f16<CG>(tmem_acc, desc_k_sw128(a_hi + koff), desc_k_sw128(b_hi + koff), idesc, (c | kk) ? 1u : 0u);
+                                umma_f16<CG>(tmem_acc, desc_k_sw128(a_hi + koff), desc_k_sw128(b_lo + koff), idesc, 1u);
+                                umma_f16<CG>(tmem_acc, desc_k_sw128(a_lo + koff), desc_k_sw128(b_hi + koff), idesc, 1u);
+                            }
+                            tc_commit<CG>(&empty[stage]);
+                            if (c == CHUNKS - 1) {
+                                tc_commit<CG>(&acc_full[a]);
+                                if (t == num_tiles - 1) tc_commit<CG>(&b_empty);  // the weights may be replaced
+                            }
+                        }
+                        __syncwarp();
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp >= FIRST_EPI_WARP) {
+        // ============================== EPILOGUE ==============================
+        const float inv_scale = (p.amax != nullptr) ? 1.0f / pow2_scale_for(__ldg(p.amax)) : 1.0f;
+        const int lane_base = (warp & 3) * 32;
+        uint32_t tile_counter = 0;
+        for (int slab = cluster_id; slab < total_slabs; slab += num_clusters) {
+            int type, row_begin, row_end;
+            locate(slab, type, row_begin, row_end);
+            const int num_tiles = (row_end - row_begin + TILE_M * CG - 1) / (TILE_M * CG);
+            const float* brow = p.bias ? p.bias + (size_t)type * p.N : nullptr;
+            for (int t = 0; t < num_tiles; ++t, ++tile_counter) {
+                const int row0 = row_begin + t * (TILE_M * CG) + (int)cta_rank * TILE_M;
+                const uint32_t a = tile_counter & 1u, ause = tile_counter >> 1;
+                mbar_wait(&acc_full[a], ause & 1u, 3);
+                tc_fence_after();
+                const int r = row0 + lane_base + lane;
+                const bool valid = r < row_end;
+                float* orow = p.out + (size_t)r * p.N;
+#pragma unroll 1
+                for (int j = 0; j < NT / 32; ++j) {
+                    float v[32];
+                    const int col = j * 32;
+                    tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(a * NT + col), v);
+                    if (valid) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float4 o = make_float4(v[4 * q] * inv_scale, v[4 * q + 1] * inv_scale, v[4 * q + 2] * inv_scale,
+                                                   v[4 * q + 3] * inv_scale);
+                            if (brow) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(brow + col) + q);
+                                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                            }
+                            reinterpret_cast<float4*>(orow + col)[q] = o;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (leader) mbar_arrive_local(&acc_empty[a]);
+                    else mbar_arrive_cluster(&acc_empty[a], 0);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == MMA_WARP) tmem_dealloc<CG>(tmem_base, 2 * NT);
+}
+
+// =====================================================================================================================
 // Weight gradient:  dW_type[m, col0 + n] += inv_scale * sum over the pair rows p of the segments of that type of
 //                   G[p, m] * X[idx[p], n]
 //   G = split table of the (pre-scaled) table gradient [2][g_rows][M], X = split table of the node states [2][x_rows][Nin].
@@ -412,7 +629,6 @@ proj_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 //   rows of G past a slab end harmless).  Work item = (slab of <= SLAB_ROWS pair rows, 128*CG-row m tile, 256-col n tile);
 //   partial tiles are added to dW with fp32 REDs (dW pre-zeroed by the caller side of the C ABI).
 // =====================================================================================================================
-constexpr int SLAB_ROWS = 4096;  // also bounds the truncating tensor-core accumulation chain (768 MMAs)
 
 struct WgParams {
     const int* idx;        // [P]
@@ -768,6 +984,34 @@ extern "C" int bl_segment_unit_prefix(const int32_t* seg_ptr, int32_t num_segs, 
 
 extern "C" int bl_tma_tile_rows(void) { return tg::TILE_M * tg::default_cg(); }
 extern "C" int bl_tma_slab_rows(void) { return tg::SLAB_ROWS; }
+
+/* 1 when bl_tma_project_stationary covers the shape (CTA pairs, 256 x 256) and BUGLAB_B200_TMA_BSTAT != 0 */
+extern "C" int bl_tma_project_stationary_supported(int32_t n_out, int32_t k_in) {
+    static const int enabled = tg::env_int("BUGLAB_B200_TMA_BSTAT", 1);
+    return enabled && tg::default_cg() == 2 && n_out == 256 && k_in == 256 && tg::encode_fn() != nullptr;
+}
+
+/* Same product as bl_tma_project with the weights held in shared memory per slab of <= bl_tma_slab_rows() pair rows
+ * (slab_ptr = bl_segment_unit_prefix(seg_ptr, bl_tma_slab_rows()), max_slabs = an upper bound of its last entry). */
+extern "C" int bl_tma_project_stationary(const void* a_split, int64_t a_rows, const int32_t* idx, const void* wparts, const float* bias,
+                                         const float* amax, const int32_t* seg_ptr, const int32_t* seg_type, const int32_t* slab_ptr,
+                                         int32_t num_segs, int32_t num_types, int64_t num_rows, int64_t max_slabs, int32_t n_out,
+                                         int32_t k_in, float* out, bl_stream_t stream_) {
+    if (num_segs <= 0 || num_types <= 0 || num_rows < 0 || a_rows <= 0 || a_rows > (1ll << 30)) return BL_ERR_INVALID_ARGUMENT;
+    if (!bl_tma_project_stationary_supported(n_out, k_in)) return BL_ERR_UNSUPPORTED;
+    if (num_rows == 0 || max_slabs <= 0) return BL_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CUtensorMap map_a, map_b;
+    int rc = tg::make_map_f16(&map_a, a_split, (uint64_t)(2 * a_rows), (uint64_t)k_in, tg::CHUNK_K, idx ? 1u : (uint32_t)tg::TILE_M);
+    if (rc) return rc;
+    rc = tg::make_map_f16(&map_b, wparts, (uint64_t)num_types * 2 * n_out, (uint64_t)k_in, tg::CHUNK_K, (uint32_t)tg::ProjBsCfg::NTL);
+    if (rc) return rc;
+    tg::ProjParams p{idx, bias, amax, seg_ptr, seg_type, slab_ptr, out, num_segs, n_out, k_in, (int)a_rows};
+    int grid = (int)std::min<int64_t>((int64_t)(num_sms() / 2), max_slabs) * 2;
+    if (grid < 2) grid = 2;
+    if (idx) return tg::launch(tg::proj_bs_kernel<true>, 2, grid, tg::ProjBsCfg::SMEM_BYTES, stream, "bl_tma_project_stationary", map_a, map_b, p);
+    return tg::launch(tg::proj_bs_kernel<false>, 2, grid, tg::ProjBsCfg::SMEM_BYTES, stream, "bl_tma_project_stationary", map_a, map_b, p);
+}
 
 extern "C" int bl_tma_project(const void* a_split, int64_t a_rows, const int32_t* idx, const void* wparts, const float* bias,
                               const float* amax, const int32_t* seg_ptr, const int32_t* seg_type, const int32_t* tile_ptr,

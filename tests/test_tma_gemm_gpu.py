@@ -29,6 +29,7 @@ PROJECT_CASES = [
     ([300, 260, 10, 700, 255, 257], [2, 0, 1, 0, 2, 1], 256, 256, True, True, False),   # segments sharing weight matrices
     ([70000, 41000], None, 256, 256, True, True, False),          # several tiles per CTA pair: ring + accumulator reuse
     ([3000, 2000], None, 512, 512, False, False, True),           # the wide layers' backward shape
+    ([9000, 4100, 50, 0, 300], None, 256, 256, False, True, True),  # contiguous 256 x 256 with several slabs per segment
 ]
 
 WGRAD_CASES = [
@@ -81,9 +82,12 @@ def run_case(case):
             _lib.check(_lib.load().bl_absmax(_lib.f32(src_d), src_d.numel(), _lib.f32(amax), _lib.stream_ptr(dev)), "bl_absmax")
         a_split = ops.rows_split(src_d, None, amax)
         parts = ops.weight_parts(weight.to(dev), n_out, k_in, col0, transposed=False)
-        out = ops.tma_project(a_split, idx.to(dev) if gather else None, parts, bias.to(dev) if use_bias else None, amax,
-                              torch.tensor(sp, dtype=torch.int32, device=dev),
-                              torch.tensor(types, dtype=torch.int32, device=dev) if seg_types is not None else None, P)
+        seg_ptr = torch.tensor(sp, dtype=torch.int32, device=dev)
+        # slab table given: 256 x 256 products take the weight-stationary kernel (pairs only), everything else the streaming one
+        slabs = ops.unit_prefix(seg_ptr, ops.tma_slab_rows()) if os.environ.get("TEST_TMA_STATIONARY", "0") == "1" else None
+        out = ops.tma_project(a_split, idx.to(dev) if gather else None, parts, bias.to(dev) if use_bias else None, amax, seg_ptr,
+                              torch.tensor(types, dtype=torch.int32, device=dev) if seg_types is not None else None, P,
+                              None, slabs)
         torch.cuda.synchronize()
         got = out.cpu().double()
         scale = float(ref.abs().max())
@@ -131,11 +135,12 @@ _CACHE = {}
 
 
 def _results(cg):
-    """All cases at cluster size ``cg``, run once per session in a child process: {(kind, index): result dict}."""
+    """All cases at cluster size ``cg`` (``"2s"`` = pairs with the weight-stationary kernel for the 256 x 256 products), run
+    once per session in a child process: {(kind, index): result dict}."""
     if cg in _CACHE:
         return _CACHE[cg]
     cases = [dict(kind="project", args=a) for a in PROJECT_CASES] + [dict(kind="wgrad", args=a) for a in WGRAD_CASES]
-    env = dict(os.environ, BUGLAB_B200_TMA_CG=str(cg))
+    env = dict(os.environ, BUGLAB_B200_TMA_CG=str(cg)[0], TEST_TMA_STATIONARY="1" if str(cg).endswith("s") else "0")
     proc = subprocess.run([sys.executable, "-c", _DRIVER.format(root=ROOT), json.dumps(cases)], env=env, capture_output=True,
                           text=True, timeout=900)
     out = {}
@@ -155,7 +160,7 @@ def _get(cg, kind, index):
     return results[(kind, index)]
 
 
-@pytest.mark.parametrize("cg", [2, 1])
+@pytest.mark.parametrize("cg", [2, 1, "2s"])
 @pytest.mark.parametrize("case_index", range(len(PROJECT_CASES)))
 def test_tma_project_matches_fp64(cuda_device, case_index, cg):
     res = _get(cg, "project", case_index)
