@@ -79,6 +79,14 @@ def main():
         out["fwd_tma_ms"] = timed(lambda: ops.tma_project(h_split, idx, parts, bias, None, type_ptr, None, P, tile_ptr),
                                   args.warmup, args.iters)
         out["fwd_tma_tflops"] = flops / out["fwd_tma_ms"] / 1e9
+        slab_ptr_f = ops.unit_prefix(type_ptr, ops.tma_slab_rows())
+        if _lib.load().bl_tma_project_stationary_supported(M, D):
+            stat = ops.tma_project(h_split, idx, parts, bias, None, type_ptr, None, P, tile_ptr, slab_ptr_f)
+            out["fwd_stationary_max_abs_diff_vs_streaming"] = float((stat - new).abs().max())
+            out["fwd_tma_stationary_ms"] = timed(
+                lambda: ops.tma_project(h_split, idx, parts, bias, None, type_ptr, None, P, tile_ptr, slab_ptr_f), args.warmup, args.iters)
+            out["fwd_tma_stationary_tflops"] = flops / out["fwd_tma_stationary_ms"] / 1e9
+            del stat
         if not args.skip_old and _lib.load().bl_pair_project_tc_supported(M, D):
             old = ops.pair_project_tc(h, idx, parts, bias, type_ptr, P)
             out["fwd_max_abs_diff_vs_gen1"] = float((old - new).abs().max())
@@ -102,6 +110,9 @@ def main():
         d_in = ops.tma_project(g_split, None, parts_t, None, amax, type_ptr, None, P, tile_ptr)
         out["bwd_in_tma_ms"] = timed(lambda: ops.tma_project(g_split, None, parts_t, None, amax, type_ptr, None, P, tile_ptr),
                                      args.warmup, args.iters)
+        if _lib.load().bl_tma_project_stationary_supported(D, M):
+            out["bwd_in_tma_stationary_ms"] = timed(
+                lambda: ops.tma_project(g_split, None, parts_t, None, amax, type_ptr, None, P, tile_ptr, slab_ptr_f), args.warmup, args.iters)
         if not args.skip_old and _lib.load().bl_pair_project_tc_supported(D, M):
             old = ops.pair_project_tc(g, None, parts_t, None, type_ptr, P, amax=amax)
             scale = float(torch.exp2(12 - torch.ceil(torch.log2(amax))))

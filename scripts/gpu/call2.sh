@@ -5,6 +5,8 @@ set -u
 mkdir -p gpurun_out
 O=gpurun_out/r2c2
 echo "== tma gemm tests, CTA pairs"; timeout 900 python -m pytest tests/test_tma_gemm_gpu.py -q -k "2]" > ${O}_tma_cg2.txt 2>&1; rc2=$?; tail -25 ${O}_tma_cg2.txt
+echo "== tma gemm tests, CTA pairs + weight-stationary"; timeout 900 python -m pytest tests/test_tma_gemm_gpu.py -q -k "2s]" > ${O}_tma_cg2s.txt 2>&1; rc2s=$?; tail -12 ${O}_tma_cg2s.txt
+if [[ $rc2s -ne 0 ]]; then export BUGLAB_B200_TMA_BSTAT=0; echo "!! weight-stationary kernel unhealthy: streaming kernel only"; fi
 echo "== tma gemm tests, single CTAs"; timeout 900 python -m pytest tests/test_tma_gemm_gpu.py -q -k "1]" > ${O}_tma_cg1.txt 2>&1; rc1=$?; tail -25 ${O}_tma_cg1.txt
 if [[ $rc2 -ne 0 ]]; then
   if [[ $rc1 -eq 0 ]]; then export BUGLAB_B200_TMA_CG=1; echo "!! falling back to single CTAs"; else export BUGLAB_B200_TMA=0; echo "!! TMA GEMMs unhealthy: first-generation kernels"; fi
