@@ -380,11 +380,12 @@ def layer_rooflines(plan, hidden, device, label, seed=0):
         P = plan.num_s_pairs
 
         def proj():
-            return ops.tma_project(h_split, plan.s_node, parts, None, None, plan.s_type_ptr, None, P, plan.s_tile_ptr)
+            return ops.tma_project(h_split, plan.s_node, parts, None, None, plan.s_type_ptr, plan.seg_type, P, plan.s_tile_ptr,
+                                   plan.s_slab_ptr)
 
         ms_proj = _time_on_stream(proj, device)
         flops = 2.0 * P * D * M * 3
-        out["projection"] = {"bound": "tensor", "kernel": "tg::proj_kernel<256, 2, gather> (bl_tma_project), U table of an H->H layer",
+        out["projection"] = {"bound": "tensor", "kernel": "tg::proj_bs_kernel<gather> / tg::proj_kernel<256, 2, gather> (bl_tma_project[_stationary]), U table of an H->H layer",
                              "achieved": flops / ms_proj / 1e9, "peak": peaks["bf16_tflops"], "peak_kind": peak_kind + " (cuBLAS bf16 burst)",
                              "unit": "TFLOP/s", "frac": flops / ms_proj / 1e9 / peaks["bf16_tflops"],
                              "traffic": ncu_traffic("proj_kernel", f"{P}x{D}x{M}"), "flops_per_launch": flops,
@@ -403,7 +404,8 @@ def rooflines(model, tensorized_batch, hidden, device):
 
     mb = pack(model, tensorized_batch, device)
     graph = mb["graph_data"]
-    plan = ops.build_edge_plan(graph["adjacency_lists"], int(graph["node_to_graph_idx"].shape[0]))
+    block_nodes = ops.plan_block_nodes_for([(hidden, hidden), (2 * hidden, 2 * hidden)])  # the layout the model's plan uses
+    plan = ops.build_edge_plan(graph["adjacency_lists"], int(graph["node_to_graph_idx"].shape[0]), block_nodes)
     del mb, graph
     here = layer_rooflines(plan, hidden, device, "this workload (configs[1])")
     del plan
@@ -411,7 +413,8 @@ def rooflines(model, tensorized_batch, hidden, device):
     result = {"roofline": here.get("projection", here["edge"]), "roofline_edge": here["edge"], "roofline_layer": here["layer"]}
     # BASELINE configs[2]: 1 M nodes / 10 M edges / 14 edge kinds, directly synthesised packed batch
     src, tgt, etype = packed_edge_batch(1_000_000, 10_000_000, 14, 0)
-    plan = ops.build_edge_plan_from_flat(*(torch.from_numpy(a).to(device) for a in (src, tgt, etype)), 1_000_000, 14)
+    plan = ops.build_edge_plan_from_flat(*(torch.from_numpy(a).to(device) for a in (src, tgt, etype)), 1_000_000, 14,
+                                         ops.plan_block_nodes_for([(256, 256)]))
     c3 = layer_rooflines(plan, 256, device, "configs[2] (1M nodes / 10M edges / 14 kinds)")
     result["roofline_c3"] = {"layer": c3["layer"], "edge": c3["edge"], "projection": c3.get("projection")}
     del plan
