@@ -655,6 +655,10 @@ def _single_segment(rows: int, device) -> torch.Tensor:
     return seg
 
 
+# Diagnostics only (scripts/diag_precision.py): evaluate the node-update Linear's FORWARD with a plain fp32 library GEMM
+DENSE_FORWARD_FP32_REFEREE = os.environ.get("BUGLAB_B200_DENSE_FP32_REFEREE", "0") == "1"
+
+
 class DenseLinearTma(torch.autograd.Function):
     """y = x @ weight.T (no bias) for x [R, K_in], weight [N_out, K_in] on the TMA-fed tcgen05 kernels: the node-update
     ``Linear(M -> D_out)`` of the message-passing layer.  Same split-fp16 arithmetic as the projections (fp32-class
@@ -669,8 +673,11 @@ class DenseLinearTma(torch.autograd.Function):
         seg = _single_segment(R, x.device)
         x_split = rows_split(x)
         slabs = unit_prefix(seg, tma_slab_rows())
-        y = tma_project(x_split, None, weight_parts(weight.view(1, N_out, K_in), N_out, K_in, 0, False), None, None, seg, None, R,
-                        None, slabs)
+        if DENSE_FORWARD_FP32_REFEREE:
+            y = torch.mm(x, weight.t())
+        else:
+            y = tma_project(x_split, None, weight_parts(weight.view(1, N_out, K_in), N_out, K_in, 0, False), None, None, seg, None,
+                            R, None, slabs)
         ctx.save_for_backward(x_split, weight, seg, slabs)
         return y
 

@@ -32,7 +32,7 @@ def install() -> None:
     for module in (mp_pkg, mlp_mod, gnnlayerdefs):
         module.MlpMessagePassingLayer = mp_ref.MlpMessagePassingLayer
     srm.SubtokenUnitEmbedder = mp_ref.SubtokenUnitEmbedder
-    gnn_mod.plan_for = lambda adjacency_lists, num_nodes: None
+    gnn_mod.plan_for = lambda adjacency_lists, num_nodes, block_nodes=None: None
 
     ops.layer_norm = lambda x, g, b, eps=1e-5: torch.nn.functional.layer_norm(x, (x.shape[-1],), g, b, eps)
     ops.segment_log_softmax = lambda src, index, eps=1e-12, num_segments=None: scatter_ref.scatter_log_softmax(src, index.long())

@@ -66,7 +66,7 @@ def install_cpu_reference_backend():
     mp_pkg.MlpMessagePassingLayer = mp_ref.MlpMessagePassingLayer
     mlp_mod.MlpMessagePassingLayer = mp_ref.MlpMessagePassingLayer
     srm.SubtokenUnitEmbedder = mp_ref.SubtokenUnitEmbedder
-    gnn_mod.plan_for = lambda adjacency_lists, num_nodes: None  # the plan is a GPU-side object; the oracle needs none
+    gnn_mod.plan_for = lambda adjacency_lists, num_nodes, block_nodes=None: None  # the plan is a GPU-side object; the oracle needs none
 
 
 def main():
