@@ -204,6 +204,16 @@ USE_TMA = os.environ.get("BUGLAB_B200_TMA", "1") != "0"
 # Edge backward that writes the gradient tables as fp16 split tables with one writer per row (bl_edge_bwd_targets/_sources)
 # instead of fp32 tables + REDs + a split pass; BUGLAB_B200_SPLIT_EDGE_BWD=0 keeps round 1's bl_edge_segmax_bwd.
 USE_SPLIT_EDGE_BACKWARD = os.environ.get("BUGLAB_B200_SPLIT_EDGE_BWD", "1") != "0"
+# Run the by-source half of the edge backward on a side stream, concurrently with the T-table GEMMs (BUGLAB_B200_OVERLAP=0: off)
+OVERLAP_EDGE_BACKWARD = os.environ.get("BUGLAB_B200_OVERLAP", "1") != "0"
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device)
+    return _SIDE_STREAMS[key]
 
 
 def _tma_proj_ok(n_out: int, k_in: int) -> bool:
@@ -459,19 +469,31 @@ class TypedEdgeMessageMax(torch.autograd.Function):
                                           N, M, K, plan.num_t_pairs, f32(amax_in), f32(amax), f32(g_rows), dv_split.data_ptr(),
                                           f32(d_bias) if d_bias is not None else None, stream_ptr(dev)), "bl_edge_bwd_targets")
             du_split = torch.empty((2, plan.num_s_pairs + 1, M), device=dev, dtype=torch.float16)
-            check(lib.bl_edge_bwd_sources(f32(g_rows), i32(ewin), i32(plan.s_edge_ptr), i32(plan.s_edge_idx), i32(plan.e_tgt),
-                                          plan.num_s_pairs, M, f32(amax), du_split.data_ptr(), stream_ptr(dev)), "bl_edge_bwd_sources")
-            del g_rows
+            # The by-source kernel is latency/HBM-bound and independent of the T-table GEMMs: run it on a side stream so it
+            # overlaps those tensor-bound kernels (its blocks co-reside with the persistent GEMM CTAs), then join.
+            main = torch.cuda.current_stream(dev)
+            side = _side_stream(dev) if OVERLAP_EDGE_BACKWARD else None
+            if side is not None:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    check(lib.bl_edge_bwd_sources(f32(g_rows), i32(ewin), i32(plan.s_edge_ptr), i32(plan.s_edge_idx), i32(plan.e_tgt),
+                                                  plan.num_s_pairs, M, f32(amax), du_split.data_ptr(), stream_ptr(dev)),
+                          "bl_edge_bwd_sources")
+            else:
+                check(lib.bl_edge_bwd_sources(f32(g_rows), i32(ewin), i32(plan.s_edge_ptr), i32(plan.s_edge_idx), i32(plan.e_tgt),
+                                              plan.num_s_pairs, M, f32(amax), du_split.data_ptr(), stream_ptr(dev)), "bl_edge_bwd_sources")
             h_split = ctx.h_split if ctx.h_split is not None else rows_split(h)
             d_weight = torch.empty_like(weight)
-            d_rows = []
-            for rows_idx, g_split, col0, type_ptr_dev, tile_ptr, slab_ptr in (
-                    (plan.s_node, du_split, 0, plan.s_type_ptr, plan.s_tile_ptr, plan.s_slab_ptr),
-                    (plan.t_node, dv_split, D, plan.t_type_ptr, plan.t_tile_ptr, plan.t_slab_ptr)):
-                d_rows.append(tma_project(g_split, None, weight_parts(weight, D, M, col0, True), None, amax, type_ptr_dev,
-                                          plan.seg_type, int(rows_idx.shape[0]), tile_ptr, slab_ptr))
+            d_rows = [None, None]
+            for slot, rows_idx, g_split, col0, type_ptr_dev, tile_ptr, slab_ptr in (
+                    (1, plan.t_node, dv_split, D, plan.t_type_ptr, plan.t_tile_ptr, plan.t_slab_ptr),
+                    (0, plan.s_node, du_split, 0, plan.s_type_ptr, plan.s_tile_ptr, plan.s_slab_ptr)):
+                if slot == 0 and side is not None:
+                    main.wait_stream(side)  # dU is complete; g_rows / ewin are no longer read on the side stream
+                d_rows[slot] = tma_project(g_split, None, weight_parts(weight, D, M, col0, True), None, amax, type_ptr_dev,
+                                           plan.seg_type, int(rows_idx.shape[0]), tile_ptr, slab_ptr)
                 tma_weight_grad(g_split, h_split, rows_idx, amax, type_ptr_dev, plan.seg_type, d_weight, col0, slab_ptr)
-            del du_split, dv_split
+            del du_split, dv_split, g_rows
             d_h = torch.empty_like(h)
             check(lib.bl_rows_segment_sum(f32(d_rows[0]), i32(plan.s_by_node_ptr), i32(plan.s_by_node_idx),
                                           f32(d_rows[1]), i32(plan.t_by_node_ptr), i32(plan.t_by_node_idx),
