@@ -152,9 +152,11 @@ int bl_absmax(const float* x, int64_t n, float* amax, bl_stream_t stream);
  * the split table never exists in HBM.   out[p, 0:n_out] = s * src[idx[p], 0:k_in] . W_k^T (+ bias_k),  p in type k.
  *   parts  = bl_weight_parts_f16 output [num_types, 2 (hi,lo), n_out, k_in] fp16
  *   idx    may be NULL (identity), amax may be NULL (s = 1), bias may be NULL; type_ptr is a DEVICE array.
- * Supported shapes: k_in % 64 == 0 and n_out in {128, 256, 512, 768, 1024} (bl_pair_project_tc_supported). */
+ * Supported shapes: k_in % 64 == 0 and n_out in {128, 256, 512, 768, 1024} (bl_pair_project_tc_supported).
+ * bl_weight_parts_f16: amax (nullable) = device scalar max|weight|: the parts are pre-scaled by the power of two derived
+ * from it (only the bl_tma_* kernels undo it, through their amax_b argument; pass NULL for bl_pair_project_tc). */
 int bl_weight_parts_f16(const float* weight, int32_t num_types, int32_t n_out, int32_t k_in, int32_t ld, int32_t col0,
-                        int32_t transposed, void* parts, bl_stream_t stream);
+                        int32_t transposed, const float* amax, void* parts, bl_stream_t stream);
 int bl_pair_project_tc_supported(int32_t n_out, int32_t k_in);
 int bl_pair_project_tc(const float* src, const int32_t* idx, const float* amax, const void* parts, const float* bias,
                        const int32_t* type_ptr, int32_t num_types, int64_t num_rows, int32_t n_out, int32_t k_in,
@@ -210,24 +212,27 @@ int bl_segment_unit_prefix(const int32_t* seg_ptr, int32_t num_segs, int32_t uni
 int bl_tma_tile_rows(void);
 int bl_tma_slab_rows(void);
 int bl_tma_gemm_supported(int32_t n_out, int32_t k_in);
-/* out[p, 0:n_out] = (1/s) * A[row(p), :] . W_type[0:n_out, 0:k_in]^T (+ bias_type);  row(p) = idx[p] or p (idx NULL);
- * a_rows = rows per part of a_split (incl. the zero row); wparts as written by bl_weight_parts_f16; s from *amax. */
+/* out[p, 0:n_out] = (1/(s_a*s_b)) * A[row(p), :] . W_type[0:n_out, 0:k_in]^T (+ bias_type);  row(p) = idx[p] or p (idx
+ * NULL); a_rows = rows per part of a_split (incl. the zero row); wparts as written by bl_weight_parts_f16; s_a / s_b =
+ * the power-of-two pre-scales of the A table / the weight parts, from *amax / *amax_b (NULL: 1).  Pre-scaling BOTH
+ * operands keeps their fp16 lo parts out of the subnormal range. */
 int bl_tma_project(const void* a_split, int64_t a_rows, const int32_t* idx, const void* wparts, const float* bias,
-                   const float* amax, const int32_t* seg_ptr, const int32_t* seg_type, const int32_t* tile_ptr,
+                   const float* amax, const float* amax_b, const int32_t* seg_ptr, const int32_t* seg_type, const int32_t* tile_ptr,
                    int32_t num_segs, int32_t num_types, int64_t num_rows, int64_t max_tiles, int32_t n_out, int32_t k_in,
                    float* out, bl_stream_t stream);
 /* Weight-stationary variant for the 256 x 256 products (CTA pairs): the pair keeps a slab's weight matrix (hi and lo, its
  * 128 output columns per CTA: 128 KB) in shared memory and streams only A.  slab_ptr = bl_segment_unit_prefix(seg_ptr,
- * bl_tma_slab_rows()).  BUGLAB_B200_TMA_BSTAT=0 switches it off (the streaming kernel is used instead). */
+ * bl_tma_slab_rows()).  Opt-in (BUGLAB_B200_TMA_BSTAT=1): the streaming kernel measured faster on B200. */
 int bl_tma_project_stationary_supported(int32_t n_out, int32_t k_in);
 int bl_tma_project_stationary(const void* a_split, int64_t a_rows, const int32_t* idx, const void* wparts, const float* bias,
-                              const float* amax, const int32_t* seg_ptr, const int32_t* seg_type, const int32_t* slab_ptr,
+                              const float* amax, const float* amax_b, const int32_t* seg_ptr, const int32_t* seg_type, const int32_t* slab_ptr,
                               int32_t num_segs, int32_t num_types, int64_t num_rows, int64_t max_slabs, int32_t n_out,
                               int32_t k_in, float* out, bl_stream_t stream);
 int bl_tma_weight_grad_supported(int32_t m_out, int32_t n_in);
-/* d_weight[type, 0:m_out, col0:col0+n_in] = (1/s) * sum over pair rows of G[p, :]^T X[idx[p], :]  (block zeroed first) */
+/* d_weight[type, 0:m_out, col0:col0+n_in] = (1/(s_g*s_x)) * sum over pair rows of G[p, :]^T X[idx[p], :]  (block zeroed
+ * first); s_g / s_x from *amax / *amax_x (NULL: 1). */
 int bl_tma_weight_grad(const void* g_split, int64_t g_rows, const void* x_split, int64_t x_rows, const int32_t* idx,
-                       const float* amax, const int32_t* seg_ptr, const int32_t* seg_type, const int32_t* slab_ptr,
+                       const float* amax, const float* amax_x, const int32_t* seg_ptr, const int32_t* seg_type, const int32_t* slab_ptr,
                        int32_t num_segs, int32_t num_types, int64_t num_rows, int64_t max_slabs, int32_t m_out,
                        int32_t n_in, float* d_weight, int32_t ld, int32_t col0, bl_stream_t stream);
 

@@ -42,7 +42,7 @@ _SIGNATURES = {
     "bl_pair_project_bwd_weight": (c_i32, [c_ptr, c_i32, c_i32, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_ptr]),
     "bl_grouped_colsum": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_ptr, c_ptr]),
     "bl_absmax": (c_i32, [c_ptr, c_i64, c_ptr, c_ptr]),
-    "bl_weight_parts_f16": (c_i32, [c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr, c_ptr]),
+    "bl_weight_parts_f16": (c_i32, [c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
     "bl_pair_project_tc_supported": (c_i32, [c_i32, c_i32]),
     "bl_pair_project_tc": (c_i32, [c_ptr] * 6 + [c_i32, c_i64, c_i32, c_i32, c_ptr, c_ptr]),
     "bl_pair_weight_grad_tc_supported": (c_i32, [c_i32, c_i32]),
@@ -52,11 +52,11 @@ _SIGNATURES = {
     "bl_tma_tile_rows": (c_i32, []),
     "bl_tma_slab_rows": (c_i32, []),
     "bl_tma_gemm_supported": (c_i32, [c_i32, c_i32]),
-    "bl_tma_project": (c_i32, [c_ptr, c_i64] + [c_ptr] * 7 + [c_i32, c_i32, c_i64, c_i64, c_i32, c_i32, c_ptr, c_ptr]),
+    "bl_tma_project": (c_i32, [c_ptr, c_i64] + [c_ptr] * 8 + [c_i32, c_i32, c_i64, c_i64, c_i32, c_i32, c_ptr, c_ptr]),
     "bl_tma_project_stationary_supported": (c_i32, [c_i32, c_i32]),
-    "bl_tma_project_stationary": (c_i32, [c_ptr, c_i64] + [c_ptr] * 7 + [c_i32, c_i32, c_i64, c_i64, c_i32, c_i32, c_ptr, c_ptr]),
+    "bl_tma_project_stationary": (c_i32, [c_ptr, c_i64] + [c_ptr] * 8 + [c_i32, c_i32, c_i64, c_i64, c_i32, c_i32, c_ptr, c_ptr]),
     "bl_tma_weight_grad_supported": (c_i32, [c_i32, c_i32]),
-    "bl_tma_weight_grad": (c_i32, [c_ptr, c_i64, c_ptr, c_i64] + [c_ptr] * 5 + [c_i32, c_i32, c_i64, c_i64, c_i32, c_i32,
+    "bl_tma_weight_grad": (c_i32, [c_ptr, c_i64, c_ptr, c_i64] + [c_ptr] * 6 + [c_i32, c_i32, c_i64, c_i64, c_i32, c_i32,
                                    c_ptr, c_i32, c_i32, c_ptr]),
     "bl_edge_segmax_fwd": (c_i32, [c_ptr] * 5 + [c_i64, c_i32] + [c_ptr] * 3 + [c_ptr]),
     "bl_edge_segmax_bwd": (c_i32, [c_ptr] * 6 + [c_i64, c_i32, c_i64, c_i64] + [c_ptr] * 3 + [c_ptr]),

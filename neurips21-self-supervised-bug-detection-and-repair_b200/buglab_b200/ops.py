@@ -206,6 +206,9 @@ USE_TMA = os.environ.get("BUGLAB_B200_TMA", "1") != "0"
 USE_SPLIT_EDGE_BACKWARD = os.environ.get("BUGLAB_B200_SPLIT_EDGE_BWD", "1") != "0"
 # Run the by-source half of the edge backward on a side stream, concurrently with the T-table GEMMs (BUGLAB_B200_OVERLAP=0: off)
 OVERLAP_EDGE_BACKWARD = os.environ.get("BUGLAB_B200_OVERLAP", "1") != "0"
+# Pre-scale BOTH operands of the TMA GEMMs by powers of two (activations and weights to ~2^12) so that their fp16 lo parts
+# are normal numbers (unscaled, the lo part of a typical weight is a subnormal: ~17 instead of 22 significant bits)
+PRESCALE_OPERANDS = os.environ.get("BUGLAB_B200_PRESCALE", "1") != "0"
 _SIDE_STREAMS = {}
 
 
@@ -258,13 +261,23 @@ def _split3_weights(weight: torch.Tensor, bias: Optional[torch.Tensor], col0: in
     return w3, b3
 
 
-def weight_parts(weight: torch.Tensor, n_out: int, k_in: int, col0: int, transposed: bool) -> torch.Tensor:
-    """fp16 hi/lo parts [K, 2, n_out, k_in] of weight[:, :, col0:...] (or of its transpose) for the tcgen05 kernel."""
+def weight_parts(weight: torch.Tensor, n_out: int, k_in: int, col0: int, transposed: bool,
+                 amax: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp16 hi/lo parts [K, 2, n_out, k_in] of weight[:, :, col0:...] (or of its transpose) for the tcgen05 kernels,
+    pre-scaled by the power of two derived from ``amax`` (TMA kernels only: they undo it through ``amax_b``)."""
     K, _, ld = weight.shape
     parts = torch.empty((K, 2, n_out, k_in), device=weight.device, dtype=torch.float16)
-    check(_lib.load().bl_weight_parts_f16(f32(weight), K, n_out, k_in, ld, col0, 1 if transposed else 0, parts.data_ptr(),
+    check(_lib.load().bl_weight_parts_f16(f32(weight), K, n_out, k_in, ld, col0, 1 if transposed else 0,
+                                          f32(amax) if amax is not None else None, parts.data_ptr(),
                                           stream_ptr(weight.device)), "bl_weight_parts_f16")
     return parts
+
+
+def absmax(x: torch.Tensor) -> torch.Tensor:
+    """Device scalar max|x| (source of the power-of-two pre-scales of the split tables); no host sync."""
+    out = torch.empty(1, device=x.device, dtype=torch.float32)
+    check(_lib.load().bl_absmax(f32(x), x.numel(), f32(out), stream_ptr(x.device)), "bl_absmax")
+    return out
 
 
 def pair_project_tc(src: torch.Tensor, idx: Optional[torch.Tensor], parts: torch.Tensor, bias: Optional[torch.Tensor],
@@ -321,7 +334,8 @@ def tma_slab_rows() -> int:
 
 def tma_project(a_split: torch.Tensor, idx: Optional[torch.Tensor], parts: torch.Tensor, bias: Optional[torch.Tensor],
                 amax: Optional[torch.Tensor], seg_ptr: torch.Tensor, seg_type: Optional[torch.Tensor], num_rows: int,
-                tile_ptr: Optional[torch.Tensor] = None, slab_ptr: Optional[torch.Tensor] = None) -> torch.Tensor:
+                tile_ptr: Optional[torch.Tensor] = None, slab_ptr: Optional[torch.Tensor] = None,
+                amax_b: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``out[p] = (1/s) * A[row(p)] @ W_type.T (+ bias_type)`` on the TMA-fed tcgen05 kernels; ``a_split`` from
     :func:`rows_split`, ``parts`` from :func:`weight_parts`.  256 x 256 products run on the weight-stationary variant
     (one weight load per slab of pair rows) when ``slab_ptr`` is given."""
@@ -333,7 +347,8 @@ def tma_project(a_split: torch.Tensor, idx: Optional[torch.Tensor], parts: torch
         max_slabs = num_rows // tma_slab_rows() + num_segs
         check(lib.bl_tma_project_stationary(a_split.data_ptr(), int(a_split.shape[1]), i32(idx) if idx is not None else None,
                                             parts.data_ptr(), f32(bias) if bias is not None else None,
-                                            f32(amax) if amax is not None else None, i32(seg_ptr),
+                                            f32(amax) if amax is not None else None,
+                                            f32(amax_b) if amax_b is not None else None, i32(seg_ptr),
                                             i32(seg_type) if seg_type is not None else None, i32(slab_ptr), num_segs, num_types,
                                             num_rows, max_slabs, n_out, k_in, f32(out), stream_ptr(a_split.device)),
               "bl_tma_project_stationary")
@@ -343,7 +358,8 @@ def tma_project(a_split: torch.Tensor, idx: Optional[torch.Tensor], parts: torch
     max_tiles = num_rows // tma_tile_rows() + num_segs
     check(_lib.load().bl_tma_project(a_split.data_ptr(), int(a_split.shape[1]), i32(idx) if idx is not None else None,
                                      parts.data_ptr(), f32(bias) if bias is not None else None,
-                                     f32(amax) if amax is not None else None, i32(seg_ptr),
+                                     f32(amax) if amax is not None else None,
+                                     f32(amax_b) if amax_b is not None else None, i32(seg_ptr),
                                      i32(seg_type) if seg_type is not None else None, i32(tile_ptr), num_segs, num_types,
                                      num_rows, max_tiles, n_out, k_in, f32(out), stream_ptr(a_split.device)), "bl_tma_project")
     return out
@@ -351,7 +367,7 @@ def tma_project(a_split: torch.Tensor, idx: Optional[torch.Tensor], parts: torch
 
 def tma_weight_grad(g_split: torch.Tensor, x_split: torch.Tensor, idx: torch.Tensor, amax: Optional[torch.Tensor],
                     seg_ptr: torch.Tensor, seg_type: Optional[torch.Tensor], d_weight: torch.Tensor, col0: int,
-                    slab_ptr: Optional[torch.Tensor] = None) -> None:
+                    slab_ptr: Optional[torch.Tensor] = None, amax_x: Optional[torch.Tensor] = None) -> None:
     """``d_weight[type, :, col0:col0+n] = (1/s) * sum_p G[p]^T X[idx[p]]`` (block zeroed first) on the TMA-fed tcgen05 kernel."""
     num_types, m_out, ld = d_weight.shape
     n_in = int(x_split.shape[2])
@@ -361,7 +377,8 @@ def tma_weight_grad(g_split: torch.Tensor, x_split: torch.Tensor, idx: torch.Ten
         slab_ptr = unit_prefix(seg_ptr, tma_slab_rows())
     max_slabs = num_rows // tma_slab_rows() + num_segs
     check(_lib.load().bl_tma_weight_grad(g_split.data_ptr(), int(g_split.shape[1]), x_split.data_ptr(), int(x_split.shape[1]),
-                                         i32(idx), f32(amax) if amax is not None else None, i32(seg_ptr),
+                                         i32(idx), f32(amax) if amax is not None else None,
+                                         f32(amax_x) if amax_x is not None else None, i32(seg_ptr),
                                          i32(seg_type) if seg_type is not None else None, i32(slab_ptr), num_segs, num_types,
                                          num_rows, max_slabs, m_out, n_in, f32(d_weight), ld, col0,
                                          stream_ptr(g_split.device)), "bl_tma_weight_grad")
@@ -406,15 +423,18 @@ class TypedEdgeMessageMax(torch.autograd.Function):
         if twoD != 2 * D or K != plan.num_edge_types or N != plan.num_nodes:
             raise ValueError(f"shape mismatch: h {tuple(h.shape)}, weight {tuple(weight.shape)}, plan K={plan.num_edge_types} N={plan.num_nodes}")
         bias_c = bias.contiguous() if bias is not None else None
-        h_split = None
+        h_split = amax_h = amax_w = None
         with torch.no_grad():
             if _tma_proj_ok(M, D) and plan.s_tile_ptr is not None:
-                # split h ONCE per layer at node granularity; both projections gather its rows by TMA
-                h_split = rows_split(h)
-                u_rows = tma_project(h_split, plan.s_node, weight_parts(weight, M, D, 0, False), None, None,
-                                     plan.s_type_ptr, plan.seg_type, plan.num_s_pairs, plan.s_tile_ptr, plan.s_slab_ptr)
-                v_rows = tma_project(h_split, plan.t_node, weight_parts(weight, M, D, D, False), bias_c, None,
-                                     plan.t_type_ptr, plan.seg_type, plan.num_t_pairs, plan.t_tile_ptr, plan.t_slab_ptr)
+                # split h ONCE per layer at node granularity; both projections gather its rows by TMA.  Both operands are
+                # pre-scaled by exact powers of two (their absolute maxima brought to ~2^12) so that the lo parts are normal
+                # fp16 numbers; the kernels' epilogues undo both scales.
+                amax_h, amax_w = (absmax(h), absmax(weight)) if PRESCALE_OPERANDS else (None, None)
+                h_split = rows_split(h, None, amax_h)
+                u_rows = tma_project(h_split, plan.s_node, weight_parts(weight, M, D, 0, False, amax_w), None, amax_h,
+                                     plan.s_type_ptr, plan.seg_type, plan.num_s_pairs, plan.s_tile_ptr, plan.s_slab_ptr, amax_w)
+                v_rows = tma_project(h_split, plan.t_node, weight_parts(weight, M, D, D, False, amax_w), bias_c, amax_h,
+                                     plan.t_type_ptr, plan.seg_type, plan.num_t_pairs, plan.t_tile_ptr, plan.t_slab_ptr, amax_w)
             elif plan.block_nodes > 0:
                 raise _lib.BuglabB200Error(f"a node-blocked plan needs the TMA GEMMs, which do not cover (D={D}, M={M})")
             elif PROJECTION_MODE == "f16x3":
@@ -442,6 +462,7 @@ class TypedEdgeMessageMax(torch.autograd.Function):
         ctx.has_bias = bias is not None
         ctx.mode = PROJECTION_MODE
         ctx.h_split = h_split if (h_split is not None and _tma_wgrad_ok(M, D)) else None  # x operand of the weight gradient
+        ctx.amax_h, ctx.amax_w = (amax_h, amax_w) if ctx.h_split is not None else (None, None)
         ctx.save_for_backward(h, weight, xwin, ewin)
         return agg
 
@@ -482,7 +503,11 @@ class TypedEdgeMessageMax(torch.autograd.Function):
             else:
                 check(lib.bl_edge_bwd_sources(f32(g_rows), i32(ewin), i32(plan.s_edge_ptr), i32(plan.s_edge_idx), i32(plan.e_tgt),
                                               plan.num_s_pairs, M, f32(amax), du_split.data_ptr(), stream_ptr(dev)), "bl_edge_bwd_sources")
-            h_split = ctx.h_split if ctx.h_split is not None else rows_split(h)
+            if ctx.h_split is not None:
+                h_split, amax_h, amax_w = ctx.h_split, ctx.amax_h, ctx.amax_w
+            else:
+                amax_h, amax_w = (absmax(h), absmax(weight)) if PRESCALE_OPERANDS else (None, None)
+                h_split = rows_split(h, None, amax_h)
             d_weight = torch.empty_like(weight)
             d_rows = [None, None]
             for slot, rows_idx, g_split, col0, type_ptr_dev, tile_ptr, slab_ptr in (
@@ -490,9 +515,9 @@ class TypedEdgeMessageMax(torch.autograd.Function):
                     (0, plan.s_node, du_split, 0, plan.s_type_ptr, plan.s_tile_ptr, plan.s_slab_ptr)):
                 if slot == 0 and side is not None:
                     main.wait_stream(side)  # dU is complete; g_rows / ewin are no longer read on the side stream
-                d_rows[slot] = tma_project(g_split, None, weight_parts(weight, D, M, col0, True), None, amax, type_ptr_dev,
-                                           plan.seg_type, int(rows_idx.shape[0]), tile_ptr, slab_ptr)
-                tma_weight_grad(g_split, h_split, rows_idx, amax, type_ptr_dev, plan.seg_type, d_weight, col0, slab_ptr)
+                d_rows[slot] = tma_project(g_split, None, weight_parts(weight, D, M, col0, True, amax_w), None, amax, type_ptr_dev,
+                                           plan.seg_type, int(rows_idx.shape[0]), tile_ptr, slab_ptr, amax_w)
+                tma_weight_grad(g_split, h_split, rows_idx, amax, type_ptr_dev, plan.seg_type, d_weight, col0, slab_ptr, amax_h)
             del du_split, dv_split, g_rows
             d_h = torch.empty_like(h)
             check(lib.bl_rows_segment_sum(f32(d_rows[0]), i32(plan.s_by_node_ptr), i32(plan.s_by_node_idx),
@@ -520,15 +545,21 @@ class TypedEdgeMessageMax(torch.autograd.Function):
             if d_bias is not None:
                 check(lib.bl_grouped_colsum(f32(dv), i32(plan.t_type_ptr), K, M, f32(d_bias), stream_ptr(dev)), "bl_grouped_colsum")
             wg_ok = _tma_wgrad_ok(M, D)
-            h_split = ctx.h_split if ctx.h_split is not None else (rows_split(h) if wg_ok else None)
+            amax_h, amax_w = ctx.amax_h, ctx.amax_w
+            h_split = ctx.h_split
+            if h_split is None and wg_ok:
+                amax_h = absmax(h) if PRESCALE_OPERANDS else None
+                h_split = rows_split(h, None, amax_h)
+            if amax_w is None and PRESCALE_OPERANDS:
+                amax_w = absmax(weight)
             for rows_idx, d_tab, col0, type_ptr, type_ptr_dev, tile_ptr, slab_ptr in (
                     (plan.s_node, du, 0, plan.s_type_ptr_host, plan.s_type_ptr, plan.s_tile_ptr, plan.s_slab_ptr),
                     (plan.t_node, dv, D, plan.t_type_ptr_host, plan.t_type_ptr, plan.t_tile_ptr, plan.t_slab_ptr)):
                 g_split = rows_split(d_tab, None, amax)
-                d_rows.append(tma_project(g_split, None, weight_parts(weight, D, M, col0, True), None, amax, type_ptr_dev, None,
-                                          int(rows_idx.shape[0]), tile_ptr, slab_ptr))
+                d_rows.append(tma_project(g_split, None, weight_parts(weight, D, M, col0, True, amax_w), None, amax, type_ptr_dev, None,
+                                          int(rows_idx.shape[0]), tile_ptr, slab_ptr, amax_w))
                 if wg_ok:
-                    tma_weight_grad(g_split, h_split, rows_idx, amax, type_ptr_dev, None, d_weight, col0, slab_ptr)
+                    tma_weight_grad(g_split, h_split, rows_idx, amax, type_ptr_dev, None, d_weight, col0, slab_ptr, amax_h)
                 else:  # widths the weight-gradient kernel does not cover (e.g. 128): round 1's split + library GEMM
                     g2 = _split2_rows(d_tab, None, amax)
                     a2 = _split2_rows(h, rows_idx)
@@ -693,20 +724,26 @@ class DenseLinearTma(torch.autograd.Function):
         R, K_in = x.shape
         N_out = weight.shape[0]
         seg = _single_segment(R, x.device)
-        x_split = rows_split(x)
+        amax_x, amax_w = (absmax(x), absmax(weight)) if PRESCALE_OPERANDS else (None, None)
+        x_split = rows_split(x, None, amax_x)
         slabs = unit_prefix(seg, tma_slab_rows())
         if DENSE_FORWARD_FP32_REFEREE:
             y = torch.mm(x, weight.t())
         else:
-            y = tma_project(x_split, None, weight_parts(weight.view(1, N_out, K_in), N_out, K_in, 0, False), None, None, seg, None,
-                            R, None, slabs)
-        ctx.save_for_backward(x_split, weight, seg, slabs)
+            y = tma_project(x_split, None, weight_parts(weight.view(1, N_out, K_in), N_out, K_in, 0, False, amax_w), None, amax_x,
+                            seg, None, R, None, slabs, amax_w)
+        none = torch.empty(0, device=x.device)
+        ctx.prescaled = amax_x is not None
+        ctx.save_for_backward(x_split, weight, seg, slabs, amax_x if amax_x is not None else none,
+                              amax_w if amax_w is not None else none)
         return y
 
     @staticmethod
     def backward(ctx, dy: torch.Tensor):
         lib = _lib.load()
-        x_split, weight, seg, slabs = ctx.saved_tensors
+        x_split, weight, seg, slabs, amax_x, amax_w = ctx.saved_tensors
+        if not ctx.prescaled:
+            amax_x = amax_w = None
         dy = dy.contiguous()
         R, N_out = dy.shape
         K_in = weight.shape[1]
@@ -714,11 +751,11 @@ class DenseLinearTma(torch.autograd.Function):
         amax = torch.empty(1, device=dev, dtype=torch.float32)
         check(lib.bl_absmax(f32(dy), dy.numel(), f32(amax), stream_ptr(dev)), "bl_absmax")
         g_split = rows_split(dy, None, amax)
-        dx = tma_project(g_split, None, weight_parts(weight.view(1, N_out, K_in), K_in, N_out, 0, True), None, amax, seg, None, R,
-                         None, slabs)
+        dx = tma_project(g_split, None, weight_parts(weight.view(1, N_out, K_in), K_in, N_out, 0, True, amax_w), None, amax, seg,
+                         None, R, None, slabs, amax_w)
         dw = torch.empty_like(weight)
         identity = torch.arange(R, device=dev, dtype=torch.int32)
-        tma_weight_grad(g_split, x_split, identity, amax, seg, None, dw.view(1, N_out, K_in), 0, slabs)
+        tma_weight_grad(g_split, x_split, identity, amax, seg, None, dw.view(1, N_out, K_in), 0, slabs, amax_x)
         return dx, dw
 
 

@@ -208,6 +208,48 @@ __device__ __forceinline__ int find_segment(const int* __restrict__ tile_ptr, in
     return lo;
 }
 
+// ------------------------------------------------------------------------------------------------ coalesced epilogue
+// After tcgen05.ld a thread holds 32 consecutive columns of ITS row: storing them directly makes every warp-level store
+// touch 32 different 128-byte lines (measured: L1TEX 66-74 % busy, the tensor pipe waiting on the epilogue).  Each
+// epilogue warp therefore transposes a 32 x 32 fp32 block through a private 4 KB shared-memory tile (16-byte chunks
+// XOR-swizzled by row & 7: conflict-free both ways) and writes 4 full 128-byte row segments per instruction.
+constexpr int EPI_STAGE_FLOATS = 32 * 32;
+
+__device__ __forceinline__ void epi_stage_write(float* stage, const float* v, int lane, float scale) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(stage + lane * 32 + ((q ^ (lane & 7)) << 2)) =
+            make_float4(v[4 * q] * scale, v[4 * q + 1] * scale, v[4 * q + 2] * scale, v[4 * q + 3] * scale);
+    __syncwarp();
+}
+// rows [0, rows_valid) of the staged block -> out[r * ld + 0..31]  (+ bias[0..31])
+__device__ __forceinline__ void epi_store_rows(const float* stage, int lane, float* out, int64_t ld, int rows_valid,
+                                               const float* bias) {
+    const int sub = lane >> 3, ch = lane & 7;
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(bias) + ch);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + sub;
+        float4 o = *reinterpret_cast<const float4*>(stage + r * 32 + ((ch ^ (r & 7)) << 2));
+        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+        if (r < rows_valid) *reinterpret_cast<float4*>(out + (int64_t)r * ld + (ch << 2)) = o;
+    }
+    __syncwarp();
+}
+// same, added to the destination with one 16-byte vector RED per lane (weight-gradient partial tiles)
+__device__ __forceinline__ void epi_red_rows(const float* stage, int lane, float* out, int64_t ld) {
+    const int sub = lane >> 3, ch = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + sub;
+        const float4 o = *reinterpret_cast<const float4*>(stage + r * 32 + ((ch ^ (r & 7)) << 2));
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + (int64_t)r * ld + (ch << 2)), "f"(o.x), "f"(o.y),
+                     "f"(o.z), "f"(o.w) : "memory");
+    }
+    __syncwarp();
+}
+
 // =====================================================================================================================
 // Projection:  out[p, 0:N] = inv_scale * A[row(p), 0:Kin] . W_type(seg(p))[0:N, 0:Kin]^T (+ bias_type)
 //   A is a split table  [2 parts][a_rows][Kin] fp16  (part 0 = hi, part 1 = lo; its LAST row of each part is zero and
@@ -218,6 +260,7 @@ struct ProjParams {
     const int* idx;       // [P] rows of the split table, or nullptr (contiguous: row(p) = p)
     const float* bias;    // [num_types, N] or nullptr
     const float* amax;    // nullable: out is multiplied by 1 / pow2_scale_for(*amax)  (undoes the pre-scale of A)
+    const float* amax_b;  // nullable: the same for the pre-scale of the weight parts
     const int* seg_ptr;   // [num_segs + 1]
     const int* seg_type;  // [num_segs] or nullptr (identity)
     const int* tile_ptr;  // [num_segs + 1] prefix sums of ceil(rows / (128 * CG))
@@ -246,6 +289,7 @@ proj_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
     __shared__ uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) float epi_stage[4][EPI_STAGE_FLOATS];  // one 32 x 32 transposition tile per epilogue warp
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -357,8 +401,10 @@ proj_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
     } else if (warp >= FIRST_EPI_WARP) {
         // ============================== EPILOGUE (warps 5-8: TMEM lane quarter = warp % 4) ==============================
-        const float inv_scale = (p.amax != nullptr) ? 1.0f / pow2_scale_for(__ldg(p.amax)) : 1.0f;
+        const float inv_scale = ((p.amax != nullptr) ? 1.0f / pow2_scale_for(__ldg(p.amax)) : 1.0f) *
+                                ((p.amax_b != nullptr) ? 1.0f / pow2_scale_for(__ldg(p.amax_b)) : 1.0f);
         const int lane_base = (warp & 3) * 32;
+        float* stage_tile = epi_stage[warp & 3];
         uint32_t tile_counter = 0;
         for (int work = cluster_id; work < total_work; work += num_clusters, ++tile_counter) {
             const int tile = work / n_splits, split = work - tile * n_splits;
@@ -370,27 +416,16 @@ proj_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             const uint32_t a = tile_counter & 1u, ause = tile_counter >> 1;
             mbar_wait(&acc_full[a], ause & 1u, 3);
             tc_fence_after();
-            const int r = row0 + lane_base + lane;
-            const bool valid = r < row_end;
-            float* orow = p.out + (size_t)r * p.N + col0;
+            const int rows_valid = max(0, min(32, row_end - (row0 + lane_base)));
+            float* oblock = p.out + (size_t)(row0 + lane_base) * p.N + col0;
             const float* brow = p.bias ? p.bias + (size_t)type * p.N + col0 : nullptr;
 #pragma unroll 1
             for (int j = 0; j < NT / 32; ++j) {
                 float v[32];
                 const int col = j * 32;
                 tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(a * NT + col), v);
-                if (valid) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        float4 o = make_float4(v[4 * q] * inv_scale, v[4 * q + 1] * inv_scale, v[4 * q + 2] * inv_scale,
-                                               v[4 * q + 3] * inv_scale);
-                        if (brow) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(brow + col) + q);
-                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                        }
-                        reinterpret_cast<float4*>(orow + col)[q] = o;
-                    }
-                }
+                epi_stage_write(stage_tile, v, lane, inv_scale);
+                epi_store_rows(stage_tile, lane, oblock + col, p.N, rows_valid, brow ? brow + col : nullptr);
             }
             tc_fence_before();
             __syncwarp();
@@ -419,7 +454,7 @@ struct ProjBsCfg {
     static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES;               // A hi + lo of one 64-wide chunk
     static constexpr uint32_t B_CHUNK_BYTES = NTL * 128;               // one part of one chunk of the weights
     static constexpr uint32_t B_BYTES = CHUNKS * 2 * B_CHUNK_BYTES;    // 128 KB
-    static constexpr int STAGES = 3;
+    static constexpr int STAGES = 2;  // 128 KB of weights + 2 x 32 KB of A + 16 KB of epilogue staging (static)
     static constexpr uint32_t SMEM_BYTES = B_BYTES + STAGES * STAGE_BYTES + 1024;
 };
 
@@ -435,6 +470,7 @@ proj_bs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     __shared__ uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2], b_full, b_empty;
     __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) float epi_stage[4][EPI_STAGE_FLOATS];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t cta_rank = cluster_ctarank();
@@ -572,8 +608,10 @@ proj_bs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else if (warp >= FIRST_EPI_WARP) {
         // ============================== EPILOGUE ==============================
-        const float inv_scale = (p.amax != nullptr) ? 1.0f / pow2_scale_for(__ldg(p.amax)) : 1.0f;
+        const float inv_scale = ((p.amax != nullptr) ? 1.0f / pow2_scale_for(__ldg(p.amax)) : 1.0f) *
+                                ((p.amax_b != nullptr) ? 1.0f / pow2_scale_for(__ldg(p.amax_b)) : 1.0f);
         const int lane_base = (warp & 3) * 32;
+        float* stage_tile = epi_stage[warp & 3];
         uint32_t tile_counter = 0;
         for (int slab = cluster_id; slab < total_slabs; slab += num_clusters) {
             int type, row_begin, row_end;
@@ -585,26 +623,15 @@ proj_bs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const uint32_t a = tile_counter & 1u, ause = tile_counter >> 1;
                 mbar_wait(&acc_full[a], ause & 1u, 3);
                 tc_fence_after();
-                const int r = row0 + lane_base + lane;
-                const bool valid = r < row_end;
-                float* orow = p.out + (size_t)r * p.N;
+                const int rows_valid = max(0, min(32, row_end - (row0 + lane_base)));
+                float* oblock = p.out + (size_t)(row0 + lane_base) * p.N;
 #pragma unroll 1
                 for (int j = 0; j < NT / 32; ++j) {
                     float v[32];
                     const int col = j * 32;
                     tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(a * NT + col), v);
-                    if (valid) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            float4 o = make_float4(v[4 * q] * inv_scale, v[4 * q + 1] * inv_scale, v[4 * q + 2] * inv_scale,
-                                                   v[4 * q + 3] * inv_scale);
-                            if (brow) {
-                                const float4 b = __ldg(reinterpret_cast<const float4*>(brow + col) + q);
-                                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                            }
-                            reinterpret_cast<float4*>(orow + col)[q] = o;
-                        }
-                    }
+                    epi_stage_write(stage_tile, v, lane, inv_scale);
+                    epi_store_rows(stage_tile, lane, oblock + col, p.N, rows_valid, brow ? brow + col : nullptr);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -633,6 +660,7 @@ proj_bs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 struct WgParams {
     const int* idx;        // [P]
     const float* amax;     // pre-scale source of G (nullable)
+    const float* amax_x;   // pre-scale source of X (nullable)
     const int* seg_ptr;    // [num_segs + 1]
     const int* seg_type;   // nullable
     const int* slab_ptr;   // [num_segs + 1] prefix sums of ceil(rows / SLAB_ROWS)
@@ -664,6 +692,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ 
 
     __shared__ uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) float epi_stage[4][EPI_STAGE_FLOATS];  // one 32 x 32 transposition tile per epilogue warp
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -790,8 +819,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ 
         }
     } else if (warp >= FIRST_EPI_WARP) {
         // ============================== EPILOGUE: fp32 REDs into dW ==============================
-        const float inv_scale = (p.amax != nullptr) ? 1.0f / pow2_scale_for(__ldg(p.amax)) : 1.0f;
+        const float inv_scale = ((p.amax != nullptr) ? 1.0f / pow2_scale_for(__ldg(p.amax)) : 1.0f) *
+                                ((p.amax_x != nullptr) ? 1.0f / pow2_scale_for(__ldg(p.amax_x)) : 1.0f);
         const int lane_base = (warp & 3) * 32;
+        float* stage_tile = epi_stage[warp & 3];
         uint32_t tile_counter = 0;
         for (int work = cluster_id; work < total_work; work += num_clusters, ++tile_counter) {
             int type, row_begin, row_end, m0, n0;
@@ -799,14 +830,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ 
             const uint32_t a = tile_counter & 1u, ause = tile_counter >> 1;
             mbar_wait(&acc_full[a], ause & 1u, 3);
             tc_fence_after();
-            float* wrow = p.d_weight + ((size_t)type * p.M + m0 + lane_base + lane) * p.ld + p.col0 + n0;
+            float* wblock = p.d_weight + ((size_t)type * p.M + m0 + lane_base) * p.ld + p.col0 + n0;
 #pragma unroll 1
             for (int j = 0; j < NT / 32; ++j) {
                 float v[32];
                 const int col = j * 32;
                 tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(a * NT + col), v);
-#pragma unroll
-                for (int q = 0; q < 32; ++q) atomicAdd(wrow + col + q, v[q] * inv_scale);
+                epi_stage_write(stage_tile, v, lane, inv_scale);
+                epi_red_rows(stage_tile, lane, wblock + col, p.ld);
             }
             tc_fence_before();
             __syncwarp();
@@ -985,16 +1016,18 @@ extern "C" int bl_segment_unit_prefix(const int32_t* seg_ptr, int32_t num_segs, 
 extern "C" int bl_tma_tile_rows(void) { return tg::TILE_M * tg::default_cg(); }
 extern "C" int bl_tma_slab_rows(void) { return tg::SLAB_ROWS; }
 
-/* 1 when bl_tma_project_stationary covers the shape (CTA pairs, 256 x 256) and BUGLAB_B200_TMA_BSTAT != 0 */
+/* 1 when bl_tma_project_stationary covers the shape (CTA pairs, 256 x 256) and BUGLAB_B200_TMA_BSTAT=1 (default 0: on
+ * B200 the streaming kernel measured faster — 2.51 vs 2.57 ms forward, 2.52 vs 2.86 ms backward-input at 5 M rows — because
+ * the kernels were bound by the epilogue's store pattern, not by L2->SM weight traffic; profiles/r2_gemm_microbench*.jsonl) */
 extern "C" int bl_tma_project_stationary_supported(int32_t n_out, int32_t k_in) {
-    static const int enabled = tg::env_int("BUGLAB_B200_TMA_BSTAT", 1);
+    static const int enabled = tg::env_int("BUGLAB_B200_TMA_BSTAT", 0);
     return enabled && tg::default_cg() == 2 && n_out == 256 && k_in == 256 && tg::encode_fn() != nullptr;
 }
 
 /* Same product as bl_tma_project with the weights held in shared memory per slab of <= bl_tma_slab_rows() pair rows
  * (slab_ptr = bl_segment_unit_prefix(seg_ptr, bl_tma_slab_rows()), max_slabs = an upper bound of its last entry). */
 extern "C" int bl_tma_project_stationary(const void* a_split, int64_t a_rows, const int32_t* idx, const void* wparts, const float* bias,
-                                         const float* amax, const int32_t* seg_ptr, const int32_t* seg_type, const int32_t* slab_ptr,
+                                         const float* amax, const float* amax_b, const int32_t* seg_ptr, const int32_t* seg_type, const int32_t* slab_ptr,
                                          int32_t num_segs, int32_t num_types, int64_t num_rows, int64_t max_slabs, int32_t n_out,
                                          int32_t k_in, float* out, bl_stream_t stream_) {
     if (num_segs <= 0 || num_types <= 0 || num_rows < 0 || a_rows <= 0 || a_rows > (1ll << 30)) return BL_ERR_INVALID_ARGUMENT;
@@ -1006,7 +1039,7 @@ extern "C" int bl_tma_project_stationary(const void* a_split, int64_t a_rows, co
     if (rc) return rc;
     rc = tg::make_map_f16(&map_b, wparts, (uint64_t)num_types * 2 * n_out, (uint64_t)k_in, tg::CHUNK_K, (uint32_t)tg::ProjBsCfg::NTL);
     if (rc) return rc;
-    tg::ProjParams p{idx, bias, amax, seg_ptr, seg_type, slab_ptr, out, num_segs, n_out, k_in, (int)a_rows};
+    tg::ProjParams p{idx, bias, amax, amax_b, seg_ptr, seg_type, slab_ptr, out, num_segs, n_out, k_in, (int)a_rows};
     int grid = (int)std::min<int64_t>((int64_t)(num_sms() / 2), max_slabs) * 2;
     if (grid < 2) grid = 2;
     if (idx) return tg::launch(tg::proj_bs_kernel<true>, 2, grid, tg::ProjBsCfg::SMEM_BYTES, stream, "bl_tma_project_stationary", map_a, map_b, p);
@@ -1014,7 +1047,7 @@ extern "C" int bl_tma_project_stationary(const void* a_split, int64_t a_rows, co
 }
 
 extern "C" int bl_tma_project(const void* a_split, int64_t a_rows, const int32_t* idx, const void* wparts, const float* bias,
-                              const float* amax, const int32_t* seg_ptr, const int32_t* seg_type, const int32_t* tile_ptr,
+                              const float* amax, const float* amax_b, const int32_t* seg_ptr, const int32_t* seg_type, const int32_t* tile_ptr,
                               int32_t num_segs, int32_t num_types, int64_t num_rows, int64_t max_tiles, int32_t n_out,
                               int32_t k_in, float* out, bl_stream_t stream_) {
     if (num_segs <= 0 || num_types <= 0 || num_rows < 0 || a_rows <= 0 || a_rows > (1ll << 30)) return BL_ERR_INVALID_ARGUMENT;
@@ -1029,7 +1062,7 @@ extern "C" int bl_tma_project(const void* a_split, int64_t a_rows, const int32_t
     if (rc) return rc;
     rc = tg::make_map_f16(&map_b, wparts, (uint64_t)num_types * 2 * n_out, (uint64_t)k_in, tg::CHUNK_K, (uint32_t)ntl);
     if (rc) return rc;
-    tg::ProjParams p{idx, bias, amax, seg_ptr, seg_type, tile_ptr, out, num_segs, n_out, k_in, (int)a_rows};
+    tg::ProjParams p{idx, bias, amax, amax_b, seg_ptr, seg_type, tile_ptr, out, num_segs, n_out, k_in, (int)a_rows};
     int sms = num_sms();
     int grid = (int)std::min<int64_t>((int64_t)(sms / cg), max_tiles * (n_out / nt)) * cg;
     if (grid < cg) grid = cg;
@@ -1049,7 +1082,7 @@ extern "C" int bl_tma_weight_grad_supported(int32_t m_out, int32_t n_in) {
 
 /* d_weight[type, 0:m_out, col0:col0+n_in] = (1/scale) sum over pair rows of G[p,:]^T X[idx[p],:]  (zeroes that block first) */
 extern "C" int bl_tma_weight_grad(const void* g_split, int64_t g_rows, const void* x_split, int64_t x_rows, const int32_t* idx,
-                                  const float* amax, const int32_t* seg_ptr, const int32_t* seg_type, const int32_t* slab_ptr,
+                                  const float* amax, const float* amax_x, const int32_t* seg_ptr, const int32_t* seg_type, const int32_t* slab_ptr,
                                   int32_t num_segs, int32_t num_types, int64_t num_rows, int64_t max_slabs, int32_t m_out,
                                   int32_t n_in, float* d_weight, int32_t ld, int32_t col0, bl_stream_t stream_) {
     if (num_segs <= 0 || num_types <= 0 || num_rows < 0 || idx == nullptr || g_rows <= 0 || x_rows <= 0) return BL_ERR_INVALID_ARGUMENT;
@@ -1065,7 +1098,7 @@ extern "C" int bl_tma_weight_grad(const void* g_split, int64_t g_rows, const voi
     if (rc) return rc;
     rc = tg::make_map_f16(&map_x, x_split, (uint64_t)(2 * x_rows), (uint64_t)n_in, 64, 1);
     if (rc) return rc;
-    tg::WgParams p{idx, amax, seg_ptr, seg_type, slab_ptr, d_weight, num_segs, m_out, n_in, ld, col0, (int)g_rows, (int)x_rows};
+    tg::WgParams p{idx, amax, amax_x, seg_ptr, seg_type, slab_ptr, d_weight, num_segs, m_out, n_in, ld, col0, (int)g_rows, (int)x_rows};
     const int64_t items = max_slabs * (m_out / (tg::TILE_M * cg)) * (n_in / 256);
     int grid = (int)std::min<int64_t>((int64_t)(num_sms() / cg), items) * cg;
     if (grid < cg) grid = cg;

@@ -347,13 +347,16 @@ __global__ void __launch_bounds__(THREADS_V2, 1) pair_project_tc_v2_kernel(const
 // wparts[k, part, n, kin] = hi/lo of W[k, n, col0 + kin]              (transposed == 0, W is [K, N, ld])
 //                         = hi/lo of W[k, kin, col0 + n]              (transposed != 0, W is [K, Kin, ld])
 __global__ void weight_parts_kernel(const float* __restrict__ W, int num_types, int N, int Kin, int ld, int col0,
-                                    int transposed, __half* __restrict__ out) {
+                                    int transposed, const float* __restrict__ amax, __half* __restrict__ out) {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (int64_t)num_types * N * Kin) return;
     const int kin = (int)(gid % Kin);
     const int n = (int)((gid / Kin) % N);
     const int64_t k = gid / ((int64_t)Kin * N);
-    const float w = transposed ? W[(k * Kin + kin) * ld + col0 + n] : W[(k * N + n) * ld + col0 + kin];
+    // optional power-of-two pre-scale: without it the lo parts of typical weights (|w| ~ 0.05 -> lo ~ 1e-5) are fp16
+    // SUBNORMALS (spacing 6e-8), i.e. the pair hi+lo carries ~17 significant bits instead of 22
+    const float scale = (amax != nullptr) ? pow2_scale_for(__ldg(amax)) : 1.0f;
+    const float w = scale * (transposed ? W[(k * Kin + kin) * ld + col0 + n] : W[(k * N + n) * ld + col0 + kin]);
     const __half hi = __float2half_rn(w);
     const __half lo = __float2half_rn(w - __half2float(hi));
     out[((k * 2 + 0) * N + n) * Kin + kin] = hi;
@@ -537,10 +540,10 @@ __global__ void __launch_bounds__(THREADS, 1) pair_weight_grad_tc_kernel(const W
 using namespace bl;
 
 extern "C" int bl_weight_parts_f16(const float* weight, int32_t num_types, int32_t n_out, int32_t k_in, int32_t ld,
-                                   int32_t col0, int32_t transposed, void* parts, bl_stream_t stream) {
+                                   int32_t col0, int32_t transposed, const float* amax, void* parts, bl_stream_t stream) {
     if (num_types <= 0 || n_out <= 0 || k_in <= 0) return BL_ERR_INVALID_ARGUMENT;
     tc::weight_parts_kernel<<<grid_for((int64_t)num_types * n_out * k_in, 256), 256, 0, (cudaStream_t)stream>>>(
-        weight, num_types, n_out, k_in, ld, col0, transposed, (__half*)parts);
+        weight, num_types, n_out, k_in, ld, col0, transposed, amax, (__half*)parts);
     return check_launch("bl_weight_parts_f16");
 }
 

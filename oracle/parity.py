@@ -98,3 +98,17 @@ def assert_routing_is_valid(audits, what: str = "", max_relative_deficit: float 
         worst["differing_frac"] = max(worst["differing_frac"], frac)
         worst["max_relative_deficit"] = max(worst["max_relative_deficit"], a["max_relative_deficit"])
     return worst
+
+
+def assert_grad_close_to_scale(actual: torch.Tensor, expected: torch.Tensor, what: str = "", rel_to_max: float = 1e-4,
+                               max_rel_l2: float = 1e-4) -> None:
+    """For gradients that are long sums (weight gradients: thousands of terms with cancellation) the rounding error of an
+    entry scales with the magnitude of the TERMS, not of the entry, so an abs+rel criterion per entry misfires on entries
+    near zero.  Required here: max |a - e| <= rel_to_max * max|e| (fp32-class accuracy at the tensor's own scale) and a
+    relative Frobenius error <= max_rel_l2.  Use only under identical max-routing."""
+    a, e = actual.detach().cpu().double(), expected.detach().cpu().double()
+    scale = float(e.abs().max()) if e.numel() else 0.0
+    worst = float((a - e).abs().max()) if e.numel() else 0.0
+    rel_l2 = float((a - e).norm()) / max(float(e.norm()), 1e-30)
+    assert worst <= rel_to_max * scale + 1e-7, f"{what}: max abs diff {worst:.2e} vs {rel_to_max:.0e} * max|expected| = {rel_to_max * scale:.2e}"
+    assert rel_l2 <= max_rel_l2, f"{what}: relative L2 error {rel_l2:.2e} (allowed {max_rel_l2:.0e})"

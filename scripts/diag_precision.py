@@ -40,7 +40,8 @@ print(f"hidden={hidden} nodes={r64.shape[0]}; oracle fp32 vs fp64 per state: "
                  for i in range(len(widths))))
 
 CONFIGS = [
-    ("tma (default: TMA projections + TMA node update)", dict(USE_TMA=True, PROJECTION_MODE="f16x3", DENSE_FORWARD_FP32_REFEREE=False)),
+    ("tma (default: TMA projections + TMA node update, operands pre-scaled)", dict(USE_TMA=True, PROJECTION_MODE="f16x3", DENSE_FORWARD_FP32_REFEREE=False, PRESCALE_OPERANDS=True)),
+    ("tma, operands NOT pre-scaled (lo parts of the weights are fp16 subnormals)", dict(USE_TMA=True, PROJECTION_MODE="f16x3", DENSE_FORWARD_FP32_REFEREE=False, PRESCALE_OPERANDS=False)),
     ("tma projections, fp32 library GEMM node update", dict(USE_TMA=True, PROJECTION_MODE="f16x3", DENSE_FORWARD_FP32_REFEREE=True)),
     ("first-generation path (round 1)", dict(USE_TMA=False, PROJECTION_MODE="f16x3", DENSE_FORWARD_FP32_REFEREE=False)),
     ("fp32 library GEMMs everywhere (referee)", dict(USE_TMA=False, PROJECTION_MODE="fp32", DENSE_FORWARD_FP32_REFEREE=False)),

@@ -75,19 +75,20 @@ def run_case(case):
             ref[lo:hi] = rows[lo:hi].double() @ weight[k, :, col0:col0 + k_in].double().t()
             if use_bias:
                 ref[lo:hi] += bias[k].double()
-        src_d = src.to(dev)
-        amax = None
-        if prescale:
-            amax = torch.empty(1, device=dev)
-            _lib.check(_lib.load().bl_absmax(_lib.f32(src_d), src_d.numel(), _lib.f32(amax), _lib.stream_ptr(dev)), "bl_absmax")
+        src_d, weight_d = src.to(dev), weight.to(dev)
+        # both operands pre-scaled by powers of two, as the model path does (mandatory for the tiny-gradient cases, optional
+        # otherwise: odd case indices exercise the unscaled entry too)
+        scaled = prescale or (case["index"] % 2 == 0)
+        amax = ops.absmax(src_d) if scaled else None
+        amax_w = ops.absmax(weight_d) if scaled else None
         a_split = ops.rows_split(src_d, None, amax)
-        parts = ops.weight_parts(weight.to(dev), n_out, k_in, col0, transposed=False)
+        parts = ops.weight_parts(weight_d, n_out, k_in, col0, transposed=False, amax=amax_w)
         seg_ptr = torch.tensor(sp, dtype=torch.int32, device=dev)
         # slab table given: 256 x 256 products take the weight-stationary kernel (pairs only), everything else the streaming one
         slabs = ops.unit_prefix(seg_ptr, ops.tma_slab_rows()) if os.environ.get("TEST_TMA_STATIONARY", "0") == "1" else None
         out = ops.tma_project(a_split, idx.to(dev) if gather else None, parts, bias.to(dev) if use_bias else None, amax, seg_ptr,
                               torch.tensor(types, dtype=torch.int32, device=dev) if seg_types is not None else None, P,
-                              None, slabs)
+                              None, slabs, amax_w)
         torch.cuda.synchronize()
         got = out.cpu().double()
         scale = float(ref.abs().max())
@@ -113,10 +114,13 @@ def run_case(case):
         amax = torch.empty(1, device=dev)
         _lib.check(_lib.load().bl_absmax(_lib.f32(grad_d), grad_d.numel(), _lib.f32(amax), _lib.stream_ptr(dev)), "bl_absmax")
         g_split = ops.rows_split(grad_d, None, amax)
-        x_split = ops.rows_split(x.to(dev))
+        x_d = x.to(dev)
+        amax_x = ops.absmax(x_d) if case["index"] % 2 == 0 else None
+        x_split = ops.rows_split(x_d, None, amax_x)
         d_weight = torch.full((K, m_out, ld), 7.0, device=dev)
         ops.tma_weight_grad(g_split, x_split, idx.to(dev), amax, torch.tensor(sp, dtype=torch.int32, device=dev),
-                            torch.tensor(types, dtype=torch.int32, device=dev) if seg_types is not None else None, d_weight, col0)
+                            torch.tensor(types, dtype=torch.int32, device=dev) if seg_types is not None else None, d_weight, col0,
+                            None, amax_x)
         torch.cuda.synchronize()
         got = d_weight[:, :, col0:col0 + n_in].cpu().double()
         untouched = bool((d_weight[:, :, :col0] == 7.0).all()) and bool((d_weight[:, :, col0 + n_in:] == 7.0).all())
@@ -125,6 +129,7 @@ def run_case(case):
         return (dict(ok=bool(err <= 1e-4 * scale) and untouched, max_err=err, scale=scale, rel=err / scale, untouched=untouched))
 
 for i, case in enumerate(cases):
+    case["index"] = i
     res = run_case(case)
     res["index"] = i
     print("RESULT " + json.dumps(res), flush=True)
@@ -140,7 +145,8 @@ def _results(cg):
     if cg in _CACHE:
         return _CACHE[cg]
     cases = [dict(kind="project", args=a) for a in PROJECT_CASES] + [dict(kind="wgrad", args=a) for a in WGRAD_CASES]
-    env = dict(os.environ, BUGLAB_B200_TMA_CG=str(cg)[0], TEST_TMA_STATIONARY="1" if str(cg).endswith("s") else "0")
+    stationary = "1" if str(cg).endswith("s") else "0"
+    env = dict(os.environ, BUGLAB_B200_TMA_CG=str(cg)[0], TEST_TMA_STATIONARY=stationary, BUGLAB_B200_TMA_BSTAT=stationary)
     proc = subprocess.run([sys.executable, "-c", _DRIVER.format(root=ROOT), json.dumps(cases)], env=env, capture_output=True,
                           text=True, timeout=900)
     out = {}
