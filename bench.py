@@ -374,18 +374,17 @@ def layer_rooflines(plan, hidden, device, label, seed=0):
     del u, v, agg, xwin, ewin
 
     # (3) the dominant kernel: one projection (U table) on the TMA-fed tcgen05 kernel
-    if ops.USE_TMA and plan.s_tile_ptr is not None and lib.bl_tma_gemm_supported(M, D):
+    if ops.USE_TMA and plan.s_tiles is not None and lib.bl_tma_gemm_supported(M, D):
         h_split = ops.rows_split(h)
         parts = ops.weight_parts(weight, M, D, 0, False)
         P = plan.num_s_pairs
 
         def proj():
-            return ops.tma_project(h_split, plan.s_node, parts, None, None, plan.s_type_ptr, plan.seg_type, P, plan.s_tile_ptr,
-                                   plan.s_slab_ptr)
+            return ops.tma_project(h_split, plan.s_node, parts, None, None, plan.s_tiles, P, plan.s_slabs)
 
         ms_proj = _time_on_stream(proj, device)
         flops = 2.0 * P * D * M * 3
-        out["projection"] = {"bound": "tensor", "kernel": "tg::proj_bs_kernel<gather> / tg::proj_kernel<256, 2, gather> (bl_tma_project[_stationary]), U table of an H->H layer",
+        out["projection"] = {"bound": "tensor", "kernel": "tg::proj_kernel<256, 2, gather> (bl_tma_project), U table of an H->H layer",
                              "achieved": flops / ms_proj / 1e9, "peak": peaks["bf16_tflops"], "peak_kind": peak_kind + " (cuBLAS bf16 burst)",
                              "unit": "TFLOP/s", "frac": flops / ms_proj / 1e9 / peaks["bf16_tflops"],
                              "traffic": ncu_traffic("proj_kernel", f"{P}x{D}x{M}"), "flops_per_launch": flops,
@@ -524,9 +523,10 @@ def config1_gpu(device):
     import torch
 
     work = tempfile.mkdtemp(prefix="buglab_bench_config1_")
-    # ~15 graphs (30 000 nodes) per step: epoch 1 = 2 warm-up steps' worth is too short to settle the allocator, so the
-    # warm-up epoch has 10 steps too; epoch 2 is the timed one
-    rate, steps, graphs, seconds = _train_entry_rate(_config1_arguments(work, CONFIG1_HIDDEN, epochs=2, epoch_samples=150,
+    # ~15 graphs (30 000 nodes) per step.  An epoch is the whole 500-graph shard (~34 steps): the entry point re-opens and
+    # inflates the shard at every epoch start, which a 10-step epoch would charge to 150 graphs.  Epoch 1 warms up, epoch 2
+    # is the timed one.
+    rate, steps, graphs, seconds = _train_entry_rate(_config1_arguments(work, CONFIG1_HIDDEN, epochs=2, epoch_samples=CONFIG1_GRAPHS,
                                                                         sequential=False))
     torch.cuda.synchronize(device)
     torch.cuda.empty_cache()

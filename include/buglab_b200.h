@@ -202,38 +202,43 @@ int bl_edge_bwd_sources(const float* g_rows, const int32_t* ewin, const int32_t*
  * last row of each part is zero (the padding row the kernels read for rows past a segment end).
  * s = pow2 pre-scale derived from *amax (NULL: 1).
  *
- * Segments: pair rows are grouped in num_segs ranges [seg_ptr[s], seg_ptr[s+1]) that share weight matrix
- * seg_type[s] (NULL: s).  tile_ptr / slab_ptr = bl_segment_unit_prefix(seg_ptr, unit) with unit =
- * bl_tma_tile_rows() / bl_tma_slab_rows(); max_tiles / max_slabs = any upper bound of their last entry
- * (sizes the persistent grid without a device->host copy). */
+ * Segments and work units: pair rows are grouped in num_segs ranges [seg_ptr[s], seg_ptr[s+1]) that share weight matrix
+ * seg_type[s] (NULL: s).  The GEMMs walk a device-side table of work units built once per plan by bl_segment_units:
+ * units[u] = int32 {first row, end row, weight matrix, segment} for every run of <= `unit` consecutive pair rows of one
+ * segment (unit = bl_tma_tile_rows() for the projections, bl_tma_slab_rows() for the weight gradient and the
+ * weight-stationary projection); *count = number of units.  max_units (>= num_rows / unit + num_segs) sizes the table and
+ * the persistent grid without a device->host copy. */
 int bl_rows_split_f16(const float* x, const int32_t* idx, int64_t rows, int32_t dim, const float* amax, void* out,
                       bl_stream_t stream);
 int bl_segment_unit_prefix(const int32_t* seg_ptr, int32_t num_segs, int32_t unit, int32_t* prefix, bl_stream_t stream);
+int bl_segment_units(const int32_t* seg_ptr, const int32_t* seg_type, int32_t num_segs, int32_t unit, int64_t max_units,
+                     int32_t* prefix_ws, void* units, int32_t* count, bl_stream_t stream);
 int bl_tma_tile_rows(void);
 int bl_tma_slab_rows(void);
 int bl_tma_gemm_supported(int32_t n_out, int32_t k_in);
 /* out[p, 0:n_out] = (1/(s_a*s_b)) * A[row(p), :] . W_type[0:n_out, 0:k_in]^T (+ bias_type);  row(p) = idx[p] or p (idx
  * NULL); a_rows = rows per part of a_split (incl. the zero row); wparts as written by bl_weight_parts_f16; s_a / s_b =
  * the power-of-two pre-scales of the A table / the weight parts, from *amax / *amax_b (NULL: 1).  Pre-scaling BOTH
- * operands keeps their fp16 lo parts out of the subnormal range. */
+ * operands keeps their fp16 lo parts out of the subnormal range.  tiles / num_tiles: bl_segment_units
+ * with unit bl_tma_tile_rows(). */
 int bl_tma_project(const void* a_split, int64_t a_rows, const int32_t* idx, const void* wparts, const float* bias,
-                   const float* amax, const float* amax_b, const int32_t* seg_ptr, const int32_t* seg_type, const int32_t* tile_ptr,
-                   int32_t num_segs, int32_t num_types, int64_t num_rows, int64_t max_tiles, int32_t n_out, int32_t k_in,
+                   const float* amax, const float* amax_b, const void* tiles, const int32_t* num_tiles,
+                   int32_t num_types, int64_t num_rows, int64_t max_tiles, int32_t n_out, int32_t k_in,
                    float* out, bl_stream_t stream);
 /* Weight-stationary variant for the 256 x 256 products (CTA pairs): the pair keeps a slab's weight matrix (hi and lo, its
- * 128 output columns per CTA: 128 KB) in shared memory and streams only A.  slab_ptr = bl_segment_unit_prefix(seg_ptr,
- * bl_tma_slab_rows()).  Opt-in (BUGLAB_B200_TMA_BSTAT=1): the streaming kernel measured faster on B200. */
+ * 128 output columns per CTA: 128 KB) in shared memory and streams only A.  slabs / num_slabs: bl_segment_units with unit
+ * bl_tma_slab_rows().  Opt-in (BUGLAB_B200_TMA_BSTAT=1): the streaming kernel measured faster on B200. */
 int bl_tma_project_stationary_supported(int32_t n_out, int32_t k_in);
 int bl_tma_project_stationary(const void* a_split, int64_t a_rows, const int32_t* idx, const void* wparts, const float* bias,
-                              const float* amax, const float* amax_b, const int32_t* seg_ptr, const int32_t* seg_type, const int32_t* slab_ptr,
-                              int32_t num_segs, int32_t num_types, int64_t num_rows, int64_t max_slabs, int32_t n_out,
+                              const float* amax, const float* amax_b, const void* slabs, const int32_t* num_slabs,
+                              int32_t num_types, int64_t num_rows, int64_t max_slabs, int32_t n_out,
                               int32_t k_in, float* out, bl_stream_t stream);
 int bl_tma_weight_grad_supported(int32_t m_out, int32_t n_in);
 /* d_weight[type, 0:m_out, col0:col0+n_in] = (1/(s_g*s_x)) * sum over pair rows of G[p, :]^T X[idx[p], :]  (block zeroed
  * first); s_g / s_x from *amax / *amax_x (NULL: 1). */
 int bl_tma_weight_grad(const void* g_split, int64_t g_rows, const void* x_split, int64_t x_rows, const int32_t* idx,
-                       const float* amax, const float* amax_x, const int32_t* seg_ptr, const int32_t* seg_type, const int32_t* slab_ptr,
-                       int32_t num_segs, int32_t num_types, int64_t num_rows, int64_t max_slabs, int32_t m_out,
+                       const float* amax, const float* amax_x, const void* slabs, const int32_t* num_slabs,
+                       int32_t num_types, int64_t num_rows, int64_t max_slabs, int32_t m_out,
                        int32_t n_in, float* d_weight, int32_t ld, int32_t col0, bl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -49,14 +49,15 @@ _SIGNATURES = {
     "bl_pair_weight_grad_tc": (c_i32, [c_ptr] * 5 + [c_i32, c_i64, c_i32, c_i32, c_ptr, c_i32, c_i32, c_ptr]),
     "bl_rows_split_f16": (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_ptr, c_ptr, c_ptr]),
     "bl_segment_unit_prefix": (c_i32, [c_ptr, c_i32, c_i32, c_ptr, c_ptr]),
+    "bl_segment_units": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
     "bl_tma_tile_rows": (c_i32, []),
     "bl_tma_slab_rows": (c_i32, []),
     "bl_tma_gemm_supported": (c_i32, [c_i32, c_i32]),
-    "bl_tma_project": (c_i32, [c_ptr, c_i64] + [c_ptr] * 8 + [c_i32, c_i32, c_i64, c_i64, c_i32, c_i32, c_ptr, c_ptr]),
+    "bl_tma_project": (c_i32, [c_ptr, c_i64] + [c_ptr] * 7 + [c_i32, c_i64, c_i64, c_i32, c_i32, c_ptr, c_ptr]),
     "bl_tma_project_stationary_supported": (c_i32, [c_i32, c_i32]),
-    "bl_tma_project_stationary": (c_i32, [c_ptr, c_i64] + [c_ptr] * 8 + [c_i32, c_i32, c_i64, c_i64, c_i32, c_i32, c_ptr, c_ptr]),
+    "bl_tma_project_stationary": (c_i32, [c_ptr, c_i64] + [c_ptr] * 7 + [c_i32, c_i64, c_i64, c_i32, c_i32, c_ptr, c_ptr]),
     "bl_tma_weight_grad_supported": (c_i32, [c_i32, c_i32]),
-    "bl_tma_weight_grad": (c_i32, [c_ptr, c_i64, c_ptr, c_i64] + [c_ptr] * 6 + [c_i32, c_i32, c_i64, c_i64, c_i32, c_i32,
+    "bl_tma_weight_grad": (c_i32, [c_ptr, c_i64, c_ptr, c_i64] + [c_ptr] * 5 + [c_i32, c_i64, c_i64, c_i32, c_i32,
                                    c_ptr, c_i32, c_i32, c_ptr]),
     "bl_edge_segmax_fwd": (c_i32, [c_ptr] * 5 + [c_i64, c_i32] + [c_ptr] * 3 + [c_ptr]),
     "bl_edge_segmax_bwd": (c_i32, [c_ptr] * 6 + [c_i64, c_i32, c_i64, c_i64] + [c_ptr] * 3 + [c_ptr]),
@@ -123,7 +124,7 @@ KERNELS_PER_CALL = {
     "bl_rows_split3_f16": 1, "bl_unscale_pow2": 1, "bl_weights_split3_f16": 2, "bl_pair_project_fwd": 0, "bl_pair_project_bwd_input": 0,
     "bl_pair_project_bwd_weight": 1, "bl_rows_split2_f16": 1, "bl_grouped_colsum": 1, "bl_absmax": 1, "bl_weight_parts_f16": 1,
     "bl_pair_project_tc": 1, "bl_pair_weight_grad_tc": 1, "bl_tma_project": 1, "bl_tma_project_stationary": 1, "bl_tma_weight_grad": 1,
-    "bl_segment_unit_prefix": 1, "bl_seq_attention_fwd": 1, "bl_seq_attention_bwd": 2,
+    "bl_segment_unit_prefix": 1, "bl_segment_units": 2, "bl_seq_attention_fwd": 1, "bl_seq_attention_bwd": 2,
 }
 launch_counter = {"kernels": 0, "calls": 0}
 

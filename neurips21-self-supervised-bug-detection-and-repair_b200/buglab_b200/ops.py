@@ -46,11 +46,12 @@ class EdgePlan(NamedTuple):
     num_t_pairs: int
     s_type_ptr_host: Tuple[int, ...]
     t_type_ptr_host: Tuple[int, ...]
-    # tile / slab prefix tables of the TMA GEMMs over the S- and T-pair segments (device, int32 [K+1])
-    s_tile_ptr: Optional[torch.Tensor] = None
-    t_tile_ptr: Optional[torch.Tensor] = None
-    s_slab_ptr: Optional[torch.Tensor] = None
-    t_slab_ptr: Optional[torch.Tensor] = None
+    # work-unit tables of the TMA GEMMs over the S- and T-pair segments (``Units``: tiles of tma_tile_rows() rows for the
+    # projections, slabs of tma_slab_rows() rows for the weight gradient); None when the TMA path is off
+    s_tiles: Optional["Units"] = None
+    t_tiles: Optional["Units"] = None
+    s_slabs: Optional["Units"] = None
+    t_slabs: Optional["Units"] = None
     # S-pair -> its sorted edges (CSR) and the target node of every sorted edge: by-source half of the edge backward
     s_edge_ptr: Optional[torch.Tensor] = None
     s_edge_idx: Optional[torch.Tensor] = None
@@ -121,14 +122,14 @@ def build_edge_plan_from_flat(
         ),
         "bl_plan_build",
     )
+    seg_type = torch.arange(S, device=device, dtype=torch.int32).remainder_(K) if B > 0 else None
     tables = [None] * 4
     if USE_TMA:
+        # P_s, P_t <= E: size the unit tables by that bound so that no host value is needed before the (single) sync below
         tile_rows, slab_rows = tma_tile_rows(), tma_slab_rows()
-        tables = [unit_prefix(s_type_ptr, tile_rows), unit_prefix(t_type_ptr, tile_rows),
-                  unit_prefix(s_type_ptr, slab_rows), unit_prefix(t_type_ptr, slab_rows)]
-    seg_type = None
+        tables = [segment_units(s_type_ptr, seg_type, tile_rows, E), segment_units(t_type_ptr, seg_type, tile_rows, E),
+                  segment_units(s_type_ptr, seg_type, slab_rows, E), segment_units(t_type_ptr, seg_type, slab_rows, E)]
     if B > 0:
-        seg_type = torch.arange(S, device=device, dtype=torch.int32).remainder_(K)
         P_s, P_t = meta[:2].cpu().tolist()  # the one host sync of the plan
         s_tp = t_tp = ()
     else:
@@ -316,12 +317,37 @@ def rows_split(x: torch.Tensor, idx: Optional[torch.Tensor] = None, amax: Option
 
 
 def unit_prefix(seg_ptr: torch.Tensor, unit: int) -> torch.Tensor:
-    """``prefix[s] = sum_{s' < s} ceil(rows(s') / unit)`` on the device (tile / slab tables of the TMA GEMMs)."""
+    """``prefix[s] = sum_{s' < s} ceil(rows(s') / unit)`` on the device."""
     num_segs = int(seg_ptr.shape[0]) - 1
     out = torch.empty(num_segs + 1, device=seg_ptr.device, dtype=torch.int32)
     check(_lib.load().bl_segment_unit_prefix(i32(seg_ptr), num_segs, int(unit), i32(out), stream_ptr(seg_ptr.device)),
           "bl_segment_unit_prefix")
     return out
+
+
+class Units(NamedTuple):
+    """Device-side work-unit table of the TMA GEMMs (``bl_segment_units``): ``table[u] = (first row, end row, weight matrix,
+    segment)`` for every run of <= ``unit`` consecutive pair rows of one segment; ``count`` = number of units (device scalar);
+    ``capacity`` = rows of ``table`` (an upper bound of the count known without a host sync)."""
+
+    table: torch.Tensor
+    count: torch.Tensor
+    capacity: int
+    unit: int
+
+
+def segment_units(seg_ptr: torch.Tensor, seg_type: Optional[torch.Tensor], unit: int, max_rows: int) -> Units:
+    """Work units of ``unit`` rows over the segments ``[seg_ptr[s], seg_ptr[s+1])`` (weight matrix ``seg_type[s]``, or ``s``);
+    ``max_rows`` = any upper bound of the total number of pair rows."""
+    num_segs = int(seg_ptr.shape[0]) - 1
+    capacity = max(1, int(max_rows) // int(unit) + num_segs)
+    dev = seg_ptr.device
+    table = torch.empty((capacity, 4), device=dev, dtype=torch.int32)
+    count = torch.empty(1, device=dev, dtype=torch.int32)
+    scratch = torch.empty(num_segs + 1, device=dev, dtype=torch.int32)
+    check(_lib.load().bl_segment_units(i32(seg_ptr), i32(seg_type) if seg_type is not None else None, num_segs, int(unit),
+                                       capacity, i32(scratch), table.data_ptr(), i32(count), stream_ptr(dev)), "bl_segment_units")
+    return Units(table, count, capacity, int(unit))
 
 
 def tma_tile_rows() -> int:
@@ -333,54 +359,38 @@ def tma_slab_rows() -> int:
 
 
 def tma_project(a_split: torch.Tensor, idx: Optional[torch.Tensor], parts: torch.Tensor, bias: Optional[torch.Tensor],
-                amax: Optional[torch.Tensor], seg_ptr: torch.Tensor, seg_type: Optional[torch.Tensor], num_rows: int,
-                tile_ptr: Optional[torch.Tensor] = None, slab_ptr: Optional[torch.Tensor] = None,
+                amax: Optional[torch.Tensor], tiles: Units, num_rows: int, slabs: Optional[Units] = None,
                 amax_b: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """``out[p] = (1/s) * A[row(p)] @ W_type.T (+ bias_type)`` on the TMA-fed tcgen05 kernels; ``a_split`` from
-    :func:`rows_split`, ``parts`` from :func:`weight_parts`.  256 x 256 products run on the weight-stationary variant
-    (one weight load per slab of pair rows) when ``slab_ptr`` is given."""
+    """``out[p] = (1/(s_a s_b)) * A[row(p)] @ W_type.T (+ bias_type)`` on the TMA-fed tcgen05 kernels; ``a_split`` from
+    :func:`rows_split`, ``parts`` from :func:`weight_parts`, ``tiles`` from :func:`segment_units` (unit ``tma_tile_rows()``).
+    256 x 256 products run on the weight-stationary variant when it is enabled and ``slabs`` is given."""
     num_types, _, n_out, k_in = parts.shape
-    num_segs = int(seg_ptr.shape[0]) - 1
     out = torch.empty((num_rows, n_out), device=a_split.device, dtype=torch.float32)
     lib = _lib.load()
-    if slab_ptr is not None and lib.bl_tma_project_stationary_supported(n_out, k_in):
-        max_slabs = num_rows // tma_slab_rows() + num_segs
-        check(lib.bl_tma_project_stationary(a_split.data_ptr(), int(a_split.shape[1]), i32(idx) if idx is not None else None,
-                                            parts.data_ptr(), f32(bias) if bias is not None else None,
-                                            f32(amax) if amax is not None else None,
-                                            f32(amax_b) if amax_b is not None else None, i32(seg_ptr),
-                                            i32(seg_type) if seg_type is not None else None, i32(slab_ptr), num_segs, num_types,
-                                            num_rows, max_slabs, n_out, k_in, f32(out), stream_ptr(a_split.device)),
-              "bl_tma_project_stationary")
+    common = (a_split.data_ptr(), int(a_split.shape[1]), i32(idx) if idx is not None else None, parts.data_ptr(),
+              f32(bias) if bias is not None else None, f32(amax) if amax is not None else None,
+              f32(amax_b) if amax_b is not None else None)
+    if slabs is not None and lib.bl_tma_project_stationary_supported(n_out, k_in):
+        check(lib.bl_tma_project_stationary(*common, slabs.table.data_ptr(), i32(slabs.count), num_types, num_rows,
+                                            slabs.capacity, n_out, k_in, f32(out),
+                                            stream_ptr(a_split.device)), "bl_tma_project_stationary")
         return out
-    if tile_ptr is None:
-        tile_ptr = unit_prefix(seg_ptr, tma_tile_rows())
-    max_tiles = num_rows // tma_tile_rows() + num_segs
-    check(_lib.load().bl_tma_project(a_split.data_ptr(), int(a_split.shape[1]), i32(idx) if idx is not None else None,
-                                     parts.data_ptr(), f32(bias) if bias is not None else None,
-                                     f32(amax) if amax is not None else None,
-                                     f32(amax_b) if amax_b is not None else None, i32(seg_ptr),
-                                     i32(seg_type) if seg_type is not None else None, i32(tile_ptr), num_segs, num_types,
-                                     num_rows, max_tiles, n_out, k_in, f32(out), stream_ptr(a_split.device)), "bl_tma_project")
+    check(lib.bl_tma_project(*common, tiles.table.data_ptr(), i32(tiles.count), num_types, num_rows, tiles.capacity, n_out, k_in,
+                             f32(out), stream_ptr(a_split.device)), "bl_tma_project")
     return out
 
 
 def tma_weight_grad(g_split: torch.Tensor, x_split: torch.Tensor, idx: torch.Tensor, amax: Optional[torch.Tensor],
-                    seg_ptr: torch.Tensor, seg_type: Optional[torch.Tensor], d_weight: torch.Tensor, col0: int,
-                    slab_ptr: Optional[torch.Tensor] = None, amax_x: Optional[torch.Tensor] = None) -> None:
-    """``d_weight[type, :, col0:col0+n] = (1/s) * sum_p G[p]^T X[idx[p]]`` (block zeroed first) on the TMA-fed tcgen05 kernel."""
+                    slabs: Units, d_weight: torch.Tensor, col0: int, amax_x: Optional[torch.Tensor] = None) -> None:
+    """``d_weight[type, :, col0:col0+n] = (1/(s_g s_x)) * sum_p G[p]^T X[idx[p]]`` (block zeroed first) on the TMA-fed
+    tcgen05 kernel; ``slabs`` from :func:`segment_units` (unit ``tma_slab_rows()``)."""
     num_types, m_out, ld = d_weight.shape
     n_in = int(x_split.shape[2])
-    num_segs = int(seg_ptr.shape[0]) - 1
     num_rows = int(idx.shape[0])
-    if slab_ptr is None:
-        slab_ptr = unit_prefix(seg_ptr, tma_slab_rows())
-    max_slabs = num_rows // tma_slab_rows() + num_segs
     check(_lib.load().bl_tma_weight_grad(g_split.data_ptr(), int(g_split.shape[1]), x_split.data_ptr(), int(x_split.shape[1]),
                                          i32(idx), f32(amax) if amax is not None else None,
-                                         f32(amax_x) if amax_x is not None else None, i32(seg_ptr),
-                                         i32(seg_type) if seg_type is not None else None, i32(slab_ptr), num_segs, num_types,
-                                         num_rows, max_slabs, m_out, n_in, f32(d_weight), ld, col0,
+                                         f32(amax_x) if amax_x is not None else None, slabs.table.data_ptr(), i32(slabs.count),
+                                         num_types, num_rows, slabs.capacity, m_out, n_in, f32(d_weight), ld, col0,
                                          stream_ptr(g_split.device)), "bl_tma_weight_grad")
 
 
@@ -425,16 +435,16 @@ class TypedEdgeMessageMax(torch.autograd.Function):
         bias_c = bias.contiguous() if bias is not None else None
         h_split = amax_h = amax_w = None
         with torch.no_grad():
-            if _tma_proj_ok(M, D) and plan.s_tile_ptr is not None:
+            if _tma_proj_ok(M, D) and plan.s_tiles is not None:
                 # split h ONCE per layer at node granularity; both projections gather its rows by TMA.  Both operands are
                 # pre-scaled by exact powers of two (their absolute maxima brought to ~2^12) so that the lo parts are normal
                 # fp16 numbers; the kernels' epilogues undo both scales.
                 amax_h, amax_w = (absmax(h), absmax(weight)) if PRESCALE_OPERANDS else (None, None)
                 h_split = rows_split(h, None, amax_h)
                 u_rows = tma_project(h_split, plan.s_node, weight_parts(weight, M, D, 0, False, amax_w), None, amax_h,
-                                     plan.s_type_ptr, plan.seg_type, plan.num_s_pairs, plan.s_tile_ptr, plan.s_slab_ptr, amax_w)
+                                     plan.s_tiles, plan.num_s_pairs, plan.s_slabs, amax_w)
                 v_rows = tma_project(h_split, plan.t_node, weight_parts(weight, M, D, D, False, amax_w), bias_c, amax_h,
-                                     plan.t_type_ptr, plan.seg_type, plan.num_t_pairs, plan.t_tile_ptr, plan.t_slab_ptr, amax_w)
+                                     plan.t_tiles, plan.num_t_pairs, plan.t_slabs, amax_w)
             elif plan.block_nodes > 0:
                 raise _lib.BuglabB200Error(f"a node-blocked plan needs the TMA GEMMs, which do not cover (D={D}, M={M})")
             elif PROJECTION_MODE == "f16x3":
@@ -477,7 +487,7 @@ class TypedEdgeMessageMax(torch.autograd.Function):
         dev = h.device
         d_bias = torch.zeros((K, M), device=dev, dtype=torch.float32) if ctx.has_bias else None
         if (ctx.mode == "f16x3" and USE_SPLIT_EDGE_BACKWARD and M in (128, 256, 512) and _tma_proj_ok(D, M) and _tma_wgrad_ok(M, D)
-                and plan.s_tile_ptr is not None and plan.s_edge_ptr is not None):
+                and plan.s_tiles is not None and plan.s_edge_ptr is not None):
             # Second-generation backward, end to end: the edge kernels write both gradient tables directly as pre-scaled
             # fp16 hi/lo split tables (one writer per row, no memset, no atomics on the tables) and fold the bias column
             # sums in; the TMA-fed tcgen05 kernels take it from there.
@@ -510,14 +520,14 @@ class TypedEdgeMessageMax(torch.autograd.Function):
                 h_split = rows_split(h, None, amax_h)
             d_weight = torch.empty_like(weight)
             d_rows = [None, None]
-            for slot, rows_idx, g_split, col0, type_ptr_dev, tile_ptr, slab_ptr in (
-                    (1, plan.t_node, dv_split, D, plan.t_type_ptr, plan.t_tile_ptr, plan.t_slab_ptr),
-                    (0, plan.s_node, du_split, 0, plan.s_type_ptr, plan.s_tile_ptr, plan.s_slab_ptr)):
+            for slot, rows_idx, g_split, col0, tiles, slabs in (
+                    (1, plan.t_node, dv_split, D, plan.t_tiles, plan.t_slabs),
+                    (0, plan.s_node, du_split, 0, plan.s_tiles, plan.s_slabs)):
                 if slot == 0 and side is not None:
                     main.wait_stream(side)  # dU is complete; g_rows / ewin are no longer read on the side stream
-                d_rows[slot] = tma_project(g_split, None, weight_parts(weight, D, M, col0, True, amax_w), None, amax, type_ptr_dev,
-                                           plan.seg_type, int(rows_idx.shape[0]), tile_ptr, slab_ptr, amax_w)
-                tma_weight_grad(g_split, h_split, rows_idx, amax, type_ptr_dev, plan.seg_type, d_weight, col0, slab_ptr, amax_h)
+                d_rows[slot] = tma_project(g_split, None, weight_parts(weight, D, M, col0, True, amax_w), None, amax, tiles,
+                                           int(rows_idx.shape[0]), slabs, amax_w)
+                tma_weight_grad(g_split, h_split, rows_idx, amax, slabs, d_weight, col0, amax_h)
             del du_split, dv_split, g_rows
             d_h = torch.empty_like(h)
             check(lib.bl_rows_segment_sum(f32(d_rows[0]), i32(plan.s_by_node_ptr), i32(plan.s_by_node_idx),
@@ -538,7 +548,7 @@ class TypedEdgeMessageMax(torch.autograd.Function):
         )
         d_rows = []
         unscaled = False
-        if ctx.mode == "f16x3" and _tma_proj_ok(D, M) and plan.s_tile_ptr is not None:
+        if ctx.mode == "f16x3" and _tma_proj_ok(D, M) and plan.s_tiles is not None:
             # second-generation path: split each gradient table once (pre-scaled), then TMA-fed tcgen05 for both products
             unscaled = True  # the projection epilogue undoes the pre-scale
             d_weight = torch.empty_like(weight)
@@ -552,14 +562,14 @@ class TypedEdgeMessageMax(torch.autograd.Function):
                 h_split = rows_split(h, None, amax_h)
             if amax_w is None and PRESCALE_OPERANDS:
                 amax_w = absmax(weight)
-            for rows_idx, d_tab, col0, type_ptr, type_ptr_dev, tile_ptr, slab_ptr in (
-                    (plan.s_node, du, 0, plan.s_type_ptr_host, plan.s_type_ptr, plan.s_tile_ptr, plan.s_slab_ptr),
-                    (plan.t_node, dv, D, plan.t_type_ptr_host, plan.t_type_ptr, plan.t_tile_ptr, plan.t_slab_ptr)):
+            for rows_idx, d_tab, col0, type_ptr, tiles, slabs in (
+                    (plan.s_node, du, 0, plan.s_type_ptr_host, plan.s_tiles, plan.s_slabs),
+                    (plan.t_node, dv, D, plan.t_type_ptr_host, plan.t_tiles, plan.t_slabs)):
                 g_split = rows_split(d_tab, None, amax)
-                d_rows.append(tma_project(g_split, None, weight_parts(weight, D, M, col0, True, amax_w), None, amax, type_ptr_dev, None,
-                                          int(rows_idx.shape[0]), tile_ptr, slab_ptr, amax_w))
+                d_rows.append(tma_project(g_split, None, weight_parts(weight, D, M, col0, True, amax_w), None, amax, tiles,
+                                          int(rows_idx.shape[0]), slabs, amax_w))
                 if wg_ok:
-                    tma_weight_grad(g_split, h_split, rows_idx, amax, type_ptr_dev, None, d_weight, col0, slab_ptr, amax_h)
+                    tma_weight_grad(g_split, h_split, rows_idx, amax, slabs, d_weight, col0, amax_h)
                 else:  # widths the weight-gradient kernel does not cover (e.g. 128): round 1's split + library GEMM
                     g2 = _split2_rows(d_tab, None, amax)
                     a2 = _split2_rows(h, rows_idx)
@@ -726,24 +736,22 @@ class DenseLinearTma(torch.autograd.Function):
         seg = _single_segment(R, x.device)
         amax_x, amax_w = (absmax(x), absmax(weight)) if PRESCALE_OPERANDS else (None, None)
         x_split = rows_split(x, None, amax_x)
-        slabs = unit_prefix(seg, tma_slab_rows())
+        tiles, slabs = segment_units(seg, None, tma_tile_rows(), R), segment_units(seg, None, tma_slab_rows(), R)
         if DENSE_FORWARD_FP32_REFEREE:
             y = torch.mm(x, weight.t())
         else:
             y = tma_project(x_split, None, weight_parts(weight.view(1, N_out, K_in), N_out, K_in, 0, False, amax_w), None, amax_x,
-                            seg, None, R, None, slabs, amax_w)
-        none = torch.empty(0, device=x.device)
-        ctx.prescaled = amax_x is not None
-        ctx.save_for_backward(x_split, weight, seg, slabs, amax_x if amax_x is not None else none,
-                              amax_w if amax_w is not None else none)
+                            tiles, R, slabs, amax_w)
+        ctx.units = (tiles, slabs)
+        ctx.amax = (amax_x, amax_w)
+        ctx.save_for_backward(x_split, weight)
         return y
 
     @staticmethod
     def backward(ctx, dy: torch.Tensor):
         lib = _lib.load()
-        x_split, weight, seg, slabs, amax_x, amax_w = ctx.saved_tensors
-        if not ctx.prescaled:
-            amax_x = amax_w = None
+        x_split, weight = ctx.saved_tensors
+        (tiles, slabs), (amax_x, amax_w) = ctx.units, ctx.amax
         dy = dy.contiguous()
         R, N_out = dy.shape
         K_in = weight.shape[1]
@@ -751,11 +759,11 @@ class DenseLinearTma(torch.autograd.Function):
         amax = torch.empty(1, device=dev, dtype=torch.float32)
         check(lib.bl_absmax(f32(dy), dy.numel(), f32(amax), stream_ptr(dev)), "bl_absmax")
         g_split = rows_split(dy, None, amax)
-        dx = tma_project(g_split, None, weight_parts(weight.view(1, N_out, K_in), K_in, N_out, 0, True, amax_w), None, amax, seg,
-                         None, R, None, slabs, amax_w)
+        dx = tma_project(g_split, None, weight_parts(weight.view(1, N_out, K_in), K_in, N_out, 0, True, amax_w), None, amax, tiles,
+                         R, slabs, amax_w)
         dw = torch.empty_like(weight)
         identity = torch.arange(R, device=dev, dtype=torch.int32)
-        tma_weight_grad(g_split, x_split, identity, amax, seg, None, dw.view(1, N_out, K_in), 0, slabs, amax_x)
+        tma_weight_grad(g_split, x_split, identity, amax, slabs, dw.view(1, N_out, K_in), 0, amax_x)
         return dx, dw
 
 

@@ -254,18 +254,21 @@ __device__ __forceinline__ void epi_red_rows(const float* stage, int lane, float
 // Projection:  out[p, 0:N] = inv_scale * A[row(p), 0:Kin] . W_type(seg(p))[0:N, 0:Kin]^T (+ bias_type)
 //   A is a split table  [2 parts][a_rows][Kin] fp16  (part 0 = hi, part 1 = lo; its LAST row of each part is zero and
 //   serves as the padding row);  row(p) = idx[p] (GATHER) or p.
-//   Pair rows are grouped in `num_segs` segments [seg_ptr[s], seg_ptr[s+1]) that share one weight matrix seg_type[s].
+//   Pair rows are grouped in segments that share one weight matrix; the kernels walk a device-side table of work units
+//   (row range + matrix id per tile / slab, built once per plan by bl_segment_units: one 16-byte load locates a tile —
+//   a binary search over ~1 200 (node block, type) segments per tile cost the producers ~1.4 us of dependent L2 latency
+//   per 3 us tile).
 // =====================================================================================================================
 struct ProjParams {
     const int* idx;       // [P] rows of the split table, or nullptr (contiguous: row(p) = p)
     const float* bias;    // [num_types, N] or nullptr
     const float* amax;    // nullable: out is multiplied by 1 / pow2_scale_for(*amax)  (undoes the pre-scale of A)
     const float* amax_b;  // nullable: the same for the pre-scale of the weight parts
-    const int* seg_ptr;   // [num_segs + 1]
-    const int* seg_type;  // [num_segs] or nullptr (identity)
-    const int* tile_ptr;  // [num_segs + 1] prefix sums of ceil(rows / (128 * CG))
+    const int4* units;    // work units {first pair row, end pair row, weight matrix, -}: tiles of <= 128*CG rows of one
+                          // segment (proj_kernel) or slabs of <= SLAB_ROWS rows (proj_bs_kernel); bl_segment_units
+    const int* num_units; // device scalar: number of valid entries of `units`
     float* out;           // [P, N]
-    int num_segs, N, Kin, a_rows;
+    int N, Kin, a_rows;
 };
 
 template <int NT, int CG>
@@ -319,7 +322,7 @@ proj_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const uint32_t tmem_base = tmem_base_smem;
 
     const int n_splits = p.N / NT;
-    const int total_work = __ldg(p.tile_ptr + p.num_segs) * n_splits;
+    const int total_work = __ldg(p.num_units) * n_splits;
     const int num_chunks = p.Kin / CHUNK_K;
 
     if (warp < 4) {
@@ -330,10 +333,8 @@ proj_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         uint32_t phase = 0, chunk_counter = 0;
         for (int work = cluster_id; work < total_work; work += num_clusters) {
             const int tile = work / n_splits, split = work - tile * n_splits;
-            const int s = find_segment(p.tile_ptr, p.num_segs, tile);
-            const int row0 = __ldg(p.seg_ptr + s) + (tile - __ldg(p.tile_ptr + s)) * (TILE_M * CG) + (int)cta_rank * TILE_M;
-            const int row_end = __ldg(p.seg_ptr + s + 1);
-            const int type = p.seg_type ? __ldg(p.seg_type + s) : s;
+            const int4 unit = __ldg(p.units + tile);
+            const int row0 = unit.x + (int)cta_rank * TILE_M, row_end = unit.y, type = unit.z;
             int rows[4];
             if (GATHER) {
 #pragma unroll
@@ -408,10 +409,8 @@ proj_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         uint32_t tile_counter = 0;
         for (int work = cluster_id; work < total_work; work += num_clusters, ++tile_counter) {
             const int tile = work / n_splits, split = work - tile * n_splits;
-            const int s = find_segment(p.tile_ptr, p.num_segs, tile);
-            const int row0 = __ldg(p.seg_ptr + s) + (tile - __ldg(p.tile_ptr + s)) * (TILE_M * CG) + (int)cta_rank * TILE_M;
-            const int row_end = __ldg(p.seg_ptr + s + 1);
-            const int type = p.seg_type ? __ldg(p.seg_type + s) : s;
+            const int4 unit = __ldg(p.units + tile);
+            const int row0 = unit.x + (int)cta_rank * TILE_M, row_end = unit.y, type = unit.z;
             const int col0 = split * NT;
             const uint32_t a = tile_counter & 1u, ause = tile_counter >> 1;
             mbar_wait(&acc_full[a], ause & 1u, 3);
@@ -501,13 +500,11 @@ proj_bs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
-    // p.tile_ptr holds the SLAB prefix here (unit SLAB_ROWS); a slab has <= SLAB_ROWS / 256 row tiles
-    const int total_slabs = __ldg(p.tile_ptr + p.num_segs);
+    // p.units holds SLABS here (<= SLAB_ROWS rows); a slab has <= SLAB_ROWS / 256 row tiles
+    const int total_slabs = __ldg(p.num_units);
     auto locate = [&](int slab, int& type, int& row_begin, int& row_end) {
-        const int s = find_segment(p.tile_ptr, p.num_segs, slab);
-        type = p.seg_type ? __ldg(p.seg_type + s) : s;
-        row_begin = __ldg(p.seg_ptr + s) + (slab - __ldg(p.tile_ptr + s)) * SLAB_ROWS;
-        row_end = min(row_begin + SLAB_ROWS, __ldg(p.seg_ptr + s + 1));
+        const int4 unit = __ldg(p.units + slab);
+        row_begin = unit.x; row_end = unit.y; type = unit.z;
     };
 
     if (warp < 4) {
@@ -661,11 +658,10 @@ struct WgParams {
     const int* idx;        // [P]
     const float* amax;     // pre-scale source of G (nullable)
     const float* amax_x;   // pre-scale source of X (nullable)
-    const int* seg_ptr;    // [num_segs + 1]
-    const int* seg_type;   // nullable
-    const int* slab_ptr;   // [num_segs + 1] prefix sums of ceil(rows / SLAB_ROWS)
+    const int4* units;     // slabs {first pair row, end pair row, weight matrix, -} (bl_segment_units, unit SLAB_ROWS)
+    const int* num_units;  // device scalar
     float* d_weight;       // [num_types, M, ld]; this call accumulates into columns [col0, col0 + Nin)
-    int num_segs, M, Nin, ld, col0, g_rows, x_rows;
+    int M, Nin, ld, col0, g_rows, x_rows;
 };
 
 template <int CG>
@@ -723,16 +719,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ 
 
     const int m_tiles = p.M / (TILE_M * CG), n_tiles = p.Nin / NT;
     const int per_slab = m_tiles * n_tiles;
-    const int total_work = __ldg(p.slab_ptr + p.num_segs) * per_slab;
+    const int total_work = __ldg(p.num_units) * per_slab;
 
     // (slab, m tile, n tile) -> pair-row range and output offsets
     auto locate = [&](int work, int& type, int& row_begin, int& row_end, int& m0, int& n0) {
         const int slab = work / per_slab, mn = work - slab * per_slab;
         const int mt = mn / n_tiles, nt = mn - mt * n_tiles;
-        const int s = find_segment(p.slab_ptr, p.num_segs, slab);
-        type = p.seg_type ? __ldg(p.seg_type + s) : s;
-        row_begin = __ldg(p.seg_ptr + s) + (slab - __ldg(p.slab_ptr + s)) * SLAB_ROWS;
-        row_end = min(row_begin + SLAB_ROWS, __ldg(p.seg_ptr + s + 1));
+        const int4 unit = __ldg(p.units + slab);
+        type = unit.z; row_begin = unit.x; row_end = unit.y;
         m0 = mt * (TILE_M * CG) + (int)cta_rank * TILE_M;  // this CTA's 128 rows of dW
         n0 = nt * NT;                                      // the pair's 256 columns; this CTA stages NTL of them
     };
@@ -919,6 +913,18 @@ __global__ void unit_prefix_kernel(const int* __restrict__ seg_ptr, int num_segs
     if (tid == 0) prefix[num_segs] = carry;
 }
 
+// units[u] = {first row, end row, matrix id, segment} of work unit u (<= `unit` consecutive rows of one segment), u < prefix[num_segs]
+__global__ void unit_table_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ seg_type, const int* __restrict__ prefix,
+                                  int num_segs, int unit, int64_t max_units, int4* __restrict__ units, int* __restrict__ count) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = prefix[num_segs];
+    if (u == 0) *count = (int)min((int64_t)total, max_units);
+    if (u >= total || u >= max_units) return;
+    const int s = find_segment(prefix, num_segs, (int)u);
+    const int row_begin = seg_ptr[s] + ((int)u - prefix[s]) * unit;
+    units[u] = make_int4(row_begin, min(row_begin + unit, seg_ptr[s + 1]), seg_type ? seg_type[s] : s, s);
+}
+
 // ------------------------------------------------------------------------------------------------ host helpers
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1013,6 +1019,19 @@ extern "C" int bl_segment_unit_prefix(const int32_t* seg_ptr, int32_t num_segs, 
     return check_launch("bl_segment_unit_prefix");
 }
 
+/* Work-unit table of the TMA GEMMs: units[u] = {first row, end row, weight matrix (seg_type[s] or s), segment} for every
+ * run of <= `unit` consecutive pair rows of one segment, in row order; *count = number of units (<= max_units, which must
+ * be >= num_rows / unit + num_segs).  prefix_ws: scratch of num_segs + 1 ints.  Device to device, no sync. */
+extern "C" int bl_segment_units(const int32_t* seg_ptr, const int32_t* seg_type, int32_t num_segs, int32_t unit, int64_t max_units,
+                                int32_t* prefix_ws, void* units, int32_t* count, bl_stream_t stream_) {
+    if (num_segs <= 0 || unit <= 0 || max_units <= 0) return BL_ERR_INVALID_ARGUMENT;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    tg::unit_prefix_kernel<<<1, 1024, 0, stream>>>(seg_ptr, num_segs, unit, prefix_ws);
+    tg::unit_table_kernel<<<grid_for(max_units, 256), 256, 0, stream>>>(seg_ptr, seg_type, prefix_ws, num_segs, unit, max_units,
+                                                                        (int4*)units, count);
+    return check_launch("bl_segment_units");
+}
+
 extern "C" int bl_tma_tile_rows(void) { return tg::TILE_M * tg::default_cg(); }
 extern "C" int bl_tma_slab_rows(void) { return tg::SLAB_ROWS; }
 
@@ -1027,10 +1046,10 @@ extern "C" int bl_tma_project_stationary_supported(int32_t n_out, int32_t k_in) 
 /* Same product as bl_tma_project with the weights held in shared memory per slab of <= bl_tma_slab_rows() pair rows
  * (slab_ptr = bl_segment_unit_prefix(seg_ptr, bl_tma_slab_rows()), max_slabs = an upper bound of its last entry). */
 extern "C" int bl_tma_project_stationary(const void* a_split, int64_t a_rows, const int32_t* idx, const void* wparts, const float* bias,
-                                         const float* amax, const float* amax_b, const int32_t* seg_ptr, const int32_t* seg_type, const int32_t* slab_ptr,
-                                         int32_t num_segs, int32_t num_types, int64_t num_rows, int64_t max_slabs, int32_t n_out,
+                                         const float* amax, const float* amax_b, const void* slabs, const int32_t* num_slabs,
+                                         int32_t num_types, int64_t num_rows, int64_t max_slabs, int32_t n_out,
                                          int32_t k_in, float* out, bl_stream_t stream_) {
-    if (num_segs <= 0 || num_types <= 0 || num_rows < 0 || a_rows <= 0 || a_rows > (1ll << 30)) return BL_ERR_INVALID_ARGUMENT;
+    if (slabs == nullptr || num_slabs == nullptr || num_types <= 0 || num_rows < 0 || a_rows <= 0 || a_rows > (1ll << 30)) return BL_ERR_INVALID_ARGUMENT;
     if (!bl_tma_project_stationary_supported(n_out, k_in)) return BL_ERR_UNSUPPORTED;
     if (num_rows == 0 || max_slabs <= 0) return BL_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -1039,7 +1058,7 @@ extern "C" int bl_tma_project_stationary(const void* a_split, int64_t a_rows, co
     if (rc) return rc;
     rc = tg::make_map_f16(&map_b, wparts, (uint64_t)num_types * 2 * n_out, (uint64_t)k_in, tg::CHUNK_K, (uint32_t)tg::ProjBsCfg::NTL);
     if (rc) return rc;
-    tg::ProjParams p{idx, bias, amax, amax_b, seg_ptr, seg_type, slab_ptr, out, num_segs, n_out, k_in, (int)a_rows};
+    tg::ProjParams p{idx, bias, amax, amax_b, (const int4*)slabs, num_slabs, out, n_out, k_in, (int)a_rows};
     int grid = (int)std::min<int64_t>((int64_t)(num_sms() / 2), max_slabs) * 2;
     if (grid < 2) grid = 2;
     if (idx) return tg::launch(tg::proj_bs_kernel<true>, 2, grid, tg::ProjBsCfg::SMEM_BYTES, stream, "bl_tma_project_stationary", map_a, map_b, p);
@@ -1047,10 +1066,10 @@ extern "C" int bl_tma_project_stationary(const void* a_split, int64_t a_rows, co
 }
 
 extern "C" int bl_tma_project(const void* a_split, int64_t a_rows, const int32_t* idx, const void* wparts, const float* bias,
-                              const float* amax, const float* amax_b, const int32_t* seg_ptr, const int32_t* seg_type, const int32_t* tile_ptr,
-                              int32_t num_segs, int32_t num_types, int64_t num_rows, int64_t max_tiles, int32_t n_out,
+                              const float* amax, const float* amax_b, const void* tiles, const int32_t* num_tiles,
+                              int32_t num_types, int64_t num_rows, int64_t max_tiles, int32_t n_out,
                               int32_t k_in, float* out, bl_stream_t stream_) {
-    if (num_segs <= 0 || num_types <= 0 || num_rows < 0 || a_rows <= 0 || a_rows > (1ll << 30)) return BL_ERR_INVALID_ARGUMENT;
+    if (tiles == nullptr || num_tiles == nullptr || num_types <= 0 || num_rows < 0 || a_rows <= 0 || a_rows > (1ll << 30)) return BL_ERR_INVALID_ARGUMENT;
     if (!bl_tma_gemm_supported(n_out, k_in)) return BL_ERR_UNSUPPORTED;
     if (num_rows == 0 || max_tiles <= 0) return BL_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -1062,7 +1081,7 @@ extern "C" int bl_tma_project(const void* a_split, int64_t a_rows, const int32_t
     if (rc) return rc;
     rc = tg::make_map_f16(&map_b, wparts, (uint64_t)num_types * 2 * n_out, (uint64_t)k_in, tg::CHUNK_K, (uint32_t)ntl);
     if (rc) return rc;
-    tg::ProjParams p{idx, bias, amax, amax_b, seg_ptr, seg_type, tile_ptr, out, num_segs, n_out, k_in, (int)a_rows};
+    tg::ProjParams p{idx, bias, amax, amax_b, (const int4*)tiles, num_tiles, out, n_out, k_in, (int)a_rows};
     int sms = num_sms();
     int grid = (int)std::min<int64_t>((int64_t)(sms / cg), max_tiles * (n_out / nt)) * cg;
     if (grid < cg) grid = cg;
@@ -1082,10 +1101,10 @@ extern "C" int bl_tma_weight_grad_supported(int32_t m_out, int32_t n_in) {
 
 /* d_weight[type, 0:m_out, col0:col0+n_in] = (1/scale) sum over pair rows of G[p,:]^T X[idx[p],:]  (zeroes that block first) */
 extern "C" int bl_tma_weight_grad(const void* g_split, int64_t g_rows, const void* x_split, int64_t x_rows, const int32_t* idx,
-                                  const float* amax, const float* amax_x, const int32_t* seg_ptr, const int32_t* seg_type, const int32_t* slab_ptr,
-                                  int32_t num_segs, int32_t num_types, int64_t num_rows, int64_t max_slabs, int32_t m_out,
+                                  const float* amax, const float* amax_x, const void* slabs, const int32_t* num_slabs,
+                                  int32_t num_types, int64_t num_rows, int64_t max_slabs, int32_t m_out,
                                   int32_t n_in, float* d_weight, int32_t ld, int32_t col0, bl_stream_t stream_) {
-    if (num_segs <= 0 || num_types <= 0 || num_rows < 0 || idx == nullptr || g_rows <= 0 || x_rows <= 0) return BL_ERR_INVALID_ARGUMENT;
+    if (slabs == nullptr || num_slabs == nullptr || num_types <= 0 || num_rows < 0 || idx == nullptr || g_rows <= 0 || x_rows <= 0) return BL_ERR_INVALID_ARGUMENT;
     if (!bl_tma_weight_grad_supported(m_out, n_in)) return BL_ERR_UNSUPPORTED;
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc = check_cuda(cudaMemset2DAsync(d_weight + col0, (size_t)ld * sizeof(float), 0, (size_t)n_in * sizeof(float),
@@ -1098,7 +1117,7 @@ extern "C" int bl_tma_weight_grad(const void* g_split, int64_t g_rows, const voi
     if (rc) return rc;
     rc = tg::make_map_f16(&map_x, x_split, (uint64_t)(2 * x_rows), (uint64_t)n_in, 64, 1);
     if (rc) return rc;
-    tg::WgParams p{idx, amax, amax_x, seg_ptr, seg_type, slab_ptr, d_weight, num_segs, m_out, n_in, ld, col0, (int)g_rows, (int)x_rows};
+    tg::WgParams p{idx, amax, amax_x, (const int4*)slabs, num_slabs, d_weight, m_out, n_in, ld, col0, (int)g_rows, (int)x_rows};
     const int64_t items = max_slabs * (m_out / (tg::TILE_M * cg)) * (n_in / 256);
     int grid = (int)std::min<int64_t>((int64_t)(num_sms() / cg), items) * cg;
     if (grid < cg) grid = cg;

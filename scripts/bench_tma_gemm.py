@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--shapes", default="256x256,512x512")
     ap.add_argument("--skip-old", action="store_true")
+    ap.add_argument("--block-nodes", type=int, default=0, help="order the pair rows by (node block, type, node) like the model's plan")
     args = ap.parse_args()
 
     import torch
@@ -60,6 +61,8 @@ def main():
         type_ptr_host.append(type_ptr_host[-1] + c)
     idx = torch.cat([torch.sort(torch.randint(0, N, (int(c),), dtype=torch.int32))[0] for c in counts.tolist()]).to(dev)
     type_ptr = torch.tensor(type_ptr_host, dtype=torch.int32, device=dev)
+    if args.block_nodes > 0:
+        raise SystemExit("--block-nodes: use bench.py's roofline legs (they time the kernels on the model's blocked plan)")
     cg = os.environ.get("BUGLAB_B200_TMA_CG", "2")
 
     for shape in args.shapes.split(","):
@@ -73,18 +76,17 @@ def main():
         # ---- forward projection (gathered rows) ----
         parts = ops.weight_parts(weight, M, D, 0, False)
         h_split = ops.rows_split(h)
-        tile_ptr = ops.unit_prefix(type_ptr, ops.tma_tile_rows())
-        new = ops.tma_project(h_split, idx, parts, bias, None, type_ptr, None, P, tile_ptr)
+        tiles = ops.segment_units(type_ptr, None, ops.tma_tile_rows(), P)
+        slabs = ops.segment_units(type_ptr, None, ops.tma_slab_rows(), P)
+        new = ops.tma_project(h_split, idx, parts, bias, None, tiles, P)
         out["split_ms"] = timed(lambda: ops.rows_split(h), args.warmup, args.iters)
-        out["fwd_tma_ms"] = timed(lambda: ops.tma_project(h_split, idx, parts, bias, None, type_ptr, None, P, tile_ptr),
-                                  args.warmup, args.iters)
+        out["fwd_tma_ms"] = timed(lambda: ops.tma_project(h_split, idx, parts, bias, None, tiles, P), args.warmup, args.iters)
         out["fwd_tma_tflops"] = flops / out["fwd_tma_ms"] / 1e9
-        slab_ptr_f = ops.unit_prefix(type_ptr, ops.tma_slab_rows())
         if _lib.load().bl_tma_project_stationary_supported(M, D):
-            stat = ops.tma_project(h_split, idx, parts, bias, None, type_ptr, None, P, tile_ptr, slab_ptr_f)
+            stat = ops.tma_project(h_split, idx, parts, bias, None, tiles, P, slabs)
             out["fwd_stationary_max_abs_diff_vs_streaming"] = float((stat - new).abs().max())
-            out["fwd_tma_stationary_ms"] = timed(
-                lambda: ops.tma_project(h_split, idx, parts, bias, None, type_ptr, None, P, tile_ptr, slab_ptr_f), args.warmup, args.iters)
+            out["fwd_tma_stationary_ms"] = timed(lambda: ops.tma_project(h_split, idx, parts, bias, None, tiles, P, slabs),
+                                                 args.warmup, args.iters)
             out["fwd_tma_stationary_tflops"] = flops / out["fwd_tma_stationary_ms"] / 1e9
             del stat
         if not args.skip_old and _lib.load().bl_pair_project_tc_supported(M, D):
@@ -105,14 +107,12 @@ def main():
         _lib.check(_lib.load().bl_absmax(_lib.f32(g), g.numel(), _lib.f32(amax), _lib.stream_ptr(dev)), "bl_absmax")
         parts_t = ops.weight_parts(weight, D, M, 0, True)
         g_split = ops.rows_split(g, None, amax)
-        tile_ptr = ops.unit_prefix(type_ptr, ops.tma_tile_rows())
         out["gsplit_ms"] = timed(lambda: ops.rows_split(g, None, amax), args.warmup, args.iters)
-        d_in = ops.tma_project(g_split, None, parts_t, None, amax, type_ptr, None, P, tile_ptr)
-        out["bwd_in_tma_ms"] = timed(lambda: ops.tma_project(g_split, None, parts_t, None, amax, type_ptr, None, P, tile_ptr),
-                                     args.warmup, args.iters)
+        d_in = ops.tma_project(g_split, None, parts_t, None, amax, tiles, P)
+        out["bwd_in_tma_ms"] = timed(lambda: ops.tma_project(g_split, None, parts_t, None, amax, tiles, P), args.warmup, args.iters)
         if _lib.load().bl_tma_project_stationary_supported(D, M):
-            out["bwd_in_tma_stationary_ms"] = timed(
-                lambda: ops.tma_project(g_split, None, parts_t, None, amax, type_ptr, None, P, tile_ptr, slab_ptr_f), args.warmup, args.iters)
+            out["bwd_in_tma_stationary_ms"] = timed(lambda: ops.tma_project(g_split, None, parts_t, None, amax, tiles, P, slabs),
+                                                    args.warmup, args.iters)
         if not args.skip_old and _lib.load().bl_pair_project_tc_supported(D, M):
             old = ops.pair_project_tc(g, None, parts_t, None, type_ptr, P, amax=amax)
             scale = float(torch.exp2(12 - torch.ceil(torch.log2(amax))))
@@ -124,10 +124,8 @@ def main():
 
         # ---- weight gradient ----
         d_weight = torch.zeros(K, M, 2 * D, device=dev)
-        slab_ptr = ops.unit_prefix(type_ptr, ops.tma_slab_rows())
-        ops.tma_weight_grad(g_split, h_split, idx, amax, type_ptr, None, d_weight, 0, slab_ptr)
-        out["wgrad_tma_ms"] = timed(lambda: ops.tma_weight_grad(g_split, h_split, idx, amax, type_ptr, None, d_weight, 0, slab_ptr),
-                                    args.warmup, args.iters)
+        ops.tma_weight_grad(g_split, h_split, idx, amax, slabs, d_weight, 0)
+        out["wgrad_tma_ms"] = timed(lambda: ops.tma_weight_grad(g_split, h_split, idx, amax, slabs, d_weight, 0), args.warmup, args.iters)
         k_small = K - 1  # the smallest type: cheap exact reference
         lo, hi = type_ptr_host[k_small], type_ptr_host[k_small + 1]
         ref = g[lo:hi].double().t() @ h[idx[lo:hi].long()].double()

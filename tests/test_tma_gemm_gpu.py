@@ -84,11 +84,12 @@ def run_case(case):
         a_split = ops.rows_split(src_d, None, amax)
         parts = ops.weight_parts(weight_d, n_out, k_in, col0, transposed=False, amax=amax_w)
         seg_ptr = torch.tensor(sp, dtype=torch.int32, device=dev)
+        seg_type = torch.tensor(types, dtype=torch.int32, device=dev) if seg_types is not None else None
+        tiles = ops.segment_units(seg_ptr, seg_type, ops.tma_tile_rows(), P)
         # slab table given: 256 x 256 products take the weight-stationary kernel (pairs only), everything else the streaming one
-        slabs = ops.unit_prefix(seg_ptr, ops.tma_slab_rows()) if os.environ.get("TEST_TMA_STATIONARY", "0") == "1" else None
-        out = ops.tma_project(a_split, idx.to(dev) if gather else None, parts, bias.to(dev) if use_bias else None, amax, seg_ptr,
-                              torch.tensor(types, dtype=torch.int32, device=dev) if seg_types is not None else None, P,
-                              None, slabs, amax_w)
+        slabs = ops.segment_units(seg_ptr, seg_type, ops.tma_slab_rows(), P) if os.environ.get("TEST_TMA_STATIONARY", "0") == "1" else None
+        out = ops.tma_project(a_split, idx.to(dev) if gather else None, parts, bias.to(dev) if use_bias else None, amax, tiles, P,
+                              slabs, amax_w)
         torch.cuda.synchronize()
         got = out.cpu().double()
         scale = float(ref.abs().max())
@@ -118,9 +119,10 @@ def run_case(case):
         amax_x = ops.absmax(x_d) if case["index"] % 2 == 0 else None
         x_split = ops.rows_split(x_d, None, amax_x)
         d_weight = torch.full((K, m_out, ld), 7.0, device=dev)
-        ops.tma_weight_grad(g_split, x_split, idx.to(dev), amax, torch.tensor(sp, dtype=torch.int32, device=dev),
-                            torch.tensor(types, dtype=torch.int32, device=dev) if seg_types is not None else None, d_weight, col0,
-                            None, amax_x)
+        seg_ptr = torch.tensor(sp, dtype=torch.int32, device=dev)
+        seg_type = torch.tensor(types, dtype=torch.int32, device=dev) if seg_types is not None else None
+        ops.tma_weight_grad(g_split, x_split, idx.to(dev), amax, ops.segment_units(seg_ptr, seg_type, ops.tma_slab_rows(), P),
+                            d_weight, col0, amax_x)
         torch.cuda.synchronize()
         got = d_weight[:, :, col0:col0 + n_in].cpu().double()
         untouched = bool((d_weight[:, :, :col0] == 7.0).all()) and bool((d_weight[:, :, col0 + n_in:] == 7.0).all())
