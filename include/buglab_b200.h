@@ -66,7 +66,8 @@ const char* bl_error_string(int code);
  *                  segment s = (node block s / K, type s % K); only the segment-aware GEMMs (bl_tma_*) accept this
  *                  layout (they then sweep the node states once per layer instead of once per type).
  *   s_edge_ptr[E+1], s_edge_idx[E]  (nullable) CSR S-pair -> its sorted edges (ascending): the edges whose U row
- *                  is that pair; e_tgt[E] (nullable) target node of every sorted edge.  Both feed the by-source half
+ *                  is that pair; e_tgt[E] (nullable) target node of every sorted edge; s_edge_tgt[E] (nullable) =
+ *                  e_tgt[s_edge_idx[.]], the same targets in S-pair order.  They feed the by-source half
  *                  of the edge kernel's backward (bl_edge_bwd_sources).
  * ------------------------------------------------------------------------------------------------ */
 size_t bl_plan_workspace_bytes(int64_t num_edges, int64_t num_nodes, int32_t num_edge_types);
@@ -77,7 +78,8 @@ int bl_plan_build(const int32_t* src, const int32_t* tgt, const int32_t* etype,
                   int32_t* urow, int32_t* vrow,
                   int32_t* s_node, int32_t* s_type_ptr, int32_t* s_by_node_ptr, int32_t* s_by_node_idx,
                   int32_t* t_node, int32_t* t_type_ptr, int32_t* t_by_node_ptr, int32_t* t_by_node_idx,
-                  int32_t* counts, int32_t* s_edge_ptr, int32_t* s_edge_idx, int32_t* e_tgt, int32_t block_nodes,
+                  int32_t* counts, int32_t* s_edge_ptr, int32_t* s_edge_idx, int32_t* e_tgt, int32_t* s_edge_tgt,
+                  int32_t block_nodes,
                   void* workspace, size_t workspace_bytes, bl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -187,7 +189,7 @@ int bl_edge_bwd_targets(const float* d_agg, const float* xwin, const int32_t* ew
                         int32_t num_edge_types, int64_t num_t_pairs, const float* amax_in, float* amax_eff, float* g_rows,
                         void* dv_split, float* d_bias, bl_stream_t stream);
 int bl_edge_bwd_sources(const float* g_rows, const int32_t* ewin, const int32_t* s_edge_ptr, const int32_t* s_edge_idx,
-                        const int32_t* e_tgt, int64_t num_s_pairs, int32_t msg_dim, const float* amax_eff, void* du_split,
+                        const int32_t* s_edge_tgt, int64_t num_s_pairs, int32_t msg_dim, const float* amax_eff, void* du_split,
                         bl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -30,7 +30,7 @@ _SIGNATURES = {
     "bl_version": (c_i32, []),
     "bl_error_string": (ctypes.c_char_p, [c_i32]),
     "bl_plan_workspace_bytes": (c_size, [c_i64, c_i64, c_i32]),
-    "bl_plan_build": (c_i32, [c_ptr] * 3 + [c_i64, c_i64, c_i32] + [c_ptr] * 18 + [c_i32, c_ptr, c_size, c_ptr]),
+    "bl_plan_build": (c_i32, [c_ptr] * 3 + [c_i64, c_i64, c_i32] + [c_ptr] * 19 + [c_i32, c_ptr, c_size, c_ptr]),
     "bl_rows_gather": (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_ptr, c_ptr]),
     "bl_rows_segment_sum": (c_i32, [c_ptr] * 6 + [c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
     "bl_rows_split3_f16": (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_ptr, c_ptr, c_ptr]),

@@ -56,6 +56,7 @@ class EdgePlan(NamedTuple):
     s_edge_ptr: Optional[torch.Tensor] = None
     s_edge_idx: Optional[torch.Tensor] = None
     e_tgt: Optional[torch.Tensor] = None
+    s_edge_tgt: Optional[torch.Tensor] = None
     # pair layout: 0 = type-major (one segment per type); B > 0 = node-blocked, segments (node block, type) with
     # seg_type[s] = s % K (then s_type_ptr / t_type_ptr hold num_segs + 1 segment pointers and the *_host tuples are empty)
     block_nodes: int = 0
@@ -109,7 +110,8 @@ def build_edge_plan_from_flat(
     # [counts (2) | s_type_ptr (S+1) | t_type_ptr (S+1)] in one buffer -> one D2H copy (of the counts only when blocked)
     meta = torch.empty(2 + 2 * (S + 1), **opts)
     counts, s_type_ptr, t_type_ptr = meta[:2], meta[2 : S + 3], meta[S + 3 :]
-    s_edge_ptr, s_edge_idx, e_tgt = (torch.empty(Ea + 1, **opts), torch.empty(Ea, **opts), torch.empty(Ea, **opts))
+    s_edge_ptr, s_edge_idx, e_tgt, s_edge_tgt = (torch.empty(Ea + 1, **opts), torch.empty(Ea, **opts), torch.empty(Ea, **opts),
+                                                 torch.empty(Ea, **opts))
     ws_bytes = lib.bl_plan_workspace_bytes(E, N, K)
     workspace = torch.empty(ws_bytes, device=device, dtype=torch.uint8)
     check(
@@ -118,7 +120,8 @@ def build_edge_plan_from_flat(
             i32(e_perm), i32(e_src), i32(e_type), i32(row_ptr), i32(urow), i32(vrow),
             i32(s_node), s_type_ptr.data_ptr(), i32(s_by_node_ptr), i32(s_by_node_idx),
             i32(t_node), t_type_ptr.data_ptr(), i32(t_by_node_ptr), i32(t_by_node_idx),
-            counts.data_ptr(), i32(s_edge_ptr), i32(s_edge_idx), i32(e_tgt), B, workspace.data_ptr(), ws_bytes, stream_ptr(device),
+            counts.data_ptr(), i32(s_edge_ptr), i32(s_edge_idx), i32(e_tgt), i32(s_edge_tgt), B, workspace.data_ptr(), ws_bytes,
+            stream_ptr(device),
         ),
         "bl_plan_build",
     )
@@ -140,7 +143,7 @@ def build_edge_plan_from_flat(
         N, E, K, e_perm[:E], e_src[:E], e_type[:E], row_ptr, urow[:E], vrow[:E],
         s_node[:P_s], s_type_ptr, s_by_node_ptr, s_by_node_idx[:P_s],
         t_node[:P_t], t_type_ptr, t_by_node_ptr, t_by_node_idx[:P_t],
-        P_s, P_t, s_tp, t_tp, *tables, s_edge_ptr[: P_s + 1], s_edge_idx[:E], e_tgt[:E], B, S, seg_type,
+        P_s, P_t, s_tp, t_tp, *tables, s_edge_ptr[: P_s + 1], s_edge_idx[:E], e_tgt[:E], s_edge_tgt[:E], B, S, seg_type,
     )
 
 
@@ -507,11 +510,11 @@ class TypedEdgeMessageMax(torch.autograd.Function):
             if side is not None:
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
-                    check(lib.bl_edge_bwd_sources(f32(g_rows), i32(ewin), i32(plan.s_edge_ptr), i32(plan.s_edge_idx), i32(plan.e_tgt),
+                    check(lib.bl_edge_bwd_sources(f32(g_rows), i32(ewin), i32(plan.s_edge_ptr), i32(plan.s_edge_idx), i32(plan.s_edge_tgt),
                                                   plan.num_s_pairs, M, f32(amax), du_split.data_ptr(), stream_ptr(dev)),
                           "bl_edge_bwd_sources")
             else:
-                check(lib.bl_edge_bwd_sources(f32(g_rows), i32(ewin), i32(plan.s_edge_ptr), i32(plan.s_edge_idx), i32(plan.e_tgt),
+                check(lib.bl_edge_bwd_sources(f32(g_rows), i32(ewin), i32(plan.s_edge_ptr), i32(plan.s_edge_idx), i32(plan.s_edge_tgt),
                                               plan.num_s_pairs, M, f32(amax), du_split.data_ptr(), stream_ptr(dev)), "bl_edge_bwd_sources")
             if ctx.h_split is not None:
                 h_split, amax_h, amax_w = ctx.h_split, ctx.amax_h, ctx.amax_w

@@ -357,43 +357,77 @@ edge_bwd_targets_warp(const float* __restrict__ d_agg, const float* __restrict__
     }
 }
 
-template <int ITER>
+// UNR S-pair rows per warp, walked in lock step: the chain  edge list -> ewin row of the target -> g row  is latency-bound
+// (measured: DRAM 24 %, 18 warps stalled on the scoreboard per issue with one row per warp), so every level is issued for
+// UNR rows at once; the per-edge target comes from the plan (s_edge_tgt) instead of a dependent e_tgt[e] load.
+template <int ITER, int UNR>
 __global__ void __launch_bounds__(256)
 edge_bwd_sources_warp(const float* __restrict__ g_rows, const int* __restrict__ ewin, const int* __restrict__ s_edge_ptr,
-                      const int* __restrict__ s_edge_idx, const int* __restrict__ e_tgt, int64_t num_s_pairs,
+                      const int* __restrict__ s_edge_idx, const int* __restrict__ s_edge_tgt, int64_t num_s_pairs,
                       const float* __restrict__ amax_eff, __half* __restrict__ du_split) {
     constexpr int M4 = 32 * ITER;
     constexpr int M = 128 * ITER;
-    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t row0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * UNR;
     const int lane = threadIdx.x & 31;
-    if (row > num_s_pairs) return;
-    __half* hi_row = du_split + (size_t)row * M;
-    __half* lo_row = du_split + (size_t)(num_s_pairs + 1 + row) * M;
-    float4 acc[ITER];
+    if (row0 > num_s_pairs) return;
+    float4 acc[UNR][ITER];
+    int beg[UNR], len[UNR];
+    int max_len = 0;
 #pragma unroll
-    for (int i = 0; i < ITER; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row < num_s_pairs) {  // row == num_s_pairs: the zero (padding) row
-        const int beg = __ldg(s_edge_ptr + row), end = __ldg(s_edge_ptr + row + 1);
-        for (int j = beg; j < end; ++j) {  // ascending sorted-edge id: a fixed summation order
-            const int e = __ldg(s_edge_idx + j);
-            const int t = __ldg(e_tgt + e);
+    for (int u = 0; u < UNR; ++u) {
 #pragma unroll
-            for (int i = 0; i < ITER; ++i) {
-                const size_t off = (size_t)t * M4 + lane + 32 * i;
-                const int4 w = __ldg(reinterpret_cast<const int4*>(ewin) + off);
-                if (w.x == e || w.y == e || w.z == e || w.w == e) {
-                    const float4 gv = __ldg(reinterpret_cast<const float4*>(g_rows) + off);
-                    if (w.x == e) acc[i].x += gv.x;
-                    if (w.y == e) acc[i].y += gv.y;
-                    if (w.z == e) acc[i].z += gv.z;
-                    if (w.w == e) acc[i].w += gv.w;
-                }
+        for (int i = 0; i < ITER; ++i) acc[u][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int64_t row = row0 + u;
+        beg[u] = 0;
+        len[u] = 0;
+        if (row < num_s_pairs) {  // row == num_s_pairs: the zero (padding) row
+            beg[u] = __ldg(s_edge_ptr + row);
+            len[u] = __ldg(s_edge_ptr + row + 1) - beg[u];
+        }
+        max_len = max(max_len, len[u]);
+    }
+    for (int j = 0; j < max_len; ++j) {  // ascending sorted-edge id inside a row: a fixed summation order
+        int e[UNR], t[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            e[u] = -2;  // never equals an ewin entry (>= -1)
+            t[u] = 0;
+            if (j < len[u]) {
+                e[u] = __ldg(s_edge_idx + beg[u] + j);
+                t[u] = __ldg(s_edge_tgt + beg[u] + j);
             }
         }
+        int4 w[UNR][ITER];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+#pragma unroll
+            for (int i = 0; i < ITER; ++i)
+                w[u][i] = (j < len[u]) ? __ldg(reinterpret_cast<const int4*>(ewin) + (size_t)t[u] * M4 + lane + 32 * i)
+                                       : make_int4(-1, -1, -1, -1);
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+#pragma unroll
+            for (int i = 0; i < ITER; ++i) {
+                const int4 ww = w[u][i];
+                if (ww.x == e[u] || ww.y == e[u] || ww.z == e[u] || ww.w == e[u]) {
+                    const float4 gv = __ldg(reinterpret_cast<const float4*>(g_rows) + (size_t)t[u] * M4 + lane + 32 * i);
+                    if (ww.x == e[u]) acc[u][i].x += gv.x;
+                    if (ww.y == e[u]) acc[u][i].y += gv.y;
+                    if (ww.z == e[u]) acc[u][i].z += gv.z;
+                    if (ww.w == e[u]) acc[u][i].w += gv.w;
+                }
+            }
     }
     const float scale = pow2_scale_for(__ldg(amax_eff));
 #pragma unroll
-    for (int i = 0; i < ITER; ++i) split_store_f16x4(acc[i], scale, hi_row, lo_row, lane + 32 * i);
+    for (int u = 0; u < UNR; ++u) {
+        const int64_t row = row0 + u;
+        if (row > num_s_pairs) break;
+        __half* hi_row = du_split + (size_t)row * M;
+        __half* lo_row = du_split + (size_t)(num_s_pairs + 1 + row) * M;
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) split_store_f16x4(acc[u][i], scale, hi_row, lo_row, lane + 32 * i);
+    }
 }
 
 }  // namespace bl
@@ -489,18 +523,19 @@ extern "C" int bl_edge_bwd_targets(const float* d_agg, const float* xwin, const 
 }
 
 extern "C" int bl_edge_bwd_sources(const float* g_rows, const int32_t* ewin, const int32_t* s_edge_ptr, const int32_t* s_edge_idx,
-                                   const int32_t* e_tgt, int64_t num_s_pairs, int32_t msg_dim, const float* amax_eff,
+                                   const int32_t* s_edge_tgt, int64_t num_s_pairs, int32_t msg_dim, const float* amax_eff,
                                    void* du_split, bl_stream_t stream_) {
     if (num_s_pairs < 0 || amax_eff == nullptr) return BL_ERR_INVALID_ARGUMENT;
     if (msg_dim != 128 && msg_dim != 256 && msg_dim != 512) return BL_ERR_UNSUPPORTED;
     cudaStream_t stream = (cudaStream_t)stream_;
     const int threads = 256;
-    const unsigned grid = grid_for((num_s_pairs + 1) * 32, threads);
+    constexpr int UNR = 2;
+    const unsigned grid = grid_for(((num_s_pairs + 1 + UNR - 1) / UNR) * 32, threads);
     if (msg_dim == 128)
-        edge_bwd_sources_warp<1><<<grid, threads, 0, stream>>>(g_rows, ewin, s_edge_ptr, s_edge_idx, e_tgt, num_s_pairs, amax_eff, (__half*)du_split);
+        edge_bwd_sources_warp<1, UNR><<<grid, threads, 0, stream>>>(g_rows, ewin, s_edge_ptr, s_edge_idx, s_edge_tgt, num_s_pairs, amax_eff, (__half*)du_split);
     else if (msg_dim == 256)
-        edge_bwd_sources_warp<2><<<grid, threads, 0, stream>>>(g_rows, ewin, s_edge_ptr, s_edge_idx, e_tgt, num_s_pairs, amax_eff, (__half*)du_split);
+        edge_bwd_sources_warp<2, UNR><<<grid, threads, 0, stream>>>(g_rows, ewin, s_edge_ptr, s_edge_idx, s_edge_tgt, num_s_pairs, amax_eff, (__half*)du_split);
     else
-        edge_bwd_sources_warp<4><<<grid, threads, 0, stream>>>(g_rows, ewin, s_edge_ptr, s_edge_idx, e_tgt, num_s_pairs, amax_eff, (__half*)du_split);
+        edge_bwd_sources_warp<4, UNR><<<grid, threads, 0, stream>>>(g_rows, ewin, s_edge_ptr, s_edge_idx, s_edge_tgt, num_s_pairs, amax_eff, (__half*)du_split);
     return check_launch("bl_edge_bwd_sources");
 }

@@ -87,12 +87,14 @@ __global__ void scatter_pairs(const unsigned long long* __restrict__ keys_sorted
                               const int* __restrict__ pid_incl, int64_t E, int64_t N, int K, int block,
                               int* __restrict__ row_of_edge, int* __restrict__ pair_node,
                               unsigned* __restrict__ pair_node_key, unsigned long long* __restrict__ ukeys,
-                              int* __restrict__ count_out, int* __restrict__ edge_ptr, int* __restrict__ edge_idx) {
+                              int* __restrict__ count_out, int* __restrict__ edge_ptr, int* __restrict__ edge_idx,
+                              const int* __restrict__ e_tgt_sorted, int* __restrict__ edge_tgt) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= E) return;
     const int pid = pid_incl[i] - 1;
     row_of_edge[edge_of[i]] = pid;
     if (edge_idx != nullptr) edge_idx[i] = edge_of[i];  // sorted-edge ids grouped by pair, ascending inside a pair (stable sort)
+    if (edge_tgt != nullptr) edge_tgt[i] = e_tgt_sorted[edge_of[i]];  // ... and their target nodes (saves a dependent load)
     if (flags[i]) {
         const int node = node_of_key(keys_sorted[i], N, K, block);
         pair_node[pid] = node;
@@ -185,7 +187,7 @@ static size_t carve(Workspace* ws, void* base, int64_t E) {
 static int build_pairs(const Workspace& ws, const int* e_type, const int* node_of_edge, int64_t E,
                        int64_t N, int K, int block, int* row_of_edge, int* pair_node, int* type_ptr,
                        int* by_node_ptr, int* by_node_idx, int* count_out, int* edge_ptr, int* edge_idx,
-                       cudaStream_t stream) {
+                       const int* e_tgt_sorted, int* edge_tgt, cudaStream_t stream) {
     const int T = 256;
     const unsigned g = grid_for(E, T);
     size_t tb = ws.cub_bytes;
@@ -200,7 +202,7 @@ static int build_pairs(const Workspace& ws, const int* e_type, const int* node_o
     tb = ws.cub_bytes;
     cub::DeviceScan::InclusiveSum(ws.cub_temp, tb, ws.flags, ws.scan, (int)E, stream);
     scatter_pairs<<<g, T, 0, stream>>>(ws.k64_b, ws.v32_b, ws.flags, ws.scan, E, N, K, block, row_of_edge, pair_node,
-                                       ws.k32_a, ws.ukeys, count_out, edge_ptr, edge_idx);
+                                       ws.k32_a, ws.ukeys, count_out, edge_ptr, edge_idx, e_tgt_sorted, edge_tgt);
     pad_pairs<<<g, T, 0, stream>>>(count_out, E, N, pair_node, ws.k32_a);
     type_ptr_kernel<<<grid_for(num_segs + 1, 64), 64, 0, stream>>>(ws.ukeys, count_out, unit, num_segs, type_ptr);
     // node -> pairs CSR: stable sort of pair ids by node (padding has key N and sorts last)
@@ -229,7 +231,8 @@ extern "C" int bl_plan_build(const int32_t* src, const int32_t* tgt, const int32
                              int32_t* s_type_ptr, int32_t* s_by_node_ptr, int32_t* s_by_node_idx,
                              int32_t* t_node, int32_t* t_type_ptr, int32_t* t_by_node_ptr,
                              int32_t* t_by_node_idx, int32_t* counts, int32_t* s_edge_ptr, int32_t* s_edge_idx,
-                             int32_t* e_tgt, int32_t block_nodes, void* workspace, size_t workspace_bytes, bl_stream_t stream_) {
+                             int32_t* e_tgt, int32_t* s_edge_tgt, int32_t block_nodes, void* workspace, size_t workspace_bytes,
+                             bl_stream_t stream_) {
     if (E < 0 || N <= 0 || K <= 0 || E > 0x7ffffff0LL || N > 0x7ffffff0LL || block_nodes < 0) return BL_ERR_INVALID_ARGUMENT;
     const int num_segs = block_nodes > 0 ? (int)((N + block_nodes - 1) / block_nodes) * K : K;
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -270,11 +273,11 @@ extern "C" int bl_plan_build(const int32_t* src, const int32_t* tgt, const int32
     }
     // 2. S-pairs (type, src)
     rc = build_pairs(ws, e_type, e_src, E, N, K, block_nodes, urow, s_node, s_type_ptr, s_by_node_ptr, s_by_node_idx,
-                     counts + 0, s_edge_ptr, s_edge_idx, stream);
+                     counts + 0, s_edge_ptr, s_edge_idx, e_tgt_sorted, (s_edge_ptr != nullptr) ? s_edge_tgt : nullptr, stream);
     if (rc) return rc;
     // 3. T-pairs (type, tgt).  e_tgt_sorted aliases t_by_node_idx, which build_pairs writes only in
     // its final sort, after every read of node_of_edge (make_pair_keys) has been issued in stream order.
     rc = build_pairs(ws, e_type, e_tgt_sorted, E, N, K, block_nodes, vrow, t_node, t_type_ptr, t_by_node_ptr,
-                     t_by_node_idx, counts + 1, nullptr, nullptr, stream);
+                     t_by_node_idx, counts + 1, nullptr, nullptr, nullptr, nullptr, stream);
     return rc;
 }

@@ -48,6 +48,7 @@ def build_plan_ref(src: np.ndarray, tgt: np.ndarray, etype: np.ndarray, num_node
     out["s_edge_idx"] = by_pair
     out["s_edge_ptr"] = np.searchsorted(urow[by_pair], np.arange(s_node.shape[0] + 1), side="left")
     out["e_tgt"] = e_tgt
+    out["s_edge_tgt"] = e_tgt[by_pair]
     out = {k: np.asarray(v, dtype=np.int32) for k, v in out.items()}
     out["num_s_pairs"], out["num_t_pairs"] = int(s_node.shape[0]), int(t_node.shape[0])
     return out

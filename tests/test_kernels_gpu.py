@@ -33,7 +33,7 @@ def test_plan_bit_exact(cuda_device, N, K, epk, self_edges):
     assert plan.num_s_pairs == ref["num_s_pairs"] and plan.num_t_pairs == ref["num_t_pairs"]
     for name in ("e_perm", "e_src", "e_type", "row_ptr", "urow", "vrow", "s_node", "s_type_ptr", "s_by_node_ptr",
                  "s_by_node_idx", "t_node", "t_type_ptr", "t_by_node_ptr", "t_by_node_idx", "s_edge_ptr", "s_edge_idx",
-                 "e_tgt"):
+                 "e_tgt", "s_edge_tgt"):
         got = getattr(plan, name).cpu().numpy()
         assert got.dtype == np.int32
         np.testing.assert_array_equal(got, ref[name], err_msg=name)
@@ -50,7 +50,7 @@ def test_plan_bit_exact(cuda_device, N, K, epk, self_edges):
         assert plan.num_segs == int(ref["s_type_ptr"].shape[0]) - 1 and plan.num_s_pairs == ref["num_s_pairs"]
         for name in ("e_perm", "e_src", "e_type", "row_ptr", "urow", "vrow", "s_node", "s_type_ptr", "s_by_node_ptr",
                      "s_by_node_idx", "t_node", "t_type_ptr", "t_by_node_ptr", "t_by_node_idx", "s_edge_ptr", "s_edge_idx",
-                     "e_tgt"):
+                     "e_tgt", "s_edge_tgt"):
             np.testing.assert_array_equal(getattr(plan, name).cpu().numpy(), ref[name], err_msg=f"{name} (block {block})")
         np.testing.assert_array_equal(plan.seg_type.cpu().numpy(), np.arange(plan.num_segs) % K)
 
