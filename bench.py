@@ -598,6 +598,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # the CPU arm must not see a GPU: the kept entry point trains on cuda:0 whenever one is visible (reference
+    # modelregistry.py:155 / train.py), while the oracle underneath is a host implementation.  torch is not imported yet.
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
+    for key in ("WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):  # rank 0 runs alone; no process group
+        os.environ.pop(key, None)
+    os.environ["RANK"] = "0"
     base = cpu_train_entry(args.hidden, steps=args.steps, warmup=min(args.warmup, 2), threads=args.cpu_threads)
     print(json.dumps({
         "impl": "reference",
