@@ -24,7 +24,9 @@ class _FixerMetrics(ModuleWithMetrics):
         if selected_fixes is None:
             return
         with torch.no_grad():
-            c = torch.stack((selected_fixes[targets].sum(), torch.tensor(targets.shape[0], device=targets.device))).double()
+            # torch.full, not torch.tensor: a device tensor made from a host scalar is a synchronising H2D copy
+            n = torch.full((), targets.shape[0], device=targets.device, dtype=torch.float64)
+            c = torch.stack((selected_fixes[targets].sum().double(), n))
             self._counts = c if self._counts is None else self._counts + c
 
     def _module_metrics(self) -> Dict[str, Any]:

@@ -70,8 +70,9 @@ class LocalizationModule(ModuleWithMetrics):
             predicted = scatter_max(log_probs, groups, dim_size=has_bug.shape[0])[1]
             is_correct = predicted == correct
             no_bug = has_bug.logical_not()
-            stats = torch.stack((is_correct.sum(), -per_sample.sum(), no_bug.sum(), (no_bug & is_correct).sum(),
-                                 torch.tensor(float(per_sample.shape[0]), device=per_sample.device))).double()
+            n = torch.full((), float(per_sample.shape[0]), device=per_sample.device, dtype=torch.float64)  # no H2D copy
+            stats = torch.stack((is_correct.sum().double(), -per_sample.sum().double(), no_bug.sum().double(),
+                                 (no_bug & is_correct).sum().double(), n))
             self.__stats = stats if self.__stats is None else self.__stats + stats
             self.__num_steps += 1
         weight = self._buggy_samples_weight_schedule(self._epoch_idx)

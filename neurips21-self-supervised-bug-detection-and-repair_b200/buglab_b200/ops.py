@@ -82,9 +82,14 @@ def build_edge_plan(
     E = sum(sizes)
     src = torch.cat([a[0].reshape(-1) for a in adjacency_lists]).to(torch.int32)
     tgt = torch.cat([a[1].reshape(-1) for a in adjacency_lists]).to(torch.int32)
-    etype = torch.repeat_interleave(
-        torch.arange(K, device=device, dtype=torch.int32), torch.tensor(sizes, device=device), output_size=E
-    ) if E > 0 else torch.zeros(0, device=device, dtype=torch.int32)
+    # per-type constant runs written by fill kernels: building the counts tensor from the host list would be a
+    # synchronising H2D copy in the middle of the step
+    etype = torch.empty(E, device=device, dtype=torch.int32)
+    start = 0
+    for k, n in enumerate(sizes):
+        if n:
+            etype[start:start + n].fill_(k)
+            start += n
     return build_edge_plan_from_flat(src, tgt, etype, num_nodes, K, block_nodes)
 
 
