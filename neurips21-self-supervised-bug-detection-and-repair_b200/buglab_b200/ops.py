@@ -899,10 +899,17 @@ def _num_segments(index: torch.Tensor, dim_size: Optional[int]) -> int:
     return int(index.max().item()) + 1 if index.numel() > 0 else 0
 
 
+# Test hook (like WINNER_TRACE): when set to a list, every DIFFERENTIABLE segment max / min appends its arg tensor
+# ([S, F] positions in src; src.shape[0] for empty segments) so that an oracle can be evaluated with the same routing.
+MINMAX_TRACE: Optional[list] = None
+
+
 def segment_minmax(src, index, dim=-1, dim_size=None, is_min=False):
     src2d, was_1d = _as_LF(src.float(), dim)
     S = _num_segments(index, dim_size)
     out, arg = SegmentMinMaxFn.apply(src2d, _index32(index), S, is_min)
+    if MINMAX_TRACE is not None and torch.is_grad_enabled() and src2d.requires_grad:
+        MINMAX_TRACE.append(arg.detach().to(torch.int64).cpu())
     arg = arg.to(torch.int64)
     if was_1d:
         return out.view(-1), arg.view(-1)

@@ -664,9 +664,10 @@ struct WgParams {
     int M, Nin, ld, col0, g_rows, x_rows;
 };
 
-template <int CG>
+template <int CG, int NT_>
 struct WgCfg {
-    static constexpr int NT = 256;
+    static constexpr int NT = NT_;                                          // columns of dW per work item (256, or 64 for
+                                                                            // the narrow products of the attention backward)
     static constexpr int NTL = NT / CG;
     static constexpr uint32_t BLOCK_BYTES = CHUNK_K * 128;                  // 64 pair rows x 64 outputs, fp16
     static constexpr uint32_t A_BYTES = (TILE_M / 64) * BLOCK_BYTES;        // one part: 128 outputs of G
@@ -676,10 +677,11 @@ struct WgCfg {
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
 };
 
-template <int CG>
+template <int CG, int NT_>
 __global__ void __launch_bounds__(THREADS, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_x, const WgParams p) {
-    using Cfg = WgCfg<CG>;
+    static_assert(NT_ / CG >= 64 && (NT_ / CG) % 64 == 0, "X is staged in 64-column blocks");
+    using Cfg = WgCfg<CG, NT_>;
     constexpr int NT = Cfg::NT, NTL = Cfg::NTL, STAGES = Cfg::STAGES;
     constexpr uint32_t BLOCK_BYTES = Cfg::BLOCK_BYTES, A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES,
                        STAGE_BYTES = Cfg::STAGE_BYTES;
@@ -764,11 +766,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ 
                                             part * p.g_rows + p0);
                     }
                     __syncwarp();
+                    if constexpr (NTL >= 128) {
 #pragma unroll
-                    for (int pass = 0; pass < NTL / 128; ++pass) {  // X: 16 gather4 per 64-column block
-                        const int blk = pass * 2 + sub;
-                        tma_gather4<CG>(&map_x, &full[stage], st + 2 * A_BYTES + part * B_BYTES + blk * BLOCK_BYTES + grp * 512,
-                                        x_col0 + blk * 64, rows[0], rows[1], rows[2], rows[3]);
+                        for (int pass = 0; pass < NTL / 128; ++pass) {  // X: 16 gather4 per 64-column block
+                            const int blk = pass * 2 + sub;
+                            tma_gather4<CG>(&map_x, &full[stage], st + 2 * A_BYTES + part * B_BYTES + blk * BLOCK_BYTES + grp * 512,
+                                            x_col0 + blk * 64, rows[0], rows[1], rows[2], rows[3]);
+                        }
+                    } else if (sub == 0) {  // a single 64-column block: half the warp issues
+                        tma_gather4<CG>(&map_x, &full[stage], st + 2 * A_BYTES + part * B_BYTES + grp * 512, x_col0, rows[0], rows[1],
+                                        rows[2], rows[3]);
                     }
                 }
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -1009,7 +1016,7 @@ extern "C" int bl_rows_split_f16(const float* x, const int32_t* idx, int64_t row
 }
 
 extern "C" int bl_tma_gemm_supported(int32_t n_out, int32_t k_in) {
-    return (k_in % tg::CHUNK_K == 0) && (n_out == 128 || (n_out % 256 == 0 && n_out <= 1024)) && tg::encode_fn() != nullptr;
+    return (k_in % tg::CHUNK_K == 0) && (n_out == 64 || n_out == 128 || (n_out % 256 == 0 && n_out <= 1024)) && tg::encode_fn() != nullptr;
 }
 
 /* prefix[s] = sum_{s' < s} ceil(rows(s') / unit): the tile / slab tables the GEMMs walk (device to device, no sync). */
@@ -1074,7 +1081,7 @@ extern "C" int bl_tma_project(const void* a_split, int64_t a_rows, const int32_t
     if (num_rows == 0 || max_tiles <= 0) return BL_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     const int cg = tg::default_cg();
-    const int nt = (n_out == 128) ? 128 : 256;
+    const int nt = (n_out < 256) ? n_out : 256;
     const int ntl = nt / cg;
     CUtensorMap map_a, map_b;
     int rc = tg::make_map_f16(&map_a, a_split, (uint64_t)(2 * a_rows), (uint64_t)k_in, tg::CHUNK_K, idx ? 1u : (uint32_t)tg::TILE_M);
@@ -1090,13 +1097,16 @@ extern "C" int bl_tma_project(const void* a_split, int64_t a_rows, const int32_t
                       map_a, map_b, p)                                                                                   \
          : tg::launch(tg::proj_kernel<NT_, CG_, false>, CG_, grid, tg::ProjCfg<NT_, CG_>::SMEM_BYTES, stream, "bl_tma_project", \
                       map_a, map_b, p))
+    if (nt == 64) return cg == 2 ? BL_LAUNCH_PROJ(64, 2) : BL_LAUNCH_PROJ(64, 1);
     if (nt == 128) return cg == 2 ? BL_LAUNCH_PROJ(128, 2) : BL_LAUNCH_PROJ(128, 1);
     return cg == 2 ? BL_LAUNCH_PROJ(256, 2) : BL_LAUNCH_PROJ(256, 1);
 #undef BL_LAUNCH_PROJ
 }
 
 extern "C" int bl_tma_weight_grad_supported(int32_t m_out, int32_t n_in) {
-    return (m_out % 256 == 0) && (n_in % 256 == 0) && m_out <= 1024 && n_in <= 1024 && tg::encode_fn() != nullptr;
+    if (tg::encode_fn() == nullptr) return 0;
+    if (n_in == 64) return m_out % tg::TILE_M == 0 && m_out <= 1024;  // narrow products (attention backward): single CTAs
+    return (m_out % 256 == 0) && (n_in % 256 == 0) && m_out <= 1024 && n_in <= 1024;
 }
 
 /* d_weight[type, 0:m_out, col0:col0+n_in] = (1/scale) sum over pair rows of G[p,:]^T X[idx[p],:]  (zeroes that block first) */
@@ -1111,16 +1121,18 @@ extern "C" int bl_tma_weight_grad(const void* g_split, int64_t g_rows, const voi
                                           (size_t)num_types * m_out, stream), "bl_tma_weight_grad memset");
     if (rc) return rc;
     if (num_rows == 0 || max_slabs <= 0) return BL_OK;
-    const int cg = tg::default_cg();
+    const int cg = (n_in == 64) ? 1 : tg::default_cg();
+    const int nt = (n_in == 64) ? 64 : 256;
     CUtensorMap map_g, map_x;
     rc = tg::make_map_f16(&map_g, g_split, (uint64_t)(2 * g_rows), (uint64_t)m_out, 64, 64);
     if (rc) return rc;
     rc = tg::make_map_f16(&map_x, x_split, (uint64_t)(2 * x_rows), (uint64_t)n_in, 64, 1);
     if (rc) return rc;
     tg::WgParams p{idx, amax, amax_x, (const int4*)slabs, num_slabs, d_weight, m_out, n_in, ld, col0, (int)g_rows, (int)x_rows};
-    const int64_t items = max_slabs * (m_out / (tg::TILE_M * cg)) * (n_in / 256);
+    const int64_t items = max_slabs * (m_out / (tg::TILE_M * cg)) * (n_in / nt);
     int grid = (int)std::min<int64_t>((int64_t)(num_sms() / cg), items) * cg;
     if (grid < cg) grid = cg;
-    if (cg == 2) return tg::launch(tg::wgrad_kernel<2>, 2, grid, tg::WgCfg<2>::SMEM_BYTES, stream, "bl_tma_weight_grad", map_g, map_x, p);
-    return tg::launch(tg::wgrad_kernel<1>, 1, grid, tg::WgCfg<1>::SMEM_BYTES, stream, "bl_tma_weight_grad", map_g, map_x, p);
+    if (nt == 64) return tg::launch(tg::wgrad_kernel<1, 64>, 1, grid, tg::WgCfg<1, 64>::SMEM_BYTES, stream, "bl_tma_weight_grad", map_g, map_x, p);
+    if (cg == 2) return tg::launch(tg::wgrad_kernel<2, 256>, 2, grid, tg::WgCfg<2, 256>::SMEM_BYTES, stream, "bl_tma_weight_grad", map_g, map_x, p);
+    return tg::launch(tg::wgrad_kernel<1, 256>, 1, grid, tg::WgCfg<1, 256>::SMEM_BYTES, stream, "bl_tma_weight_grad", map_g, map_x, p);
 }

@@ -124,9 +124,35 @@ class LocalizationModule(nn.Module):
         self._summary_repr = nn.Linear(dim, dim)
         self._l1 = nn.Linear(2 * dim, dim)
         self._repr_to_localization_score = nn.Linear(dim, 1, bias=False)
+        # Like the message-passing layers (mp_ref.MlpMessagePassingLayer.forced_winners): route the per-sample max over the
+        # candidates like another implementation did ([S, dim] candidate positions; C = empty) and audit that routing
+        # against this evaluation's own maximum.  Two candidates within rounding distance of each other may legitimately
+        # swap; one swap moves ~1/(S*dim) of the gradient mass, far above the elementwise gradient tolerance.
+        self.forced_summary_args = None
+        self.routing_audit = None
+
+    def _summary(self, candidate_reprs, candidate_to_sample_idx):
+        projected = self._summary_repr(candidate_reprs)
+        own_max, own_arg = scatter_max(projected, candidate_to_sample_idx, dim=0)
+        if self.forced_summary_args is None:
+            return own_max
+        arg, C = self.forced_summary_args, projected.shape[0]
+        picked = projected.gather(0, arg.clamp(max=C - 1))
+        forced = torch.where(arg >= C, torch.zeros_like(picked), picked)
+        with torch.no_grad():
+            valid = arg < C
+            sample_of_winner = candidate_to_sample_idx[arg.clamp(max=C - 1)]
+            wrong_segment = valid & (sample_of_winner != torch.arange(arg.shape[0]).view(-1, 1))
+            deficit = (own_max - forced) / (1.0 + own_max.abs())
+            self.routing_audit = dict(
+                decisions=int(arg.numel()), differing=int((arg != own_arg).sum()), wrong_segment=int(wrong_segment.sum()),
+                empty_mismatch=int(((arg >= C) != (own_arg >= C)).sum()),
+                max_relative_deficit=float(deficit.max()) if deficit.numel() else 0.0,
+                later_edge_on_exact_tie=int((valid & (own_arg < C) & (arg > own_arg) & (forced == own_max)).sum()))
+        return forced
 
     def compute_localization_logprobs(self, candidate_reprs, candidate_to_sample_idx, num_samples):  # :54-79
-        summary = scatter_max(self._summary_repr(candidate_reprs), candidate_to_sample_idx, dim=0)[0][candidate_to_sample_idx]
+        summary = self._summary(candidate_reprs, candidate_to_sample_idx)[candidate_to_sample_idx]
         l1 = torch.sigmoid(self._l1(torch.cat([candidate_reprs, summary], dim=-1)))
         scores = self._repr_to_localization_score(l1).squeeze(-1)
         arange = torch.arange(num_samples, dtype=torch.int64)
@@ -192,6 +218,23 @@ class GnnBugLabModule(nn.Module):
 
     def node_representations(self, graph_data):
         return self._gnn(graph_data["node_data"], graph_data["adjacency_lists"])
+
+    def force_routing(self, mp_winners, head_args) -> None:
+        """Evaluate with another implementation's max-routing: ``mp_winners`` = its per-layer winning edges
+        (``ops.WINNER_TRACE``), ``head_args`` = the args of its differentiable segment maxima in call order
+        (``ops.MINMAX_TRACE``; the discriminator step has exactly one: the localisation module's candidate summary).
+        ``None`` restores this module's own argmax."""
+        self._gnn.force_winners(mp_winners)
+        if head_args is not None:
+            assert len(head_args) == 1, f"expected one traced head maximum, got {len(head_args)}"
+        self.__localization_module.forced_summary_args = head_args[0] if head_args is not None else None
+
+    def routing_audits(self):
+        """Audits of the last forced routing: the message-passing layers', then the localisation summary's."""
+        audits = list(self._gnn.routing_audits())
+        if self.__localization_module.forced_summary_args is not None:
+            audits.append(self.__localization_module.routing_audit)
+        return audits
 
     def compute_localization_logprobs(self, graph_data):  # gnn.py:125-142
         states = self.node_representations(graph_data)

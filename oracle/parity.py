@@ -94,7 +94,9 @@ def assert_routing_is_valid(audits, what: str = "", max_relative_deficit: float 
         assert a["max_relative_deficit"] <= max_relative_deficit, (
             f"{what}: layer {i}: a forced winner falls short of the exact maximum by {a['max_relative_deficit']:.2e} (relative)")
         frac = a["differing"] / max(a["decisions"], 1)
-        assert frac <= max_differing_frac, f"{what}: layer {i}: {frac:.2e} of the winners differ from the exact argmax"
+        # (small audits — the localisation summary has samples x hidden decisions — may hold a handful of near-ties)
+        assert frac <= max_differing_frac or a["differing"] <= 4, (
+            f"{what}: layer {i}: {frac:.2e} of the winners differ from the exact argmax")
         worst["differing_frac"] = max(worst["differing_frac"], frac)
         worst["max_relative_deficit"] = max(worst["max_relative_deficit"], a["max_relative_deficit"])
     return worst

@@ -46,12 +46,13 @@ for label, flags in CONFIGS:
     adj.plan = None
     adj.block_nodes = ops.plan_block_nodes_for(getattr(model.gnn_model, "_mp_layer_dims", ()))
     nn.zero_grad(); ref.zero_grad(); nn.train()
-    ops.WINNER_TRACE = []
+    ops.WINNER_TRACE, ops.MINMAX_TRACE = [], []
     loss = nn(**mb)
     winners, ops.WINNER_TRACE = ops.WINNER_TRACE, None
+    head_args, ops.MINMAX_TRACE = ops.MINMAX_TRACE, None
     loss.backward()
     torch.cuda.synchronize()
-    ref._gnn.force_winners(winners)
+    ref.force_routing(winners, head_args)
     loss_ref = ref(**mb_cpu)
     loss_ref.backward()
     ref_grads = dict(ref.named_parameters())

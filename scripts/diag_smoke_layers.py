@@ -57,12 +57,13 @@ for use_tma in (True, False):
     nn.zero_grad(); ref.zero_grad(); nn.train()
     got, exp = {}, {}
     hs = hooked(gpu_layers, got) + hooked(ref_layers, exp)
-    ops.WINNER_TRACE = []
+    ops.WINNER_TRACE, ops.MINMAX_TRACE = [], []
     loss = nn(**mb)
     winners, ops.WINNER_TRACE = ops.WINNER_TRACE, None
+    head_args, ops.MINMAX_TRACE = ops.MINMAX_TRACE, None
     loss.backward()
     torch.cuda.synchronize()
-    ref._gnn.force_winners(winners)
+    ref.force_routing(winners, head_args)
     loss_ref = ref(**mb_cpu)
     loss_ref.backward()
     for h in hs:

@@ -46,12 +46,13 @@ def _check_steps(model, nn, ref, tensors, device, minibatch_size, what, max_batc
             break
         nn.zero_grad(); ref.zero_grad()
         nn.train()
-        ops.WINNER_TRACE = []
+        ops.WINNER_TRACE, ops.MINMAX_TRACE = [], []
         loss = nn(**mb)
         winners, ops.WINNER_TRACE = ops.WINNER_TRACE, None
+        head_args, ops.MINMAX_TRACE = ops.MINMAX_TRACE, None   # the localisation module's max over the candidates
         loss.backward()
         mb_cpu = model_ref.minibatch_to_cpu(mb)
-        ref._gnn.force_winners(None)
+        ref.force_routing(None, None)
         loss_ref, det = ref(**mb_cpu, return_details=True)
 
         ref64 = copy.deepcopy(ref).double()  # fp64 referee: exact evaluation of the same semantics (oracle/parity.py)
@@ -69,14 +70,15 @@ def _check_steps(model, nn, ref, tensors, device, minibatch_size, what, max_batc
 
         # ROUTING, verified independently of the conditioning below: the exact (fp64) oracle audits every winner the
         # GPU path chose against its own segment maxima (oracle/parity.py::assert_routing_is_valid)
-        ref64._gnn.force_winners(winners)
+        ref64.force_routing(winners, head_args)
         ref64(**mb_cpu)
-        routing = parity.assert_routing_is_valid(ref64._gnn.routing_audits(), what)
-        # GRADIENTS: oracle re-run with the GPU path's max-routing forced -> elementwise comparable
-        ref._gnn.force_winners(winners)
+        routing = parity.assert_routing_is_valid(ref64.routing_audits(), what)
+        # GRADIENTS: oracle re-run with the GPU path's max-routing forced (message-passing layers AND the localisation
+        # module's candidate summary) -> elementwise comparable
+        ref.force_routing(winners, head_args)
         ref.zero_grad()
         ref(**mb_cpu).backward()
-        ref._gnn.force_winners(None)
+        ref.force_routing(None, None)
         ref_params = dict(ref.named_parameters())
         worst_frac = worst_l2 = 0.0
         for name, p in nn.named_parameters():

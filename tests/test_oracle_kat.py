@@ -146,3 +146,37 @@ def test_routing_audit_accepts_the_exact_argmax_and_rejects_wrong_edges():
     bad = own_arg.clone(); bad[N - 1, 0] = 0
     with pytest.raises(AssertionError):
         parity.assert_routing_is_valid(audit(bad)[1], "edge claimed for an empty segment")
+
+
+def test_localization_summary_forced_routing_and_audit():
+    """The oracle's localisation module under forced candidate-summary routing: its own argmax reproduces the unforced
+    log-probabilities and gradients and audits clean; a winner from another sample is flagged; a near-tie swap is accepted
+    with a tiny deficit (oracle/model_ref.py::LocalizationModule._summary)."""
+    import pytest
+
+    from oracle import parity
+    from oracle.model_ref import LocalizationModule
+
+    torch.manual_seed(4)
+    dim, C, S = 8, 11, 3
+    mod = LocalizationModule(dim).double()
+    reprs = torch.randn(C, dim, dtype=torch.float64, requires_grad=True)
+    to_sample = torch.tensor([0, 0, 0, 0, 1, 1, 1, 2, 2, 2, 2])
+    _, lp, _ = mod.compute_localization_logprobs(reprs, to_sample, S)
+    lp.sum().backward()
+    grad_own = reprs.grad.clone()
+    own_arg = scatter_ref.scatter_max(mod._summary_repr(reprs), to_sample, dim=0)[1]
+
+    mod.forced_summary_args = own_arg
+    reprs.grad = None
+    _, lp_forced, _ = mod.compute_localization_logprobs(reprs, to_sample, S)
+    lp_forced.sum().backward()
+    assert torch.equal(lp_forced, lp) and torch.equal(reprs.grad, grad_own)
+    assert parity.assert_routing_is_valid([mod.routing_audit], "own argmax")["differing_frac"] == 0.0
+
+    wrong = own_arg.clone()
+    wrong[0, 0] = 5  # a candidate of sample 1 routed into sample 0
+    mod.forced_summary_args = wrong
+    mod.compute_localization_logprobs(reprs, to_sample, S)
+    with pytest.raises(AssertionError, match="not in-edges"):
+        parity.assert_routing_is_valid([mod.routing_audit], "wrong sample")
