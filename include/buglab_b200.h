@@ -360,8 +360,9 @@ int bl_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
  *   col_query / col_tab list the same entries grouped by (b, key) with ascending query rows.  Duplicates add up.
  *   p_drop / seed: dropout on the attention probabilities (multihead_attention.py:77), counter-based mask over
  *   (seed, b, h, query, key) as in the other kernels; pass the same pair to the backward call.
- * STATUS: first correct path (fp32 CUDA cores, one thread per row).  The arithmetic is pinned against the oracle through
- * the host emulation of the same source (csrc/seq_attention_core.h); B200 parity tests are gated until they have run.
+ * This is the fp32 CUDA-core path (one thread per row), kept for shapes the tensor-core path below does not cover (padded
+ * length > 512) and as its referee; its arithmetic is pinned against the oracle through the host emulation of the same
+ * source (csrc/seq_attention_core.h) and on B200 by tests/test_seq_attention_gpu.py.
  * ------------------------------------------------------------------------------------------------ */
 int bl_seq_attention_supported(int32_t head_dim);
 int bl_seq_attention_fwd(const float* q, const float* k, const float* v, const int32_t* lengths, const float* bias,
@@ -376,6 +377,31 @@ int bl_seq_attention_bwd(const float* q, const float* k, const float* v, const i
                          int32_t B, int32_t H, int32_t L, int32_t D, int32_t T2, float p_drop, uint64_t seed,
                          const float* out, const float* lse, const float* d_out, float* dq, float* dk, float* dv,
                          float* d_entry_bias, float* d_entry_vbias, float* delta, bl_stream_t stream);
+
+/* Tensor-core path of the same attention (csrc/seq_attention_tc.cu; head size <= 64 zero-padded to 64, padded length
+ * Lp in {128, 256, 512} >= L).  The GEMM-shaped products run on the TMA-fed tcgen05 kernels above, one segment per
+ * (sample, head) whose "weight matrix" is that head's K, V, Q or dO:
+ *     forward   S  = Q K^T    bl_tma_project (n_out = Lp, k_in = 64)      O  = P' V     bl_tma_project (n_out = 64, k_in = Lp)
+ *     backward  dP = dO V^T   bl_tma_project                              dQ = dS K     bl_tma_project
+ *               dK = dS^T Q,  dV = P'^T dO                                bl_tma_weight_grad (m_out = Lp, n_in = 64)
+ * and the two row kernels below do everything in between, one warp per (sample, head, query) row of the score tile.
+ *   bl_seq_softmax_fwd: scores [B*H*Lp, Lp] (in: Q K^T; out: + the typed-edge terms <q_i, bias[tab_e]>, kept for backward);
+ *     q [B*H*Lp, 64]; lse [B*H*Lp]; p_split: fp16 hi/lo split table [2][B*H*Lp + 1][Lp] of P' = dropout(softmax) scaled by
+ *     the power of two derived from *amax_p (pass 1 / (1 - p_drop)); o_extra [B*H*Lp, 64] = the value-bias terms of "rat"
+ *     (NULL iff vbias is NULL).  row_ptr / row_key / row_tab as above (indexed with the unpadded L).
+ *   bl_seq_softmax_bwd: d_scores [B*H*Lp, Lp] (in: dP = dO V^T; out: dS); out / d_out [B*H*Lp, 64]; p_split recomputed;
+ *     dq_extra [B*H*Lp, 64] = entry terms of dQ; d_entry_bias / d_entry_vbias [entries, H, d_entry_dim] as in
+ *     bl_seq_attention_bwd (d_entry_dim = the caller's unpadded head size). */
+int bl_seq_attention_tc_supported(int32_t head_dim, int32_t max_len);
+int bl_seq_softmax_fwd(float* scores, const float* q, const int32_t* lengths, const float* bias, const float* vbias,
+                       const int32_t* row_ptr, const int32_t* row_key, const int32_t* row_tab, int32_t B, int32_t H, int32_t L,
+                       int32_t Lp, int32_t T2, float p_drop, uint64_t seed, const float* amax_p, float* lse, void* p_split,
+                       float* o_extra, bl_stream_t stream);
+int bl_seq_softmax_bwd(const float* scores, const float* lse, const float* q, const int32_t* lengths, const float* bias,
+                       const float* vbias, const int32_t* row_ptr, const int32_t* row_key, const int32_t* row_tab, int32_t B,
+                       int32_t H, int32_t L, int32_t Lp, int32_t T2, float p_drop, uint64_t seed, const float* amax_p,
+                       const float* out, const float* d_out, float* d_scores, void* p_split, float* dq_extra,
+                       float* d_entry_bias, float* d_entry_vbias, int32_t d_entry_dim, bl_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -79,6 +79,9 @@ _SIGNATURES = {
     "bl_seq_attention_supported": (c_i32, [c_i32]),
     "bl_seq_attention_fwd": (c_i32, [c_ptr] * 9 + [c_i32] * 5 + [c_f32, c_u64] + [c_ptr, c_ptr, c_ptr]),
     "bl_seq_attention_bwd": (c_i32, [c_ptr] * 12 + [c_i32] * 5 + [c_f32, c_u64] + [c_ptr] * 9 + [c_ptr]),
+    "bl_seq_attention_tc_supported": (c_i32, [c_i32, c_i32]),
+    "bl_seq_softmax_fwd": (c_i32, [c_ptr] * 8 + [c_i32] * 5 + [c_f32, c_u64] + [c_ptr] * 4 + [c_ptr]),
+    "bl_seq_softmax_bwd": (c_i32, [c_ptr] * 9 + [c_i32] * 5 + [c_f32, c_u64] + [c_ptr] * 8 + [c_i32, c_ptr]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -125,6 +128,7 @@ KERNELS_PER_CALL = {
     "bl_pair_project_bwd_weight": 1, "bl_rows_split2_f16": 1, "bl_grouped_colsum": 1, "bl_absmax": 1, "bl_weight_parts_f16": 1,
     "bl_pair_project_tc": 1, "bl_pair_weight_grad_tc": 1, "bl_tma_project": 1, "bl_tma_project_stationary": 1, "bl_tma_weight_grad": 1,
     "bl_segment_unit_prefix": 1, "bl_segment_units": 2, "bl_seq_attention_fwd": 1, "bl_seq_attention_bwd": 2,
+    "bl_seq_softmax_fwd": 1, "bl_seq_softmax_bwd": 1,
 }
 launch_counter = {"kernels": 0, "calls": 0}
 

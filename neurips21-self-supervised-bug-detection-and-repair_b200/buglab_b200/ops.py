@@ -1118,11 +1118,131 @@ class SeqEdgeAttentionFn(torch.autograd.Function):
         return dq, dk, dv, d_bias, d_vbias, None, None, None
 
 
+# Tensor-core path (csrc/seq_attention_tc.cu + csrc/gemm_tma.cu).  BUGLAB_B200_SEQ_TC=0 keeps the fp32 CUDA-core kernels.
+SEQ_ATTENTION_TC = os.environ.get("BUGLAB_B200_SEQ_TC", "1") != "0"
+_SEQ_HEAD = 64  # the tensor-core path's head size (smaller heads are zero-padded)
+
+
+def _seq_tc_ok(q: torch.Tensor) -> bool:
+    if not (SEQ_ATTENTION_TC and USE_TMA and q.is_cuda):
+        return False
+    lib = _lib.load()
+    L, D = int(q.shape[2]), int(q.shape[3])
+    return bool(lib.bl_seq_attention_tc_supported(D, L)) and bool(lib.bl_tma_gemm_supported(_SEQ_HEAD, _SEQ_HEAD)) and \
+        bool(lib.bl_tma_weight_grad_supported(128, _SEQ_HEAD))
+
+
+def _pad_heads(x: torch.Tensor, Lp: int) -> torch.Tensor:
+    """[B, H, L, D] -> contiguous [B, H, Lp, 64], zero-padded."""
+    B, H, L, D = x.shape
+    if L == Lp and D == _SEQ_HEAD:
+        return x.contiguous()
+    return torch.nn.functional.pad(x, (0, _SEQ_HEAD - D, 0, Lp - L)).contiguous()
+
+
+class SeqEdgeAttentionTcFn(torch.autograd.Function):
+    """The same function as :class:`SeqEdgeAttentionFn` with the four GEMM-shaped products on the TMA-fed tcgen05 kernels
+    (split-fp16, fp32-class accuracy), one segment per (sample, head) whose "weight matrix" is that head's K / V / Q / dO,
+    and warp-per-row kernels for everything between them (entry terms, mask, softmax, dropout, split tables, entry
+    gradients).  The [B*H*Lp, Lp] score tile goes through HBM (537 MB at B=64, H=8, Lp=512: ~0.1 ms per pass)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, bias, vbias, plan: SeqAttentionPlan, p_drop: float = 0.0, seed: int = 0):
+        lib = _lib.load()
+        B, H, L, D = q.shape
+        if (B, L) != (plan.num_samples, plan.max_len) or bias.shape != (plan.num_tables, H, D):
+            raise ValueError(f"shape mismatch: q {tuple(q.shape)}, bias {tuple(bias.shape)}, plan B={plan.num_samples} "
+                             f"L={plan.max_len} tables={plan.num_tables}")
+        dev = q.device
+        Lp = 128 if L <= 128 else (256 if L <= 256 else 512)
+        G, R = B * H, B * H * Lp
+        qp, kp, vp = _pad_heads(q, Lp), _pad_heads(k, Lp), _pad_heads(v, Lp)
+        pad_d = (0, _SEQ_HEAD - D)
+        bias_p = torch.nn.functional.pad(bias, pad_d).contiguous()
+        vbias_p = torch.nn.functional.pad(vbias, pad_d).contiguous() if vbias is not None else None
+        seg = torch.arange(G + 1, device=dev, dtype=torch.int32) * Lp
+        tiles = segment_units(seg, None, tma_tile_rows(), R)
+        slabs = segment_units(seg, None, tma_slab_rows(), R)
+        amax_q, amax_k, amax_v = absmax(qp), absmax(kp), absmax(vp)
+        q_split = rows_split(qp.view(R, _SEQ_HEAD), None, amax_q)
+        scores = tma_project(q_split, None, weight_parts(kp.view(G, Lp, _SEQ_HEAD), Lp, _SEQ_HEAD, 0, False, amax_k), None,
+                             amax_q, tiles, R, None, amax_k)                                    # S = Q K^T  [R, Lp]
+        amax_p = torch.full((1,), 1.0 / (1.0 - float(p_drop)), device=dev, dtype=torch.float32)
+        p_split = torch.empty((2, R + 1, Lp), device=dev, dtype=torch.float16)
+        lse = torch.empty(R, device=dev, dtype=torch.float32)
+        o_extra = torch.empty((R, _SEQ_HEAD), device=dev, dtype=torch.float32) if vbias is not None else None
+        check(lib.bl_seq_softmax_fwd(f32(scores), f32(qp), i32(plan.lengths), f32(bias_p),
+                                     f32(vbias_p) if vbias_p is not None else None, i32(plan.row_ptr), i32(plan.row_key),
+                                     i32(plan.row_tab), B, H, L, Lp, plan.num_tables, float(p_drop), int(seed), f32(amax_p),
+                                     f32(lse), p_split.data_ptr(), f32(o_extra) if o_extra is not None else None,
+                                     stream_ptr(dev)), "bl_seq_softmax_fwd")
+        out_p = tma_project(p_split, None, weight_parts(vp.view(G, Lp, _SEQ_HEAD), _SEQ_HEAD, Lp, 0, True, amax_v), None, amax_p,
+                            tiles, R, None, amax_v)                                             # O = P' V  [R, 64]
+        if o_extra is not None:
+            out_p += o_extra
+        ctx.plan, ctx.dims = plan, (B, H, L, D, Lp)
+        ctx.dropout = (float(p_drop), int(seed))
+        ctx.has_vbias = vbias is not None
+        ctx.units = (tiles, slabs)
+        ctx.save_for_backward(qp, kp, vp, bias_p, vbias_p if vbias_p is not None else bias_p.new_zeros(0), scores, lse, out_p,
+                              amax_q, amax_k, amax_v, amax_p)
+        return out_p.view(B, H, Lp, _SEQ_HEAD)[:, :, :L, :D].contiguous()
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        qp, kp, vp, bias_p, vbias_p, scores, lse, out_p, amax_q, amax_k, amax_v, amax_p = ctx.saved_tensors
+        vbias_p = vbias_p if ctx.has_vbias else None
+        plan: SeqAttentionPlan = ctx.plan
+        B, H, L, D, Lp = ctx.dims
+        tiles, slabs = ctx.units
+        dev = qp.device
+        G, R = B * H, B * H * Lp
+        gp = _pad_heads(d_out, Lp).view(R, _SEQ_HEAD)
+        amax_g = absmax(gp)
+        g_split = rows_split(gp, None, amax_g)
+        d_scores = tma_project(g_split, None, weight_parts(vp.view(G, Lp, _SEQ_HEAD), Lp, _SEQ_HEAD, 0, False, amax_v), None,
+                               amax_g, tiles, R, None, amax_v)                                  # dP = dO V^T  [R, Lp]
+        entries = int(plan.row_key.shape[0])
+        p_split = torch.empty((2, R + 1, Lp), device=dev, dtype=torch.float16)
+        dq_extra = torch.empty((R, _SEQ_HEAD), device=dev, dtype=torch.float32)
+        d_entry_bias = torch.empty((max(entries, 1), H, D), device=dev, dtype=torch.float32)
+        d_entry_vbias = torch.empty_like(d_entry_bias) if vbias_p is not None else None
+        check(lib.bl_seq_softmax_bwd(f32(scores), f32(lse), f32(qp), i32(plan.lengths), f32(bias_p),
+                                     f32(vbias_p) if vbias_p is not None else None, i32(plan.row_ptr), i32(plan.row_key),
+                                     i32(plan.row_tab), B, H, L, Lp, plan.num_tables, ctx.dropout[0], ctx.dropout[1], f32(amax_p),
+                                     f32(out_p), f32(gp), f32(d_scores), p_split.data_ptr(), f32(dq_extra), f32(d_entry_bias),
+                                     f32(d_entry_vbias) if d_entry_vbias is not None else None, D, stream_ptr(dev)),
+              "bl_seq_softmax_bwd")                                                             # d_scores now holds dS
+        amax_ds = absmax(d_scores)
+        ds_split = rows_split(d_scores, None, amax_ds)
+        del d_scores
+        dq = tma_project(ds_split, None, weight_parts(kp.view(G, Lp, _SEQ_HEAD), _SEQ_HEAD, Lp, 0, True, amax_k), None, amax_ds,
+                         tiles, R, None, amax_k)                                                # dQ = dS K  [R, 64]
+        dq += dq_extra
+        identity = torch.arange(R, device=dev, dtype=torch.int32)
+        q_split = rows_split(qp.view(R, _SEQ_HEAD), None, amax_q)
+        dk = torch.empty((G, Lp, _SEQ_HEAD), device=dev, dtype=torch.float32)
+        tma_weight_grad(ds_split, q_split, identity, amax_ds, slabs, dk, 0, amax_q)             # dK = dS^T Q
+        dv = torch.empty((G, Lp, _SEQ_HEAD), device=dev, dtype=torch.float32)
+        tma_weight_grad(p_split, g_split, identity, amax_p, slabs, dv, 0, amax_g)               # dV = P'^T dO
+
+        def unpad(x):
+            return x.view(B, H, Lp, _SEQ_HEAD)[:, :, :L, :D].contiguous()
+
+        tabs = plan.row_tab.long()
+        d_bias = torch.zeros((plan.num_tables, H, D), device=dev, dtype=torch.float32).index_add_(0, tabs, d_entry_bias[:entries])
+        d_vbias = (torch.zeros((plan.num_tables, H, D), device=dev, dtype=torch.float32).index_add_(0, tabs, d_entry_vbias[:entries])
+                   if vbias_p is not None else None)
+        return unpad(dq), unpad(dk), unpad(dv), d_bias, d_vbias, None, None, None
+
+
 def seq_edge_attention(q, k, v, bias, vbias, plan: SeqAttentionPlan, p_drop: float = 0.0, training: bool = False) -> torch.Tensor:
     """``p_drop``: dropout on the attention probabilities (active when ``training``); the mask is a pure function of a fresh
     seed and the (sample, head, query, key) index, recomputed in backward."""
     p = float(p_drop) if training else 0.0
-    return SeqEdgeAttentionFn.apply(q, k, v, bias, vbias, plan, p, fresh_seed() if p > 0 else 0)
+    fn = SeqEdgeAttentionTcFn if _seq_tc_ok(q) else SeqEdgeAttentionFn
+    return fn.apply(q, k, v, bias, vbias, plan, p, fresh_seed() if p > 0 else 0)
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -6,7 +6,7 @@ OUT=../buglab_b200/libbuglab_b200.so
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O3 --expt-relaxed-constexpr)
 if [[ "${1:-}" == "-v" ]]; then FLAGS+=(-Xptxas -v); fi
-SRCS=(api.cu plan.cu rows.cu edge_segmax.cu gemm.cu pair_project_tc.cu gemm_tma.cu node_update.cu segment_ops.cu embed.cu optim.cu seq_attention.cu)
+SRCS=(api.cu plan.cu rows.cu edge_segmax.cu gemm.cu pair_project_tc.cu gemm_tma.cu node_update.cu segment_ops.cu embed.cu optim.cu seq_attention.cu seq_attention_tc.cu)
 OBJS=()
 pids=()
 mkdir -p build

@@ -133,7 +133,8 @@ def main():
     both_ms = start.elapsed_time(end) / args.steps
     lengths = mb["token_sequence_lengths"].double()
     flops_fwd = float((4.0 * H * d * lengths * lengths).sum())        # unmasked part of QK^T and PV
-    out["attention"] = {"padded_length": int(L), "entries": int(plan.row_key.shape[0]), "fwd_ms": round(fwd_ms, 3),
+    out["attention"] = {"backend": "tensor-core (tcgen05 GEMMs + row kernels)" if ops._seq_tc_ok(q) else "cuda-core (fp32, thread per row)",
+                        "padded_length": int(L), "entries": int(plan.row_key.shape[0]), "fwd_ms": round(fwd_ms, 3),
                         "fwd_bwd_ms": round(both_ms, 3), "fwd_tflops": round(flops_fwd / (fwd_ms / 1e3) / 1e12, 2)}
     print(json.dumps(out))
 

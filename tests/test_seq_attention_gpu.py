@@ -19,11 +19,15 @@ pytestmark = [pytest.mark.gpu,
                                  reason="seq-attention GPU parity switched off by BUGLAB_B200_SEQ_GPU=0")]
 
 
+@pytest.mark.parametrize("backend", ["tensor-core", "cuda-core"])
 @pytest.mark.parametrize("case_index", range(7))
-def test_kernels_match_oracle(cuda_device, case_index):
+def test_kernels_match_oracle(cuda_device, monkeypatch, case_index, backend):
+    """``tensor-core``: QK^T / PV / dP / dQ / dK / dV on the TMA-fed tcgen05 GEMMs + the warp-per-row softmax kernels
+    (csrc/seq_attention_tc.cu); ``cuda-core``: the fp32 one-thread-per-row kernels (csrc/seq_attention.cu)."""
     import test_seq_attention_emul as emul
     from buglab_b200 import ops
 
+    monkeypatch.setattr(ops, "SEQ_ATTENTION_TC", backend == "tensor-core")
     case = emul.CASES[case_index]
     att, x, mask, edges, edge_types, weights = emul.random_case(*case)
     types = case[6]
@@ -46,6 +50,7 @@ def test_kernels_match_oracle(cuda_device, case_index):
     vbias = None
     if att._use_edge_value_biases:
         vbias = torch.cat((params["_edge_value_biases.weight"], params["_reverse_edge_value_biases.weight"])).view(-1, H, dk)
+    assert ops._seq_tc_ok(q) == (backend == "tensor-core")
     out = ops.seq_edge_attention(q, k, v, bias, vbias, plan)
     got = out.permute(0, 2, 1, 3).reshape(B, L, -1) @ params["_out_proj.weight"].t()
     assert float((got.detach().cpu() - expected.detach())[keep].abs().max()) < 1e-5
@@ -54,6 +59,45 @@ def test_kernels_match_oracle(cuda_device, case_index):
     for name, ref in ref_grads.items():
         err = float((params[name].grad.cpu() - ref).abs().max())
         assert err <= 5e-5 * float(ref.abs().max()) + 5e-6, (name, err)
+
+
+def test_tensor_core_attention_at_config4_shape(cuda_device, monkeypatch):
+    """BASELINE config 4's attention shape (8 heads of 64, sequences up to 512 tokens; 6 samples here) with dropout on the
+    probabilities and value biases ("rat"): the tensor-core path against the fp32 CUDA-core kernels, which the cases above
+    pin to the oracle — outputs and all gradients."""
+    from buglab_b200 import ops
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(11)
+    B, H, L, D, T = 6, 8, 512, 64, 5
+    lengths = torch.tensor([512, 301, 17, 448, 129, 256])
+    n_edges = 4000
+    eb = torch.randint(0, B, (n_edges,), generator=g)
+    es = (torch.rand(n_edges, generator=g) * lengths[eb]).long()
+    et = (torch.rand(n_edges, generator=g) * lengths[eb]).long()
+    edges = torch.stack((eb, es, et))
+    edge_types = torch.randint(0, T, (n_edges,), generator=g)
+    plan = ops.build_seq_attention_plan(edges.to(dev), edge_types.to(dev), lengths.to(dev), L, T)
+
+    def run(tc: bool):
+        monkeypatch.setattr(ops, "SEQ_ATTENTION_TC", tc)
+        gen = torch.Generator().manual_seed(5)
+        leaves = [torch.randn(B, H, L, D, generator=gen).mul_(s).to(dev).requires_grad_(True) for s in (0.35, 1.0, 1.0)]
+        leaves += [(torch.randn(2 * T, H, D, generator=gen) * 0.3).to(dev).requires_grad_(True) for _ in range(2)]
+        q, k, v, bias, vbias = leaves
+        fn = ops.SeqEdgeAttentionTcFn if tc else ops.SeqEdgeAttentionFn
+        assert ops._seq_tc_ok(q) == tc
+        out = fn.apply(q, k, v, bias, vbias, plan, 0.1, 1234)
+        w = torch.randn(B, H, L, D, generator=gen).to(dev)
+        keep = (torch.arange(L, device=dev).view(1, 1, L, 1) < lengths.to(dev).view(B, 1, 1, 1)).float()
+        (out * w * keep).sum().backward()
+        return [out.detach() * keep] + [t.grad for t in leaves]
+
+    got, ref = run(True), run(False)
+    for name, a, e in zip(("out", "dq", "dk", "dv", "d_bias", "d_vbias"), got, ref):
+        scale = float(e.abs().max())
+        err = float((a - e).abs().max())
+        assert err <= 2e-5 * scale + 1e-6, (name, err, scale)
 
 
 @pytest.mark.parametrize("layer_type", ["great", "rat", "transformer", "gru"])

@@ -30,6 +30,9 @@ PROJECT_CASES = [
     ([70000, 41000], None, 256, 256, True, True, False),          # several tiles per CTA pair: ring + accumulator reuse
     ([3000, 2000], None, 512, 512, False, False, True),           # the wide layers' backward shape
     ([9000, 4100, 50, 0, 300], None, 256, 256, False, True, True),  # contiguous 256 x 256 with several slabs per segment
+    ([512, 512, 300], None, 64, 512, False, False, True),         # attention scores: one 64-deep chunk per tile
+    ([1024, 512, 77], None, 512, 64, False, False, True),         # attention P'V / dS K: 64-wide output tile
+    ([700, 33, 260], None, 256, 64, True, True, False),           # 64-wide output, gathered rows, bias
 ]
 
 WGRAD_CASES = [
@@ -38,6 +41,8 @@ WGRAD_CASES = [
     ([9000, 4100, 50], None, 256, 256),        # > one 4096-row slab per type
     ([5000, 300], None, 512, 512),             # wide layers: 2 x 2 output tiles per slab (pairs) / 4 x 2 (single CTAs)
     ([600, 500, 4200, 64], [1, 0, 1, 0], 256, 256),
+    ([512, 512, 384], None, 512, 64),          # attention dK / dV: 64-wide products on single CTAs
+    ([128, 300], None, 128, 64),
 ]
 
 _DRIVER = r"""
