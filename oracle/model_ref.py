@@ -205,10 +205,24 @@ class GnnBugLabModule(nn.Module):
 
     def __init__(self, hidden: int, num_edge_types: int, vocabulary_size: int, rewrite_vocabulary_size: int,
                  dropout_rate: float = 0.0, embedding_dropout_rate: float = 0.0, buggy_samples_weight: float = 1.0,
-                 use_message_bias: bool = True, generator_loss_type: str = "classify-max-loss"):
+                 use_message_bias: bool = True, generator_loss_type: str = "classify-max-loss",
+                 use_all_gnn_layer_outputs: bool = False):
         super().__init__()
         self._gnn = GraphNeuralNetwork(hidden, num_edge_types, vocabulary_size, dropout_rate, embedding_dropout_rate,
                                        use_message_bias)
+        self.use_all_gnn_layer_outputs = use_all_gnn_layer_outputs
+        if use_all_gnn_layer_outputs:  # gnn.py:65-69: Linear over [embedding ; every layer's output] -> output width
+            widths, remembered, cur = [hidden], None, hidden
+            for layer in self._gnn.layers:
+                if isinstance(layer, _NoParams):
+                    if layer.kind == "remember":
+                        remembered = cur
+                    else:
+                        cur = remembered + cur
+                else:
+                    cur = layer.output_state_dimension
+                widths.append(cur)
+            self.__summarization_layer = nn.Linear(sum(widths), cur)
         self.__localization_module = LocalizationModule(hidden)
         self._text_repair_module = TextRepairModule(hidden, rewrite_vocabulary_size)
         self._varmisuse_module = SingleCandidateNodeSelectorModule(hidden)
@@ -217,6 +231,8 @@ class GnnBugLabModule(nn.Module):
         self.generator_loss_type = generator_loss_type
 
     def node_representations(self, graph_data):
+        if self.use_all_gnn_layer_outputs:  # gnn.py:109-114
+            return self.__summarization_layer(self._gnn(graph_data["node_data"], graph_data["adjacency_lists"], return_all_states=True))
         return self._gnn(graph_data["node_data"], graph_data["adjacency_lists"])
 
     def force_routing(self, mp_winners, head_args) -> None:

@@ -142,6 +142,31 @@ def test_step_matches_oracle_without_message_bias(cuda_device, monkeypatch):
     _check_steps(model, nn, ref, tensors, cuda_device, 6, "no message bias, H=64", max_batches=1)
 
 
+def test_step_matches_oracle_with_all_layer_outputs(cuda_device):
+    """``use_all_gnn_layer_outputs=True`` (modelregistry.py:55, gnn.py:65-69,109-114): the heads read a Linear over the
+    concatenation of the embedding and every layer's output, so every layer receives gradient from two places."""
+    from buglab.models.modelregistry import load_model
+    from buglab_b200.synthetic import SyntheticBugLabGenerator
+    from oracle import model_ref
+
+    hidden = 64
+    torch.manual_seed(2)
+    gen = SyntheticBugLabGenerator(seed=2, mean_nodes=250, min_nodes=40)
+    data = [gen.sample() for _ in range(6)]
+    model, _, _ = load_model({"modelName": "gnn-mlp", "hidden_state_size": hidden, "dropout_rate": 0.0,
+                              "use_all_gnn_layer_outputs": True}, Path("/tmp/buglab_b200_test_all.pkl.gz"))
+    model.gnn_model.node_representation_model.dropout_rate = 0.0
+    model.compute_metadata(iter(copy.deepcopy(data)))
+    nn = model.build_neural_module().to(cuda_device)
+    assert any("summarization_layer" in k for k in nn.state_dict())
+    ref = model_ref.GnnBugLabModule(hidden, model.gnn_model.num_edge_types,
+                                    len(model.gnn_model.node_representation_model.vocabulary),
+                                    len(model._target_rewrite_ops), use_all_gnn_layer_outputs=True)
+    ref.load_state_dict({k: v.cpu() for k, v in nn.state_dict().items()})
+    tensors = list(model.tensorize_dataset(iter(copy.deepcopy(data)), parallelize=False))
+    _check_steps(model, nn, ref, tensors, cuda_device, 6, "all layer outputs, H=64", max_batches=1)
+
+
 def test_optimizer_trajectory_matches_torch_adam(cuda_device):
     """5 real training steps: the fused flat Adam + global-norm clip + linear warm-up must move the weights exactly like
     torch.optim.Adam + clip_grad_norm_(0.5) + LambdaLR (the reference's optimiser stack, utils.py:51-66 / train.py:104)
