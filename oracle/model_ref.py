@@ -104,12 +104,42 @@ class GraphNeuralNetwork(nn.Module):
         return torch.cat(states, dim=-1) if return_all_states else state
 
 
+class AuditedReLU(nn.Module):
+    """ReLU whose kink decisions (pre-activation > 0) can be forced to another implementation's — the third kind of
+    non-differentiable point on the path besides the two arg-routed maxima.  A pre-activation within rounding distance of
+    zero may legitimately fall on either side; the forward value is unaffected (|x| tiny) but the unit's whole gradient
+    switches on or off: ONE such unit among the argswap scorer's 256 moved 0.5 % of every gradient tensor in smoke().
+    ``forced_masks``: list of bool tensors consumed in call order; the audit records how far from zero the forced
+    decisions that disagree with this evaluation's own sign are (a wrong mask misses by O(1))."""
+
+    def __init__(self):
+        super().__init__()
+        self.forced_masks = None
+        self.routing_audit = None
+        self._calls = 0
+
+    def forward(self, x):
+        if self.forced_masks is None:
+            return torch.relu(x)
+        mask = self.forced_masks[self._calls]
+        self._calls += 1
+        with torch.no_grad():
+            differing = mask != (x > 0)
+            worst = float(x[differing].abs().max()) if bool(differing.any()) else 0.0
+            prev = self.routing_audit or dict(decisions=0, differing=0, wrong_segment=0, empty_mismatch=0,
+                                              max_relative_deficit=0.0, later_edge_on_exact_tie=0)
+            self.routing_audit = dict(prev, decisions=prev["decisions"] + int(mask.numel()),
+                                      differing=prev["differing"] + int(differing.sum()),
+                                      max_relative_deficit=max(prev["max_relative_deficit"], worst))
+        return torch.where(mask, x, torch.zeros_like(x))
+
+
 class MLP(nn.Module):
     def __init__(self, input_dim: int, out_dim: int, hidden_layer_dims: List[int]):
         super().__init__()
         layers, d = [], input_dim
         for h in hidden_layer_dims:
-            layers += [nn.Linear(d, h), nn.ReLU()]
+            layers += [nn.Linear(d, h), AuditedReLU()]
             d = h
         layers.append(nn.Linear(d, out_dim))
         self._layers = nn.Sequential(*layers)
@@ -235,21 +265,33 @@ class GnnBugLabModule(nn.Module):
             return self.__summarization_layer(self._gnn(graph_data["node_data"], graph_data["adjacency_lists"], return_all_states=True))
         return self._gnn(graph_data["node_data"], graph_data["adjacency_lists"])
 
-    def force_routing(self, mp_winners, head_args) -> None:
-        """Evaluate with another implementation's max-routing: ``mp_winners`` = its per-layer winning edges
+    def force_routing(self, mp_winners, head_args, relu_masks=None) -> None:
+        """Evaluate with another implementation's discrete decisions: ``mp_winners`` = its per-layer winning edges
         (``ops.WINNER_TRACE``), ``head_args`` = the args of its differentiable segment maxima in call order
-        (``ops.MINMAX_TRACE``; the discriminator step has exactly one: the localisation module's candidate summary).
-        ``None`` restores this module's own argmax."""
+        (``ops.MINMAX_TRACE``; the discriminator step has exactly one: the localisation module's candidate summary),
+        ``relu_masks`` = {name of the Linear feeding a ReLU: [pre-activation > 0 per call]} (``parity.relu_trace``).
+        ``None`` restores this module's own decisions."""
         self._gnn.force_winners(mp_winners)
         if head_args is not None:
             assert len(head_args) == 1, f"expected one traced head maximum, got {len(head_args)}"
         self.__localization_module.forced_summary_args = head_args[0] if head_args is not None else None
+        modules = dict(self.named_modules())
+        for name, module in modules.items():
+            if isinstance(module, AuditedReLU):
+                container, _, index = name.rpartition(".")
+                linear = f"{container}.{int(index) - 1}"       # MLP._layers: Linear at i - 1 feeds the ReLU at i
+                module.forced_masks = list(relu_masks[linear]) if relu_masks is not None and linear in relu_masks else None
+                module.routing_audit, module._calls = None, 0
 
     def routing_audits(self):
-        """Audits of the last forced routing: the message-passing layers', then the localisation summary's."""
+        """Audits of the last forced evaluation: the message-passing layers', the localisation summary's, the ReLU kinks'
+        (max_relative_deficit = the largest |pre-activation| whose forced side differs from this evaluation's sign)."""
         audits = list(self._gnn.routing_audits())
         if self.__localization_module.forced_summary_args is not None:
             audits.append(self.__localization_module.routing_audit)
+        for module in self.modules():
+            if isinstance(module, AuditedReLU) and module.forced_masks is not None and module.routing_audit is not None:
+                audits.append(module.routing_audit)
         return audits
 
     def compute_localization_logprobs(self, graph_data):  # gnn.py:125-142

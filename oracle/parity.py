@@ -114,3 +114,30 @@ def assert_grad_close_to_scale(actual: torch.Tensor, expected: torch.Tensor, wha
     rel_l2 = float((a - e).norm()) / max(float(e.norm()), 1e-30)
     assert worst <= rel_to_max * scale + 1e-7, f"{what}: max abs diff {worst:.2e} vs {rel_to_max:.0e} * max|expected| = {rel_to_max * scale:.2e}"
     assert rel_l2 <= max_rel_l2, f"{what}: relative L2 error {rel_l2:.2e} (allowed {max_rel_l2:.0e})"
+
+
+class relu_trace:
+    """Context manager (test infrastructure): records, for every ``torch.nn.Linear`` of ``module`` whose output feeds a
+    ReLU inside an ``nn.Sequential`` (the heads' MLP scorers, buglab/models/layers/mlp.py:6-20), the sign pattern
+    ``output > 0`` of each call: ``{qualified Linear name: [bool tensor per call]}`` — the ReLU kink decisions an oracle is
+    then evaluated under (``model_ref.GnnBugLabModule.force_routing``)."""
+
+    def __init__(self, module: torch.nn.Module):
+        self.module, self.masks, self._handles = module, {}, []
+
+    def __enter__(self):
+        for name, seq in self.module.named_modules():
+            if not isinstance(seq, torch.nn.Sequential):
+                continue
+            children = list(seq.named_children())
+            for (child_name, child), (_, following) in zip(children[:-1], children[1:]):
+                if isinstance(child, torch.nn.Linear) and (isinstance(following, torch.nn.ReLU) or type(following).__name__ == "AuditedReLU"):
+                    key = f"{name}.{child_name}"
+                    self._handles.append(child.register_forward_hook(
+                        lambda _m, _i, out, key=key: self.masks.setdefault(key, []).append((out.detach() > 0).cpu())))
+        return self.masks
+
+    def __exit__(self, *exc):
+        for h in self._handles:
+            h.remove()
+        return False

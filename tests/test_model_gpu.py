@@ -47,7 +47,8 @@ def _check_steps(model, nn, ref, tensors, device, minibatch_size, what, max_batc
         nn.zero_grad(); ref.zero_grad()
         nn.train()
         ops.WINNER_TRACE, ops.MINMAX_TRACE = [], []
-        loss = nn(**mb)
+        with parity.relu_trace(nn) as relu_masks:   # the heads' ReLU kink decisions (oracle/model_ref.py::AuditedReLU)
+            loss = nn(**mb)
         winners, ops.WINNER_TRACE = ops.WINNER_TRACE, None
         head_args, ops.MINMAX_TRACE = ops.MINMAX_TRACE, None   # the localisation module's max over the candidates
         loss.backward()
@@ -70,12 +71,12 @@ def _check_steps(model, nn, ref, tensors, device, minibatch_size, what, max_batc
 
         # ROUTING, verified independently of the conditioning below: the exact (fp64) oracle audits every winner the
         # GPU path chose against its own segment maxima (oracle/parity.py::assert_routing_is_valid)
-        ref64.force_routing(winners, head_args)
+        ref64.force_routing(winners, head_args, relu_masks)
         ref64(**mb_cpu)
         routing = parity.assert_routing_is_valid(ref64.routing_audits(), what)
         # GRADIENTS: oracle re-run with the GPU path's max-routing forced (message-passing layers AND the localisation
         # module's candidate summary) -> elementwise comparable
-        ref.force_routing(winners, head_args)
+        ref.force_routing(winners, head_args, relu_masks)
         ref.zero_grad()
         ref(**mb_cpu).backward()
         ref.force_routing(None, None)

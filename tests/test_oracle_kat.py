@@ -180,3 +180,41 @@ def test_localization_summary_forced_routing_and_audit():
     mod.compute_localization_logprobs(reprs, to_sample, S)
     with pytest.raises(AssertionError, match="not in-edges"):
         parity.assert_routing_is_valid([mod.routing_audit], "wrong sample")
+
+
+def test_forced_relu_kinks_and_their_audit():
+    """oracle/model_ref.py::AuditedReLU + parity.relu_trace: a module evaluated under its own traced kink decisions
+    reproduces itself exactly and audits clean; a forced decision on the wrong side of a pre-activation far from zero is
+    reported with that distance."""
+    import pytest
+
+    from oracle import parity
+    from oracle.model_ref import MLP, AuditedReLU
+
+    torch.manual_seed(9)
+    mlp = MLP(6, 1, [5]).double()
+    x = torch.randn(7, 6, dtype=torch.float64, requires_grad=True)
+    with parity.relu_trace(mlp) as masks:
+        y = mlp(x)
+    assert list(masks) == ["_layers.0"] and masks["_layers.0"][0].shape == (7, 5)
+    y.sum().backward()
+    grad_own = x.grad.clone()
+    relu = next(m for m in mlp.modules() if isinstance(m, AuditedReLU))
+    relu.forced_masks, relu._calls = masks["_layers.0"], 0
+    x.grad = None
+    y_forced = mlp(x)
+    y_forced.sum().backward()
+    assert torch.equal(y_forced, y) and torch.equal(x.grad, grad_own)
+    assert relu.routing_audit["differing"] == 0 and relu.routing_audit["decisions"] == 35
+    parity.assert_routing_is_valid([relu.routing_audit], "own kinks")
+
+    pre = mlp._layers[0](x).detach()
+    far = int(pre.abs().argmax())
+    wrong = masks["_layers.0"][0].clone()
+    wrong.view(-1)[far] = ~wrong.view(-1)[far]
+    relu.forced_masks, relu._calls, relu.routing_audit = [wrong], 0, None
+    mlp(x)
+    assert relu.routing_audit["differing"] == 1
+    assert abs(relu.routing_audit["max_relative_deficit"] - float(pre.abs().max())) < 1e-12
+    with pytest.raises(AssertionError, match="falls short"):
+        parity.assert_routing_is_valid([relu.routing_audit], "wrong kink")

@@ -75,7 +75,7 @@ def test_tensor_core_attention_at_config4_shape(cuda_device, monkeypatch):
     eb = torch.randint(0, B, (n_edges,), generator=g)
     es = (torch.rand(n_edges, generator=g) * lengths[eb]).long()
     et = (torch.rand(n_edges, generator=g) * lengths[eb]).long()
-    edges = torch.stack((eb, es, et))
+    edges = torch.stack((eb, es, et), dim=1)   # [E, 3] = (sample, source position, target position)
     edge_types = torch.randint(0, T, (n_edges,), generator=g)
     plan = ops.build_seq_attention_plan(edges.to(dev), edge_types.to(dev), lengths.to(dev), L, T)
 
