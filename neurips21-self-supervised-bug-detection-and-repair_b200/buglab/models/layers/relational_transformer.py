@@ -3,8 +3,10 @@
 Parameter names and semantics: reference buglab/models/layers/multihead_attention.py:7-85,
 relational_multihead_attention.py:7-178, relational_transformer.py:18-125 (a reference ``state_dict`` loads unchanged).
 What runs where: the score / softmax / weighted-sum core with the typed-edge terms is the hand-written kernel behind
-``ops.seq_edge_attention`` (``bl_seq_attention_fwd/_bwd``), LayerNorm is ``bl_layernorm_*``; the dense projections and the
-feed-forward block are plain library GEMMs (``torch.nn.functional.linear``).  Behaviours kept on purpose: "great" uses
+``ops.seq_edge_attention`` (tensor-core path: ``bl_tma_project`` / ``bl_tma_weight_grad`` + ``bl_seq_softmax_*``; CUDA-core
+path ``bl_seq_attention_fwd/_bwd``), LayerNorm is ``bl_layernorm_*``; the dense projections and the feed-forward block run
+on the same split-fp16 TMA-fed tcgen05 GEMMs (``ops.dense_linear``) where they cover the shape (config 4: all of them),
+else on plain library GEMMs (``torch.nn.functional.linear``).  Behaviours kept on purpose: "great" uses
 the query-side vector bias (the scalar switch is never set upstream) and post-norm applies ``norm1`` after both sub-layers.
 """
 from typing import Optional, Union
@@ -13,6 +15,17 @@ import torch
 from torch import nn
 
 from buglab_b200 import ops
+
+
+def _linear(lin: nn.Linear, x: torch.Tensor) -> torch.Tensor:
+    """``lin(x)`` for x [..., k]: on a GPU the product runs on the split-fp16 TMA-fed tcgen05 GEMMs (``ops.dense_linear``:
+    fp32-class accuracy, forward and both backward products) where they cover the shape, else on the fp32 library GEMM."""
+    if not x.is_cuda:
+        return lin(x)
+    y = ops.dense_linear(x.reshape(-1, x.shape[-1]), lin.weight)
+    if lin.bias is not None:
+        y = y + lin.bias
+    return y.view(*x.shape[:-1], lin.weight.shape[0])
 
 
 def _layer_norm(norm: nn.LayerNorm, x: torch.Tensor) -> torch.Tensor:
@@ -33,14 +46,14 @@ class MultiheadAttention(nn.Module):
 
     def _project(self, x: torch.Tensor):
         B, L, _ = x.shape
-        per_head = self._selfatt_head_transforms(x).view(B, L, self._num_heads, -1).permute(0, 2, 1, 3)
+        per_head = _linear(self._selfatt_head_transforms, x).view(B, L, self._num_heads, -1).permute(0, 2, 1, 3)
         dk = self._key_query_dim
         return ((per_head[..., :dk] * self._scaling).contiguous(), per_head[..., dk: 2 * dk].contiguous(),
                 per_head[..., 2 * dk:].contiguous())
 
     def _merge(self, per_head_values: torch.Tensor) -> torch.Tensor:
         B, H, L, dv = per_head_values.shape
-        return self._out_proj(per_head_values.permute(0, 2, 1, 3).reshape(B, L, H * dv))
+        return _linear(self._out_proj, per_head_values.permute(0, 2, 1, 3).reshape(B, L, H * dv))
 
 
 class RelationalMultiheadAttention(MultiheadAttention):
@@ -123,8 +136,8 @@ class RelationalTransformerEncoderLayer(nn.Module):
         src = src + self.dropout1(self._alpha1 * attended)
         if post:
             src = _layer_norm(self.norm1, src)
-        hidden = self.dropout(activation(self.linear1(_layer_norm(self.norm2, src) if pre else src)))
-        src = src + self.dropout2(self._alpha2 * self.linear2(hidden))
+        hidden = self.dropout(activation(_linear(self.linear1, _layer_norm(self.norm2, src) if pre else src)))
+        src = src + self.dropout2(self._alpha2 * _linear(self.linear2, hidden))
         if post:
             src = _layer_norm(self.norm1, src)  # sic — the reference normalises with norm1 again (relational_transformer.py:122-123)
         return src

@@ -1016,7 +1016,8 @@ extern "C" int bl_rows_split_f16(const float* x, const int32_t* idx, int64_t row
 }
 
 extern "C" int bl_tma_gemm_supported(int32_t n_out, int32_t k_in) {
-    return (k_in % tg::CHUNK_K == 0) && (n_out == 64 || n_out == 128 || (n_out % 256 == 0 && n_out <= 1024)) && tg::encode_fn() != nullptr;
+    return (k_in % tg::CHUNK_K == 0) && (n_out == 64 || n_out == 128 || (n_out % 256 == 0 && n_out <= 4096)) && k_in <= 4096 &&
+           tg::encode_fn() != nullptr;
 }
 
 /* prefix[s] = sum_{s' < s} ceil(rows(s') / unit): the tile / slab tables the GEMMs walk (device to device, no sync). */
@@ -1106,7 +1107,7 @@ extern "C" int bl_tma_project(const void* a_split, int64_t a_rows, const int32_t
 extern "C" int bl_tma_weight_grad_supported(int32_t m_out, int32_t n_in) {
     if (tg::encode_fn() == nullptr) return 0;
     if (n_in == 64) return m_out % tg::TILE_M == 0 && m_out <= 1024;  // narrow products (attention backward): single CTAs
-    return (m_out % 256 == 0) && (n_in % 256 == 0) && m_out <= 1024 && n_in <= 1024;
+    return (m_out % 256 == 0) && (n_in % 256 == 0) && m_out <= 4096 && n_in <= 4096;
 }
 
 /* d_weight[type, 0:m_out, col0:col0+n_in] = (1/scale) sum over pair rows of G[p,:]^T X[idx[p],:]  (zeroes that block first) */

@@ -33,6 +33,8 @@ PROJECT_CASES = [
     ([512, 512, 300], None, 64, 512, False, False, True),         # attention scores: one 64-deep chunk per tile
     ([1024, 512, 77], None, 512, 64, False, False, True),         # attention P'V / dS K: 64-wide output tile
     ([700, 33, 260], None, 256, 64, True, True, False),           # 64-wide output, gathered rows, bias
+    ([2500], None, 512, 1536, False, False, True),                # sequence models: q/k/v head transforms (6 column tiles)
+    ([2500], None, 2048, 512, False, False, True),                # feed-forward down projection (32 chunks deep)
 ]
 
 WGRAD_CASES = [
@@ -43,6 +45,8 @@ WGRAD_CASES = [
     ([600, 500, 4200, 64], [1, 0, 1, 0], 256, 256),
     ([512, 512, 384], None, 512, 64),          # attention dK / dV: 64-wide products on single CTAs
     ([128, 300], None, 128, 64),
+    ([5000], None, 2048, 512),                 # feed-forward weight gradients of the sequence models
+    ([5000], None, 512, 2048),
 ]
 
 _DRIVER = r"""
