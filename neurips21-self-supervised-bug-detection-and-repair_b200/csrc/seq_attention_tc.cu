@@ -121,7 +121,7 @@ softmax_fwd_kernel(const RowProblem p, float* __restrict__ scores, float* __rest
     const float scale = pow2_scale_for(__ldg(p.amax_p));
     for (int j = lane; j < p.Lp; j += 32) {
         const float s = sm[j];
-        srow[j] = s;
+        if (e1 > e0) srow[j] = s;  // rows without entries are unchanged
         const float prob = (j < len) ? expf(s - row_lse) * dropout_scale(p, b, h, i, j) : 0.f;
         sm[j] = prob;
         store_split(hi_row, lo_row, j, prob * scale);
