@@ -181,16 +181,14 @@ int bl_pair_weight_grad_tc(const float* g, const float* x, const int32_t* idx, c
  *     [2][P_t + 1][M] (pre-scaled by the power of two derived from amax_eff, last row of each part zero); adds the
  *     per-type column sums of dV (= d bias_k) into d_bias[K, M] (zero-initialised by the caller; NULL: skipped).
  *     amax_in = device scalar max|d_agg| (bl_absmax); the kernel publishes amax_eff = amax_in * 1.13 (bound of GELU') *
- *     256 (fan-in headroom of the dU sums) for the consumers' 1/scale.  win_mask[E][M / 32] (uint32): bit l of word
- *     4 * i + c of sorted edge e is set iff e won channel 4 * (l + 32 * i) + c of its target — M / 8 bytes per edge.
+ *     256 (fan-in headroom of the dU sums) for the consumers' 1/scale.
  *   bl_edge_bwd_sources: one warp per S-pair row.  dU[p] = sum over the pair's edges e (ascending) of g masked to the
- *     channels e won (read from win_mask: per edge M / 8 bytes of mask and only the 16-byte pieces of the target's g row
- *     that hold a won channel), written as the split table [2][P_s + 1][M] with the same scale. */
+ *     channels e won, written as the split table [2][P_s + 1][M] with the same scale. */
 int bl_edge_bwd_targets(const float* d_agg, const float* xwin, const int32_t* ewin, const int32_t* row_ptr,
                         const int32_t* vrow, const int32_t* e_type, int64_t num_nodes, int32_t msg_dim,
                         int32_t num_edge_types, int64_t num_t_pairs, const float* amax_in, float* amax_eff, float* g_rows,
-                        void* dv_split, float* d_bias, void* win_mask, bl_stream_t stream);
-int bl_edge_bwd_sources(const float* g_rows, const void* win_mask, const int32_t* s_edge_ptr, const int32_t* s_edge_idx,
+                        void* dv_split, float* d_bias, bl_stream_t stream);
+int bl_edge_bwd_sources(const float* g_rows, const int32_t* ewin, const int32_t* s_edge_ptr, const int32_t* s_edge_idx,
                         const int32_t* s_edge_tgt, int64_t num_s_pairs, int32_t msg_dim, const float* amax_eff, void* du_split,
                         bl_stream_t stream);
 

@@ -61,7 +61,7 @@ _SIGNATURES = {
                                    c_ptr, c_i32, c_i32, c_ptr]),
     "bl_edge_segmax_fwd": (c_i32, [c_ptr] * 5 + [c_i64, c_i32] + [c_ptr] * 3 + [c_ptr]),
     "bl_edge_segmax_bwd": (c_i32, [c_ptr] * 6 + [c_i64, c_i32, c_i64, c_i64] + [c_ptr] * 3 + [c_ptr]),
-    "bl_edge_bwd_targets": (c_i32, [c_ptr] * 6 + [c_i64, c_i32, c_i32, c_i64] + [c_ptr] * 6 + [c_ptr]),
+    "bl_edge_bwd_targets": (c_i32, [c_ptr] * 6 + [c_i64, c_i32, c_i32, c_i64] + [c_ptr] * 5 + [c_ptr]),
     "bl_edge_bwd_sources": (c_i32, [c_ptr] * 5 + [c_i64, c_i32, c_ptr, c_ptr, c_ptr]),
     "bl_layernorm_fwd": (c_i32, [c_ptr] * 3 + [c_i64, c_i32, c_f32] + [c_ptr] * 3 + [c_ptr]),
     "bl_layernorm_bwd": (c_i32, [c_ptr] * 5 + [c_i64, c_i32] + [c_ptr] * 4 + [c_ptr]),

@@ -504,12 +504,9 @@ class TypedEdgeMessageMax(torch.autograd.Function):
             amax = torch.empty(1, device=dev, dtype=torch.float32)
             g_rows = torch.empty((N, M), device=dev, dtype=torch.float32)
             dv_split = torch.empty((2, plan.num_t_pairs + 1, M), device=dev, dtype=torch.float16)
-            # one bit per (sorted edge, channel): the channels each edge won (M / 8 bytes per edge; read by the by-source kernel)
-            win_mask = torch.empty((max(plan.num_edges, 1), M // 32), device=dev, dtype=torch.int32)
             check(lib.bl_edge_bwd_targets(f32(d_agg), f32(xwin), i32(ewin), i32(plan.row_ptr), i32(plan.vrow), i32(plan.e_type),
                                           N, M, K, plan.num_t_pairs, f32(amax_in), f32(amax), f32(g_rows), dv_split.data_ptr(),
-                                          f32(d_bias) if d_bias is not None else None, win_mask.data_ptr(), stream_ptr(dev)),
-                  "bl_edge_bwd_targets")
+                                          f32(d_bias) if d_bias is not None else None, stream_ptr(dev)), "bl_edge_bwd_targets")
             du_split = torch.empty((2, plan.num_s_pairs + 1, M), device=dev, dtype=torch.float16)
             # The by-source kernel is latency/HBM-bound and independent of the T-table GEMMs: run it on a side stream so it
             # overlaps those tensor-bound kernels (its blocks co-reside with the persistent GEMM CTAs), then join.
@@ -518,11 +515,11 @@ class TypedEdgeMessageMax(torch.autograd.Function):
             if side is not None:
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
-                    check(lib.bl_edge_bwd_sources(f32(g_rows), win_mask.data_ptr(), i32(plan.s_edge_ptr), i32(plan.s_edge_idx), i32(plan.s_edge_tgt),
+                    check(lib.bl_edge_bwd_sources(f32(g_rows), i32(ewin), i32(plan.s_edge_ptr), i32(plan.s_edge_idx), i32(plan.s_edge_tgt),
                                                   plan.num_s_pairs, M, f32(amax), du_split.data_ptr(), stream_ptr(dev)),
                           "bl_edge_bwd_sources")
             else:
-                check(lib.bl_edge_bwd_sources(f32(g_rows), win_mask.data_ptr(), i32(plan.s_edge_ptr), i32(plan.s_edge_idx), i32(plan.s_edge_tgt),
+                check(lib.bl_edge_bwd_sources(f32(g_rows), i32(ewin), i32(plan.s_edge_ptr), i32(plan.s_edge_idx), i32(plan.s_edge_tgt),
                                               plan.num_s_pairs, M, f32(amax), du_split.data_ptr(), stream_ptr(dev)), "bl_edge_bwd_sources")
             if ctx.h_split is not None:
                 h_split, amax_h, amax_w = ctx.h_split, ctx.amax_h, ctx.amax_w

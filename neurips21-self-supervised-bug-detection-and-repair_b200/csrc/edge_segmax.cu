@@ -275,7 +275,7 @@ edge_bwd_targets_warp(const float* __restrict__ d_agg, const float* __restrict__
                       const int* __restrict__ row_ptr, const int* __restrict__ vrow, const int* __restrict__ e_type,
                       int num_nodes, int num_types, int64_t num_t_pairs, const float* __restrict__ amax_in,
                       float* __restrict__ amax_eff, float* __restrict__ g_rows, __half* __restrict__ dv_split,
-                      float* __restrict__ d_bias, uint32_t* __restrict__ win_mask) {
+                      float* __restrict__ d_bias) {
     constexpr int M4 = 32 * ITER;
     constexpr int M = 128 * ITER;
     extern __shared__ float bias_acc[];  // [num_types][M] when d_bias != nullptr
@@ -301,18 +301,16 @@ edge_bwd_targets_warp(const float* __restrict__ d_agg, const float* __restrict__
         const int beg = __ldg(row_ptr + node);
         const int end = __ldg(row_ptr + node + 1);
         float4 g[ITER];
-        int4 wv[ITER], we[ITER];
+        int4 wv[ITER];
 #pragma unroll
         for (int i = 0; i < ITER; ++i) {
             const size_t off = (size_t)node * M4 + lane + 32 * i;
             g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             wv[i] = make_int4(-1, -1, -1, -1);
-            we[i] = make_int4(-1, -1, -1, -1);
             if (beg != end) {  // a non-empty segment always has a winner (ewin >= 0)
                 const float4 d = __ldg(reinterpret_cast<const float4*>(d_agg) + off);
                 const float4 x = __ldg(reinterpret_cast<const float4*>(xwin) + off);
                 const int4 e = __ldg(reinterpret_cast<const int4*>(ewin) + off);
-                we[i] = e;
                 g[i] = make_float4(d.x * gelu_grad(x.x), d.y * gelu_grad(x.y), d.z * gelu_grad(x.z), d.w * gelu_grad(x.w));
                 wv[i] = make_int4(__ldg(vrow + e.x), __ldg(vrow + e.y), __ldg(vrow + e.z), __ldg(vrow + e.w));
             }
@@ -325,21 +323,6 @@ edge_bwd_targets_warp(const float* __restrict__ d_agg, const float* __restrict__
             const int my_v = __ldg(vrow + base + min(lane, cnt - 1));
             const int my_t = __ldg(e_type + base + min(lane, cnt - 1));
             for (int t = 0; t < cnt; ++t) {
-                {   // which channels this edge won: word 4 * i + c, bit l  <->  channel 4 * (l + 32 * i) + c  (the lane layout of
-                    // the float4 row pieces in both backward kernels); M / 8 bytes per edge instead of a full ewin row per edge
-                    const int pos = base + t;
-                    uint32_t word = 0u;
-#pragma unroll
-                    for (int i = 0; i < ITER; ++i) {
-                        const uint32_t bx = __ballot_sync(FULL_MASK, we[i].x == pos), by = __ballot_sync(FULL_MASK, we[i].y == pos);
-                        const uint32_t bz = __ballot_sync(FULL_MASK, we[i].z == pos), bw = __ballot_sync(FULL_MASK, we[i].w == pos);
-                        if (lane == 4 * i) word = bx;
-                        if (lane == 4 * i + 1) word = by;
-                        if (lane == 4 * i + 2) word = bz;
-                        if (lane == 4 * i + 3) word = bw;
-                    }
-                    if (lane < 4 * ITER) win_mask[(size_t)pos * (4 * ITER) + lane] = word;
-                }
                 const int v = __shfl_sync(FULL_MASK, my_v, t);
                 const int type = __shfl_sync(FULL_MASK, my_t, t);
                 if (v == prev_v) continue;  // warp-uniform
@@ -374,14 +357,12 @@ edge_bwd_targets_warp(const float* __restrict__ d_agg, const float* __restrict__
     }
 }
 
-// UNR S-pair rows per warp, walked in lock step: the chain  edge list -> win mask of the edge -> g row of its target  is
-// latency-bound (measured with full ewin rows: DRAM 24 %, 18 warps stalled on the scoreboard per issue with one row per
-// warp), so every level is issued for UNR rows at once; the per-edge target comes from the plan (s_edge_tgt).  Per edge the
-// kernel reads M / 8 bytes of win mask (written by the targets kernel) and only those 16-byte pieces of the target's g row
-// in which the edge won a channel (~9 % of the channels at the bench's fan-in) — not the target's whole ewin row.
+// UNR S-pair rows per warp, walked in lock step: the chain  edge list -> ewin row of the target -> g row  is latency-bound
+// (measured: DRAM 24 %, 18 warps stalled on the scoreboard per issue with one row per warp), so every level is issued for
+// UNR rows at once; the per-edge target comes from the plan (s_edge_tgt) instead of a dependent e_tgt[e] load.
 template <int ITER, int UNR>
 __global__ void __launch_bounds__(256)
-edge_bwd_sources_warp(const float* __restrict__ g_rows, const uint32_t* __restrict__ win_mask, const int* __restrict__ s_edge_ptr,
+edge_bwd_sources_warp(const float* __restrict__ g_rows, const int* __restrict__ ewin, const int* __restrict__ s_edge_ptr,
                       const int* __restrict__ s_edge_idx, const int* __restrict__ s_edge_tgt, int64_t num_s_pairs,
                       const float* __restrict__ amax_eff, __half* __restrict__ du_split) {
     constexpr int M4 = 32 * ITER;
@@ -409,31 +390,31 @@ edge_bwd_sources_warp(const float* __restrict__ g_rows, const uint32_t* __restri
         int e[UNR], t[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-            e[u] = -1;
+            e[u] = -2;  // never equals an ewin entry (>= -1)
             t[u] = 0;
             if (j < len[u]) {
                 e[u] = __ldg(s_edge_idx + beg[u] + j);
                 t[u] = __ldg(s_edge_tgt + beg[u] + j);
             }
         }
-        uint4 w[UNR][ITER];
+        int4 w[UNR][ITER];
 #pragma unroll
         for (int u = 0; u < UNR; ++u)
 #pragma unroll
-            for (int i = 0; i < ITER; ++i)   // the same address in every lane: one broadcast transaction
-                w[u][i] = (e[u] >= 0) ? __ldg(reinterpret_cast<const uint4*>(win_mask) + (size_t)e[u] * ITER + i) : make_uint4(0u, 0u, 0u, 0u);
+            for (int i = 0; i < ITER; ++i)
+                w[u][i] = (j < len[u]) ? __ldg(reinterpret_cast<const int4*>(ewin) + (size_t)t[u] * M4 + lane + 32 * i)
+                                       : make_int4(-1, -1, -1, -1);
 #pragma unroll
         for (int u = 0; u < UNR; ++u)
 #pragma unroll
             for (int i = 0; i < ITER; ++i) {
-                const uint4 ww = w[u][i];
-                const bool bx = (ww.x >> lane) & 1u, by = (ww.y >> lane) & 1u, bz = (ww.z >> lane) & 1u, bw = (ww.w >> lane) & 1u;
-                if (bx || by || bz || bw) {
+                const int4 ww = w[u][i];
+                if (ww.x == e[u] || ww.y == e[u] || ww.z == e[u] || ww.w == e[u]) {
                     const float4 gv = __ldg(reinterpret_cast<const float4*>(g_rows) + (size_t)t[u] * M4 + lane + 32 * i);
-                    if (bx) acc[u][i].x += gv.x;
-                    if (by) acc[u][i].y += gv.y;
-                    if (bz) acc[u][i].z += gv.z;
-                    if (bw) acc[u][i].w += gv.w;
+                    if (ww.x == e[u]) acc[u][i].x += gv.x;
+                    if (ww.y == e[u]) acc[u][i].y += gv.y;
+                    if (ww.z == e[u]) acc[u][i].z += gv.z;
+                    if (ww.w == e[u]) acc[u][i].w += gv.w;
                 }
             }
     }
@@ -514,9 +495,8 @@ extern "C" int bl_edge_segmax_bwd(const float* d_agg, const float* xwin, const i
 extern "C" int bl_edge_bwd_targets(const float* d_agg, const float* xwin, const int32_t* ewin, const int32_t* row_ptr,
                                    const int32_t* vrow, const int32_t* e_type, int64_t num_nodes, int32_t msg_dim,
                                    int32_t num_edge_types, int64_t num_t_pairs, const float* amax_in, float* amax_eff,
-                                   float* g_rows, void* dv_split, float* d_bias, void* win_mask, bl_stream_t stream_) {
-    if (num_nodes <= 0 || num_nodes > 0x7fffffffLL || num_edge_types <= 0 || num_t_pairs < 0 || amax_in == nullptr || amax_eff == nullptr ||
-        win_mask == nullptr)
+                                   float* g_rows, void* dv_split, float* d_bias, bl_stream_t stream_) {
+    if (num_nodes <= 0 || num_nodes > 0x7fffffffLL || num_edge_types <= 0 || num_t_pairs < 0 || amax_in == nullptr || amax_eff == nullptr)
         return BL_ERR_INVALID_ARGUMENT;
     if (msg_dim != 128 && msg_dim != 256 && msg_dim != 512) return BL_ERR_UNSUPPORTED;
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -533,7 +513,7 @@ extern "C" int bl_edge_bwd_targets(const float* d_agg, const float* xwin, const 
             if (rc) return rc;                                                                                         \
         }                                                                                                              \
         edge_bwd_targets_warp<ITER><<<grid, threads, smem, stream>>>(d_agg, xwin, ewin, row_ptr, vrow, e_type, n, num_edge_types, \
-                                                                     num_t_pairs, amax_in, amax_eff, g_rows, (__half*)dv_split, d_bias, (uint32_t*)win_mask); \
+                                                                     num_t_pairs, amax_in, amax_eff, g_rows, (__half*)dv_split, d_bias); \
     } while (0)
     if (msg_dim == 128) BL_LAUNCH_EBT(1);
     else if (msg_dim == 256) BL_LAUNCH_EBT(2);
@@ -542,21 +522,20 @@ extern "C" int bl_edge_bwd_targets(const float* d_agg, const float* xwin, const 
     return check_launch("bl_edge_bwd_targets");
 }
 
-extern "C" int bl_edge_bwd_sources(const float* g_rows, const void* win_mask_, const int32_t* s_edge_ptr, const int32_t* s_edge_idx,
+extern "C" int bl_edge_bwd_sources(const float* g_rows, const int32_t* ewin, const int32_t* s_edge_ptr, const int32_t* s_edge_idx,
                                    const int32_t* s_edge_tgt, int64_t num_s_pairs, int32_t msg_dim, const float* amax_eff,
                                    void* du_split, bl_stream_t stream_) {
-    if (num_s_pairs < 0 || amax_eff == nullptr || win_mask_ == nullptr) return BL_ERR_INVALID_ARGUMENT;
+    if (num_s_pairs < 0 || amax_eff == nullptr) return BL_ERR_INVALID_ARGUMENT;
     if (msg_dim != 128 && msg_dim != 256 && msg_dim != 512) return BL_ERR_UNSUPPORTED;
     cudaStream_t stream = (cudaStream_t)stream_;
-    const uint32_t* win_mask = (const uint32_t*)win_mask_;
     const int threads = 256;
     constexpr int UNR = 2;
     const unsigned grid = grid_for(((num_s_pairs + 1 + UNR - 1) / UNR) * 32, threads);
     if (msg_dim == 128)
-        edge_bwd_sources_warp<1, UNR><<<grid, threads, 0, stream>>>(g_rows, win_mask, s_edge_ptr, s_edge_idx, s_edge_tgt, num_s_pairs, amax_eff, (__half*)du_split);
+        edge_bwd_sources_warp<1, UNR><<<grid, threads, 0, stream>>>(g_rows, ewin, s_edge_ptr, s_edge_idx, s_edge_tgt, num_s_pairs, amax_eff, (__half*)du_split);
     else if (msg_dim == 256)
-        edge_bwd_sources_warp<2, UNR><<<grid, threads, 0, stream>>>(g_rows, win_mask, s_edge_ptr, s_edge_idx, s_edge_tgt, num_s_pairs, amax_eff, (__half*)du_split);
+        edge_bwd_sources_warp<2, UNR><<<grid, threads, 0, stream>>>(g_rows, ewin, s_edge_ptr, s_edge_idx, s_edge_tgt, num_s_pairs, amax_eff, (__half*)du_split);
     else
-        edge_bwd_sources_warp<4, UNR><<<grid, threads, 0, stream>>>(g_rows, win_mask, s_edge_ptr, s_edge_idx, s_edge_tgt, num_s_pairs, amax_eff, (__half*)du_split);
+        edge_bwd_sources_warp<4, UNR><<<grid, threads, 0, stream>>>(g_rows, ewin, s_edge_ptr, s_edge_idx, s_edge_tgt, num_s_pairs, amax_eff, (__half*)du_split);
     return check_launch("bl_edge_bwd_sources");
 }
