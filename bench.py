@@ -285,6 +285,7 @@ def run_ours(args):
             if world == 1:
                 result["e2e_shards"] = e2e_from_shards(args, device, result["value"])
                 result["config1"] = config1_gpu(device)
+                result["config4_seq"] = config4_seq()
         if world == 1 and not args.skip_cpu_baseline:
             result["cpu_baseline"] = cpu_arm_subprocess(args.hidden, steps=2, warmup=1, threads=args.cpu_threads)
             if "config1" in result:
@@ -552,6 +553,25 @@ def config1_gpu(device):
 # ---------------------------------------------------------------------------------------------------------------
 # CPU arm
 # ---------------------------------------------------------------------------------------------------------------
+def config4_seq():
+    """BASELINE.json configs[3] (seq-great, hidden 512, 8 heads, 5 layers, 64 sequences of <= 512 tokens): the train step
+    of the sequence model, measured by scripts/bench_seq.py in a child process (its own CUDA context, after this one has
+    released its cache).  Context only: the headline metric stays the gnn-mlp step."""
+    import subprocess
+
+    cmd = [sys.executable, os.path.join(ROOT, "scripts", "bench_seq.py"), "--steps", "8", "--warmup", "3"]
+    try:
+        proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        lines = [l for l in proc.stdout.splitlines() if l.startswith("{")]
+        if proc.returncode != 0 or not lines:
+            return {"unavailable": (proc.stderr or proc.stdout)[-300:]}
+        out = json.loads(lines[-1])
+        out["command"] = "python scripts/bench_seq.py --steps 8 --warmup 3"
+        return out
+    except Exception as exc:  # a context leg must never take the headline line down with it
+        return {"unavailable": repr(exc)[:300]}
+
+
 def cpu_thread_count(requested: int = 0) -> int:
     """Fixed thread count of the CPU arm: min(32, usable CPUs).  (os.cpu_count() over-reports inside CPU-limited
     containers: round 1's box reported 128 and ran the oracle 30x slower with 128 threads than with 32.)"""

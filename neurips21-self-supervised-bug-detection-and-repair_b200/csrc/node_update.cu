@@ -136,17 +136,34 @@ layernorm_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ x
     }
 }
 
-__global__ void layernorm_bwd_reduce(const float* __restrict__ partial, int num_partials, int dim,
-                                     float* __restrict__ d_gamma, float* __restrict__ d_beta) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= dim) return;
+// Column sums of the per-block partials: block = 32 columns x 32 row lanes (a single thread walking all 1 184 partials of
+// its column took 0.29 ms per call — 1 % of the c2 step); fixed summation order, so still deterministic.
+__global__ void __launch_bounds__(1024)
+layernorm_bwd_reduce(const float* __restrict__ partial, int num_partials, int dim,
+                     float* __restrict__ d_gamma, float* __restrict__ d_beta) {
+    __shared__ float sa[32][33], sb[32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int j = blockIdx.x * 32 + tx;
     float a = 0.f, b = 0.f;
-    for (int p = 0; p < num_partials; ++p) {
-        a += partial[(size_t)p * dim + j];
-        b += partial[(size_t)(num_partials + p) * dim + j];
+    if (j < dim) {
+        for (int p = ty; p < num_partials; p += 32) {
+            a += partial[(size_t)p * dim + j];
+            b += partial[(size_t)(num_partials + p) * dim + j];
+        }
     }
-    d_gamma[j] = a;
-    d_beta[j] = b;
+    sa[ty][tx] = a;
+    sb[ty][tx] = b;
+    __syncthreads();
+    if (ty == 0 && j < dim) {
+        float ta = 0.f, tb = 0.f;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            ta += sa[r][tx];
+            tb += sb[r][tx];
+        }
+        d_gamma[j] = ta;
+        d_beta[j] = tb;
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -219,7 +236,7 @@ extern "C" int bl_layernorm_bwd(const float* dy, const float* x, const float* ga
     else if (dim <= 512) BL_LAUNCH_LN_BWD(4);
     else BL_LAUNCH_LN_BWD(8);
 #undef BL_LAUNCH_LN_BWD
-    layernorm_bwd_reduce<<<grid_for(dim, 128), 128, 0, stream>>>(partial, BL_LN_PARTIALS, dim, d_gamma, d_beta);
+    layernorm_bwd_reduce<<<(dim + 31) / 32, dim3(32, 32), 0, stream>>>(partial, BL_LN_PARTIALS, dim, d_gamma, d_beta);
     return check_launch("bl_layernorm_bwd");
 }
 

@@ -19,25 +19,35 @@ pytestmark = [pytest.mark.gpu,
                                  reason="seq-attention GPU parity switched off by BUGLAB_B200_SEQ_GPU=0")]
 
 
-@pytest.mark.parametrize("backend", ["tensor-core", "cuda-core"])
-@pytest.mark.parametrize("case_index", range(7))
-def test_kernels_match_oracle(cuda_device, monkeypatch, case_index, backend):
-    """``tensor-core``: QK^T / PV / dP / dQ / dK / dV on the TMA-fed tcgen05 GEMMs + the warp-per-row softmax kernels
-    (csrc/seq_attention_tc.cu); ``cuda-core``: the fp32 one-thread-per-row kernels (csrc/seq_attention.cu)."""
+LARGE_CASES = [  # seed, B, L, E, d_model, heads, relation kinds, value biases  (GPU only; fp64 oracle)
+    (8, 4, 512, 6000, 512, 8, 6, True),     # BASELINE config 4's layer: 8 heads of 64, 512 tokens
+    (9, 3, 300, 2500, 512, 8, 5, False),    # padded to 512 keys
+    (10, 5, 200, 1500, 256, 4, 4, True),    # padded to 256 keys
+]
+
+
+def _check_case(case, dev, backend, monkeypatch, double_oracle=False):
+    import copy
+
     import test_seq_attention_emul as emul
     from buglab_b200 import ops
 
     monkeypatch.setattr(ops, "SEQ_ATTENTION_TC", backend == "tensor-core")
-    case = emul.CASES[case_index]
     att, x, mask, edges, edge_types, weights = emul.random_case(*case)
     types = case[6]
     keep = ~mask
-    expected = att(x, mask, edges, edge_types)
-    (expected * weights).sum().backward()
-    ref_grads = {n: p.grad.clone() for n, p in att.named_parameters()}
-    ref_dx = x.grad.clone()
+    if double_oracle:  # exact evaluation of the same layer (oracle/seq_ref.py) in fp64
+        att_ref, x_ref = copy.deepcopy(att).double(), x.detach().double().requires_grad_(True)
+        expected = att_ref(x_ref, mask, edges, edge_types)
+        (expected * weights.double()).sum().backward()
+        ref_grads = {n: p.grad.float() for n, p in att_ref.named_parameters()}
+        ref_dx, expected = x_ref.grad.float(), expected.float()
+    else:
+        expected = att(x, mask, edges, edge_types)
+        (expected * weights).sum().backward()
+        ref_grads = {n: p.grad.clone() for n, p in att.named_parameters()}
+        ref_dx = x.grad.clone()
 
-    dev = cuda_device
     B, L, _ = x.shape
     lengths = (~mask).sum(dim=1)
     plan = ops.build_seq_attention_plan(edges.to(dev), edge_types.to(dev), lengths.to(dev), L, types)
@@ -53,12 +63,30 @@ def test_kernels_match_oracle(cuda_device, monkeypatch, case_index, backend):
     assert ops._seq_tc_ok(q) == (backend == "tensor-core")
     out = ops.seq_edge_attention(q, k, v, bias, vbias, plan)
     got = out.permute(0, 2, 1, 3).reshape(B, L, -1) @ params["_out_proj.weight"].t()
-    assert float((got.detach().cpu() - expected.detach())[keep].abs().max()) < 1e-5
+    out_tol = 1e-5 if not double_oracle else 1e-5 * max(1.0, float(expected.abs().max()))
+    assert float((got.detach().cpu() - expected.detach())[keep].abs().max()) < out_tol
     (got * weights.to(dev)).sum().backward()
     assert float((xg.grad.cpu() - ref_dx).abs().max()) <= 5e-5 * float(ref_dx.abs().max()) + 5e-6
     for name, ref in ref_grads.items():
         err = float((params[name].grad.cpu() - ref).abs().max())
         assert err <= 5e-5 * float(ref.abs().max()) + 5e-6, (name, err)
+
+
+@pytest.mark.parametrize("backend", ["tensor-core", "cuda-core"])
+@pytest.mark.parametrize("case_index", range(7))
+def test_kernels_match_oracle(cuda_device, monkeypatch, case_index, backend):
+    """``tensor-core``: QK^T / PV / dP / dQ / dK / dV on the TMA-fed tcgen05 GEMMs + the warp-per-row softmax kernels
+    (csrc/seq_attention_tc.cu); ``cuda-core``: the fp32 one-thread-per-row kernels (csrc/seq_attention.cu)."""
+    import test_seq_attention_emul as emul
+
+    _check_case(emul.CASES[case_index], cuda_device, backend, monkeypatch)
+
+
+@pytest.mark.parametrize("case", LARGE_CASES, ids=lambda c: f"seed{c[0]}-L{c[2]}")
+def test_tensor_core_attention_matches_fp64_oracle_at_full_size(cuda_device, monkeypatch, case):
+    """The layer of BASELINE config 4 (d_model 512, 8 heads of 64, up to 512 tokens, thousands of typed-edge entries) on the
+    tensor-core path against the fp64 evaluation of the oracle layer: outputs and every gradient."""
+    _check_case(case, cuda_device, "tensor-core", monkeypatch, double_oracle=True)
 
 
 def test_tensor_core_attention_at_config4_shape(cuda_device, monkeypatch):
