@@ -18,10 +18,8 @@ from buglab_b200 import ops
 
 
 def _linear(lin: nn.Linear, x: torch.Tensor) -> torch.Tensor:
-    """``lin(x)`` for x [..., k]: on a GPU the product runs on the split-fp16 TMA-fed tcgen05 GEMMs (``ops.dense_linear``:
-    fp32-class accuracy, forward and both backward products) where they cover the shape, else on the fp32 library GEMM."""
-    if not x.is_cuda:
-        return lin(x)
+    """``lin(x)`` for x [..., k] on the split-fp16 TMA-fed tcgen05 GEMMs (``ops.dense_linear``: fp32-class accuracy, forward
+    and both backward products) where they cover the shape, else on the fp32 library GEMM."""
     y = ops.dense_linear(x.reshape(-1, x.shape[-1]), lin.weight)
     if lin.bias is not None:
         y = y + lin.bias

@@ -777,6 +777,8 @@ class DenseLinearTma(torch.autograd.Function):
 
 def dense_linear(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     """Bias-free Linear: split-fp16 tensor-core GEMMs by default, plain fp32 library GEMM in "fp32" mode or for odd widths."""
+    if not x.is_cuda:
+        raise _lib.BuglabB200Error("dense_linear: buglab_b200 has no CPU path (x is a CPU tensor)")
     n_out, k_in = int(weight.shape[0]), int(x.shape[1])
     if _tma_proj_ok(n_out, k_in) and _tma_proj_ok(k_in, n_out) and _tma_wgrad_ok(n_out, k_in):
         return DenseLinearTma.apply(x, weight)

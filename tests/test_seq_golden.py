@@ -234,6 +234,7 @@ def cpu_kernels(monkeypatch, request):
 
     request.getfixturevalue("host_backend")  # attention -> host emulation of csrc/seq_attention_core.h
     monkeypatch.setattr(ops, "layer_norm", lambda x, g, b, eps=1e-5: torch.nn.functional.layer_norm(x, (x.shape[-1],), g, b, eps))
+    monkeypatch.setattr(ops, "dense_linear", lambda x, w: torch.nn.functional.linear(x, w))
     monkeypatch.setattr(ops, "subtoken_maxpool", lambda emb, ids, lens, p_drop=0.0, training=False:
                         mp_ref.subtoken_maxpool_ref(emb, ids.long(), lens.long()))
     monkeypatch.setattr(ops, "segment_log_softmax", lambda src, index, eps=1e-12, num_segments=None:
