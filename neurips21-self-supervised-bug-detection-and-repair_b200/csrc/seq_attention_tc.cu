@@ -58,10 +58,15 @@ __device__ __forceinline__ float dropout_scale(const RowProblem& p, int b, int h
     return seqatt::dropout_scale(q, b, h, i, j);
 }
 
-__device__ __forceinline__ void store_split(__half* hi_row, __half* lo_row, int j, float x) {
-    const __half h = __float2half_rn(x);
-    hi_row[j] = h;
-    lo_row[j] = __float2half_rn(x - __half2float(h));
+__device__ __forceinline__ void store_split4(__half* hi_row, __half* lo_row, int j4, float4 x) {
+    const __half2 h01 = __floats2half2_rn(x.x, x.y), h23 = __floats2half2_rn(x.z, x.w);
+    const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn(x.x - b01.x, x.y - b01.y), l23 = __floats2half2_rn(x.z - b23.x, x.w - b23.y);
+    uint2 hv, lv;
+    hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+    lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+    reinterpret_cast<uint2*>(hi_row)[j4] = hv;
+    reinterpret_cast<uint2*>(lo_row)[j4] = lv;
 }
 
 // ---- forward --------------------------------------------------------------------------------------------------------------
@@ -69,10 +74,11 @@ __device__ __forceinline__ void store_split(__half* hi_row, __half* lo_row, int 
 __global__ void __launch_bounds__(kWarps * 32)
 softmax_fwd_kernel(const RowProblem p, float* __restrict__ scores, float* __restrict__ lse, __half* __restrict__ p_split,
                    float* __restrict__ o_extra) {
-    __shared__ float row_buf[kWarps][kMaxLp];
+    __shared__ __align__(16) float row_buf[kWarps][kMaxLp];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t total_rows = (int64_t)p.B * p.H * p.Lp;
     const int64_t row = (int64_t)blockIdx.x * kWarps + warp;
+    const int L4 = p.Lp >> 2;  // Lp is a multiple of 128: every lane moves whole 16-byte pieces
     __half* const hi_base = p_split;
     __half* const lo_base = p_split + (size_t)(total_rows + 1) * p.Lp;
     if (blockIdx.x == 0 && warp == 0) {  // the zero (padding) row of both parts
@@ -99,7 +105,7 @@ softmax_fwd_kernel(const RowProblem p, float* __restrict__ scores, float* __rest
         return;
     }
     float* srow = scores + (size_t)row * p.Lp;
-    for (int j = lane; j < p.Lp; j += 32) sm[j] = srow[j];
+    for (int j4 = lane; j4 < L4; j4 += 32) reinterpret_cast<float4*>(sm)[j4] = __ldg(reinterpret_cast<const float4*>(srow) + j4);
     __syncwarp();
     const int e0 = __ldg(p.row_ptr + b * p.L + i), e1 = __ldg(p.row_ptr + b * p.L + i + 1);
     const float2 q2 = __ldg(reinterpret_cast<const float2*>(p.q + (size_t)row * kD) + lane);
@@ -119,12 +125,17 @@ softmax_fwd_kernel(const RowProblem p, float* __restrict__ scores, float* __rest
     const float row_lse = m + logf(l);
     if (lane == 0) lse[row] = row_lse;
     const float scale = pow2_scale_for(__ldg(p.amax_p));
-    for (int j = lane; j < p.Lp; j += 32) {
-        const float s = sm[j];
-        if (e1 > e0) srow[j] = s;  // rows without entries are unchanged
-        const float prob = (j < len) ? expf(s - row_lse) * dropout_scale(p, b, h, i, j) : 0.f;
-        sm[j] = prob;
-        store_split(hi_row, lo_row, j, prob * scale);
+    for (int j4 = lane; j4 < L4; j4 += 32) {
+        const float4 s4 = reinterpret_cast<const float4*>(sm)[j4];
+        if (e1 > e0) reinterpret_cast<float4*>(srow)[j4] = s4;  // rows without entries are unchanged
+        const int j = 4 * j4;
+        float4 pr;
+        pr.x = (j < len) ? expf(s4.x - row_lse) * dropout_scale(p, b, h, i, j) : 0.f;
+        pr.y = (j + 1 < len) ? expf(s4.y - row_lse) * dropout_scale(p, b, h, i, j + 1) : 0.f;
+        pr.z = (j + 2 < len) ? expf(s4.z - row_lse) * dropout_scale(p, b, h, i, j + 2) : 0.f;
+        pr.w = (j + 3 < len) ? expf(s4.w - row_lse) * dropout_scale(p, b, h, i, j + 3) : 0.f;
+        reinterpret_cast<float4*>(sm)[j4] = pr;
+        store_split4(hi_row, lo_row, j4, make_float4(pr.x * scale, pr.y * scale, pr.z * scale, pr.w * scale));
     }
     if (o_extra != nullptr) {  // "rat": sum over the row's entries of p'[key] * vbias[tab]
         __syncwarp();
@@ -147,8 +158,8 @@ softmax_bwd_kernel(const RowProblem p, const float* __restrict__ scores, const f
                    const float* __restrict__ out, const float* __restrict__ d_out, float* __restrict__ d_scores,
                    __half* __restrict__ p_split, float* __restrict__ dq_extra, float* __restrict__ d_entry_bias,
                    float* __restrict__ d_entry_vbias, int d_entry_dim) {
-    __shared__ float ds_buf[kWarps][kMaxLp];
-    __shared__ float pr_buf[kWarps][kMaxLp];
+    __shared__ __align__(16) float ds_buf[kWarps][kMaxLp];
+    __shared__ __align__(16) float pr_buf[kWarps][kMaxLp];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t total_rows = (int64_t)p.B * p.H * p.Lp;
     const int64_t row = (int64_t)blockIdx.x * kWarps + warp;
@@ -196,7 +207,8 @@ softmax_bwd_kernel(const RowProblem p, const float* __restrict__ scores, const f
     const float2 o2 = __ldg(reinterpret_cast<const float2*>(out + (size_t)row * kD) + lane);
     const float2 q2 = __ldg(reinterpret_cast<const float2*>(p.q + (size_t)row * kD) + lane);
     const float delta = warp_sum(fmaf(g2.x, o2.x, g2.y * o2.y));  // sum_j p_ij dP_ij = <dO_i, O_i>
-    for (int j = lane; j < p.Lp; j += 32) ds[j] = drow[j];
+    const int L4 = p.Lp >> 2;
+    for (int j4 = lane; j4 < L4; j4 += 32) reinterpret_cast<float4*>(ds)[j4] = __ldg(reinterpret_cast<const float4*>(drow) + j4);
     __syncwarp();
     if (p.vbias != nullptr) {
         for (int e = e0; e < e1; ++e) {
@@ -210,18 +222,28 @@ softmax_bwd_kernel(const RowProblem p, const float* __restrict__ scores, const f
     const float row_lse = __ldg(lse + row);
     const float scale = pow2_scale_for(__ldg(p.amax_p));
     const float* srow = scores + (size_t)row * p.Lp;
-    for (int j = lane; j < p.Lp; j += 32) {
-        float prob_kept = 0.f, dsv = 0.f;
-        if (j < len) {
-            const float prob = expf(__ldg(srow + j) - row_lse);
-            const float mask = dropout_scale(p, b, h, i, j);
-            prob_kept = prob * mask;
-            dsv = prob * (mask * ds[j] - delta);
+    for (int j4 = lane; j4 < L4; j4 += 32) {
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(srow) + j4);
+        const float4 dp4 = reinterpret_cast<const float4*>(ds)[j4];
+        const float sv[4] = {s4.x, s4.y, s4.z, s4.w}, dpv[4] = {dp4.x, dp4.y, dp4.z, dp4.w};
+        float kept[4], dsv[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int j = 4 * j4 + c;
+            kept[c] = 0.f;
+            dsv[c] = 0.f;
+            if (j < len) {
+                const float prob = expf(sv[c] - row_lse);
+                const float mask = dropout_scale(p, b, h, i, j);
+                kept[c] = prob * mask;
+                dsv[c] = prob * (mask * dpv[c] - delta);
+            }
         }
-        ds[j] = dsv;
-        pr[j] = prob_kept;
-        drow[j] = dsv;
-        store_split(hi_row, lo_row, j, prob_kept * scale);
+        const float4 d4 = make_float4(dsv[0], dsv[1], dsv[2], dsv[3]);
+        reinterpret_cast<float4*>(ds)[j4] = d4;
+        reinterpret_cast<float4*>(pr)[j4] = make_float4(kept[0], kept[1], kept[2], kept[3]);
+        reinterpret_cast<float4*>(drow)[j4] = d4;
+        store_split4(hi_row, lo_row, j4, make_float4(kept[0] * scale, kept[1] * scale, kept[2] * scale, kept[3] * scale));
     }
     __syncwarp();
     float2 acc = make_float2(0.f, 0.f);
