@@ -535,24 +535,12 @@ class TypedEdgeMessageMax(torch.autograd.Function):
                     main.wait_stream(side)  # dU is complete; g_rows / ewin are no longer read on the side stream
                 d_rows[slot] = tma_project(g_split, None, weight_parts(weight, D, M, col0, True, amax_w), None, amax, tiles,
                                            int(rows_idx.shape[0]), slabs, amax_w)
-                if slot == 0 and side is not None:
-                    # both row tables are complete: the (HBM-bound) per-node row sum runs on the side stream under the
-                    # (tensor-bound) S-table weight gradient
-                    d_h = torch.empty_like(h)
-                    side.wait_stream(main)
-                    with torch.cuda.stream(side):
-                        check(lib.bl_rows_segment_sum(f32(d_rows[0]), i32(plan.s_by_node_ptr), i32(plan.s_by_node_idx),
-                                                      f32(d_rows[1]), i32(plan.t_by_node_ptr), i32(plan.t_by_node_idx),
-                                                      N, D, 0, None, f32(d_h), stream_ptr(dev)), "bl_rows_segment_sum")
                 tma_weight_grad(g_split, h_split, rows_idx, amax, slabs, d_weight, col0, amax_h)
-            if side is not None:
-                main.wait_stream(side)  # d_h is complete; the row tables are no longer read on the side stream
-            else:
-                d_h = torch.empty_like(h)
-                check(lib.bl_rows_segment_sum(f32(d_rows[0]), i32(plan.s_by_node_ptr), i32(plan.s_by_node_idx),
-                                              f32(d_rows[1]), i32(plan.t_by_node_ptr), i32(plan.t_by_node_idx),
-                                              N, D, 0, None, f32(d_h), stream_ptr(dev)), "bl_rows_segment_sum")
             del du_split, dv_split, g_rows
+            d_h = torch.empty_like(h)
+            check(lib.bl_rows_segment_sum(f32(d_rows[0]), i32(plan.s_by_node_ptr), i32(plan.s_by_node_idx),
+                                          f32(d_rows[1]), i32(plan.t_by_node_ptr), i32(plan.t_by_node_idx),
+                                          N, D, 0, None, f32(d_h), stream_ptr(dev)), "bl_rows_segment_sum")
             return d_h, d_weight, d_bias, None
 
         if plan.block_nodes > 0:
