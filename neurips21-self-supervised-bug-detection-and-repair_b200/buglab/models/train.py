@@ -57,7 +57,9 @@ def _data_sources(arguments, rank: int, world: int):
     the same files, shard them over ranks the same way and stop after the same number of elements."""
     credentials = arguments.get("--azure-info", None)
     files_cap = _optional_int(arguments["--max-files-per-fold"])
-    epoch_length = int(arguments["--validate-after"])
+    # --validate-after counts samples of the whole job (train.py:13 of the reference, single process): under data
+    # parallelism every rank yields its share, so that an "epoch" covers the same number of samples at any world size
+    epoch_length = max(1, -(-int(arguments["--validate-after"]) // max(world, 1)))
     folds = {name: RichPath.create(arguments[key], credentials)
              for name, key in (("train", "TRAIN_DATA_PATH"), ("valid", "VALID_DATA_PATH"))}
     if arguments.get("--host-loader"):
