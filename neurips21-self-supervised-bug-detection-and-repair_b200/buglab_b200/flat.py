@@ -69,10 +69,17 @@ class FlatAdam(torch.optim.Optimizer):
     def num_steps(self) -> int:
         return self._step
 
-    def gradient_reducer(self, bucket_bytes: int = 32 << 20):
-        """The bucketed all-reduce of this optimiser's flat gradient, overlapped with backward (created once)."""
+    def gradient_reducer(self, bucket_bytes: Optional[int] = None):
+        """The bucketed all-reduce of this optimiser's flat gradient, overlapped with backward (created once).
+        ``BUGLAB_B200_ALLREDUCE_BUCKET_MB`` overrides the bucket size (a value >= the gradient's size gives one bucket,
+        reduced after backward)."""
         if getattr(self, "_reducer", None) is None:
+            import os
+
             from .distributed import OverlappedGradientReducer
+
+            if bucket_bytes is None:
+                bucket_bytes = int(float(os.environ.get("BUGLAB_B200_ALLREDUCE_BUCKET_MB", "32")) * (1 << 20))
 
             self._reducer = OverlappedGradientReducer(self.flat_grad, self._params, self._offsets, bucket_bytes)
         return self._reducer
