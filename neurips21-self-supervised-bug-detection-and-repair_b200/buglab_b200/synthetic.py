@@ -339,14 +339,16 @@ class SyntheticProgramGenerator:
             yield self.sample()
 
 
-def write_shards(directory: str, num_shards: int, graphs_per_shard: int, seed: int = 0, **generator_kwargs) -> List[str]:
-    """Writes ``num_shards`` files ``shard_XXXX.msgpack.l.gz`` in the reference wire format."""
+def write_shards(directory: str, num_shards: int, graphs_per_shard: int, seed: int = 0, programs: bool = False,
+                 **generator_kwargs) -> List[str]:
+    """Writes ``num_shards`` files ``shard_XXXX.msgpack.l.gz`` in the reference wire format (``programs``: token-chain
+    program graphs from :class:`SyntheticProgramGenerator`, which the sequence models can project onto token sequences)."""
     import os
 
     from buglab.utils.msgpackutils import save_msgpack_l_gz
 
     os.makedirs(directory, exist_ok=True)
-    gen = SyntheticBugLabGenerator(seed=seed, **generator_kwargs)
+    gen = (SyntheticProgramGenerator if programs else SyntheticBugLabGenerator)(seed=seed, **generator_kwargs)
     paths = []
     for s in range(num_shards):
         path = os.path.join(directory, f"shard_{s:04d}.msgpack.l.gz")

@@ -181,3 +181,38 @@ def test_module_matches_reference_goldens(cuda_device, layer_type):
         if "edge_attention_biases" in name or "edge_value_biases" in name:
             grad = grad[inverse]
         assert float((grad - ref).abs().max()) <= 1e-4 * (float(ref.abs().max()) + 1e-12) + 1e-5, name
+
+
+def test_train_and_evaluate_entry_points_run_for_seq_great(cuda_device, tmp_path):
+    """python -m buglab.models.train seq-great TRAIN VALID MODEL.pkl.gz on synthetic program shards (host-language decode:
+    the native tensoriser serves the graph models), then evaluate: the trainer, the sequence model, the tensor-core
+    attention and the TMA-GEMM dense layers together (hidden 128 / 2 heads of 64: every product takes the tcgen05 path)."""
+    import logging
+
+    from buglab.models import evaluate, train
+    from buglab_b200 import ops
+    from buglab_b200.synthetic import write_shards
+
+    logging.getLogger("buglab.models.seqmodel").setLevel(logging.CRITICAL)
+    write_shards(str(tmp_path / "train"), 2, 10, seed=1, programs=True, statements=10)
+    write_shards(str(tmp_path / "valid"), 1, 6, seed=2, programs=True, statements=10)
+    model_path = tmp_path / "model.pkl.gz"
+    calls = {"attention": 0}
+    original = ops.SeqEdgeAttentionTcFn.forward
+
+    def counting(ctx, *args, **kwargs):
+        calls["attention"] += 1
+        return original(ctx, *args, **kwargs)
+
+    ops.SeqEdgeAttentionTcFn.forward = staticmethod(counting)
+    try:
+        train.main(["seq-great", str(tmp_path / "train"), str(tmp_path / "valid"), str(model_path), "--max-num-epochs=2",
+                    "--minibatch-size=5", "--quiet", "--model-spec",
+                    '{"hidden_state_size": 128, "num_heads": 2, "num_layers": 2, "max_seq_size": 256, "intermediate_dimension_size": 256}'])
+    finally:
+        ops.SeqEdgeAttentionTcFn.forward = staticmethod(original)
+    assert model_path.exists() and calls["attention"] > 0
+    args = {"MODEL_FILENAME": str(model_path), "TEST_DATA_PATH": str(tmp_path / "valid"), "--limit-num-elements": None,
+            "--sequential": True, "--azure-info": None}
+    metrics = evaluate.run(args)
+    assert metrics["num_samples"] > 0 and 0.0 <= metrics["localization_accuracy"] <= 1.0

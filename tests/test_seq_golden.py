@@ -355,3 +355,39 @@ def test_registry_defaults_build_and_checkpoints_round_trip(tmp_path):
     assert all(torch.equal(a, b) for a, b in zip(nn.state_dict().values(), restored_nn.state_dict().values()))
     sample = SyntheticProgramGenerator(seed=3).sample()
     assert model.tensorize(copy.deepcopy(sample)).node_mappings == restored.tensorize(copy.deepcopy(sample)).node_mappings
+
+
+def test_train_and_evaluate_entry_points_for_seq_great_on_cpu_kernels(cpu_kernels, monkeypatch, tmp_path):
+    """``python -m buglab.models.train seq-great …`` then ``evaluate`` over synthetic program shards, with every CUDA entry
+    point replaced as above and the fused optimiser by ``torch.optim.Adam``: the wiring of the trainer, the shard loader's
+    host-language path for non-graph models, the sequence model's minibatching, metrics and ``predict`` (the GPU twin is
+    tests/test_seq_attention_gpu.py::test_train_and_evaluate_entry_points_run_for_seq_great)."""
+    import logging
+
+    import buglab.models.train as train_mod
+    import buglab.models.utils as utils_mod
+    from buglab.models import evaluate
+    from buglab_b200.synthetic import write_shards
+
+    logging.getLogger("buglab.models.seqmodel").setLevel(logging.CRITICAL)
+    adam = lambda params, lr=0.0001: torch.optim.Adam(params, lr=lr)  # noqa: E731
+    monkeypatch.setattr(utils_mod, "optimizer", adam)
+    monkeypatch.setattr(train_mod, "optimizer", adam, raising=False)
+    write_shards(str(tmp_path / "train"), 2, 8, seed=1, programs=True, statements=6)
+    write_shards(str(tmp_path / "valid"), 1, 4, seed=2, programs=True, statements=6)
+    model_path = tmp_path / "model.pkl.gz"
+    train_mod.main(["seq-great", str(tmp_path / "train"), str(tmp_path / "valid"), str(model_path), "--max-num-epochs=1",
+                    "--minibatch-size=4", "--quiet", "--sequential", "--model-spec",
+                    '{"hidden_state_size": 32, "num_heads": 2, "num_layers": 1, "max_seq_size": 200, "intermediate_dimension_size": 64}'])
+    assert model_path.exists()
+    # evaluate.run insists on a CUDA device (no CPU path in the product): its two halves are driven here directly
+    from pathlib import Path
+
+    from buglab.models.gnn import GnnBugLabModel
+    from buglab.utils.msgpackutils import load_all_msgpack_l_gz
+    from dpu_utils.utils import RichPath
+
+    model, nn = GnnBugLabModel.restore_model(Path(model_path), torch.device("cpu"))
+    data = load_all_msgpack_l_gz(RichPath.create(str(tmp_path / "valid")), shuffle=False)
+    metrics = evaluate.evaluate_predictions(model.predict(data, nn, torch.device("cpu"), parallelize=False), False, False)
+    assert metrics["num_samples"] > 0 and 0.0 <= metrics["localization_accuracy"] <= 1.0
