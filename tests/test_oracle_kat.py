@@ -218,3 +218,26 @@ def test_forced_relu_kinks_and_their_audit():
     assert abs(relu.routing_audit["max_relative_deficit"] - float(pre.abs().max())) < 1e-12
     with pytest.raises(AssertionError, match="falls short"):
         parity.assert_routing_is_valid([relu.routing_audit], "wrong kink")
+
+
+def test_scatter_ref_values_agree_with_torch_scatter_reduce():
+    """An independent witness for the restated torch_scatter reductions (the package itself is absent):
+    PyTorch's own ``scatter_reduce`` (amax / amin / sum / mean, ``include_self=False``) must give the same VALUES on
+    non-empty segments; torch_scatter's conventions that PyTorch does not share — empty segments -> 0 and the arg output with
+    first-extreme-wins — stay pinned by the hand-computed cases above."""
+    g = torch.Generator().manual_seed(3)
+    src = torch.randn(200, 7, generator=g, dtype=torch.float64)
+    index = torch.randint(0, 23, (200,), generator=g)
+    index[index == 5] = 6   # segment 5 is empty
+    S = 25                  # 23, 24 empty too
+    idx2 = index.view(-1, 1).expand_as(src)
+    nonempty = torch.zeros(S, dtype=torch.bool).index_fill_(0, index, True)
+    for name, ref_fn in (("amax", scatter_ref.scatter_max), ("amin", scatter_ref.scatter_min)):
+        ours = ref_fn(src, index, dim=0, dim_size=S)[0]
+        theirs = torch.zeros(S, 7, dtype=torch.float64).scatter_reduce(0, idx2, src, reduce=name, include_self=False)
+        assert torch.equal(ours[nonempty], theirs[nonempty])
+        assert torch.all(ours[~nonempty] == 0)
+    assert torch.allclose(scatter_ref.scatter_sum(src, index, dim=0, dim_size=S),
+                          torch.zeros(S, 7, dtype=torch.float64).scatter_reduce(0, idx2, src, reduce="sum", include_self=False))
+    mean_theirs = torch.zeros(S, 7, dtype=torch.float64).scatter_reduce(0, idx2, src, reduce="mean", include_self=False)
+    assert torch.allclose(scatter_ref.scatter_mean(src, index, dim=0, dim_size=S)[nonempty], mean_theirs[nonempty])
