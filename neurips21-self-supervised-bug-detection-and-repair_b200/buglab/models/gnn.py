@@ -338,8 +338,12 @@ class GnnBugLabModel(AbstractNeuralModel[BugLabData, BaseTensorizedBugLabGnn, Gn
         arrays = []
         for key in _INDEX_KEYS:
             chunks = mb[key]
-            arrays.append(np.concatenate([np.atleast_1d(c) for c in chunks]).astype(np.int32, copy=False)
-                          if chunks else np.zeros(0, dtype=np.int32))
+            if not chunks:
+                arrays.append(np.zeros(0, dtype=np.int32))
+            elif np.ndim(chunks[0]) == 0:   # per-sample scalars (every chunk of a key has the same rank)
+                arrays.append(np.asarray(chunks, dtype=np.int32))
+            else:
+                arrays.append(np.concatenate(chunks).astype(np.int32, copy=False))
         arrays.append(np.asarray(mb["has_bug"], dtype=np.int32))
         sizes = [a.shape[0] for a in arrays]
         staging = torch.empty(max(sum(sizes), 1), dtype=torch.int32, pin_memory=(device.type == "cuda"))
