@@ -213,8 +213,11 @@ USE_TMA = os.environ.get("BUGLAB_B200_TMA", "1") != "0"
 # Edge backward that writes the gradient tables as fp16 split tables with one writer per row (bl_edge_bwd_targets/_sources)
 # instead of fp32 tables + REDs + a split pass; BUGLAB_B200_SPLIT_EDGE_BWD=0 keeps round 1's bl_edge_segmax_bwd.
 USE_SPLIT_EDGE_BACKWARD = os.environ.get("BUGLAB_B200_SPLIT_EDGE_BWD", "1") != "0"
-# Run the by-source half of the edge backward on a side stream, concurrently with the T-table GEMMs (BUGLAB_B200_OVERLAP=0: off)
-OVERLAP_EDGE_BACKWARD = os.environ.get("BUGLAB_B200_OVERLAP", "1") != "0"
+# BUGLAB_B200_OVERLAP=1: run the by-source half of the edge backward on a side stream, concurrently with the T-table GEMMs.
+# Off by default: measured on power-capped B200s (profiles/r2_overlap_vs_e2e.txt, same box, alternating, 3 x 20 steps each)
+# it does not change the resident step (1 064 graphs/s either way — the tensor-bound and the HBM-bound kernels share one power
+# budget) and costs ~1.3 % end to end (1 027 vs 1 041 graphs/s) with the loader's copy / plan stream as a third stream.
+OVERLAP_EDGE_BACKWARD = os.environ.get("BUGLAB_B200_OVERLAP", "0") != "0"
 # Pre-scale BOTH operands of the TMA GEMMs by powers of two (activations and weights to ~2^12) so that their fp16 lo parts
 # are normal numbers (unscaled, the lo part of a typical weight is a subnormal: ~17 instead of 22 significant bits)
 PRESCALE_OPERANDS = os.environ.get("BUGLAB_B200_PRESCALE", "1") != "0"

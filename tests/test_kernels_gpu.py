@@ -73,12 +73,15 @@ def test_plan_no_edges(cuda_device):
     (3000, 256, 256, 9, [9000, 6000, 0, 2500, 40], True, True),   # the bench's H->H layer shape
     (1500, 512, 512, 4, [6000, 3000, 900], True, False),          # the bench's wide layer shape
 ])
-@pytest.mark.parametrize("mode", ["f16x3", "fp32", "f16x3-blocked"])
+@pytest.mark.parametrize("mode", ["f16x3", "fp32", "f16x3-blocked", "f16x3-blocked-overlap"])
 def test_typed_edge_message_max_fwd_bwd(cuda_device, monkeypatch, mode, N, D, M, K, epk, self_edges, use_bias):
     from buglab_b200 import ops
     from oracle.mp_ref import typed_edge_message_max_ref
 
     block_nodes = 0
+    if mode == "f16x3-blocked-overlap":   # the optional side-stream schedule of the by-source backward (BUGLAB_B200_OVERLAP=1)
+        mode = "f16x3-blocked"
+        monkeypatch.setattr(ops, "OVERLAP_EDGE_BACKWARD", True)
     if mode == "f16x3-blocked":  # node-blocked pair tables (many small segments): only where every product runs on the TMA GEMMs
         mode = "f16x3"
         if ops.plan_block_nodes_for([(D, M)]) == 0:
