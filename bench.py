@@ -146,6 +146,17 @@ def make_workload(seed: int, graphs: int, hidden: int, mean_nodes: int, batches:
     return model, host_batches
 
 
+def workload_config(args, model, nodes_per_step, edges_per_step, world):
+    """The ``config`` object of the JSON line.  Both arms print the SAME object (the reference arm times a bounded sample
+    of this workload and says which in ``cpu_baseline.sample``), so it is built in one place."""
+    return {
+        "workload": f"gnn-mlp hidden={args.hidden}, 8 MP layers, {args.graphs} graphs/step/GPU (~{args.mean_nodes} nodes each, "
+                    f"{model.gnn_model.num_edge_types} edge kinds per layer), train step fwd+bwd+allreduce+clip+Adam, dropout {DROPOUT}",
+        "nodes_per_step": int(nodes_per_step), "edges_per_step": int(edges_per_step), "parallelism": f"dp{world}",
+        "l2_policy": "inputs larger than L2 (per-layer tables are GBs; 126 MB L2), distinct minibatches cycled",
+    }
+
+
 def pack(model, tensorized, device):
     mb = model.initialize_minibatch()
     for t in tensorized:
@@ -273,12 +284,7 @@ def run_ours(args):
         "ms_per_step": ms_resident / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {
-            "workload": f"gnn-mlp hidden={args.hidden}, 8 MP layers, {args.graphs} graphs/step/GPU (~{args.mean_nodes} nodes each, "
-                        f"{model.gnn_model.num_edge_types} edge kinds per layer), train step fwd+bwd+allreduce+clip+Adam, dropout {DROPOUT}",
-            "nodes_per_step": nodes[0], "edges_per_step": edges[0], "parallelism": f"dp{world}",
-            "l2_policy": "inputs larger than L2 (per-layer tables are GBs; 126 MB L2), distinct minibatches cycled",
-        },
+        "config": workload_config(args, model, nodes[0], edges[0], world),
         "e2e": {"value": total_graphs / (ms_e2e / 1e3), "unit": "graphs/s", "h2d_bytes_per_step": h2d_bytes[0],
                 "d2h_bytes_per_step": 4 + 4 * (2 * model.gnn_model.num_edge_types + 4), "ms_per_step": ms_e2e / args.steps,
                 "from": "host tensorised samples (numpy) -> minibatch packing -> pinned staging -> H2D -> device plan (producer thread, side stream, overlapped with the previous step as in ModelTrainer) -> step -> loss D2H (every step, read one step late); steady state: the depth-2 loader pipeline runs through warm-up and timed steps, `steps` minibatches are packed and copied inside the timed region",
@@ -651,15 +657,26 @@ def run_reference(args):
     for key in ("WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):  # rank 0 runs alone; no process group
         os.environ.pop(key, None)
     os.environ["RANK"] = "0"
-    base = cpu_train_entry(args.hidden, steps=args.steps, warmup=min(args.warmup, 2), threads=args.cpu_threads)
+    # the config object is this arm's workload exactly as the GPU arm prints it (rank 0's first minibatch: same generator,
+    # same seed; node and edge counts taken from the tensorised samples, edges incl. backward and self edges)
+    model, host_batches = make_workload(1000, args.graphs, args.hidden, args.mean_nodes, 1, DROPOUT)
+    nodes = sum(t[0].num_nodes for t in host_batches[0])
+    edges = sum(len(src) for t in host_batches[0] for src, _ in t[0].adjacency_lists)
+    config = workload_config(args, model, nodes, edges, max(1, args.gpus))
+    del model, host_batches
+    warmup = min(args.warmup, 5)  # whole minibatches of ~15 s each on the host cores: bounded
+    base = cpu_train_entry(args.hidden, steps=args.steps, warmup=warmup, threads=args.cpu_threads)
     print(json.dumps({
         "impl": "reference",
         "metric": "code-graphs/sec (train step, device-timed)", "value": base["value"], "unit": "graphs/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 2), "ms_per_step": base["ms_per_step"],
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup, "ms_per_step": base["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"gnn-mlp hidden={args.hidden}, 8 MP layers, train step (fwd+bwd+clip+Adam, dropout {DROPOUT}) on the "
-                               f"host CPU through buglab.models.train; bounded sample: minibatches of <= 30 000 nodes (~15 graphs of "
-                               f"~{MEAN_NODES} nodes), the reference's own minibatch budget", "parallelism": "cpu"},
+        "config": config,
+        "reference_arm": {"runs_on": "host CPU cores (GPUs hidden), buglab.models.train --sequential over oracle/cpu_backend.py",
+                          "bounded_sample": f"each step = one minibatch of the same generator cut by the reference's own 30 000-node "
+                                            f"budget (~15 graphs of ~{args.mean_nodes} nodes) instead of {args.graphs} graphs; "
+                                            "graphs/s is per-graph throughput, comparable across the two step sizes",
+                          "warmup_steps_run": warmup},
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
