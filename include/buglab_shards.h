@@ -109,6 +109,12 @@ void bl_sample_destroy(bl_sample* sample);
 int32_t bl_sample_decode(const bl_shard* shard, int64_t index, const bl_tokenizer* tok,
                          const char* const* edge_type_names, int32_t num_edge_types, bl_sample* sample,
                          bl_sample_view* view);
+/* The same for `count` objects in ONE call: object indices[i] is decoded into samples[i] (distinct handles) and views[i].
+ * A host loader thread decodes a whole chunk of a shard without returning to its interpreter in between (one GIL
+ * hand-off per chunk instead of one per sample).  Stops at the first error and returns its code. */
+int32_t bl_sample_decode_many(const bl_shard* shard, const int64_t* indices, int32_t count, const bl_tokenizer* tok,
+                              const char* const* edge_type_names, int32_t num_edge_types, bl_sample* const* samples,
+                              bl_sample_view* views);
 
 /* Iteration order of a CPython `set` filled with the given non-negative ints in this order (testing hook for the
  * emulation that data.py:103-108 makes load-bearing: the order decides the ids of the subtoken nodes).

@@ -65,6 +65,7 @@ _SIGNATURES = {
     "bl_sample_create": (c_i32, [ctypes.POINTER(c_ptr)]),
     "bl_sample_destroy": (None, [c_ptr]),
     "bl_sample_decode": (c_i32, [c_ptr, c_i64, c_ptr, c_ptr, c_i32, c_ptr, ctypes.POINTER(SampleView)]),
+    "bl_sample_decode_many": (c_i32, [c_ptr, c_ptr, c_i32, c_ptr, c_ptr, c_i32, c_ptr, c_ptr]),
     "bl_pyset_iteration_order": (c_i64, [c_ptr, c_i64, c_ptr]),
 }
 
@@ -223,11 +224,15 @@ class Tokenizer:
             pass
 
 
+_ITEMSIZE = {np.int32: 4, np.int64: 8}
+
+
 def _as_array(ptr: Optional[int], count: int, dtype) -> np.ndarray:
+    """A writable numpy copy of ``count`` elements at ``ptr`` (memory owned by a ``bl_sample``: valid only until its next
+    decode)."""
     if count == 0 or not ptr:
         return np.zeros(0, dtype=dtype)
-    ctype = {np.int32: ctypes.c_int32, np.int64: ctypes.c_int64}[dtype]
-    return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctype)), shape=(count,)).copy()
+    return np.frombuffer((ctypes.c_char * (count * _ITEMSIZE[dtype])).from_address(ptr), dtype=dtype).copy()
 
 
 class _SampleBuffer:
@@ -247,6 +252,17 @@ class _SampleBuffer:
             pass
 
 
+class _ChunkBuffers:
+    """Per-thread set of ``bl_sample`` handles + views for ``bl_sample_decode_many`` (one chunk of a shard per call)."""
+
+    def __init__(self, capacity: int):
+        self.capacity = capacity
+        self.samples = [_SampleBuffer() for _ in range(capacity)]
+        self.handles = (c_ptr * capacity)(*[b.handle for b in self.samples])
+        self.views = (SampleView * capacity)()
+        self.indices = (c_i64 * capacity)()
+
+
 class NativeShardTensorizer:
     """``shard file -> BaseTensorizedBugLabGnn`` for a ``GnnBugLabModel`` whose metadata is finalised."""
 
@@ -262,6 +278,7 @@ class NativeShardTensorizer:
         self._edge_names = (ctypes.c_char_p * max(1, len(names)))(*names)
         self._num_edge_types = len(names)
         self._local = threading.local()
+        self._stats_lock = threading.Lock()
         self.num_native = 0   # samples produced by the native path / handed to the host path (statistics)
         self.num_host = 0
 
@@ -278,27 +295,38 @@ class NativeShardTensorizer:
         v = buf.view
         check(lib().bl_sample_decode(shard._h, index, self._tokenizer._h, self._edge_names, self._num_edge_types,
                                      buf.handle, ctypes.byref(v)), "decode")
+        return self._from_view(v)
+
+    def _from_view(self, v: SampleView):
+        """The ``BaseTensorizedBugLabGnn`` tuple of one decoded sample (``None``: nil object, or dropped by the model)."""
         if v.status == SAMPLE_NIL:
             return None
         if v.status == SAMPLE_NEEDS_HOST:
-            self.num_host += 1
+            with self._stats_lock:
+                self.num_host += 1
             datapoint = msgpack.unpackb(ctypes.string_at(v.raw, v.raw_len), raw=False)
             return self._model.tensorize(datapoint)
-        self.num_native += 1
+        with self._stats_lock:
+            self.num_native += 1
         model, gnn_model = self._model, self._gnn_model
 
-        raw = ctypes.string_at(v.raw, v.raw_len)
-        rewrites = msgpack.unpackb(raw[v.rewrites_off: v.rewrites_off + v.rewrites_len], raw=False)
-        metadata = msgpack.unpackb(raw[v.metadata_off: v.metadata_off + v.metadata_len], raw=False)
+        # the three small candidate-rewrite fields are decoded by the host from their byte ranges (a few hundred bytes; the
+        # sample's full raw bytes are never copied)
+        raw = v.raw
+        rewrites = msgpack.unpackb(ctypes.string_at(raw + v.rewrites_off, v.rewrites_len), raw=False)
+        metadata = msgpack.unpackb(ctypes.string_at(raw + v.metadata_off, v.metadata_len), raw=False)
         logprobs = None
         has_logprobs = v.logprobs_len > 0
         if has_logprobs:
             assert not model._tensorize_only_at_target_location_rewrites
-            logprobs = msgpack.unpackb(raw[v.logprobs_off: v.logprobs_off + v.logprobs_len], raw=False)
+            logprobs = msgpack.unpackb(ctypes.string_at(raw + v.logprobs_off, v.logprobs_len), raw=False)
 
-        reference_nodes = _as_array(v.reference_nodes, v.num_reference_nodes, np.int32).tolist()
+        reference_array = _as_array(v.reference_nodes, v.num_reference_nodes, np.int32)
+        reference_nodes = reference_array.tolist()
         target_action = int(v.target_fix_action_idx) if v.has_target else None
-        candidate_nodes, inverse = np.unique(reference_nodes, return_inverse=True)
+        # np.unique over the int64 array np.unique would build from the list of Python ints (data.py:141): same values, same
+        # dtypes, without the per-element conversion
+        candidate_nodes, inverse = np.unique(reference_array.astype(np.int64), return_inverse=True)
         target_node_idx = None if target_action is None else inverse[target_action]
 
         call_args: Dict[int, List[int]] = defaultdict(list)
@@ -324,18 +352,52 @@ class NativeShardTensorizer:
 
     # ---- whole shards ---------------------------------------------------------------------------
     _DROPPED = object()  # a sample the model declined (too many nodes): counted by the loader, not yielded
+    CHUNK = 32           # samples per work item: files are inflated whole, then decoded chunk by chunk by the workers
+    DECODE_WORKERS = 2   # threads decoding chunks (the rest of ``num_threads`` only inflate files ahead)
 
-    def _shard_items(self, path: str, rank: int, world_size: int) -> List:
+    @staticmethod
+    def _indices(shard: Shard, rank: int, world_size: int) -> List[int]:
+        n = len(shard)
+        return list(range(n)) if world_size <= 1 else list(range(rank, n, world_size))
+
+    def _decode_chunk(self, shard: Shard, indices: Sequence[int]) -> List:
+        """Tensorised samples of one chunk of a shard, in order (nil objects skipped, dropped samples as ``_DROPPED``)."""
+        bufs = getattr(self._local, "chunk", None)
+        if bufs is None:
+            bufs = self._local.chunk = _ChunkBuffers(self.CHUNK)
         out: List = []
-        with Shard(path) as shard:
-            for i in range(len(shard)):
-                if world_size > 1 and i % world_size != rank:
-                    continue
-                buf = self._buffer()
-                t = self.tensorize_object(shard, i)
-                if t is None and buf.view.status == SAMPLE_NIL:
+        for start in range(0, len(indices), bufs.capacity):
+            part = indices[start: start + bufs.capacity]
+            n = len(part)
+            bufs.indices[:n] = part
+            # ONE native call (outside the GIL) for the whole chunk, then the host-side assembly of its samples
+            check(lib().bl_sample_decode_many(shard._h, bufs.indices, n, self._tokenizer._h, self._edge_names,
+                                              self._num_edge_types, bufs.handles, bufs.views), "decode")
+            for k in range(n):
+                v = bufs.views[k]
+                t = self._from_view(v)
+                if t is None and v.status == SAMPLE_NIL:
                     continue
                 out.append(self._DROPPED if t is None else t)
+        return out
+
+    @staticmethod
+    def _open(path: str) -> Optional[Shard]:
+        try:
+            return Shard(path)
+        except RuntimeError as e:  # unreadable shard: skipped like the reference does (msgpackutils.py:44-45)
+            print(f"Error loading {path}: {e}.")
+            return None
+
+    @staticmethod
+    def _finish(shard: Shard) -> None:
+        if shard.status != 0:
+            print(f"Error loading {shard.path}: {lib().bl_shards_error_string(shard.status).decode()}.")
+        shard.close()
+
+    def _shard_items(self, path: str, rank: int, world_size: int) -> List:
+        with Shard(path) as shard:
+            out = self._decode_chunk(shard, self._indices(shard, rank, world_size))
             if shard.status != 0:
                 print(f"Error loading {path}: {lib().bl_shards_error_string(shard.status).decode()}.")
         return out
@@ -347,56 +409,116 @@ class NativeShardTensorizer:
             if t is not self._DROPPED:
                 yield t
 
+    def _chunks_sequential(self, paths: Sequence[str], shard_args: Tuple[int, int]) -> Iterator[List]:
+        for path in paths:
+            shard = self._open(path)
+            if shard is None:
+                continue
+            try:
+                indices = self._indices(shard, *shard_args)
+                for c in range(0, len(indices), self.CHUNK):
+                    yield self._decode_chunk(shard, indices[c: c + self.CHUNK])
+            finally:
+                self._finish(shard)
+
+    def _chunks_parallel(self, paths: Sequence[str], shard_args: Tuple[int, int], num_threads: int) -> Iterator[List]:
+        """Chunks of tensorised samples in file order from a pool of ``num_threads`` workers.  Two kinds of work items share
+        the pool: *open* (inflate + index one file, a few files ahead of the one being decoded) and *decode* (one chunk of
+        ``CHUNK`` samples of an open file) — so a single 500-graph shard keeps every worker busy and its first samples are
+        available as soon as the file is inflated, instead of after the whole file has been decoded by one thread.  A shard
+        is shared read-only by the workers (``include/buglab_shards.h``: immutable after creation) and closed once its last
+        chunk has been consumed.  Look-ahead is bounded: ``open_ahead`` inflated files, ``2 * num_threads`` chunks."""
+        from collections import deque
+
+        # the decode items end with host-side assembly under the GIL (~0.25 ms per sample): beyond DECODE_WORKERS threads they
+        # only contend with each other and with the consumer; inflating (zlib, outside the GIL, ~2/3 of the work) scales
+        decode_workers = min(num_threads, self.DECODE_WORKERS)
+        pool = ThreadPoolExecutor(max_workers=decode_workers)
+        open_pool = ThreadPoolExecutor(max_workers=num_threads)
+        open_ahead = num_threads
+        max_inflight = 2 * decode_workers
+        opened: List[Shard] = []  # every shard this call opened and has not closed yet (closed in `finally` on early exit)
+        opening: "deque" = deque()  # files being inflated ahead of the one being decoded (futures)
+
+        def work_items() -> Iterator[Tuple[str, Any, Any]]:
+            it = iter(paths)
+
+            def open_next() -> None:
+                p = next(it, None)
+                if p is not None:
+                    opening.append(open_pool.submit(self._open, p))
+
+            for _ in range(open_ahead):
+                open_next()
+            while opening:
+                shard = opening.popleft().result()
+                open_next()
+                if shard is None:
+                    continue
+                opened.append(shard)
+                indices = self._indices(shard, *shard_args)
+                for c in range(0, len(indices), self.CHUNK):
+                    yield "chunk", shard, indices[c: c + self.CHUNK]
+                yield "end", shard, None
+
+        items = work_items()
+        window: "deque" = deque()
+
+        def fill() -> None:
+            while len(window) < max_inflight:
+                item = next(items, None)
+                if item is None:
+                    return
+                kind, shard, indices = item
+                window.append((kind, shard, pool.submit(self._decode_chunk, shard, indices) if kind == "chunk" else None))
+
+        try:
+            fill()
+            while window:
+                kind, shard, future = window.popleft()
+                if kind == "chunk":
+                    result = future.result()
+                    fill()
+                    yield result
+                else:
+                    opened.remove(shard)
+                    self._finish(shard)
+                    fill()
+        finally:
+            # a consumer that stops early (element limit, closed generator): no worker may still be decoding from a shard
+            # when it is closed
+            pool.shutdown(wait=True, cancel_futures=True)
+            open_pool.shutdown(wait=True, cancel_futures=True)
+            for future in opening:  # files inflated ahead whose turn never came
+                if not future.cancelled() and future.exception() is None and future.result() is not None:
+                    future.result().close()
+            for shard in opened:
+                shard.close()
+
     def tensorize_files(self, paths: Iterable[str], num_threads: Optional[int] = None, rank: int = 0, world_size: int = 1,
                         element_sharding: bool = False, limit_num_elements: Optional[int] = None
                         ) -> Iterator[Tuple[Any, None]]:
-        """``(tensorised, None)`` pairs — the shape ``tensorize_dataset`` yields — over many shard files.  Files are
-        decoded by ``num_threads`` workers (the native calls run outside the GIL); results come back in file order.
-        ``limit_num_elements`` counts non-nil file elements the way load_all_msgpack_l_gz does (it stops after the
-        element that EXCEEDS the limit, as the reference's loop does)."""
+        """``(tensorised, None)`` pairs — the shape ``tensorize_dataset`` yields — over many shard files, in file order.
+        Files are inflated and their samples decoded by ``num_threads`` workers (the native calls run outside the GIL),
+        chunk by chunk (:meth:`_chunks_parallel`).  ``limit_num_elements`` counts non-nil file elements the way
+        load_all_msgpack_l_gz does (it stops after the element that EXCEEDS the limit, as the reference's loop does)."""
         paths = list(paths)
         if num_threads is None:
-            num_threads = max(1, min(8, (os.cpu_count() or 2) - 1))
+            num_threads = max(1, min(4, (os.cpu_count() or 2) - 1))  # the host-side assembly holds the GIL: more workers only contend
         shard_args = (rank, world_size) if element_sharding else (0, 1)
-
-        def work(path):
-            try:
-                return self._shard_items(path, *shard_args)
-            except RuntimeError as e:  # unreadable shard: skipped like the reference does (msgpackutils.py:44-45)
-                print(f"Error loading {path}: {e}.")
-                return []
-
-        def per_file() -> Iterator[List]:
-            if num_threads <= 1 or len(paths) <= 1:
-                for path in paths:
-                    yield work(path)
-                return
-            pool = ThreadPoolExecutor(max_workers=num_threads)
-            try:
-                window: List = []
-                it = iter(paths)
-                for _ in range(num_threads + 1):
-                    p = next(it, None)
-                    if p is None:
-                        break
-                    window.append(pool.submit(work, p))
-                while window:
-                    fut = window.pop(0)
-                    p = next(it, None)
-                    if p is not None:
-                        window.append(pool.submit(work, p))
-                    yield fut.result()
-            finally:
-                pool.shutdown(wait=True, cancel_futures=True)
-
+        chunks = self._chunks_sequential(paths, shard_args) if num_threads <= 1 else \
+            self._chunks_parallel(paths, shard_args, num_threads)
         num_seen = 0
-        for items in per_file():
-            for t in items:
-                num_seen += 1
-                if t is not self._DROPPED:
-                    yield t, None
-                if limit_num_elements is not None and num_seen > limit_num_elements:
-                    return
+        try:
+            for items in chunks:
+                for t in items:
+                    num_seen += 1
+                    if t is not self._DROPPED:
+                        yield t, None
+                    if limit_num_elements is not None and num_seen > limit_num_elements:
+                        return
+        finally:
+            chunks.close()
 
 
 class ShardDataset:

@@ -876,6 +876,17 @@ int32_t bl_sample_decode(const bl_shard* shard, int64_t index, const bl_tokenize
   }
 }
 
+int32_t bl_sample_decode_many(const bl_shard* shard, const int64_t* indices, int32_t count, const bl_tokenizer* tok,
+                              const char* const* edge_type_names, int32_t num_edge_types, bl_sample* const* samples,
+                              bl_sample_view* views) {
+  if (count < 0 || (count > 0 && (!indices || !samples || !views))) return BL_SHARDS_ERR_ARG;
+  for (int32_t i = 0; i < count; ++i) {
+    int32_t rc = bl_sample_decode(shard, indices[i], tok, edge_type_names, num_edge_types, samples[i], &views[i]);
+    if (rc != BL_SHARDS_OK) return rc;
+  }
+  return BL_SHARDS_OK;
+}
+
 int64_t bl_pyset_iteration_order(const int64_t* values, int64_t n, int64_t* out) {
   if (n < 0 || (n > 0 && (!values || !out))) return -1;
   try {

@@ -378,10 +378,13 @@ class ModelTrainer:
         validation_loss = total / samples
         metrics = dict(nn.report_metrics())
         if self._target_metric is not None:
-            target_metric = metrics[self._target_metric]
             if dist.is_distributed():
-                # per-sample ratios: sum(metric_r * n_r) / sum(n_r) is the metric over the union of the ranks' shards
-                target_metric = dist.all_ranks_sum(float(target_metric) * num_samples, device) / samples
+                # per-sample ratios: sum(metric_r * n_r) / sum(n_r) is the metric over the union of the ranks' shards; a rank
+                # whose share of a tiny validation set is empty reports no metrics and contributes 0 * 0
+                local = float(metrics[self._target_metric]) if num_samples > 0 else 0.0
+                target_metric = dist.all_ranks_sum(local * num_samples, device) / samples
+            else:
+                target_metric = metrics[self._target_metric]
             improved = target_metric > best_target_metric if self._target_metric_higher_is_better \
                 else target_metric < best_target_metric
         else:

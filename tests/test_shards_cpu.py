@@ -468,6 +468,103 @@ def test_shard_dataset_matches_host_loader(model, tmp_path):
     assert len(list(shards.ShardDataset(rich))) == 35
 
 
+def test_chunked_parallel_decode_keeps_file_order_and_cleans_up(model, tmp_path, monkeypatch, capsys):
+    """Files are inflated whole and decoded chunk by chunk by a worker pool: several chunks per shard (CHUNK lowered to 3),
+    nil objects, a truncated file and an unreadable one in the middle; every thread count yields the sequential order;
+    a consumer that stops early leaves no worker running and no shard open."""
+    import threading
+
+    from buglab.utils.msgpackutils import load_all_msgpack_l_gz
+    from buglab_b200.synthetic import SyntheticBugLabGenerator
+    from dpu_utils.utils import RichPath
+
+    monkeypatch.setattr(shards.NativeShardTensorizer, "CHUNK", 3)
+    gen = SyntheticBugLabGenerator(seed=21, mean_nodes=90, min_nodes=30)
+    directory = tmp_path / "d"
+    directory.mkdir()
+    for f in range(4):
+        objects = [gen.sample() for _ in range(11 + f)]
+        objects.insert(2, None)          # nil objects are skipped (msgpackutils.py:38) without shifting the chunk order
+        objects.insert(7, None)
+        write_objects(str(directory / f"shard{f}.msgpack.l.gz"), objects)
+    (directory / "shard2.msgpack.l.gz").write_bytes(b"")          # unreadable / empty file in the middle
+    rich = RichPath.create(str(directory))
+
+    def native(threads, **kw):
+        ds = shards.ShardDataset(rich, num_threads=threads, **kw)
+        return [t for t, _ in ds.tensorized(model)]
+
+    cases = (dict(), dict(rank=2, world_size=8), dict(limit_num_yielded_elements=17), dict(rank=1, world_size=2))
+    for truncated in (False, True):
+        if truncated:
+            # a truncated stream: the objects before the break are served, then the error is reported (how many objects the
+            # host-language reader salvages from a truncated stream depends on its read-ahead, so only the native orders
+            # are compared with each other here)
+            whole = (directory / "shard1.msgpack.l.gz").read_bytes()
+            (directory / "shard1.msgpack.l.gz").write_bytes(whole[: len(whole) * 2 // 3])
+            capsys.readouterr()
+        for kw in cases:
+            expected = native(1, **kw)
+            assert len(expected) > 0, kw
+            if not truncated:
+                host = [t for t in (model.tensorize(dp) for dp in load_all_msgpack_l_gz(rich, **kw)) if t is not None]
+                assert len(expected) == len(host), kw
+                for a, b in zip(host, expected):
+                    assert_same(a, b, f"sequential {kw}")
+            for threads in (2, 3, 8):
+                got = native(threads, **kw)
+                assert len(got) == len(expected), (kw, threads)
+                for a, b in zip(expected, got):
+                    assert_same(a, b, f"{threads} threads {kw}")
+    assert "shard1.msgpack.l.gz: corrupt or truncated gzip stream" in capsys.readouterr().out
+
+    # early stop: close the generator after a few samples
+    before = threading.active_count()
+    tensorizer = shards.NativeShardTensorizer(model)
+    opened = []
+    real_open = shards.NativeShardTensorizer._open
+
+    def tracking_open(path):
+        shard = real_open(path)
+        if shard is not None:
+            opened.append(shard)
+        return shard
+
+    monkeypatch.setattr(shards.NativeShardTensorizer, "_open", staticmethod(tracking_open))
+    paths = sorted(str(p) for p in directory.iterdir())
+    it = tensorizer.tensorize_files(paths, num_threads=4)
+    for _ in range(5):
+        next(it)
+    it.close()
+    assert opened and all(s._h is None for s in opened)        # every shard that was opened has been closed
+    assert threading.active_count() <= before                   # the pool's workers are gone
+    assert tensorizer.num_native >= 5
+
+
+def test_decode_many_equals_one_call_per_sample(model, tmp_path):
+    """bl_sample_decode_many (one native call per chunk) fills the same views as bl_sample_decode per object."""
+    import ctypes
+
+    from buglab_b200.synthetic import write_shards
+
+    path = write_shards(str(tmp_path / "d"), 1, 9, seed=4, mean_nodes=100, min_nodes=30)[0]
+    tz = shards.NativeShardTensorizer(model)
+    with shards.Shard(path) as shard:
+        one_by_one = [tz.tensorize_object(shard, i) for i in range(len(shard))]
+        chunked = tz._decode_chunk(shard, list(range(len(shard))))
+        assert len(chunked) == len(one_by_one) == 9
+        for a, b in zip(one_by_one, chunked):
+            assert_same(a, b)
+        # argument checking of the chunk entry point
+        lib = shards.lib()
+        assert lib.bl_sample_decode_many(shard._h, None, 0, tz._tokenizer._h, tz._edge_names, tz._num_edge_types, None, None) == 0
+        assert lib.bl_sample_decode_many(shard._h, None, 2, tz._tokenizer._h, tz._edge_names, tz._num_edge_types, None, None) != 0
+        bufs = shards._ChunkBuffers(2)
+        bufs.indices[:2] = [0, len(shard)]                       # second index out of range: the call reports it
+        assert lib.bl_sample_decode_many(shard._h, bufs.indices, 2, tz._tokenizer._h, tz._edge_names, tz._num_edge_types,
+                                         bufs.handles, bufs.views) != 0
+
+
 def test_trainer_consumes_self_tensorizing_datasets(model, tmp_path):
     """ModelTrainer.train asks a data source with ``tensorized`` for tensors; minibatches packed from them are the ones the
     host loader gives (host-side packing only — no device work)."""
