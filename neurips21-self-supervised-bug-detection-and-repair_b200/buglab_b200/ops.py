@@ -1,13 +1,21 @@
 """PyTorch-facing operators over the buglab_b200 C ABI (``include/buglab_b200.h``).
 
 PyTorch is plumbing here: it owns device memory, streams and the autograd tape; every arithmetic step of
-the gnn-mlp hot path runs in the kernels of ``csrc/``.  The per-type projections are split-fp16 ("f16x3") tensor-core
-GEMMs — the hand-written tcgen05 kernels of ``csrc/pair_project_tc.cu`` for widths <= ``TC_MAX_WIDTH``, split kernels +
-cuBLAS fp16 GEMMs otherwise; ``PROJECTION_MODE = "fp32"`` (plain cuBLAS SGEMM through ``torch.mm``, TF32 disabled) is
-kept as the exact referee for tests.
+the gnn-mlp hot path runs in the kernels of ``csrc/``.  The per-type projections, their backward products and the
+node-update Linear are split-fp16 ("f16x3") tensor-core GEMMs with fp32-class accuracy.  Dispatch, in order:
+
+* the TMA-fed tcgen05 family of ``csrc/gemm_tma.cu`` (``bl_tma_project`` / ``bl_tma_weight_grad``: operands split once
+  per table, CTA pairs) for every shape it covers — all of the registry's hidden-256 model, forward and backward, and the
+  forward / backward-input products of hidden 128;
+* the first-generation tcgen05 kernels of ``csrc/pair_project_tc.cu`` (gather + split inside the loader) for widths
+  <= ``TC_MAX_WIDTH`` when ``BUGLAB_B200_TMA=0``, and split kernels + ``cublasGemmEx`` for the widths neither covers
+  (hidden 128's message weight gradient);
+* ``PROJECTION_MODE = "fp32"`` (plain cuBLAS SGEMM through ``torch.mm``, TF32 disabled) is kept as the exact referee for
+  tests and error budgeting.
 
 Reference semantics replaced: P4/P5 ``MlpMessagePassingLayer`` message+aggregate,
-A9/A10 scatter ops (``buglab/models/utils.py:15-48``), P2 subtoken max-pool, A12 optimiser.
+A9/A10 scatter ops (``buglab/models/utils.py:15-48``), P2 subtoken max-pool, A12 optimiser; §8(f) row 2: the relational
+attention of the sequence models.
 """
 import ctypes
 import os
