@@ -30,7 +30,6 @@ from docopt import docopt
 from dpu_utils.utils import RichPath, run_and_debug
 
 from buglab.models.gnn import GnnBugLabModel
-from buglab.utils.msgpackutils import load_all_msgpack_l_gz
 
 
 def _logsumexp(values) -> float:
@@ -94,15 +93,27 @@ def evaluate_predictions(predictions, assume_buggy: bool = False, eval_only_no_b
     return metrics
 
 
+def evaluation_data(data_path: RichPath, limit_num_elements=None, sequential: bool = False):
+    """The held-out shards as ``predict``'s data source.  ``ShardDataset`` iterates like ``load_all_msgpack_l_gz`` (sequence
+    models, anything that wants raw datapoints) and additionally lets a graph model pull tensorised samples straight from
+    the native shard decoder; the datapoints handed back next to the predictions are lazy views that serve the fields
+    :func:`evaluate_predictions` reads without unpacking the graph (the Python chain — gzip + msgpack + tensorize — makes
+    ~100 graphs/s per process and would leave the GPU idle > 95 % of an evaluation run)."""
+    from buglab_b200.shards import ShardDataset
+
+    return ShardDataset(data_path, shuffle=True, limit_num_yielded_elements=limit_num_elements,
+                        num_threads=1 if sequential else None, lazy_input_data=True)
+
+
 def run(arguments) -> Dict[str, float]:
     data_path = RichPath.create(arguments["TEST_DATA_PATH"], arguments.get("--azure-info", None))
     lim = None if arguments["--limit-num-elements"] is None else int(arguments["--limit-num-elements"])
-    data = load_all_msgpack_l_gz(data_path, shuffle=True, limit_num_yielded_elements=lim)
     if not torch.cuda.is_available():
         raise RuntimeError("evaluate.py needs a CUDA device; the B200 build has no CPU path")
     device = torch.device("cuda")
     model, nn = GnnBugLabModel.restore_model(Path(arguments["MODEL_FILENAME"]), device)
-    predictions = model.predict(data, nn, device, parallelize=not arguments["--sequential"])
+    predictions = model.predict(evaluation_data(data_path, lim, sequential=bool(arguments["--sequential"])), nn, device,
+                                parallelize=not arguments["--sequential"])
     metrics = evaluate_predictions(predictions, arguments.get("--assume-buggy", False),
                                    arguments.get("--eval-only-no-bug", False))
     for name, value in metrics.items():

@@ -374,9 +374,15 @@ class GnnBugLabModel(AbstractNeuralModel[BugLabData, BaseTensorizedBugLabGnn, Gn
         EVERY location (reference gnn.py:606-645; minibatches of <= 50 graphs)."""
         trained_nn.eval()
         with torch.no_grad(), self._tensorize_all_location_rewrites():
+            if hasattr(data, "tensorized"):
+                # a data source that tensorises itself (buglab_b200.shards.ShardDataset: native shard decoder, ~10x the
+                # host chain) pairs every sample with its raw datapoint, as tensorize_dataset(return_input_data=True) does
+                samples = data.tensorized(self, return_input_data=True,
+                                          lazy_input_data=getattr(data, "lazy_input_data", False))
+            else:
+                samples = self.tensorize_dataset(data, return_input_data=True, parallelize=parallelize)
             for mb_data, original_datapoints in self.minibatch_iterator(
-                    self.tensorize_dataset(data, return_input_data=True, parallelize=parallelize), device,
-                    max_minibatch_size=50, parallelize=parallelize):
+                    samples, device, max_minibatch_size=50, parallelize=parallelize):
                 groups, log_probs, gnn_output, _ = trained_nn.compute_localization_logprobs(mb_data["graph_data"])
                 swap_lp, text_lp, misuse_lp, _ = trained_nn._compute_repair_logprobs(
                     gnn_output, mb_data["target_rewrites"], mb_data["rewrite_to_location_group"],

@@ -15,6 +15,7 @@ import os
 import threading
 from collections import defaultdict
 from concurrent.futures import ThreadPoolExecutor
+from collections.abc import Mapping
 from typing import Any, Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
 
 import msgpack
@@ -252,6 +253,64 @@ class _SampleBuffer:
             pass
 
 
+def _unpack_like_the_host_chain(sample_bytes: bytes) -> Dict[str, Any]:
+    """``msgpack.unpackb`` + the in-place graph extension ``BugLabData.as_graph_data`` performs while tensorising: the
+    object a consumer of ``tensorize_dataset(return_input_data=True)`` / ``predict`` receives from the host chain."""
+    from buglab.representations.data import add_open_vocab_nodes_and_edges
+
+    datapoint = msgpack.unpackb(sample_bytes, raw=False)
+    add_open_vocab_nodes_and_edges(datapoint["graph"])
+    return datapoint
+
+
+class LazyDatapoint(Mapping):
+    """A raw datapoint (``BugLabData``) whose msgpack bytes are unpacked only if somebody asks for a field the native
+    decoder has not already produced.  Served without unpacking: ``target_fix_action_idx``, ``candidate_rewrites``,
+    ``candidate_rewrite_metadata`` and ``graph["reference_nodes"]`` — everything ``predict`` and ``evaluate`` read
+    (basemodel.py:240-346, evaluate.py:60-173).  Any other key, iteration, ``len`` or comparison unpacks the whole object
+    once and extends its graph the way tensorisation does in the host chain (~5 ms for a 2 000-node graph, which is why it is
+    not done up front), so every field equals what the reference-shaped path hands back.  Read-only; ``dict(dp)`` gives a
+    plain mutable copy."""
+
+    __slots__ = ("_raw", "_known", "_full")
+
+    def __init__(self, raw: bytes, known: Dict[str, Any], graph_known: Optional[Dict[str, Any]] = None):
+        self._raw = raw
+        self._known = known
+        self._full: Optional[Dict[str, Any]] = None
+        if graph_known is not None:
+            known["graph"] = LazyDatapoint._sub(self, "graph", graph_known)
+
+    @classmethod
+    def _sub(cls, parent: "LazyDatapoint", key: str, known: Dict[str, Any]) -> "LazyDatapoint":
+        sub = cls.__new__(cls)
+        sub._raw, sub._known, sub._full = (parent, key), known, None
+        return sub
+
+    def unpacked(self) -> Dict[str, Any]:
+        """The fully unpacked object, cached: exactly what the host chain hands back next to a prediction, i.e. the stored
+        object AFTER tensorisation appended the open-vocabulary subtoken nodes and ``HasSubtoken`` edges to its graph
+        (the reference mutates its input there, data.py:97-121 via :139-167)."""
+        if self._full is None:
+            raw = self._raw
+            self._full = raw[0].unpacked()[raw[1]] if isinstance(raw, tuple) else _unpack_like_the_host_chain(raw)
+        return self._full
+
+    def __getitem__(self, key):
+        if self._full is None and key in self._known:
+            return self._known[key]
+        return self.unpacked()[key]
+
+    def __iter__(self):
+        return iter(self.unpacked())
+
+    def __len__(self) -> int:
+        return len(self.unpacked())
+
+    def __repr__(self) -> str:
+        return f"LazyDatapoint({'unpacked' if self._full is not None else 'packed'}, known={sorted(self._known)})"
+
+
 class _ChunkBuffers:
     """Per-thread set of ``bl_sample`` handles + views for ``bl_sample_decode_many`` (one chunk of a shard per call)."""
 
@@ -297,15 +356,20 @@ class NativeShardTensorizer:
                                      buf.handle, ctypes.byref(v)), "decode")
         return self._from_view(v)
 
-    def _from_view(self, v: SampleView):
-        """The ``BaseTensorizedBugLabGnn`` tuple of one decoded sample (``None``: nil object, or dropped by the model)."""
+    NO_DATAPOINTS, FULL_DATAPOINTS, LAZY_DATAPOINTS = 0, 1, 2
+
+    def _from_view(self, v: SampleView, datapoints: int = 0):
+        """The ``BaseTensorizedBugLabGnn`` tuple of one decoded sample (``None``: nil object, or dropped by the model).
+        With ``datapoints`` != 0 the result is ``(tuple or None, raw datapoint)``: the unpacked dict (``FULL_DATAPOINTS``) or
+        a :class:`LazyDatapoint` over a copy of the sample's bytes (``LAZY_DATAPOINTS``) — what ``predict`` hands back."""
         if v.status == SAMPLE_NIL:
-            return None
+            return None if not datapoints else (None, None)
         if v.status == SAMPLE_NEEDS_HOST:
             with self._stats_lock:
                 self.num_host += 1
             datapoint = msgpack.unpackb(ctypes.string_at(v.raw, v.raw_len), raw=False)
-            return self._model.tensorize(datapoint)
+            tensorized = self._model.tensorize(datapoint)
+            return tensorized if not datapoints else (tensorized, datapoint)
         with self._stats_lock:
             self.num_native += 1
         model, gnn_model = self._model, self._gnn_model
@@ -346,9 +410,19 @@ class NativeShardTensorizer:
         tgt = _as_array(v.edge_tgt, int(offsets[-1]) if offsets.size else 0, np.int32)
         forward = [(src[offsets[k]: offsets[k + 1]], tgt[offsets[k]: offsets[k + 1]]) for k in range(self._num_edge_types)]
         tensorized_graph = gnn_model.tensorize_arrays(n, (ids, lens), forward, refs)
-        if tensorized_graph is None:
-            return None
-        return model._assemble_tensorized(tensorized_graph, target_node_idx, rewrite_data, logprobs)
+        tensorized = None if tensorized_graph is None else \
+            model._assemble_tensorized(tensorized_graph, target_node_idx, rewrite_data, logprobs)
+        if not datapoints:
+            return tensorized
+        if tensorized is None:
+            return None, None
+        sample_bytes = ctypes.string_at(raw, v.raw_len)  # the shard (owner of `raw`) may be closed before the consumer looks
+        if datapoints == self.FULL_DATAPOINTS:
+            return tensorized, _unpack_like_the_host_chain(sample_bytes)
+        known = {"target_fix_action_idx": target_action, "candidate_rewrites": rewrites, "candidate_rewrite_metadata": metadata}
+        if has_logprobs:
+            known["candidate_rewrite_logprobs"] = logprobs
+        return tensorized, LazyDatapoint(sample_bytes, known, {"reference_nodes": reference_nodes})
 
     # ---- whole shards ---------------------------------------------------------------------------
     _DROPPED = object()  # a sample the model declined (too many nodes): counted by the loader, not yielded
@@ -360,8 +434,9 @@ class NativeShardTensorizer:
         n = len(shard)
         return list(range(n)) if world_size <= 1 else list(range(rank, n, world_size))
 
-    def _decode_chunk(self, shard: Shard, indices: Sequence[int]) -> List:
-        """Tensorised samples of one chunk of a shard, in order (nil objects skipped, dropped samples as ``_DROPPED``)."""
+    def _decode_chunk(self, shard: Shard, indices: Sequence[int], datapoints: int = 0) -> List:
+        """Tensorised samples of one chunk of a shard, in order (nil objects skipped, dropped samples as ``_DROPPED``);
+        with ``datapoints`` != 0 the items are ``(tensorised, raw datapoint)`` pairs (see :meth:`_from_view`)."""
         bufs = getattr(self._local, "chunk", None)
         if bufs is None:
             bufs = self._local.chunk = _ChunkBuffers(self.CHUNK)
@@ -375,10 +450,13 @@ class NativeShardTensorizer:
                                               self._num_edge_types, bufs.handles, bufs.views), "decode")
             for k in range(n):
                 v = bufs.views[k]
-                t = self._from_view(v)
-                if t is None and v.status == SAMPLE_NIL:
+                if v.status == SAMPLE_NIL:
                     continue
-                out.append(self._DROPPED if t is None else t)
+                t = self._from_view(v, datapoints)
+                if datapoints:
+                    out.append(self._DROPPED if t[0] is None else t)
+                else:
+                    out.append(self._DROPPED if t is None else t)
         return out
 
     @staticmethod
@@ -409,7 +487,7 @@ class NativeShardTensorizer:
             if t is not self._DROPPED:
                 yield t
 
-    def _chunks_sequential(self, paths: Sequence[str], shard_args: Tuple[int, int]) -> Iterator[List]:
+    def _chunks_sequential(self, paths: Sequence[str], shard_args: Tuple[int, int], datapoints: int = 0) -> Iterator[List]:
         for path in paths:
             shard = self._open(path)
             if shard is None:
@@ -417,11 +495,12 @@ class NativeShardTensorizer:
             try:
                 indices = self._indices(shard, *shard_args)
                 for c in range(0, len(indices), self.CHUNK):
-                    yield self._decode_chunk(shard, indices[c: c + self.CHUNK])
+                    yield self._decode_chunk(shard, indices[c: c + self.CHUNK], datapoints)
             finally:
                 self._finish(shard)
 
-    def _chunks_parallel(self, paths: Sequence[str], shard_args: Tuple[int, int], num_threads: int) -> Iterator[List]:
+    def _chunks_parallel(self, paths: Sequence[str], shard_args: Tuple[int, int], num_threads: int,
+                         datapoints: int = 0) -> Iterator[List]:
         """Chunks of tensorised samples in file order from a pool of ``num_threads`` workers.  Two kinds of work items share
         the pool: *open* (inflate + index one file, a few files ahead of the one being decoded) and *decode* (one chunk of
         ``CHUNK`` samples of an open file) — so a single 500-graph shard keeps every worker busy and its first samples are
@@ -470,7 +549,7 @@ class NativeShardTensorizer:
                 if item is None:
                     return
                 kind, shard, indices = item
-                window.append((kind, shard, pool.submit(self._decode_chunk, shard, indices) if kind == "chunk" else None))
+                window.append((kind, shard, pool.submit(self._decode_chunk, shard, indices, datapoints) if kind == "chunk" else None))
 
         try:
             fill()
@@ -496,25 +575,27 @@ class NativeShardTensorizer:
                 shard.close()
 
     def tensorize_files(self, paths: Iterable[str], num_threads: Optional[int] = None, rank: int = 0, world_size: int = 1,
-                        element_sharding: bool = False, limit_num_elements: Optional[int] = None
-                        ) -> Iterator[Tuple[Any, None]]:
+                        element_sharding: bool = False, limit_num_elements: Optional[int] = None, datapoints: int = 0
+                        ) -> Iterator[Tuple[Any, Any]]:
         """``(tensorised, None)`` pairs — the shape ``tensorize_dataset`` yields — over many shard files, in file order.
         Files are inflated and their samples decoded by ``num_threads`` workers (the native calls run outside the GIL),
         chunk by chunk (:meth:`_chunks_parallel`).  ``limit_num_elements`` counts non-nil file elements the way
-        load_all_msgpack_l_gz does (it stops after the element that EXCEEDS the limit, as the reference's loop does)."""
+        load_all_msgpack_l_gz does (it stops after the element that EXCEEDS the limit, as the reference's loop does).
+        ``datapoints``: ``FULL_DATAPOINTS`` / ``LAZY_DATAPOINTS`` pair every sample with its raw datapoint
+        (``tensorize_dataset(return_input_data=True)``: what ``predict`` needs) instead of ``None``."""
         paths = list(paths)
         if num_threads is None:
             num_threads = max(1, min(4, (os.cpu_count() or 2) - 1))  # the host-side assembly holds the GIL: more workers only contend
         shard_args = (rank, world_size) if element_sharding else (0, 1)
-        chunks = self._chunks_sequential(paths, shard_args) if num_threads <= 1 else \
-            self._chunks_parallel(paths, shard_args, num_threads)
+        chunks = self._chunks_sequential(paths, shard_args, datapoints) if num_threads <= 1 else \
+            self._chunks_parallel(paths, shard_args, num_threads, datapoints)
         num_seen = 0
         try:
             for items in chunks:
                 for t in items:
                     num_seen += 1
                     if t is not self._DROPPED:
-                        yield t, None
+                        yield t if datapoints else (t, None)
                     if limit_num_elements is not None and num_seen > limit_num_elements:
                         return
         finally:
@@ -530,7 +611,10 @@ class ShardDataset:
 
     def __init__(self, data_path, shuffle: bool = False, take_only_first_n_files: Optional[int] = None,
                  limit_num_yielded_elements: Optional[int] = None, rank: int = 0, world_size: int = 1,
-                 num_threads: Optional[int] = None):
+                 num_threads: Optional[int] = None, lazy_input_data: bool = False):
+        # lazy_input_data: when a consumer asks for the raw datapoints next to the tensorised samples (``predict``), hand out
+        # read-only LazyDatapoint views instead of unpacked dicts (for consumers that read only the fields predict/evaluate use)
+        self.lazy_input_data = bool(lazy_input_data)
         self._path, self._shuffle, self._first_n = data_path, shuffle, take_only_first_n_files
         self._limit, self._rank, self._world, self._threads = limit_num_yielded_elements, rank, world_size, num_threads
         self._tensorizer: Optional[NativeShardTensorizer] = None
@@ -542,7 +626,10 @@ class ShardDataset:
         return load_all_msgpack_l_gz(self._path, shuffle=self._shuffle, take_only_first_n_files=self._first_n,
                                      limit_num_yielded_elements=self._limit, rank=self._rank, world_size=self._world)
 
-    def tensorized(self, model) -> Iterator[Tuple[Any, None]]:
+    def tensorized(self, model, return_input_data: bool = False, lazy_input_data: bool = False) -> Iterator[Tuple[Any, Any]]:
+        """``(tensorised, raw datapoint or None)`` pairs, the shape of ``model.tensorize_dataset``.  ``return_input_data``
+        pairs every sample with its raw datapoint (``predict``); with ``lazy_input_data`` that datapoint is a read-only
+        :class:`LazyDatapoint` that is only unpacked if a field the decoder did not produce is read (``evaluate``)."""
         from buglab.utils.msgpackutils import select_shard_files
 
         if not hasattr(model, "gnn_model"):
@@ -550,12 +637,16 @@ class ShardDataset:
             # models project graphs onto token sequences in host code) get the reference-shaped chain, said out loud
             LOGGER.info("%s is not a graph model: shards are decoded and tensorised by the host-language path.",
                         type(model).__name__)
-            return model.tensorize_dataset(iter(self), return_input_data=False, parallelize=(self._threads or 2) > 1)
+            return model.tensorize_dataset(iter(self), return_input_data=return_input_data,
+                                           parallelize=(self._threads or 2) > 1)
         if self._tensorizer is None or self._tensorizer_model is not model:
             self._tensorizer, self._tensorizer_model = NativeShardTensorizer(model), model
         files, shard_elements = select_shard_files(self._path, self._shuffle, self._first_n, self._rank, self._world)
         paths = [f.to_local_path().path for f in files]
-        return self._tensorizer.tensorize_files(paths, self._threads, self._rank, self._world, shard_elements, self._limit)
+        mode = NativeShardTensorizer.NO_DATAPOINTS if not return_input_data else \
+            (NativeShardTensorizer.LAZY_DATAPOINTS if lazy_input_data else NativeShardTensorizer.FULL_DATAPOINTS)
+        return self._tensorizer.tensorize_files(paths, self._threads, self._rank, self._world, shard_elements, self._limit,
+                                                mode)
 
     @property
     def tensorizer(self) -> Optional[NativeShardTensorizer]:

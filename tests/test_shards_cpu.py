@@ -565,6 +565,57 @@ def test_decode_many_equals_one_call_per_sample(model, tmp_path):
                                          bufs.handles, bufs.views) != 0
 
 
+def test_predict_from_native_shards_equals_the_host_chain(tmp_path):
+    """``model.predict`` over shard files through the reference-shaped loader, ShardDataset (unpacked datapoints) and
+    ShardDataset (lazy datapoints: what ``python -m buglab.models.evaluate`` uses): identical predictions, datapoints and
+    evaluation metrics, and the lazy datapoints are never unpacked by predict + evaluate.  Runs in a child process because the
+    CPU oracle backend it computes with patches the package process-wide."""
+    import json
+    import subprocess
+
+    proc = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "predict_sources_child.py"), str(tmp_path)],
+                          capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stderr[-3000:]
+    line = json.loads([l for l in proc.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["samples"] == 120
+    assert line["lazy_still_packed_after_predict"] == 120 and line["lazy_still_packed_after_metrics"] == 120
+
+
+def test_lazy_datapoint_is_a_faithful_read_only_view(model, tmp_path):
+    from buglab.utils.msgpackutils import load_msgpack_l_gz
+    from buglab_b200.synthetic import write_shards
+
+    path = write_shards(str(tmp_path / "d"), 1, 5, seed=8, mean_nodes=90, min_nodes=30)[0]
+    host = [dp for dp in load_msgpack_l_gz(path)]
+    for dp in host:
+        model.tensorize(dp)          # the host chain extends the graph in place while tensorising (data.py:97-121)
+    tz = shards.NativeShardTensorizer(model)
+    pairs = list(tz.tensorize_files([path], 1, datapoints=tz.LAZY_DATAPOINTS))
+    assert len(pairs) == len(host) == 5
+    for (t, lazy), dp in zip(pairs, host):
+        assert isinstance(lazy, shards.LazyDatapoint) and lazy._full is None
+        assert lazy["target_fix_action_idx"] == dp["target_fix_action_idx"]
+        assert lazy["candidate_rewrites"] == dp["candidate_rewrites"]
+        assert lazy["candidate_rewrite_metadata"] == dp["candidate_rewrite_metadata"]
+        graph = lazy["graph"]
+        assert graph["reference_nodes"] == dp["graph"]["reference_nodes"] and type(graph["reference_nodes"]) is list
+        assert lazy.get("target_fix_action_idx", "x") == dp["target_fix_action_idx"] and "graph" in lazy
+        assert lazy._full is None and graph._full is None                    # nothing above needed the graph
+        assert graph["nodes"] == dp["graph"]["nodes"]                        # ... this does: incl. the appended subtoken nodes
+        assert lazy._full is not None
+        assert lazy == dp and dict(lazy) == dp and list(lazy) == list(dp) and len(lazy) == len(dp)
+        assert graph == dp["graph"] and lazy["graph"]["edges"]["HasSubtoken"] == dp["graph"]["edges"]["HasSubtoken"]
+        assert lazy.get("no_such_key") is None and "no_such_key" not in lazy
+        with pytest.raises(KeyError):
+            lazy["no_such_key"]
+        with pytest.raises(TypeError):
+            lazy["x"] = 1                                                    # read-only
+    full = list(tz.tensorize_files([path], 1, datapoints=tz.FULL_DATAPOINTS))
+    for (t, dp_full), (t_lazy, _), dp in zip(full, pairs, host):
+        assert type(dp_full) is dict and dp_full == dp
+        assert_same(t, t_lazy)
+
+
 def test_trainer_consumes_self_tensorizing_datasets(model, tmp_path):
     """ModelTrainer.train asks a data source with ``tensorized`` for tensors; minibatches packed from them are the ones the
     host loader gives (host-side packing only — no device work)."""
