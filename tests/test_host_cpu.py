@@ -294,6 +294,44 @@ def test_prefetcher_stops_its_producer_when_the_consumer_leaves_early():
         list(_Prefetcher(failing, torch.device("cpu")))
 
 
+def test_tensorize_dataset_background_producer_matches_sequential():
+    """``tensorize_dataset(parallelize=True)``: one producer thread, same pairs in the same order as the sequential loop,
+    dropped samples dropped, ``return_input_data`` honoured, a failing ``tensorize`` surfaces in the consumer, and a
+    consumer that stops early leaves no thread behind."""
+    import threading
+
+    import pytest
+
+    from buglab_b200.synthetic import SyntheticBugLabGenerator
+
+    gen = SyntheticBugLabGenerator(seed=17, mean_nodes=70, min_nodes=30, max_nodes=110)
+    samples = [gen.sample() for _ in range(40)]
+    model = _tiny_model(samples)
+    model.gnn_model.max_nodes_per_graph = sorted(len(s["graph"]["nodes"]) for s in samples)[-4]   # a few samples are dropped
+    sequential = list(model.tensorize_dataset(iter(copy.deepcopy(samples)), return_input_data=True, parallelize=False))
+    assert 30 <= len(sequential) < 40
+    before = threading.active_count()
+    background = list(model.tensorize_dataset(iter(copy.deepcopy(samples)), return_input_data=True, parallelize=True))
+    assert len(background) == len(sequential)
+    for (t_a, dp_a), (t_b, dp_b) in zip(sequential, background):
+        assert dp_a == dp_b and dp_a is not None
+        assert t_a.graph_data.num_nodes == t_b.graph_data.num_nodes
+        for (s_a, g_a), (s_b, g_b) in zip(t_a.graph_data.adjacency_lists, t_b.graph_data.adjacency_lists):
+            assert np.array_equal(s_a, s_b) and np.array_equal(g_a, g_b)
+    assert all(dp is None for _, dp in model.tensorize_dataset(iter(copy.deepcopy(samples[:5])), parallelize=True))
+
+    it = model.tensorize_dataset(iter(copy.deepcopy(samples)), parallelize=True)
+    next(it), next(it)
+    it.close()                                                   # early stop: the producer thread is stopped and joined
+    assert threading.active_count() <= before
+
+    broken = copy.deepcopy(samples[:6])
+    del broken[3]["graph"]["reference_nodes"]
+    with pytest.raises(KeyError):
+        list(model.tensorize_dataset(iter(broken), parallelize=True))
+    assert threading.active_count() <= before
+
+
 def test_buffered_shuffle_is_a_permutation_and_streams():
     import random
 
