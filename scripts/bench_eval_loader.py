@@ -3,7 +3,7 @@
 pairs -> minibatches of <= 50 graphs (gnn.py:606-645), on the host cores only (no GPU, no model compute).
 
   host        the reference-shaped chain: gzip + msgpack.Unpacker -> dicts -> GnnBugLabModel.tensorize (1 thread, and the
-              tensorize_dataset thread pool)
+              tensorize_dataset background producer thread)
   native      ShardDataset.tensorized(model, return_input_data=True): native decode, datapoints unpacked (and their graphs
               extended as the host chain's tensorisation does) next to every sample
   native-lazy the same with LazyDatapoint views (what evaluate.py uses): nothing is unpacked unless a consumer asks
@@ -57,7 +57,7 @@ def main():
 
     sources = {
         "host_1thread": lambda: model.tensorize_dataset(load_all_msgpack_l_gz(rich), return_input_data=True, parallelize=False),
-        "host_threadpool": lambda: model.tensorize_dataset(load_all_msgpack_l_gz(rich), return_input_data=True, parallelize=True),
+        "host_background_thread": lambda: model.tensorize_dataset(load_all_msgpack_l_gz(rich), return_input_data=True, parallelize=True),
         "native_1thread": lambda: ShardDataset(rich, num_threads=1).tensorized(model, return_input_data=True),
         "native_4thread": lambda: ShardDataset(rich, num_threads=4).tensorized(model, return_input_data=True),
         "native_lazy_1thread": lambda: ShardDataset(rich, num_threads=1).tensorized(model, True, True),

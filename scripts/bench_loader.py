@@ -3,7 +3,7 @@
 
 Times, on the host cores only (no GPU involved):
   host      the reference-shaped Python chain (gzip + msgpack.Unpacker -> dicts -> GnnBugLabModel.tensorize), 1 thread and
-            through tensorize_dataset's thread pool (GIL-bound);
+            through tensorize_dataset's background producer thread;
   native    libbuglab_shards.so (include/buglab_shards.h) through ShardDataset.tensorized at 1..N threads;
   + pack    the same with minibatch packing (extend_minibatch_with / finalize_minibatch to CPU tensors) on the consumer.
 Prints one JSON line; graphs are the c2-shaped synthetic samples bench.py trains on.
@@ -72,7 +72,7 @@ def main():
         tag = "+pack" if pack else ""
         results[f"host_1thread{tag}"] = consume(
             model.tensorize_dataset(load_all_msgpack_l_gz(rich), parallelize=False), pack)
-        results[f"host_threadpool{tag}"] = consume(
+        results[f"host_background_thread{tag}"] = consume(
             model.tensorize_dataset(load_all_msgpack_l_gz(rich), parallelize=True), pack)
         for threads in [int(x) for x in args.threads.split(",")]:
             ds = ShardDataset(rich, num_threads=threads)
