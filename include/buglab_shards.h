@@ -116,6 +116,30 @@ int32_t bl_sample_decode_many(const bl_shard* shard, const int64_t* indices, int
                               const char* const* edge_type_names, int32_t num_edge_types, bl_sample* const* samples,
                               bl_sample_view* views);
 
+/* ---- metadata pass (vocabulary + edge types) -----------------------------------------------------------------------------
+ * What the reference does once before training, one Python object at a time: `model.compute_metadata(data)` ->
+ * GnnBugLabModel.update_metadata_from (buglab/models/gnn.py:350-358) -> BugLabData.as_graph_data (data.py:139-167, incl. the
+ * open-vocabulary nodes) -> the node model counts the (sub)tokens of every node label, the graph model records the edge-type
+ * names.  Both results are order independent, so shards are counted in parallel into per-thread accumulators and merged. */
+typedef struct bl_metadata bl_metadata;
+int32_t bl_metadata_create(bl_metadata** out);
+void bl_metadata_destroy(bl_metadata* md);
+/* Writes the indices of the non-nil objects of the shard (capacity bl_shard_num_objects) and returns their number;
+ * `indices` may be NULL to count only.  (The loader's element limit counts non-nil objects, msgpackutils.py:38-43.) */
+int64_t bl_shard_non_nil(const bl_shard* shard, int64_t* indices);
+/* Adds objects indices[0..count) to `md`.  `tok`: a tokenizer made by bl_tokenizer_create (only its splitting kind and
+ * code-point table are used; it may hold no vocabulary).  `scratch`: a bl_sample of the calling thread.  Objects the native
+ * path declines (anything the decoder would hand to the host, see BL_SAMPLE_NEEDS_HOST) are NOT added: their positions in
+ * `indices` are written to needs_host (capacity count) and counted in *num_needs_host, for the host to add. */
+int32_t bl_metadata_add(bl_metadata* md, const bl_shard* shard, const int64_t* indices, int32_t count, const bl_tokenizer* tok,
+                        bl_sample* scratch, int32_t* needs_host, int32_t* num_needs_host);
+int64_t bl_metadata_num_samples(const bl_metadata* md);
+/* which = 0: (sub)token counts; which = 1: edge-type names (count = number of samples that have the type).
+ * bl_metadata_size returns the number of entries and the total UTF-8 bytes of their keys; bl_metadata_export writes the keys
+ * back to back into blob with offsets[entries + 1] and counts[entries] (unspecified order). */
+int64_t bl_metadata_size(const bl_metadata* md, int32_t which, int64_t* blob_bytes);
+int32_t bl_metadata_export(const bl_metadata* md, int32_t which, uint8_t* blob, int64_t* offsets, int64_t* counts);
+
 /* Iteration order of a CPython `set` filled with the given non-negative ints in this order (testing hook for the
  * emulation that data.py:103-108 makes load-bearing: the order decides the ids of the subtoken nodes).
  * Returns the number of distinct values written to `out` (capacity n), or -1 for unsupported values. */

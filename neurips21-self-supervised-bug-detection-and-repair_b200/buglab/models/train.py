@@ -77,8 +77,13 @@ def _data_sources(arguments, rank: int, world: int):
         validation = ShardDataset(folds["valid"], **common)
     # Every rank computes metadata from the SAME unsharded, unshuffled prefix of the training fold, so vocabularies and the
     # relation layout agree everywhere without a broadcast (the reference, single-process, samples a shuffled prefix).
-    metadata = LazyDataIterable(construct_data_loading_callable(folds["train"], shuffle=False,
-                                                                limit_num_yielded_elements=250_000))
+    if arguments.get("--host-loader"):
+        metadata = LazyDataIterable(construct_data_loading_callable(folds["train"], shuffle=False,
+                                                                    limit_num_yielded_elements=250_000))
+    else:
+        # same prefix; a graph model's vocabulary / edge-type pass is counted by the native decoder's worker threads
+        # (~6x per thread, and it scales with them), any other model iterates the raw datapoints as above
+        metadata = ShardDataset(folds["train"], shuffle=False, limit_num_yielded_elements=250_000, num_threads=threads)
     return training, validation, metadata
 
 

@@ -68,6 +68,13 @@ _SIGNATURES = {
     "bl_sample_decode": (c_i32, [c_ptr, c_i64, c_ptr, c_ptr, c_i32, c_ptr, ctypes.POINTER(SampleView)]),
     "bl_sample_decode_many": (c_i32, [c_ptr, c_ptr, c_i32, c_ptr, c_ptr, c_i32, c_ptr, c_ptr]),
     "bl_pyset_iteration_order": (c_i64, [c_ptr, c_i64, c_ptr]),
+    "bl_shard_non_nil": (c_i64, [c_ptr, c_ptr]),
+    "bl_metadata_create": (c_i32, [ctypes.POINTER(c_ptr)]),
+    "bl_metadata_destroy": (None, [c_ptr]),
+    "bl_metadata_add": (c_i32, [c_ptr, c_ptr, c_ptr, c_i32, c_ptr, c_ptr, c_ptr, ctypes.POINTER(c_i32)]),
+    "bl_metadata_num_samples": (c_i64, [c_ptr]),
+    "bl_metadata_size": (c_i64, [c_ptr, c_i32, ctypes.POINTER(c_i64)]),
+    "bl_metadata_export": (c_i32, [c_ptr, c_i32, c_ptr, c_ptr, c_ptr]),
 }
 
 
@@ -167,6 +174,12 @@ class Shard:
         """0, or the error code that cut the stream short (objects before the break are still served)."""
         return int(lib().bl_shard_status(self._h))
 
+    def non_nil_indices(self) -> List[int]:
+        """Indices of the objects that are not msgpack nil (the loader's element limit counts those, msgpackutils.py:38-43)."""
+        out = (c_i64 * max(1, len(self)))()
+        n = lib().bl_shard_non_nil(self._h, out)
+        return list(out[:n])
+
     def object_bytes(self, index: int) -> bytes:
         data, n = c_ptr(), c_i64()
         check(lib().bl_shard_object(self._h, index, ctypes.byref(data), ctypes.byref(n)), "object")
@@ -194,13 +207,15 @@ class Tokenizer:
     """The node-label vocabulary handed to the native side (ptgnn StrElementRepresentationModel semantics)."""
 
     def __init__(self, vocabulary, splitting_kind: str, max_num_subtokens: int):
-        tokens = list(vocabulary.token_to_id.items())
+        # vocabulary None: a splitter only (metadata pass: the vocabulary is what is being computed)
+        tokens = list(vocabulary.token_to_id.items()) if vocabulary is not None else []
         encoded = [t.encode("utf-8", "surrogatepass") for t, _ in tokens]
         offsets = np.zeros(len(encoded) + 1, dtype=np.int64)
-        np.cumsum([len(e) for e in encoded], out=offsets[1:])
+        if encoded:
+            np.cumsum([len(e) for e in encoded], out=offsets[1:])
         blob = np.frombuffer(b"".join(encoded) or b"\0", dtype=np.uint8)
         ids = np.array([i for _, i in tokens], dtype=np.int32)
-        unk = vocabulary.token_to_id.get(vocabulary.get_unk(), -1)
+        unk = vocabulary.token_to_id.get(vocabulary.get_unk(), -1) if vocabulary is not None else -1
         variants = lower_variant_codepoints()
         kind = {"token": SPLIT_TOKEN, "subtoken": SPLIT_SUBTOKEN}[splitting_kind]
         handle = c_ptr()
@@ -487,20 +502,28 @@ class NativeShardTensorizer:
             if t is not self._DROPPED:
                 yield t
 
-    def _chunks_sequential(self, paths: Sequence[str], shard_args: Tuple[int, int], datapoints: int = 0) -> Iterator[List]:
+    def _chunks_sequential(self, paths: Sequence[str], shard_args: Tuple[int, int], datapoints: int = 0,
+                           work=None, select=None) -> Iterator[List]:
+        """``work(shard, indices)`` per chunk (default: :meth:`_decode_chunk`); ``select(shard, indices)`` may narrow a file's
+        object indices before they are chunked, or return None to end the pass (element budgets)."""
+        work = work or (lambda shard, indices: self._decode_chunk(shard, indices, datapoints))
         for path in paths:
             shard = self._open(path)
             if shard is None:
                 continue
             try:
                 indices = self._indices(shard, *shard_args)
+                if select is not None:
+                    indices = select(shard, indices)
+                    if indices is None:
+                        return
                 for c in range(0, len(indices), self.CHUNK):
-                    yield self._decode_chunk(shard, indices[c: c + self.CHUNK], datapoints)
+                    yield work(shard, indices[c: c + self.CHUNK])
             finally:
                 self._finish(shard)
 
     def _chunks_parallel(self, paths: Sequence[str], shard_args: Tuple[int, int], num_threads: int,
-                         datapoints: int = 0) -> Iterator[List]:
+                         datapoints: int = 0, work=None, select=None) -> Iterator[List]:
         """Chunks of tensorised samples in file order from a pool of ``num_threads`` workers.  Two kinds of work items share
         the pool: *open* (inflate + index one file, a few files ahead of the one being decoded) and *decode* (one chunk of
         ``CHUNK`` samples of an open file) — so a single 500-graph shard keeps every worker busy and its first samples are
@@ -509,6 +532,7 @@ class NativeShardTensorizer:
         chunk has been consumed.  Look-ahead is bounded: ``open_ahead`` inflated files, ``2 * num_threads`` chunks."""
         from collections import deque
 
+        work = work or (lambda shard, indices: self._decode_chunk(shard, indices, datapoints))
         # the decode items end with host-side assembly under the GIL (~0.25 ms per sample): beyond DECODE_WORKERS threads they
         # only contend with each other and with the consumer; inflating (zlib, outside the GIL, ~2/3 of the work) scales
         decode_workers = min(num_threads, self.DECODE_WORKERS)
@@ -536,6 +560,11 @@ class NativeShardTensorizer:
                     continue
                 opened.append(shard)
                 indices = self._indices(shard, *shard_args)
+                if select is not None:
+                    indices = select(shard, indices)
+                    if indices is None:
+                        yield "end", shard, None
+                        return
                 for c in range(0, len(indices), self.CHUNK):
                     yield "chunk", shard, indices[c: c + self.CHUNK]
                 yield "end", shard, None
@@ -549,7 +578,7 @@ class NativeShardTensorizer:
                 if item is None:
                     return
                 kind, shard, indices = item
-                window.append((kind, shard, pool.submit(self._decode_chunk, shard, indices, datapoints) if kind == "chunk" else None))
+                window.append((kind, shard, pool.submit(work, shard, indices) if kind == "chunk" else None))
 
         try:
             fill()
@@ -602,6 +631,99 @@ class NativeShardTensorizer:
             chunks.close()
 
 
+class NativeMetadataPass(NativeShardTensorizer):
+    """The metadata pass of a graph model over shard files — ``model.compute_metadata(data)`` without building a Python
+    object per graph (reference: ptgnn ``compute_metadata`` -> GnnBugLabModel.update_metadata_from, buglab/models/gnn.py:350-358
+    -> BugLabData.as_graph_data -> StrElementRepresentationModel / GraphNeuralNetworkModel ``update_metadata_from``).
+    Files are inflated and counted by the same worker scheme as the tensoriser; every worker thread counts into its own
+    native accumulator (``bl_metadata``), the accumulators are merged at the end (counts and name sets are order
+    independent).  Samples the native path declines are unpacked and go through ``model.update_metadata_from``."""
+
+    def __init__(self, model):
+        lib()
+        self._model = model
+        node_model = model.gnn_model.node_representation_model
+        self._tokenizer = Tokenizer(None, node_model.splitting_kind, node_model.max_num_subtokens or 1)
+        self._local = threading.local()
+        self._stats_lock = threading.Lock()
+        self._accumulators: List[c_ptr] = []
+        self.num_native = 0
+        self.num_host = 0
+
+    def _accumulator(self) -> c_ptr:
+        acc = getattr(self._local, "metadata", None)
+        if acc is None:
+            acc = c_ptr()
+            check(lib().bl_metadata_create(ctypes.byref(acc)), "metadata")
+            self._local.metadata = acc
+            with self._stats_lock:
+                self._accumulators.append(acc)
+        return acc
+
+    def _count_chunk(self, shard: Shard, indices: Sequence[int]) -> List[bytes]:
+        """Adds one chunk to this thread's accumulator; returns the raw bytes of the samples left to the host."""
+        n = len(indices)
+        idx = (c_i64 * n)(*indices)
+        declined = (c_i32 * max(1, n))()
+        num_declined = c_i32()
+        check(lib().bl_metadata_add(self._accumulator(), shard._h, idx, n, self._tokenizer._h, self._buffer().handle,
+                                    declined, ctypes.byref(num_declined)), "metadata")
+        return [shard.object_bytes(indices[declined[k]]) for k in range(num_declined.value)]
+
+    def run(self, paths: Iterable[str], num_threads: Optional[int] = None, rank: int = 0, world_size: int = 1,
+            element_sharding: bool = False, limit_num_elements: Optional[int] = None) -> Tuple[Dict[str, int], List[str], int]:
+        """``(token counts, edge-type names, number of samples)`` over the files, with the file selection, rank sharding and
+        element limit semantics of ``load_all_msgpack_l_gz`` (the pass covers ``limit + 1`` elements when there are more)."""
+        paths = list(paths)
+        if num_threads is None:
+            num_threads = max(1, min(4, (os.cpu_count() or 2) - 1))
+        shard_args = (rank, world_size) if element_sharding else (0, 1)
+        budget = [None if limit_num_elements is None else limit_num_elements + 1]
+
+        def select(shard: Shard, indices: List[int]) -> Optional[List[int]]:
+            if budget[0] is not None and budget[0] <= 0:
+                return None
+            not_nil = set(shard.non_nil_indices())
+            chosen = [i for i in indices if i in not_nil]
+            if budget[0] is not None:
+                chosen = chosen[: budget[0]]
+                budget[0] -= len(chosen)
+            return chosen
+
+        chunks = self._chunks_sequential(paths, shard_args, work=self._count_chunk, select=select) if num_threads <= 1 else \
+            self._chunks_parallel(paths, shard_args, num_threads, work=self._count_chunk, select=select)
+        model = self._model
+        try:
+            for declined in chunks:
+                for sample_bytes in declined:  # the reference-shaped path for what the decoder does not take
+                    self.num_host += 1
+                    model.update_metadata_from(msgpack.unpackb(sample_bytes, raw=False))
+        finally:
+            chunks.close()
+        counts: Dict[str, int] = {}
+        edge_types: Dict[str, int] = {}
+        num_samples = 0
+        for acc in self._accumulators:
+            num_samples += int(lib().bl_metadata_num_samples(acc))
+            for which, into in ((0, counts), (1, edge_types)):
+                blob_bytes = c_i64()
+                n = int(lib().bl_metadata_size(acc, which, ctypes.byref(blob_bytes)))
+                blob = np.empty(max(1, blob_bytes.value), dtype=np.uint8)
+                offsets = np.empty(n + 1, dtype=np.int64)
+                values = np.empty(max(1, n), dtype=np.int64)
+                check(lib().bl_metadata_export(acc, which, blob.ctypes.data, offsets.ctypes.data, values.ctypes.data), "export")
+                data = blob.tobytes()
+                bounds = offsets.tolist()
+                for k, count in enumerate(values[:n].tolist()):
+                    token = data[bounds[k]: bounds[k + 1]].decode("utf-8", "surrogatepass")
+                    into[token] = into.get(token, 0) + count
+            lib().bl_metadata_destroy(acc)
+        self._accumulators = []
+        self._local = threading.local()
+        self.num_native = num_samples
+        return counts, sorted(edge_types), num_samples + self.num_host
+
+
 class ShardDataset:
     """A directory of ``.msgpack.l.gz`` shards as the trainer's data source.
 
@@ -648,6 +770,34 @@ class ShardDataset:
         return self._tensorizer.tensorize_files(paths, self._threads, self._rank, self._world, shard_elements, self._limit,
                                                 mode)
 
+    def update_model_metadata(self, model) -> bool:
+        """The metadata pass (``model.compute_metadata``) over this data source in native code.  Returns False — nothing
+        done, the caller iterates the raw datapoints instead — for models whose metadata the native pass does not cover
+        (anything but a graph model with a string node-representation model, i.e. the sequence models)."""
+        from buglab.utils.msgpackutils import select_shard_files
+
+        gnn_model = getattr(model, "gnn_model", None)
+        node_model = getattr(gnn_model, "node_representation_model", None)
+        if gnn_model is None or not hasattr(node_model, "update_metadata_from_token_counts") or \
+                not hasattr(gnn_model, "update_metadata_from_edge_types") or type(model).update_metadata_from is not \
+                _graph_model_update_metadata_from(model):
+            return False
+        files, shard_elements = select_shard_files(self._path, self._shuffle, self._first_n, self._rank, self._world)
+        paths = [f.to_local_path().path for f in files]
+        counts, edge_types, _ = NativeMetadataPass(model).run(paths, self._threads, self._rank, self._world, shard_elements,
+                                                              self._limit)
+        node_model.update_metadata_from_token_counts(counts)
+        gnn_model.update_metadata_from_edge_types(edge_types)
+        return True
+
     @property
     def tensorizer(self) -> Optional[NativeShardTensorizer]:
         return self._tensorizer
+
+
+def _graph_model_update_metadata_from(model):
+    """``GnnBugLabModel.update_metadata_from`` — the one implementation whose effect the native pass reproduces (a subclass
+    that overrides it collects something else and must see the raw datapoints)."""
+    from buglab.models.gnn import GnnBugLabModel
+
+    return GnnBugLabModel.update_metadata_from

@@ -436,6 +436,14 @@ struct bl_sample {
   }
 };
 
+// Accumulator of the model metadata a pass over the training data collects (mirror gnn.py:223-225 ->
+// graphneuralnetwork.py update_metadata_from): (sub)token counts of the node labels and the set of edge-type names.
+struct bl_metadata {
+  std::unordered_map<std::string, int64_t> token_counts;
+  std::unordered_map<std::string, int64_t> edge_types;  // name -> number of samples that have it
+  int64_t num_samples = 0;
+};
+
 namespace {
 
 int32_t as_i32(int64_t v) {
@@ -671,6 +679,66 @@ int32_t decode_sample(const bl_shard& shard, int64_t index, const bl_tokenizer& 
   return BL_SHARDS_OK;
 }
 
+// One object's contribution to the metadata: what GnnBugLabModel.update_metadata_from does with it in the host chain —
+// BugLabData.as_graph_data (needs graph.nodes / graph.reference_nodes / target_fix_action_idx, appends the open-vocabulary
+// nodes and the HasSubtoken edges), then the node model counts the (sub)tokens of every node label and the graph model
+// records the edge-type names.  Returns BL_SAMPLE_OK / BL_SAMPLE_NIL / BL_SAMPLE_NEEDS_HOST; nothing is added unless OK.
+int32_t collect_metadata(const bl_shard& shard, int64_t index, const bl_tokenizer& tok, bl_sample& s, bl_metadata& md) {
+  const uint8_t* begin = shard.raw.data() + shard.offsets[(size_t)index];
+  const uint8_t* end = shard.raw.data() + shard.offsets[(size_t)index + 1];
+  Cursor c{begin, end};
+  if (c.at_nil()) return BL_SAMPLE_NIL;
+  try {
+    uint64_t n;
+    if (!c.map_header(n)) throw NeedsHost();
+    bool have_graph = false, have_nodes = false, have_refs = false, have_target_key = false, has_target = false;
+    int64_t target = 0;
+    s.num_edge_lists = 0;
+    s.labels.clear();
+    s.reference_nodes.clear();
+    for (uint64_t i = 0; i < n; ++i) {
+      std::string_view key;
+      if (!c.str(key)) throw NeedsHost();
+      if (key == "graph") {
+        have_nodes = have_refs = false;
+        parse_graph(c, s, have_nodes, have_refs);
+        have_graph = true;
+      } else if (key == "target_fix_action_idx") {
+        have_target_key = true;
+        if (c.at_nil()) { ++c.p; has_target = false; }
+        else {
+          if (!c.integer(target)) throw NeedsHost();
+          has_target = true;
+        }
+      } else {
+        c.skip(1);
+      }
+    }
+    if (!have_graph || !have_nodes || !have_refs || !have_target_key) throw NeedsHost();  // KeyError territory
+    if (has_target && (target < 0 || target >= (int64_t)s.reference_nodes.size())) throw NeedsHost();  // inverse[target]
+    for (std::string_view label : s.labels)
+      if (!tok.label_supported(label)) throw NeedsHost();
+    add_open_vocab_nodes_and_edges(s, tok);
+  } catch (const NeedsHost&) {
+    return BL_SAMPLE_NEEDS_HOST;
+  } catch (const ParseError&) {
+    return BL_SAMPLE_NEEDS_HOST;
+  }
+  // from here on nothing throws NeedsHost: the sample is counted as a whole
+  for (std::string_view label : s.labels) {
+    if (tok.kind == BL_SPLIT_TOKEN) {
+      md.token_counts[std::string(label)] += 1;
+    } else {
+      split_identifier(label, s.parts);
+      for (const auto& span : s.parts.spans)
+        md.token_counts[std::string(s.parts.lowered.data() + span.first, span.second)] += 1;
+    }
+  }
+  for (size_t i = 0; i < s.num_edge_lists; ++i) md.edge_types[std::string(s.edge_lists[i].name)] += 1;
+  md.num_samples += 1;
+  return BL_SAMPLE_OK;
+}
+
 // gzip (RFC 1952) members back to back, as Python's gzip module reads them.
 int32_t inflate_all(const uint8_t* gz, size_t gz_len, std::vector<uint8_t>& out) {
   z_stream zs;
@@ -883,6 +951,76 @@ int32_t bl_sample_decode_many(const bl_shard* shard, const int64_t* indices, int
   for (int32_t i = 0; i < count; ++i) {
     int32_t rc = bl_sample_decode(shard, indices[i], tok, edge_type_names, num_edge_types, samples[i], &views[i]);
     if (rc != BL_SHARDS_OK) return rc;
+  }
+  return BL_SHARDS_OK;
+}
+
+int64_t bl_shard_non_nil(const bl_shard* shard, int64_t* indices) {
+  if (!shard) return -1;
+  int64_t k = 0;
+  const int64_t n = (int64_t)shard->offsets.size() - 1;
+  for (int64_t i = 0; i < n; ++i) {
+    const bool nil = shard->offsets[(size_t)i + 1] - shard->offsets[(size_t)i] == 1 && shard->raw[(size_t)shard->offsets[(size_t)i]] == 0xc0;
+    if (!nil) {
+      if (indices) indices[k] = i;
+      ++k;
+    }
+  }
+  return k;
+}
+
+int32_t bl_metadata_create(bl_metadata** out) {
+  if (!out) return BL_SHARDS_ERR_ARG;
+  try {
+    *out = new bl_metadata();
+  } catch (...) {
+    return BL_SHARDS_ERR_NOMEM;
+  }
+  return BL_SHARDS_OK;
+}
+
+void bl_metadata_destroy(bl_metadata* md) { delete md; }
+
+int32_t bl_metadata_add(bl_metadata* md, const bl_shard* shard, const int64_t* indices, int32_t count, const bl_tokenizer* tok,
+                        bl_sample* scratch, int32_t* needs_host, int32_t* num_needs_host) {
+  if (!md || !shard || !tok || !scratch || !num_needs_host || count < 0 || (count > 0 && (!indices || !needs_host)))
+    return BL_SHARDS_ERR_ARG;
+  *num_needs_host = 0;
+  try {
+    for (int32_t i = 0; i < count; ++i) {
+      if (indices[i] < 0 || indices[i] >= bl_shard_num_objects(shard)) return BL_SHARDS_ERR_ARG;
+      if (collect_metadata(*shard, indices[i], *tok, *scratch, *md) == BL_SAMPLE_NEEDS_HOST) needs_host[(*num_needs_host)++] = i;
+    }
+  } catch (...) {
+    return BL_SHARDS_ERR_NOMEM;
+  }
+  return BL_SHARDS_OK;
+}
+
+int64_t bl_metadata_num_samples(const bl_metadata* md) { return md ? md->num_samples : -1; }
+
+int64_t bl_metadata_size(const bl_metadata* md, int32_t which, int64_t* blob_bytes) {
+  if (!md || (which != 0 && which != 1)) return -1;
+  const auto& table = which == 0 ? md->token_counts : md->edge_types;
+  int64_t bytes = 0;
+  for (const auto& kv : table) bytes += (int64_t)kv.first.size();
+  if (blob_bytes) *blob_bytes = bytes;
+  return (int64_t)table.size();
+}
+
+int32_t bl_metadata_export(const bl_metadata* md, int32_t which, uint8_t* blob, int64_t* offsets, int64_t* counts) {
+  if (!md || (which != 0 && which != 1) || !offsets) return BL_SHARDS_ERR_ARG;
+  const auto& table = which == 0 ? md->token_counts : md->edge_types;
+  int64_t off = 0, k = 0;
+  offsets[0] = 0;
+  for (const auto& kv : table) {
+    if (!kv.first.empty()) {
+      if (!blob) return BL_SHARDS_ERR_ARG;
+      memcpy(blob + off, kv.first.data(), kv.first.size());
+    }
+    off += (int64_t)kv.first.size();
+    if (counts) counts[k] = kv.second;
+    offsets[++k] = off;
   }
   return BL_SHARDS_OK;
 }

@@ -54,8 +54,12 @@ class AbstractNeuralModel(ABC, Generic[TRawDatapoint, TTensorizedDatapoint, TNeu
         Metadata construction is order-independent here (sorted vocabularies / edge types), so all
         data-parallel ranks that see the same data build identical metadata."""
         assert not self.metadata_initialized, "Metadata has already been initialized."
-        for datapoint in dataset_iterator:
-            self.update_metadata_from(datapoint)
+        # a data source that can run the pass itself (buglab_b200.shards.ShardDataset: native shard decoder, counts per
+        # worker thread) is asked to; it declines (False) for models it does not cover
+        native = getattr(dataset_iterator, "update_model_metadata", None)
+        if native is None or not native(self):
+            for datapoint in dataset_iterator:
+                self.update_metadata_from(datapoint)
         self._finalize_metadata_recursive()
 
     # ---- neural module --------------------------------------------------------------------------

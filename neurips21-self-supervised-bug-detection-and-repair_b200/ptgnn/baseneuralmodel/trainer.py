@@ -271,7 +271,8 @@ class ModelTrainer:
     def load_metadata_and_create_network(self, training_data: Iterable, parallelize: bool = True,
                                          show_progress_bar: bool = True) -> None:
         LOGGER.info("Computing model metadata...")
-        self.__model.compute_metadata(iter(training_data), parallelize)
+        self.__model.compute_metadata(training_data if hasattr(training_data, "update_model_metadata") else iter(training_data),
+                                      parallelize)
         self.__neural_network = self.__model.build_neural_module()
         LOGGER.info("Model has %s trainable parameters.",
                     sum(p.numel() for p in self.__neural_network.parameters() if p.requires_grad))

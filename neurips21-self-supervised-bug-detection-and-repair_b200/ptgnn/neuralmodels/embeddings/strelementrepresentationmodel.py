@@ -103,6 +103,11 @@ class StrElementRepresentationModel(
                 for part in split_identifier_into_parts(token):
                     self.__tok_counter[part] += count
 
+    def update_metadata_from_token_counts(self, counts: Dict[str, int]) -> None:
+        """Adds already-split (sub)token counts — the result of ``update_metadata_from_many`` over many graphs, computed
+        elsewhere (buglab_b200.shards.NativeMetadataPass)."""
+        self.__tok_counter.update(counts)
+
     def finalize_metadata(self) -> None:
         self.__vocabulary = Vocabulary.create_vocabulary(
             self.__tok_counter, max_size=self.max_vocabulary_size, count_threshold=self.min_freq_threshold, add_pad=True)

@@ -132,6 +132,10 @@ class GraphNeuralNetworkModel(AbstractNeuralModel[GraphData, TensorizedGraphData
                 model.update_metadata_from(node)
         self.__edge_types_mdata.update(datapoint.edges.keys())
 
+    def update_metadata_from_edge_types(self, edge_type_names) -> None:
+        """Adds edge-type names collected elsewhere (buglab_b200.shards.NativeMetadataPass) to the metadata."""
+        self.__edge_types_mdata.update(edge_type_names)
+
     def finalize_metadata(self) -> None:
         self.__edge_types = tuple(sorted(self.__edge_types_mdata))
         self.__edge_types_mdata = None

@@ -616,6 +616,85 @@ def test_lazy_datapoint_is_a_faithful_read_only_view(model, tmp_path):
         assert_same(t, t_lazy)
 
 
+def test_native_metadata_pass_equals_the_host_pass(tmp_path, base_sample):
+    """``model.compute_metadata(ShardDataset(...))`` — subtoken counts and edge-type names counted by the native decoder's
+    worker threads — builds the same vocabulary (ids included) and edge-type tuple as the pass over raw datapoints, for every
+    thread count, element limit and rank sharding, with nil objects, samples the decoder declines (non-ASCII identifiers,
+    stale HasSubtoken, no NextToken, ...), and token-level splitting."""
+    from pathlib import Path
+
+    from buglab.models.modelregistry import load_model
+    from buglab.utils.msgpackutils import load_all_msgpack_l_gz
+    from buglab_b200.synthetic import SyntheticBugLabGenerator
+    from dpu_utils.utils import RichPath
+
+    gen = SyntheticBugLabGenerator(seed=31, mean_nodes=120, min_nodes=40)
+    directory = tmp_path / "d"
+    directory.mkdir()
+    irregular = list(_variants(base_sample).values())
+    for f in range(3):
+        objects = [gen.sample() for _ in range(37 + f)]
+        objects.insert(5, None)
+        objects[10:10] = irregular[f::3]
+        write_objects(str(directory / f"shard{f}.msgpack.l.gz"), objects)
+    rich = RichPath.create(str(directory))
+
+    def fresh(**spec):
+        m, _, _ = load_model({"modelName": "gnn-mlp", "hidden_state_size": 16, **spec}, Path(str(tmp_path / "m.pkl.gz")))
+        return m
+
+    def metadata_of(m):
+        vocab = m.gnn_model.node_representation_model.vocabulary
+        return dict(vocab.token_to_id), list(vocab.id_to_token), m.gnn_model.edge_types
+
+    cases = [dict(), dict(limit_num_yielded_elements=40), dict(limit_num_yielded_elements=1), dict(rank=1, world_size=2),
+             dict(rank=5, world_size=8, limit_num_yielded_elements=9), dict(take_only_first_n_files=2)]
+    for spec in (dict(), dict(node_representations={"token_splitting": "token"})):
+        for kw in cases:
+            host = fresh(**spec)
+            host.compute_metadata(load_all_msgpack_l_gz(rich, **kw))
+            for threads in (1, 3):
+                native = fresh(**spec)
+                source = shards.ShardDataset(rich, num_threads=threads, **kw)
+                assert source.update_model_metadata(fresh(**spec)) is True        # the pass is taken, not declined
+                native.compute_metadata(source)
+                assert metadata_of(native) == metadata_of(host), (spec, kw, threads)
+    assert len(metadata_of(host)[0]) > 20
+
+    # models the native pass does not cover are told so and get the raw datapoints
+    class Other:
+        pass
+
+    assert shards.ShardDataset(rich).update_model_metadata(Other()) is False
+
+
+def test_metadata_accumulator_c_abi(model, tmp_path):
+    import ctypes
+
+    from buglab_b200.synthetic import write_shards
+
+    path = write_shards(str(tmp_path / "d"), 1, 4, seed=6, mean_nodes=80, min_nodes=30)[0]
+    lib = shards.lib()
+    acc = ctypes.c_void_p()
+    assert lib.bl_metadata_create(ctypes.byref(acc)) == 0
+    splitter = shards.Tokenizer(None, "subtoken", 6)
+    sample = shards._SampleBuffer()
+    with shards.Shard(path) as shard:
+        assert shard.non_nil_indices() == [0, 1, 2, 3]
+        idx = (ctypes.c_int64 * 4)(0, 1, 2, 3)
+        declined, n_declined = (ctypes.c_int32 * 4)(), ctypes.c_int32()
+        assert lib.bl_metadata_add(acc, shard._h, idx, 4, splitter._h, sample.handle, declined, ctypes.byref(n_declined)) == 0
+        assert n_declined.value == 0 and lib.bl_metadata_num_samples(acc) == 4
+        bad = (ctypes.c_int64 * 1)(9)
+        assert lib.bl_metadata_add(acc, shard._h, bad, 1, splitter._h, sample.handle, declined, ctypes.byref(n_declined)) != 0
+        assert lib.bl_metadata_add(None, shard._h, idx, 4, splitter._h, sample.handle, declined, ctypes.byref(n_declined)) != 0
+    nbytes = ctypes.c_int64()
+    n_tokens = lib.bl_metadata_size(acc, 0, ctypes.byref(nbytes))
+    n_types = lib.bl_metadata_size(acc, 1, None)
+    assert n_tokens > 10 and nbytes.value > n_tokens and n_types >= 3 and lib.bl_metadata_size(acc, 2, None) == -1
+    lib.bl_metadata_destroy(acc)
+
+
 def test_trainer_consumes_self_tensorizing_datasets(model, tmp_path):
     """ModelTrainer.train asks a data source with ``tensorized`` for tensors; minibatches packed from them are the ones the
     host loader gives (host-side packing only — no device work)."""
