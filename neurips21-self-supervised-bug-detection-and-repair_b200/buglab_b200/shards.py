@@ -698,6 +698,11 @@ class NativeMetadataPass(NativeShardTensorizer):
                 for sample_bytes in declined:  # the reference-shaped path for what the decoder does not take
                     self.num_host += 1
                     model.update_metadata_from(msgpack.unpackb(sample_bytes, raw=False))
+        except BaseException:
+            for acc in self._accumulators:  # a malformed sample raised in the host pass, as it does there: nothing is merged
+                lib().bl_metadata_destroy(acc)
+            self._accumulators, self._local = [], threading.local()
+            raise
         finally:
             chunks.close()
         counts: Dict[str, int] = {}
