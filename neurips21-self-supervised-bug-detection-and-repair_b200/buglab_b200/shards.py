@@ -693,18 +693,19 @@ class NativeMetadataPass(NativeShardTensorizer):
         chunks = self._chunks_sequential(paths, shard_args, work=self._count_chunk, select=select) if num_threads <= 1 else \
             self._chunks_parallel(paths, shard_args, num_threads, work=self._count_chunk, select=select)
         model = self._model
+        completed = False
         try:
             for declined in chunks:
                 for sample_bytes in declined:  # the reference-shaped path for what the decoder does not take
                     self.num_host += 1
                     model.update_metadata_from(msgpack.unpackb(sample_bytes, raw=False))
-        except BaseException:
-            for acc in self._accumulators:  # a malformed sample raised in the host pass, as it does there: nothing is merged
-                lib().bl_metadata_destroy(acc)
-            self._accumulators, self._local = [], threading.local()
-            raise
+            completed = True
         finally:
-            chunks.close()
+            chunks.close()  # waits for the workers: no thread is counting into an accumulator after this line
+            if not completed:  # a malformed sample raised in the host pass, as it does there: nothing is merged
+                for acc in self._accumulators:
+                    lib().bl_metadata_destroy(acc)
+                self._accumulators, self._local = [], threading.local()
         counts: Dict[str, int] = {}
         edge_types: Dict[str, int] = {}
         num_samples = 0
