@@ -661,6 +661,19 @@ def test_native_metadata_pass_equals_the_host_pass(tmp_path, base_sample):
                 assert metadata_of(native) == metadata_of(host), (spec, kw, threads)
     assert len(metadata_of(host)[0]) > 20
 
+    # a malformed sample raises in the native pass exactly as in the host pass (it is handed to model.update_metadata_from)
+    broken = copy.deepcopy(base_sample)
+    del broken["graph"]["reference_nodes"]
+    bad_dir = tmp_path / "bad"
+    bad_dir.mkdir()
+    write_objects(str(bad_dir / "shard0.msgpack.l.gz"), [gen.sample() for _ in range(40)] + [broken] + [gen.sample() for _ in range(40)])
+    bad = RichPath.create(str(bad_dir))
+    with pytest.raises(KeyError):
+        fresh().compute_metadata(load_all_msgpack_l_gz(bad))
+    for threads in (1, 3):
+        with pytest.raises(KeyError):
+            fresh().compute_metadata(shards.ShardDataset(bad, num_threads=threads))
+
     # models the native pass does not cover are told so and get the raw datapoints
     class Other:
         pass
