@@ -524,12 +524,13 @@ class NativeShardTensorizer:
 
     def _chunks_parallel(self, paths: Sequence[str], shard_args: Tuple[int, int], num_threads: int,
                          datapoints: int = 0, work=None, select=None) -> Iterator[List]:
-        """Chunks of tensorised samples in file order from a pool of ``num_threads`` workers.  Two kinds of work items share
-        the pool: *open* (inflate + index one file, a few files ahead of the one being decoded) and *decode* (one chunk of
-        ``CHUNK`` samples of an open file) — so a single 500-graph shard keeps every worker busy and its first samples are
-        available as soon as the file is inflated, instead of after the whole file has been decoded by one thread.  A shard
-        is shared read-only by the workers (``include/buglab_shards.h``: immutable after creation) and closed once its last
-        chunk has been consumed.  Look-ahead is bounded: ``open_ahead`` inflated files, ``2 * num_threads`` chunks."""
+        """Chunk results in file order.  Two kinds of work items: *open* (inflate + index one file, outside the GIL, on up to
+        ``num_threads`` workers, a few files ahead of the one being decoded) and *decode* (``work`` on one chunk of ``CHUNK``
+        objects of an open file, on ``DECODE_WORKERS`` workers) — so a single 500-graph shard keeps the workers busy and its
+        first samples are available as soon as the file is inflated, instead of after the whole file has been decoded by one
+        thread.  A shard is shared read-only by the workers (``include/buglab_shards.h``: immutable after creation) and closed
+        once its last chunk has been consumed.  Look-ahead is bounded: ``num_threads`` inflated files, ``2 * DECODE_WORKERS``
+        chunks.  ``work`` / ``select``: see :meth:`_chunks_sequential`."""
         from collections import deque
 
         work = work or (lambda shard, indices: self._decode_chunk(shard, indices, datapoints))
