@@ -176,9 +176,23 @@ class _RankSync:
       ``weight`` = B_rank * world / sum(B) is what the local gradient must be scaled by BEFORE the all-reduce so that the
       data-parallel step equals the single-device step on the union minibatch (1.0 when every rank has the same B)."""
 
-    def __init__(self, device):
+    _host_group = None  # process-wide: a gloo group over all ranks for host-side agreement (created once, by every rank)
+
+    def __init__(self, device, host_side: Optional[bool] = None):
         self.weight = 1.0
         self._device = device if torch.device(device).type == "cuda" else "cpu"
+        self._host_side = host_side
+
+    @classmethod
+    def _host_side_group(cls):
+        """With NCCL the count exchange would be a device collective ordered BEHIND the kernels of the step before it, and
+        reading its result would stall the host once per step — the launch work of step i+1 could never overlap the device
+        work of step i.  The counts are host integers, so they are exchanged over a gloo group (host memory, no stream)."""
+        import torch.distributed as tdist
+
+        if cls._host_group is None:
+            cls._host_group = tdist.new_group(backend="gloo")
+        return cls._host_group
 
     def batches(self, batches: Iterator) -> Iterator:
         dist = _distributed()
@@ -188,6 +202,9 @@ class _RankSync:
         import torch.distributed as tdist
 
         world = dist.world_size()
+        host_side = self._host_side if self._host_side is not None else (tdist.get_backend() == "nccl")
+        group = self._host_side_group() if host_side else None
+        device = "cpu" if host_side else self._device
         it = iter(batches)
         while True:
             try:
@@ -195,9 +212,9 @@ class _RankSync:
                 local = len(item[1])  # (minibatch, raw datapoints)
             except StopIteration:
                 item, local = None, -1
-            mine = torch.tensor([local], dtype=torch.int64, device=self._device)
+            mine = torch.tensor([local], dtype=torch.int64, device=device)
             everyone = [torch.empty_like(mine) for _ in range(world)]
-            tdist.all_gather(everyone, mine)
+            tdist.all_gather(everyone, mine, group=group)
             sizes = [int(t.item()) for t in everyone]
             if min(sizes) < 0:
                 return

@@ -90,13 +90,19 @@ def _uneven_worker(rank: int, world: int, port: int, out_dir: str):
     starts = [[0, 5, 9, 20, 30], [4, 7, 12]][rank]
     my_batches = [(data[s: s + n], [None] * n) for s, n in zip(starts, sizes)]
     w = torch.nn.Parameter(torch.tensor([0.5, -1.0, 2.0]))
-    sync = _RankSync("cpu")
+    # host_side=True: the count exchange over the separate gloo group the trainer uses next to NCCL (here next to gloo)
+    sync = _RankSync("cpu", host_side=True)
+    assert _RankSync._host_group is None
     seen = []
     for x, raw in sync.batches(iter(my_batches)):
         w.grad = None
         ((x @ w) ** 2).mean().backward()           # local mean over the local graphs, like the model's losses
         _allreduce_dense_gradients([w], world, sync.weight)   # the per-step collective that would dead-lock on uneven epochs
         seen.append((len(raw), sync.weight, w.grad.clone()))
+    assert _RankSync._host_group is not None
+    # the default (device-side exchange on the main group, what a gloo run uses) gives the same schedule
+    again = [(len(raw), _s.weight) for _s in [_RankSync("cpu")] for x, raw in _s.batches(iter(my_batches))]
+    assert again == [(n, wgt) for n, wgt, _ in seen]
     torch.save(seen, os.path.join(out_dir, f"uneven{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
