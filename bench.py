@@ -668,7 +668,7 @@ def run_reference(args):
     edges = sum(len(src) for t in host_batches[0] for src, _ in t[0].adjacency_lists)
     config = workload_config(args, model, nodes, edges, max(1, args.gpus))
     del model, host_batches
-    warmup = min(args.warmup, 5)  # whole minibatches of ~15 s each on the host cores: bounded
+    warmup = min(args.warmup, 2)  # whole minibatches of ~15 s each on the host cores: bounded (the line prints what was run)
     base = cpu_train_entry(args.hidden, steps=args.steps, warmup=warmup, threads=args.cpu_threads)
     print(json.dumps({
         "impl": "reference",
